@@ -1,0 +1,84 @@
+"""Synthetic KITTI-shaped scan pairs -- input manufacture only, not the hot path."""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+_CSRC = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "csrc")
+_LIB = None
+
+
+def build_synth(force=False):
+    so = os.path.join(_CSRC, "libb200synth.so")
+    src = os.path.join(_CSRC, "synth.cpp")
+    if force or not os.path.exists(so) or os.path.getmtime(src) > os.path.getmtime(so):
+        subprocess.check_call(["/usr/bin/g++", "-O2", "-fopenmp", "-shared", "-fPIC", src, "-o", so])
+    return so
+
+
+def _lib():
+    global _LIB
+    if _LIB is None:
+        _LIB = C.CDLL(build_synth())
+    return _LIB
+
+
+def se3(yaw=0.0, pitch=0.0, roll=0.0, t=(0.0, 0.0, 0.0)):
+    cy, sy, cp, sp, cr, sr = np.cos(yaw), np.sin(yaw), np.cos(pitch), np.sin(pitch), np.cos(roll), np.sin(roll)
+    Rz = np.array([[cy, -sy, 0], [sy, cy, 0], [0, 0, 1.0]])
+    Ry = np.array([[cp, 0, sp], [0, 1, 0], [-sp, 0, cp]])
+    Rx = np.array([[1, 0, 0], [0, cr, -sr], [0, sr, cr]])
+    T = np.eye(4)
+    T[:3, :3] = Rz @ Ry @ Rx
+    T[:3, 3] = t
+    return T
+
+
+def scan(scene_seed, scan_seed, pose, n):
+    """n x 4 float32 (x, y, z, intensity) in the SENSOR frame."""
+    pose = np.ascontiguousarray(pose, np.float64)
+    out = np.empty((n, 4), np.float32)
+    rc = _lib().b200synth_scan(C.c_uint64(scene_seed), C.c_uint64(scan_seed), pose.ctypes.data_as(C.POINTER(C.c_double)),
+                               n, out.ctypes.data_as(C.POINTER(C.c_float)))
+    if rc != n:
+        raise RuntimeError("b200synth_scan failed: %d" % rc)
+    return out
+
+
+def to_map_frame(pts, T):
+    """utilities.hpp:164-175 transformPcd: double math, cast to float; keeps intensity."""
+    out = pts.copy()
+    out[:, :3] = (pts[:, :3].astype(np.float64) @ T[:3, :3].T + T[:3, 3]).astype(np.float32)
+    return out
+
+
+def make_pair(pair_seed, n_src, n_tgt=None, mode="gicp"):
+    """One loop-closure candidate pair in the common map frame.
+
+    dst = scan at true pose A; src = scan at true pose B = A * T_gt, placed in the map with an
+    odometry pose that drifted by D (mode "gicp": <= 0.5 m / 2 deg; "quatro": <= 10 m / 15 deg yaw).
+    Registration must return T ~= inv(D) (maps src onto dst).  Returns (src, dst, T_expected).
+    """
+    n_tgt = n_tgt or n_src
+    rng = np.random.default_rng(pair_seed)
+    A = se3(yaw=rng.uniform(-0.1, 0.1), t=(rng.uniform(-20, 20), rng.uniform(-1.5, 1.5), 1.73))
+    Tgt = se3(yaw=np.deg2rad(rng.uniform(-15, 15)), pitch=np.deg2rad(rng.uniform(-1, 1)),
+              roll=np.deg2rad(rng.uniform(-1, 1)), t=(rng.uniform(-3, 3), rng.uniform(-3, 3), rng.uniform(-0.2, 0.2)))
+    B = A @ Tgt
+    if mode == "gicp":
+        D = se3(yaw=np.deg2rad(rng.uniform(-2, 2)), pitch=np.deg2rad(rng.uniform(-0.3, 0.3)),
+                roll=np.deg2rad(rng.uniform(-0.3, 0.3)),
+                t=(rng.uniform(-0.35, 0.35), rng.uniform(-0.35, 0.35), rng.uniform(-0.05, 0.05)))
+    else:
+        D = se3(yaw=np.deg2rad(rng.uniform(-15, 15)), t=(rng.uniform(-7, 7), rng.uniform(-7, 7), rng.uniform(-0.3, 0.3)))
+    dst = to_map_frame(scan(pair_seed, 2 * pair_seed + 1, A, n_tgt), A)
+    src = to_map_frame(scan(pair_seed, 2 * pair_seed + 2, B, n_src), D @ B)
+    return src, dst, np.linalg.inv(D)
+
+
+def se3_error(T_est, T_ref):
+    """(rotation angle [rad], translation norm [m]) of inv(T_ref) * T_est."""
+    E = np.linalg.inv(T_ref) @ T_est
+    c = np.clip((np.trace(E[:3, :3]) - 1.0) / 2.0, -1.0, 1.0)
+    return float(np.arccos(c)), float(np.linalg.norm(E[:3, 3]))

@@ -1,0 +1,179 @@
+"""ctypes binding of the CPU oracle (oracle/liboracle.so) -- TEST INFRASTRUCTURE ONLY.
+
+Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference
+leg may import this module.  The product (fast-lio-sam-qn_b200/) never does.
+"""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB = None
+
+
+class GicpParams(C.Structure):
+    # effective defaults of the reference deployment
+    _fields_ = [("k_correspondences", C.c_int), ("max_iterations", C.c_int), ("max_corr_dist", C.c_double),
+                ("transformation_eps", C.c_double), ("rotation_eps", C.c_double), ("lm_max_iterations", C.c_int),
+                ("lm_init_lambda_factor", C.c_double)]
+
+    @staticmethod
+    def default():
+        return GicpParams(15, 32, 52.5, 0.01, 2e-3, 10, 1e-9)
+
+
+class GicpResult(C.Structure):
+    _fields_ = [("T", C.c_double * 16), ("Tf", C.c_float * 16), ("fitness", C.c_double), ("converged", C.c_int),
+                ("iterations", C.c_int), ("n_linearize", C.c_int), ("n_error", C.c_int), ("lm_failed", C.c_int),
+                ("pad", C.c_int), ("ms_build", C.c_double), ("ms_cov", C.c_double), ("ms_align", C.c_double),
+                ("ms_fitness", C.c_double)]
+
+
+def build(force=False):
+    """Compile liboracle.so (+ oracle/_ref when /root/reference is present)."""
+    so = os.path.join(_HERE, "liboracle.so")
+    srcs = [os.path.join(_HERE, f) for f in ("oracle_gicp.cpp", "oracle_quatro.cpp", "linalg.hpp", "Makefile")]
+    stale = force or not os.path.exists(so) or any(os.path.getmtime(s) > os.path.getmtime(so) for s in srcs)
+    if stale:
+        subprocess.check_call(["make", "-C", _HERE, "-s", "all"], stdout=subprocess.DEVNULL)
+    elif not os.path.exists(ref_so_path()) and os.path.exists("/root/reference"):
+        subprocess.check_call(["make", "-C", _HERE, "-s", "ref"], stdout=subprocess.DEVNULL)
+    return so
+
+
+def ref_so_path():
+    return os.path.join(_HERE, "_ref", "libref_nanoflann.so")
+
+
+def lib():
+    global _LIB
+    if _LIB is None:
+        _LIB = C.CDLL(build())
+        _LIB.orc_linearize.restype = C.c_double
+        _LIB.orc_num_threads.restype = C.c_int
+    return _LIB
+
+
+def _f32(a):
+    a = np.ascontiguousarray(a, dtype=np.float32)
+    assert a.ndim == 2 and a.shape[1] >= 3
+    return a
+
+
+def _p(a, t):
+    return a.ctypes.data_as(C.POINTER(t))
+
+
+def num_threads():
+    return lib().orc_num_threads()
+
+
+def use_ref_nanoflann(enable=True):
+    """Route the oracle's kNN through the reference's own nanoflann (oracle/_ref)."""
+    if not enable:
+        return lib().orc_use_ref_nanoflann(None)
+    p = ref_so_path()
+    if not os.path.exists(p):
+        return -1
+    return lib().orc_use_ref_nanoflann(p.encode())
+
+
+def knn(pts, queries, k, brute=False):
+    pts, queries = _f32(pts), _f32(queries)
+    idx = np.empty((len(queries), k), np.int32)
+    d2 = np.empty((len(queries), k), np.float32)
+    fn = lib().orc_knn_bruteforce if brute else lib().orc_knn
+    fn(_p(pts, C.c_float), len(pts), pts.shape[1], _p(queries, C.c_float), len(queries), queries.shape[1], k,
+       _p(idx, C.c_int), _p(d2, C.c_float))
+    return idx, d2
+
+
+class RefNanoflann:
+    """The reference's kd-tree (third_party/nano_gicp/.../nanoflann_impl.hpp) via oracle/_ref."""
+
+    def __init__(self, pts):
+        self.l = C.CDLL(ref_so_path())
+        self.l.ref_nf_build.restype = C.c_void_p
+        self.pts = _f32(pts)
+        self.h = C.c_void_p(self.l.ref_nf_build(_p(self.pts, C.c_float), len(self.pts), self.pts.shape[1]))
+
+    def knn(self, queries, k):
+        q = _f32(queries)
+        idx = np.empty((len(q), k), np.int32)
+        d2 = np.empty((len(q), k), np.float32)
+        self.l.ref_nf_knn(self.h, _p(q, C.c_float), len(q), q.shape[1], k, _p(idx, C.c_int), _p(d2, C.c_float))
+        return idx, d2
+
+    def __del__(self):
+        try:
+            self.l.ref_nf_free(self.h)
+        except Exception:
+            pass
+
+
+def covariances(pts, k=15, return_knn=False):
+    pts = _f32(pts)
+    cov = np.empty((len(pts), 3, 3), np.float64)
+    kidx = np.empty((len(pts), k), np.int32)
+    lib().orc_covariances(_p(pts, C.c_float), len(pts), pts.shape[1], k, _p(cov, C.c_double), _p(kidx, C.c_int))
+    return (cov, kidx) if return_knn else cov
+
+
+def transform_queries(T, pts):
+    pts = _f32(pts)
+    T = np.ascontiguousarray(T, np.float64)
+    out = np.empty((len(pts), 3), np.float32)
+    lib().orc_transform_queries(_p(T, C.c_double), _p(pts, C.c_float), len(pts), pts.shape[1], _p(out, C.c_float))
+    return out
+
+
+def transform_output(Tf, pts):
+    pts = _f32(pts)
+    Tf = np.ascontiguousarray(Tf, np.float32)
+    out = np.empty((len(pts), 3), np.float32)
+    lib().orc_transform_output(_p(Tf, C.c_float), _p(pts, C.c_float), len(pts), pts.shape[1], _p(out, C.c_float))
+    return out
+
+
+def linearize(src, tgt, cov_src, cov_tgt, T, max_corr_dist=52.5):
+    src, tgt = _f32(src), _f32(tgt)
+    cov_src = np.ascontiguousarray(cov_src, np.float64)
+    cov_tgt = np.ascontiguousarray(cov_tgt, np.float64)
+    T = np.ascontiguousarray(T, np.float64)
+    H = np.empty((6, 6), np.float64)
+    b = np.empty(6, np.float64)
+    corr = np.empty(len(src), np.int32)
+    sqd = np.empty(len(src), np.float32)
+    mah = np.empty((len(src), 3, 3), np.float64)
+    y = lib().orc_linearize(_p(src, C.c_float), len(src), src.shape[1], _p(tgt, C.c_float), len(tgt), tgt.shape[1],
+                            _p(cov_src, C.c_double), _p(cov_tgt, C.c_double), _p(T, C.c_double),
+                            C.c_double(max_corr_dist), _p(H, C.c_double), _p(b, C.c_double), _p(corr, C.c_int),
+                            _p(sqd, C.c_float), _p(mah, C.c_double))
+    return dict(H=H, b=b, err=y, corr=corr, sqd=sqd, mahal=mah)
+
+
+def gicp_align(src, tgt, params=None, guess=None, want_aligned=False, want_trace=False):
+    """LoopClosure::icpAlignment restated (fast_lio_sam_qn/src/loop_closure.cpp:110-136)."""
+    src, tgt = _f32(src), _f32(tgt)
+    prm = params or GicpParams.default()
+    res = GicpResult()
+    aligned = np.empty((len(src), 3), np.float32) if want_aligned else None
+    trace = np.zeros((prm.max_iterations, 64), np.float64) if want_trace else None
+    g = None if guess is None else np.ascontiguousarray(guess, np.float64)
+    rc = lib().orc_gicp_align(_p(src, C.c_float), len(src), src.shape[1], _p(tgt, C.c_float), len(tgt), tgt.shape[1],
+                              C.byref(prm), None if g is None else _p(g, C.c_double), C.byref(res),
+                              None if aligned is None else _p(aligned, C.c_float),
+                              None if trace is None else _p(trace, C.c_double), prm.max_iterations)
+    if rc != 0:
+        raise RuntimeError("orc_gicp_align failed: %d" % rc)
+    out = dict(T=np.array(res.T).reshape(4, 4), Tf=np.array(res.Tf, np.float32).reshape(4, 4), fitness=res.fitness,
+               converged=bool(res.converged), iterations=res.iterations, n_linearize=res.n_linearize,
+               n_error=res.n_error, lm_failed=bool(res.lm_failed), ms_build=res.ms_build, ms_cov=res.ms_cov,
+               ms_align=res.ms_align, ms_fitness=res.ms_fitness)
+    if want_aligned:
+        out["aligned"] = aligned
+    if want_trace:
+        out["trace"] = trace[:res.n_linearize]
+    return out
