@@ -1,0 +1,7 @@
+"""b200reg -- B200-native loop-closure registration engine (Nano-GICP + Quatro path of FAST-LIO-SAM-QN).
+
+Python here is plumbing only (ctypes over the C ABI in include/b200reg.h, synthetic inputs,
+torch.distributed sharding); the product is csrc/*.cu.
+"""
+from . import synth  # noqa: F401
+from .native import B200RegError, Context, GicpParams, Result, default_params  # noqa: F401

@@ -1,0 +1,212 @@
+"""ctypes binding of libb200reg.so -- the C ABI of include/b200reg.h.
+
+The product path: every call below lands in hand-written sm_100a kernels.  There is no CPU
+fallback; if the library or a GPU is missing these functions raise.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+from .build import LIB, build_native
+
+_lib = None
+
+
+class GicpParams(C.Structure):
+    _fields_ = [("k_correspondences", C.c_int32), ("max_iterations", C.c_int32), ("max_corr_dist", C.c_double),
+                ("transformation_eps", C.c_double), ("rotation_eps", C.c_double), ("lm_max_iterations", C.c_int32),
+                ("reserved", C.c_int32), ("lm_init_lambda_factor", C.c_double), ("icp_score_thr", C.c_double)]
+
+
+class Result(C.Structure):
+    _fields_ = [("T", C.c_double * 16), ("Tf", C.c_float * 16), ("fitness", C.c_double), ("converged", C.c_int32),
+                ("valid", C.c_int32), ("iterations", C.c_int32), ("n_linearize", C.c_int32), ("n_error", C.c_int32),
+                ("lm_failed", C.c_int32), ("status", C.c_int32), ("reserved", C.c_int32)]
+
+    def as_dict(self):
+        return dict(T=np.array(self.T).reshape(4, 4), Tf=np.array(self.Tf, np.float32).reshape(4, 4),
+                    fitness=self.fitness, converged=bool(self.converged), valid=bool(self.valid),
+                    iterations=self.iterations, n_linearize=self.n_linearize, n_error=self.n_error,
+                    lm_failed=bool(self.lm_failed), status=self.status)
+
+
+EXPORTS = [
+    "b200reg_default_gicp_params", "b200reg_last_error", "b200reg_version", "b200reg_ctx_create",
+    "b200reg_ctx_destroy", "b200reg_ctx_set_stream", "b200reg_ctx_synchronize", "b200reg_ctx_launch_count",
+    "b200reg_clouds_create", "b200reg_cloud_destroy", "b200reg_cloud_size", "b200reg_clouds_covariances",
+    "b200reg_gicp_align", "b200reg_icp_alignment", "b200reg_transform_cloud", "b200reg_knn",
+    "b200reg_get_covariances", "b200reg_linearize",
+]
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        path = LIB if os.path.exists(LIB) and not os.path.exists("/usr/local/cuda/bin/nvcc") else build_native()
+        _lib = C.CDLL(path)
+        _lib.b200reg_last_error.restype = C.c_char_p
+        _lib.b200reg_version.restype = C.c_char_p
+        _lib.b200reg_ctx_launch_count.restype = C.c_int64
+        _lib.b200reg_cloud_size.restype = C.c_size_t
+    return _lib
+
+
+class B200RegError(RuntimeError):
+    pass
+
+
+def _check(rc):
+    if rc != 0:
+        raise B200RegError("b200reg error %d: %s" % (rc, lib().b200reg_last_error().decode()))
+
+
+def default_params():
+    p = GicpParams()
+    lib().b200reg_default_gicp_params(C.byref(p))
+    return p
+
+
+def _pts(a):
+    a = np.ascontiguousarray(a, dtype=np.float32)
+    assert a.ndim == 2 and a.shape[1] >= 3
+    return a
+
+
+class Cloud:
+    def __init__(self, ctx, handle, n):
+        self.ctx, self.h, self.n = ctx, handle, n
+
+    def destroy(self):
+        if self.h:
+            lib().b200reg_cloud_destroy(self.ctx.h, self.h)
+            self.h = None
+
+
+class Context:
+    """One context per GPU rank / host thread (wraps b200reg_ctx)."""
+
+    def __init__(self, device=0):
+        self.h = C.c_void_p()
+        _check(lib().b200reg_ctx_create(int(device), C.byref(self.h)))
+
+    def close(self):
+        if self.h:
+            lib().b200reg_ctx_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def set_stream(self, cuda_stream_ptr):
+        _check(lib().b200reg_ctx_set_stream(self.h, C.c_void_p(cuda_stream_ptr)))
+
+    def synchronize(self):
+        _check(lib().b200reg_ctx_synchronize(self.h))
+
+    @property
+    def launch_count(self):
+        return int(lib().b200reg_ctx_launch_count(self.h))
+
+    # -- clouds ------------------------------------------------------------------------
+    def create_clouds(self, arrays):
+        """arrays: list of host float32 (n, >=3) arrays (strided records) -> list[Cloud]."""
+        arrs = [_pts(a) for a in arrays]
+        stride = arrs[0].shape[1] * 4
+        assert all(a.shape[1] * 4 == stride for a in arrs)
+        cnt = len(arrs)
+        ptrs = (C.c_void_p * cnt)(*[a.ctypes.data for a in arrs])
+        ns = (C.c_size_t * cnt)(*[len(a) for a in arrs])
+        outs = (C.c_void_p * cnt)()
+        _check(lib().b200reg_clouds_create(self.h, cnt, ptrs, ns, C.c_size_t(stride), 0, outs))
+        return [Cloud(self, C.c_void_p(outs[i]), len(arrs[i])) for i in range(cnt)]
+
+    def create_clouds_device(self, dev_ptrs, ns, stride_bytes):
+        cnt = len(dev_ptrs)
+        ptrs = (C.c_void_p * cnt)(*dev_ptrs)
+        nsa = (C.c_size_t * cnt)(*ns)
+        outs = (C.c_void_p * cnt)()
+        _check(lib().b200reg_clouds_create(self.h, cnt, ptrs, nsa, C.c_size_t(stride_bytes), 1, outs))
+        return [Cloud(self, C.c_void_p(outs[i]), ns[i]) for i in range(cnt)]
+
+    def covariances(self, clouds, k=15):
+        arr = (C.c_void_p * len(clouds))(*[c.h for c in clouds])
+        _check(lib().b200reg_clouds_covariances(self.h, len(clouds), arr, int(k)))
+
+    # -- registration ------------------------------------------------------------------
+    def gicp_align(self, srcs, tgts, params=None, guesses=None):
+        cnt = len(srcs)
+        prm = params or default_params()
+        sa = (C.c_void_p * cnt)(*[c.h for c in srcs])
+        ta = (C.c_void_p * cnt)(*[c.h for c in tgts])
+        res = (Result * cnt)()
+        g = None
+        if guesses is not None:
+            g = np.ascontiguousarray(guesses, np.float64).reshape(cnt, 16)
+        _check(lib().b200reg_gicp_align(self.h, cnt, sa, ta, None if g is None else g.ctypes.data_as(C.c_void_p),
+                                        C.byref(prm), res))
+        return [r.as_dict() for r in res]
+
+    def icp_alignment(self, src_arrays, tgt_arrays, params=None, raw=False):
+        """LoopClosure::icpAlignment for a batch of host (pinned or pageable) buffers."""
+        srcs = [_pts(a) for a in src_arrays]
+        tgts = [_pts(a) for a in tgt_arrays]
+        stride = srcs[0].shape[1] * 4
+        cnt = len(srcs)
+        prm = params or default_params()
+        sp = (C.c_void_p * cnt)(*[a.ctypes.data for a in srcs])
+        tp = (C.c_void_p * cnt)(*[a.ctypes.data for a in tgts])
+        sn = (C.c_size_t * cnt)(*[len(a) for a in srcs])
+        tn = (C.c_size_t * cnt)(*[len(a) for a in tgts])
+        res = (Result * cnt)()
+        _check(lib().b200reg_icp_alignment(self.h, cnt, sp, sn, tp, tn, C.c_size_t(stride), 0, C.byref(prm), res))
+        return res if raw else [r.as_dict() for r in res]
+
+    def icp_alignment_ptrs(self, src_ptrs, src_ns, tgt_ptrs, tgt_ns, stride_bytes, on_device, params=None):
+        """Same, from raw addresses (pinned host or device memory owned by the caller, e.g. torch tensors)."""
+        cnt = len(src_ptrs)
+        prm = params or default_params()
+        sp = (C.c_void_p * cnt)(*src_ptrs)
+        tp = (C.c_void_p * cnt)(*tgt_ptrs)
+        sn = (C.c_size_t * cnt)(*src_ns)
+        tn = (C.c_size_t * cnt)(*tgt_ns)
+        res = (Result * cnt)()
+        _check(lib().b200reg_icp_alignment(self.h, cnt, sp, sn, tp, tn, C.c_size_t(stride_bytes), int(bool(on_device)),
+                                           C.byref(prm), res))
+        return res
+
+    def transform_cloud(self, cloud, Tf):
+        Tf = np.ascontiguousarray(Tf, np.float32).reshape(16)
+        out = np.empty((cloud.n, 3), np.float32)
+        _check(lib().b200reg_transform_cloud(self.h, cloud.h, Tf.ctypes.data_as(C.c_void_p), out.ctypes.data_as(C.c_void_p)))
+        return out
+
+    # -- debug taps ----------------------------------------------------------------------
+    def knn(self, cloud, queries, k):
+        q = _pts(queries)
+        idx = np.empty((len(q), k), np.int32)
+        d2 = np.empty((len(q), k), np.float32)
+        _check(lib().b200reg_knn(self.h, cloud.h, q.ctypes.data_as(C.c_void_p), C.c_size_t(len(q)),
+                                 C.c_size_t(q.shape[1] * 4), int(k), idx.ctypes.data_as(C.c_void_p),
+                                 d2.ctypes.data_as(C.c_void_p)))
+        return idx, d2
+
+    def get_covariances(self, cloud):
+        out = np.empty((cloud.n, 3, 3), np.float64)
+        _check(lib().b200reg_get_covariances(self.h, cloud.h, out.ctypes.data_as(C.c_void_p)))
+        return out
+
+    def linearize(self, src, tgt, T, max_corr_dist=52.5):
+        T = np.ascontiguousarray(T, np.float64).reshape(16)
+        H = np.empty((6, 6), np.float64)
+        b = np.empty(6, np.float64)
+        err = C.c_double()
+        corr = np.empty(src.n, np.int32)
+        sqd = np.empty(src.n, np.float32)
+        _check(lib().b200reg_linearize(self.h, src.h, tgt.h, T.ctypes.data_as(C.c_void_p), C.c_double(max_corr_dist),
+                                       H.ctypes.data_as(C.c_void_p), b.ctypes.data_as(C.c_void_p), C.byref(err),
+                                       corr.ctypes.data_as(C.c_void_p), sqd.ctypes.data_as(C.c_void_p)))
+        return dict(H=H, b=b, err=err.value, corr=corr, sqd=sqd)

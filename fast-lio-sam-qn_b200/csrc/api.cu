@@ -1,0 +1,522 @@
+// api.cu -- the C ABI declared in include/b200reg.h: contexts, cloud objects, batched drivers.
+// Host orchestration only; every arithmetic step of the path runs in the kernels of
+// index_build.cu / gicp.cu.  There is no CPU fallback anywhere in this library.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/b200reg.h"
+#include "internal.cuh"
+
+namespace b200 {
+int launch_index_build(const CloudDev* d_clouds, int count, int max_n, int max_nlp, cudaStream_t s);
+int launch_covariances(const CloudDev* d_clouds, int count, int max_n, int k, cudaStream_t s);
+void launch_gicp_init(PairState* states, const double* d_guess, int count, const GicpParamsDev& prm, cudaStream_t s);
+void launch_gicp_step(const PairDev* pairs, PairState* states, int count, int max_n, const GicpParamsDev& prm,
+                      int* done_counter, cudaStream_t s);
+int launch_knn_queries(const CloudDev& c, const float* d_q, int nq, int qstride, int k, int* idx, float* d2, cudaStream_t s);
+void launch_transform_out(const CloudDev& c, const float* d_Tf, float* d_out3, cudaStream_t s);
+}  // namespace b200
+
+using namespace b200;
+
+static thread_local std::string g_err;
+static int fail(int code, const std::string& msg) {
+  g_err = msg;
+  return code;
+}
+#define CU(call)                                                                                              \
+  do {                                                                                                        \
+    cudaError_t _e = (call);                                                                                  \
+    if (_e != cudaSuccess)                                                                                    \
+      return fail(B200REG_ECUDA, std::string(#call) + ": " + cudaGetErrorString(_e) + " @" + __FILE__ + ":" + \
+                                     std::to_string(__LINE__));                                               \
+  } while (0)
+
+struct b200reg_ctx {
+  int device = 0;
+  cudaStream_t own_stream = nullptr;
+  cudaStream_t stream = nullptr;
+  int* d_done = nullptr;   // device counter of finished pairs
+  int* h_done = nullptr;   // pinned mirror
+  int64_t launches = 0;
+  int step_chunk = 8;      // step kernels issued between two host polls
+};
+
+struct b200reg_cloud {
+  CloudDev dev;            // device pointers + sizes
+  void* slab = nullptr;    // persistent allocation (pts, boxes, cov, rank)
+  bool has_cov = false;
+  int cov_k = 0;
+};
+
+static size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+extern "C" {
+
+void b200reg_default_gicp_params(b200reg_gicp_params* p) {
+  if (!p) return;
+  p->k_correspondences = 15;
+  p->max_iterations = 32;
+  p->max_corr_dist = 52.5;
+  p->transformation_eps = 0.01;
+  p->rotation_eps = 2e-3;
+  p->lm_max_iterations = 10;
+  p->reserved = 0;
+  p->lm_init_lambda_factor = 1e-9;
+  p->icp_score_thr = 1.5;
+}
+
+const char* b200reg_last_error(void) { return g_err.c_str(); }
+const char* b200reg_version(void) { return "b200reg 0.1 (sm_100a)"; }
+
+int b200reg_ctx_create(int device, b200reg_ctx** out) {
+  if (!out) return fail(B200REG_EINVAL, "out is NULL");
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0 || device < 0 || device >= ndev)
+    return fail(B200REG_ENODEV, "no usable CUDA device (this library has no CPU fallback)");
+  CU(cudaSetDevice(device));
+  b200reg_ctx* c = new b200reg_ctx;
+  c->device = device;
+  CU(cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking));
+  c->stream = c->own_stream;
+  cudaMemPool_t pool;
+  CU(cudaDeviceGetDefaultMemPool(&pool, device));
+  uint64_t thr = UINT64_MAX;
+  CU(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr));
+  CU(cudaMalloc(&c->d_done, sizeof(int)));
+  CU(cudaMallocHost(&c->h_done, sizeof(int)));
+  *out = c;
+  return B200REG_OK;
+}
+
+int b200reg_ctx_destroy(b200reg_ctx* c) {
+  if (!c) return B200REG_OK;
+  cudaSetDevice(c->device);
+  cudaStreamSynchronize(c->stream);
+  cudaFree(c->d_done);
+  cudaFreeHost(c->h_done);
+  cudaStreamDestroy(c->own_stream);
+  delete c;
+  return B200REG_OK;
+}
+
+int b200reg_ctx_set_stream(b200reg_ctx* c, void* s) {
+  if (!c) return fail(B200REG_EINVAL, "ctx is NULL");
+  c->stream = s ? (cudaStream_t)s : c->own_stream;
+  return B200REG_OK;
+}
+
+int b200reg_ctx_synchronize(b200reg_ctx* c) {
+  if (!c) return fail(B200REG_EINVAL, "ctx is NULL");
+  CU(cudaSetDevice(c->device));
+  CU(cudaStreamSynchronize(c->stream));
+  return B200REG_OK;
+}
+
+int64_t b200reg_ctx_launch_count(const b200reg_ctx* c) { return c ? c->launches : 0; }
+
+size_t b200reg_cloud_size(const b200reg_cloud* cl) { return cl ? (size_t)cl->dev.n : 0; }
+
+// ------------------------------------------------------------------------------------------
+int b200reg_clouds_create(b200reg_ctx* c, int count, const float* const* xyz, const size_t* n, size_t stride_bytes,
+                          int on_device, b200reg_cloud** out) {
+  if (!c || count <= 0 || !xyz || !n || !out) return fail(B200REG_EINVAL, "bad argument");
+  if (stride_bytes < 12 || stride_bytes % 4) return fail(B200REG_EINVAL, "stride_bytes must be a multiple of 4, >= 12");
+  for (int i = 0; i < count; i++)
+    if (!xyz[i] || n[i] == 0 || n[i] > (size_t)(1u << 26)) return fail(B200REG_EINVAL, "empty or oversized cloud");
+  CU(cudaSetDevice(c->device));
+  cudaStream_t s = c->stream;
+  std::vector<CloudDev> descs(count);
+  std::vector<void*> temps;  // freed (stream-ordered) after the build
+  int max_n = 0, max_nlp = 0;
+  for (int i = 0; i < count; i++) {
+    b200reg_cloud* cl = new b200reg_cloud;
+    CloudDev& d = cl->dev;
+    d.n = (int)n[i];
+    d.nl = (d.n + LEAF - 1) / LEAF;
+    d.nlp = 1;
+    d.depth = 0;
+    while (d.nlp < d.nl) {
+      d.nlp <<= 1;
+      d.depth++;
+    }
+    d.raw_stride = (int)(stride_bytes / 4);
+    const int ntiles = (d.n + SORT_TILE - 1) / SORT_TILE;
+    // persistent slab
+    size_t o_pts = 0;
+    size_t o_box = align_up(o_pts + (size_t)d.nl * LEAF * sizeof(float4), 256);
+    size_t o_cov = align_up(o_box + (size_t)4 * d.nlp * sizeof(float4), 256);
+    size_t o_rank = align_up(o_cov + (size_t)6 * d.n * sizeof(double), 256);
+    size_t total = align_up(o_rank + (size_t)d.n * sizeof(int), 256);
+    char* slab = nullptr;
+    CU(cudaMallocAsync((void**)&slab, total, s));
+    cl->slab = slab;
+    d.pts = (float4*)(slab + o_pts);
+    d.boxes = (float4*)(slab + o_box);
+    d.cov = (double*)(slab + o_cov);
+    d.rank = (int*)(slab + o_rank);
+    // temporary slab (sort buffers, histogram, flags, bbox, and the raw records when uploading)
+    size_t t_k0 = 0;
+    size_t t_k1 = align_up(t_k0 + (size_t)d.n * 4, 256);
+    size_t t_v0 = align_up(t_k1 + (size_t)d.n * 4, 256);
+    size_t t_v1 = align_up(t_v0 + (size_t)d.n * 4, 256);
+    size_t t_h = align_up(t_v1 + (size_t)d.n * 4, 256);
+    size_t t_f = align_up(t_h + (size_t)RADIX * ntiles * 4, 256);
+    size_t t_b = align_up(t_f + (size_t)d.nlp * 4, 256);
+    size_t t_raw = align_up(t_b + 32, 256);
+    size_t t_total = t_raw + (on_device ? 0 : align_up((size_t)d.n * stride_bytes, 256));
+    char* tmp = nullptr;
+    CU(cudaMallocAsync((void**)&tmp, t_total, s));
+    temps.push_back(tmp);
+    d.keys[0] = (uint32_t*)(tmp + t_k0);
+    d.keys[1] = (uint32_t*)(tmp + t_k1);
+    d.vals[0] = (uint32_t*)(tmp + t_v0);
+    d.vals[1] = (uint32_t*)(tmp + t_v1);
+    d.hist = (uint32_t*)(tmp + t_h);
+    d.flags = (uint32_t*)(tmp + t_f);
+    d.bbox = (float*)(tmp + t_b);
+    CU(cudaMemsetAsync(d.flags, 0, (size_t)d.nlp * 4, s));
+    if (on_device) {
+      d.raw = xyz[i];
+    } else {
+      CU(cudaMemcpyAsync(tmp + t_raw, xyz[i], (size_t)d.n * stride_bytes, cudaMemcpyHostToDevice, s));
+      d.raw = (const float*)(tmp + t_raw);
+    }
+    descs[i] = d;
+    out[i] = cl;
+    max_n = std::max(max_n, d.n);
+    max_nlp = std::max(max_nlp, d.nlp);
+  }
+  CloudDev* d_descs = nullptr;
+  CU(cudaMallocAsync((void**)&d_descs, sizeof(CloudDev) * count, s));
+  CU(cudaMemcpyAsync(d_descs, descs.data(), sizeof(CloudDev) * count, cudaMemcpyHostToDevice, s));
+  c->launches += launch_index_build(d_descs, count, max_n, max_nlp, s);
+  CU(cudaGetLastError());
+  CU(cudaFreeAsync(d_descs, s));
+  for (void* t : temps) CU(cudaFreeAsync(t, s));
+  for (int i = 0; i < count; i++) {  // the temporaries are gone once the build has run
+    CloudDev& d = out[i]->dev;
+    d.raw = nullptr;
+    d.keys[0] = d.keys[1] = d.vals[0] = d.vals[1] = d.hist = d.flags = nullptr;
+    d.bbox = nullptr;
+  }
+  return B200REG_OK;
+}
+
+int b200reg_cloud_destroy(b200reg_ctx* c, b200reg_cloud* cl) {
+  if (!cl) return B200REG_OK;
+  if (!c) return fail(B200REG_EINVAL, "ctx is NULL");
+  CU(cudaSetDevice(c->device));
+  if (cl->slab) CU(cudaFreeAsync(cl->slab, c->stream));
+  delete cl;
+  return B200REG_OK;
+}
+
+int b200reg_clouds_covariances(b200reg_ctx* c, int count, b200reg_cloud* const* clouds, int k) {
+  if (!c || count <= 0 || !clouds) return fail(B200REG_EINVAL, "bad argument");
+  if (k != 10 && k != 15 && k != 20) return fail(B200REG_EINVAL, "k_correspondences must be 10, 15 or 20 in this build");
+  CU(cudaSetDevice(c->device));
+  cudaStream_t s = c->stream;
+  std::vector<CloudDev> descs;
+  int max_n = 0;
+  for (int i = 0; i < count; i++) {
+    if (!clouds[i]) return fail(B200REG_EINVAL, "NULL cloud");
+    if (clouds[i]->has_cov && clouds[i]->cov_k == k) continue;
+    bool dup = false;
+    for (int j = 0; j < i; j++) dup |= clouds[j] == clouds[i];
+    if (dup) continue;
+    descs.push_back(clouds[i]->dev);
+    max_n = std::max(max_n, clouds[i]->dev.n);
+  }
+  if (descs.empty()) return B200REG_OK;
+  CloudDev* d_descs = nullptr;
+  CU(cudaMallocAsync((void**)&d_descs, sizeof(CloudDev) * descs.size(), s));
+  CU(cudaMemcpyAsync(d_descs, descs.data(), sizeof(CloudDev) * descs.size(), cudaMemcpyHostToDevice, s));
+  int l = launch_covariances(d_descs, (int)descs.size(), max_n, k, s);
+  if (l < 0) return fail(B200REG_EINVAL, "unsupported k");
+  c->launches += l;
+  CU(cudaGetLastError());
+  CU(cudaFreeAsync(d_descs, s));
+  for (int i = 0; i < count; i++) {
+    clouds[i]->has_cov = true;
+    clouds[i]->cov_k = k;
+  }
+  return B200REG_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+static GicpParamsDev to_dev(const b200reg_gicp_params& p) {
+  GicpParamsDev d;
+  d.max_iterations = p.max_iterations;
+  d.lm_max_iterations = p.lm_max_iterations;
+  d.max_corr_dist2 = p.max_corr_dist * p.max_corr_dist;
+  d.transformation_eps = p.transformation_eps;
+  d.rotation_eps = p.rotation_eps;
+  d.lm_init_lambda_factor = p.lm_init_lambda_factor;
+  d.icp_score_thr = p.icp_score_thr;
+  return d;
+}
+
+struct PairWork {
+  std::vector<PairDev> pairs;
+  std::vector<void*> slabs;
+  PairDev* d_pairs = nullptr;
+  PairState* d_states = nullptr;
+  int max_n = 0;
+};
+
+static int make_pair_work(b200reg_ctx* c, int count, b200reg_cloud* const* src, b200reg_cloud* const* tgt, PairWork& w) {
+  cudaStream_t s = c->stream;
+  w.pairs.resize(count);
+  for (int i = 0; i < count; i++) {
+    PairDev& p = w.pairs[i];
+    p.src = src[i]->dev;
+    p.tgt = tgt[i]->dev;
+    const int N = p.src.n;
+    const int nblk = (N + STEP_THREADS - 1) / STEP_THREADS;
+    size_t o_corr = 0;
+    size_t o_sqd = align_up(o_corr + (size_t)N * 4, 256);
+    size_t o_mah = align_up(o_sqd + (size_t)N * 4, 256);
+    size_t o_par = align_up(o_mah + (size_t)N * 6 * 8, 256);
+    size_t total = align_up(o_par + (size_t)nblk * NRED * 8, 256);
+    char* slab = nullptr;
+    CU(cudaMallocAsync((void**)&slab, total, s));
+    w.slabs.push_back(slab);
+    p.corr = (int*)(slab + o_corr);
+    p.sqd = (float*)(slab + o_sqd);
+    p.mahal = (double*)(slab + o_mah);
+    p.partial = (double*)(slab + o_par);
+    w.max_n = std::max(w.max_n, N);
+  }
+  CU(cudaMallocAsync((void**)&w.d_pairs, sizeof(PairDev) * count, s));
+  CU(cudaMallocAsync((void**)&w.d_states, sizeof(PairState) * count, s));
+  CU(cudaMemcpyAsync(w.d_pairs, w.pairs.data(), sizeof(PairDev) * count, cudaMemcpyHostToDevice, s));
+  return B200REG_OK;
+}
+
+static int free_pair_work(b200reg_ctx* c, PairWork& w) {
+  cudaStream_t s = c->stream;
+  for (void* p : w.slabs) CU(cudaFreeAsync(p, s));
+  if (w.d_pairs) CU(cudaFreeAsync(w.d_pairs, s));
+  if (w.d_states) CU(cudaFreeAsync(w.d_states, s));
+  w.slabs.clear();
+  w.d_pairs = nullptr;
+  w.d_states = nullptr;
+  return B200REG_OK;
+}
+
+int b200reg_gicp_align(b200reg_ctx* c, int count, b200reg_cloud* const* src, b200reg_cloud* const* tgt,
+                       const double* guess16, const b200reg_gicp_params* params, b200reg_result* out) {
+  if (!c || count <= 0 || !src || !tgt || !params || !out) return fail(B200REG_EINVAL, "bad argument");
+  CU(cudaSetDevice(c->device));
+  cudaStream_t s = c->stream;
+  int rc;
+  // covariances on demand (nano_gicp_impl.hpp:162-167)
+  {
+    std::vector<b200reg_cloud*> need;
+    for (int i = 0; i < count; i++) {
+      if (!src[i] || !tgt[i]) return fail(B200REG_EINVAL, "NULL cloud");
+      if (!src[i]->has_cov || src[i]->cov_k != params->k_correspondences) need.push_back(src[i]);
+      if (!tgt[i]->has_cov || tgt[i]->cov_k != params->k_correspondences) need.push_back(tgt[i]);
+    }
+    if (!need.empty() && (rc = b200reg_clouds_covariances(c, (int)need.size(), need.data(), params->k_correspondences)))
+      return rc;
+  }
+  PairWork w;
+  if ((rc = make_pair_work(c, count, src, tgt, w))) return rc;
+  const GicpParamsDev prm = to_dev(*params);
+  double* d_guess = nullptr;
+  if (guess16) {
+    CU(cudaMallocAsync((void**)&d_guess, sizeof(double) * 16 * count, s));
+    CU(cudaMemcpyAsync(d_guess, guess16, sizeof(double) * 16 * count, cudaMemcpyHostToDevice, s));
+  }
+  CU(cudaMemsetAsync(c->d_done, 0, sizeof(int), s));
+  launch_gicp_init(w.d_states, d_guess, count, prm, s);
+  c->launches++;
+  // worst case: every outer iteration burns lm_max_iterations trials, plus the fitness pass
+  const long max_steps = (long)std::max(params->max_iterations, 0) * (1 + std::max(params->lm_max_iterations, 1)) + 2;
+  long steps = 0;
+  for (;;) {
+    for (int j = 0; j < c->step_chunk; j++) {
+      launch_gicp_step(w.d_pairs, w.d_states, count, w.max_n, prm, c->d_done, s);
+      c->launches++;
+      steps++;
+    }
+    CU(cudaMemcpyAsync(c->h_done, c->d_done, sizeof(int), cudaMemcpyDeviceToHost, s));
+    CU(cudaStreamSynchronize(s));
+    if (*c->h_done >= count) break;
+    if (steps > max_steps) {
+      free_pair_work(c, w);
+      return fail(B200REG_ESTATE, "LM state machine did not terminate");
+    }
+  }
+  std::vector<PairState> states(count);
+  CU(cudaMemcpyAsync(states.data(), w.d_states, sizeof(PairState) * count, cudaMemcpyDeviceToHost, s));
+  CU(cudaStreamSynchronize(s));
+  for (int i = 0; i < count; i++) {
+    const PairState& st = states[i];
+    b200reg_result& r = out[i];
+    memset(&r, 0, sizeof(r));
+    for (int a = 0; a < 3; a++) {
+      for (int b = 0; b < 3; b++) r.T[4 * a + b] = st.R[3 * a + b];
+      r.T[4 * a + 3] = st.t[a];
+    }
+    r.T[15] = 1.0;
+    for (int a = 0; a < 12; a++) r.Tf[a] = st.Tf[a];
+    r.Tf[15] = 1.0f;
+    r.fitness = st.fitness;
+    r.converged = st.converged;
+    r.valid = (st.converged && st.fitness < params->icp_score_thr) ? 1 : 0;
+    r.iterations = st.nr_iterations;
+    r.n_linearize = st.n_lin;
+    r.n_error = st.n_err;
+    r.lm_failed = st.lm_failed;
+    r.status = 0;
+  }
+  if (d_guess) CU(cudaFreeAsync(d_guess, s));
+  return free_pair_work(c, w);
+}
+
+int b200reg_icp_alignment(b200reg_ctx* c, int count, const float* const* src_xyz, const size_t* src_n,
+                          const float* const* tgt_xyz, const size_t* tgt_n, size_t stride_bytes, int on_device,
+                          const b200reg_gicp_params* params, b200reg_result* out) {
+  if (!c || count <= 0 || !src_xyz || !src_n || !tgt_xyz || !tgt_n || !params || !out)
+    return fail(B200REG_EINVAL, "bad argument");
+  std::vector<const float*> ptrs(2 * count);
+  std::vector<size_t> ns(2 * count);
+  for (int i = 0; i < count; i++) {
+    ptrs[i] = src_xyz[i];
+    ns[i] = src_n[i];
+    ptrs[count + i] = tgt_xyz[i];
+    ns[count + i] = tgt_n[i];
+  }
+  std::vector<b200reg_cloud*> clouds(2 * count, nullptr);
+  int rc = b200reg_clouds_create(c, 2 * count, ptrs.data(), ns.data(), stride_bytes, on_device, clouds.data());
+  if (rc) return rc;
+  rc = b200reg_clouds_covariances(c, 2 * count, clouds.data(), params->k_correspondences);
+  if (!rc) rc = b200reg_gicp_align(c, count, clouds.data(), clouds.data() + count, nullptr, params, out);
+  for (b200reg_cloud* cl : clouds) b200reg_cloud_destroy(c, cl);
+  return rc;
+}
+
+int b200reg_transform_cloud(b200reg_ctx* c, const b200reg_cloud* cl, const float* Tf16, float* out_xyz) {
+  if (!c || !cl || !Tf16 || !out_xyz) return fail(B200REG_EINVAL, "bad argument");
+  CU(cudaSetDevice(c->device));
+  cudaStream_t s = c->stream;
+  float* d_T = nullptr;
+  float* d_out = nullptr;
+  CU(cudaMallocAsync((void**)&d_T, 64, s));
+  CU(cudaMallocAsync((void**)&d_out, (size_t)cl->dev.n * 12, s));
+  CU(cudaMemcpyAsync(d_T, Tf16, 64, cudaMemcpyHostToDevice, s));
+  launch_transform_out(cl->dev, d_T, d_out, s);
+  c->launches++;
+  CU(cudaMemcpyAsync(out_xyz, d_out, (size_t)cl->dev.n * 12, cudaMemcpyDeviceToHost, s));
+  CU(cudaStreamSynchronize(s));
+  CU(cudaFreeAsync(d_T, s));
+  CU(cudaFreeAsync(d_out, s));
+  return B200REG_OK;
+}
+
+// ---- debug taps --------------------------------------------------------------------------
+int b200reg_knn(b200reg_ctx* c, const b200reg_cloud* cl, const float* queries, size_t nq, size_t qstride_bytes, int k,
+                int32_t* idx_out, float* d2_out) {
+  if (!c || !cl || !queries || nq == 0 || k <= 0 || k > 20 || !idx_out || !d2_out || qstride_bytes < 12 || qstride_bytes % 4)
+    return fail(B200REG_EINVAL, "bad argument (k must be 1..20)");
+  CU(cudaSetDevice(c->device));
+  cudaStream_t s = c->stream;
+  float* d_q = nullptr;
+  int* d_idx = nullptr;
+  float* d_d2 = nullptr;
+  CU(cudaMallocAsync((void**)&d_q, nq * qstride_bytes, s));
+  CU(cudaMallocAsync((void**)&d_idx, nq * k * 4, s));
+  CU(cudaMallocAsync((void**)&d_d2, nq * k * 4, s));
+  CU(cudaMemcpyAsync(d_q, queries, nq * qstride_bytes, cudaMemcpyHostToDevice, s));
+  if (launch_knn_queries(cl->dev, d_q, (int)nq, (int)(qstride_bytes / 4), k, d_idx, d_d2, s) < 0)
+    return fail(B200REG_EINVAL, "unsupported k");
+  c->launches++;
+  CU(cudaGetLastError());
+  CU(cudaMemcpyAsync(idx_out, d_idx, nq * k * 4, cudaMemcpyDeviceToHost, s));
+  CU(cudaMemcpyAsync(d2_out, d_d2, nq * k * 4, cudaMemcpyDeviceToHost, s));
+  CU(cudaStreamSynchronize(s));
+  CU(cudaFreeAsync(d_q, s));
+  CU(cudaFreeAsync(d_idx, s));
+  CU(cudaFreeAsync(d_d2, s));
+  return B200REG_OK;
+}
+
+int b200reg_get_covariances(b200reg_ctx* c, const b200reg_cloud* cl, double* cov9_out) {
+  if (!c || !cl || !cov9_out) return fail(B200REG_EINVAL, "bad argument");
+  if (!cl->has_cov) return fail(B200REG_ESTATE, "covariances not computed");
+  CU(cudaSetDevice(c->device));
+  cudaStream_t s = c->stream;
+  const int n = cl->dev.n;
+  std::vector<double> cov((size_t)n * 6);
+  std::vector<float4> pts(n);
+  CU(cudaMemcpyAsync(cov.data(), cl->dev.cov, (size_t)n * 48, cudaMemcpyDeviceToHost, s));
+  CU(cudaMemcpyAsync(pts.data(), cl->dev.pts, (size_t)n * 16, cudaMemcpyDeviceToHost, s));
+  CU(cudaStreamSynchronize(s));
+  for (int p = 0; p < n; p++) {
+    int o;
+    memcpy(&o, &pts[p].w, 4);
+    const double* a = &cov[(size_t)p * 6];
+    double* m = &cov9_out[(size_t)o * 9];
+    m[0] = a[0]; m[1] = a[1]; m[2] = a[2];
+    m[3] = a[1]; m[4] = a[3]; m[5] = a[4];
+    m[6] = a[2]; m[7] = a[4]; m[8] = a[5];
+  }
+  return B200REG_OK;
+}
+
+int b200reg_linearize(b200reg_ctx* c, const b200reg_cloud* src, const b200reg_cloud* tgt, const double* T16,
+                      double max_corr_dist, double* H36, double* b6, double* err, int32_t* corr_out, float* sqd_out) {
+  if (!c || !src || !tgt || !T16) return fail(B200REG_EINVAL, "bad argument");
+  if (!src->has_cov || !tgt->has_cov) return fail(B200REG_ESTATE, "covariances not computed");
+  CU(cudaSetDevice(c->device));
+  cudaStream_t s = c->stream;
+  PairWork w;
+  b200reg_cloud* sp = const_cast<b200reg_cloud*>(src);
+  b200reg_cloud* tp = const_cast<b200reg_cloud*>(tgt);
+  int rc;
+  if ((rc = make_pair_work(c, 1, &sp, &tp, w))) return rc;
+  b200reg_gicp_params p;
+  b200reg_default_gicp_params(&p);
+  p.max_corr_dist = max_corr_dist;
+  const GicpParamsDev prm = to_dev(p);
+  double* d_guess = nullptr;
+  CU(cudaMallocAsync((void**)&d_guess, sizeof(double) * 16, s));
+  CU(cudaMemcpyAsync(d_guess, T16, sizeof(double) * 16, cudaMemcpyHostToDevice, s));
+  CU(cudaMemsetAsync(c->d_done, 0, sizeof(int), s));
+  launch_gicp_init(w.d_states, d_guess, 1, prm, s);
+  launch_gicp_step(w.d_pairs, w.d_states, 1, w.max_n, prm, c->d_done, s);  // exactly one linearize pass
+  c->launches += 2;
+  PairState st;
+  const int N = src->dev.n, M = tgt->dev.n;
+  std::vector<int> corr(N);
+  std::vector<float> sqd(N);
+  std::vector<float4> sp_pts(N), tp_pts(M);
+  CU(cudaMemcpyAsync(&st, w.d_states, sizeof(PairState), cudaMemcpyDeviceToHost, s));
+  CU(cudaMemcpyAsync(corr.data(), w.pairs[0].corr, (size_t)N * 4, cudaMemcpyDeviceToHost, s));
+  CU(cudaMemcpyAsync(sqd.data(), w.pairs[0].sqd, (size_t)N * 4, cudaMemcpyDeviceToHost, s));
+  CU(cudaMemcpyAsync(sp_pts.data(), src->dev.pts, (size_t)N * 16, cudaMemcpyDeviceToHost, s));
+  CU(cudaMemcpyAsync(tp_pts.data(), tgt->dev.pts, (size_t)M * 16, cudaMemcpyDeviceToHost, s));
+  CU(cudaStreamSynchronize(s));
+  if (H36) memcpy(H36, st.H, sizeof(double) * 36);
+  if (b6) memcpy(b6, st.b, sizeof(double) * 6);
+  if (err) *err = st.y0;
+  for (int p_ = 0; p_ < N; p_++) {
+    int o, to = -1;
+    memcpy(&o, &sp_pts[p_].w, 4);
+    if (corr[p_] >= 0) memcpy(&to, &tp_pts[corr[p_]].w, 4);
+    if (corr_out) corr_out[o] = to;
+    if (sqd_out) sqd_out[o] = sqd[p_];
+  }
+  CU(cudaFreeAsync(d_guess, s));
+  return free_pair_work(c, w);
+}
+
+}  // extern "C"

@@ -1,0 +1,553 @@
+// gicp.cu -- Nano-GICP on the GPU: k-NN covariances, the fused correspondence + Mahalanobis +
+// linearize pass, compute_error, fitness and the Levenberg-Marquardt controller, all batched
+// over pairs (blockIdx.y = pair) and driven by a per-pair device-side state machine so that the
+// host never synchronises inside an LM iteration.
+//
+// Reference behaviour being replaced (paths relative to /root/reference):
+//   third_party/nano_gicp/include/nano_gicp/impl/nano_gicp_impl.hpp
+//       calculate_covariances :298-357, update_correspondences :173-211, linearize :213-270,
+//       compute_error :272-296
+//   third_party/nano_gicp/include/nano_gicp/impl/lsq_registration_impl.hpp
+//       computeTransformation :88-115, is_converged :117-127, step_lm :160-208
+//   third_party/nano_gicp/include/nano_gicp/gicp/so3.hpp  so3_exp :99-118
+//   pcl::Registration::getFitnessScore (call site fast_lio_sam_qn/src/loop_closure.cpp:127)
+#include "internal.cuh"
+#include "knn.cuh"
+
+namespace b200 {
+
+// ---------------------------------------------------------------------------------------
+// small fp64 helpers
+// ---------------------------------------------------------------------------------------
+// eigenvector of the smallest eigenvalue of a symmetric 3x3 (cyclic Jacobi, fp64)
+__device__ __forceinline__ void sym3_smallest_evec(double a00, double a01, double a02, double a11, double a12,
+                                                   double a22, double n[3]) {
+  double A[3][3] = {{a00, a01, a02}, {a01, a11, a12}, {a02, a12, a22}};
+  double V[3][3] = {{1, 0, 0}, {0, 1, 0}, {0, 0, 1}};
+  for (int sweep = 0; sweep < 12; sweep++) {
+    double off = A[0][1] * A[0][1] + A[0][2] * A[0][2] + A[1][2] * A[1][2];
+    double dg = A[0][0] * A[0][0] + A[1][1] * A[1][1] + A[2][2] * A[2][2];
+    if (off <= 1e-34 * dg || off == 0.0) break;
+#pragma unroll
+    for (int pq = 0; pq < 3; pq++) {
+      const int p = pq == 2 ? 1 : 0;
+      const int q = pq == 0 ? 1 : 2;
+      const int r = 3 - p - q;
+      double apq = A[p][q];
+      if (apq == 0.0) continue;
+      double theta = (A[q][q] - A[p][p]) / (2.0 * apq);
+      double t = (theta >= 0 ? 1.0 : -1.0) / (fabs(theta) + sqrt(theta * theta + 1.0));
+      double c = 1.0 / sqrt(t * t + 1.0), s = t * c;
+      A[p][p] -= t * apq;
+      A[q][q] += t * apq;
+      A[p][q] = A[q][p] = 0.0;
+      double arp = A[r][p], arq = A[r][q];
+      A[r][p] = A[p][r] = c * arp - s * arq;
+      A[r][q] = A[q][r] = s * arp + c * arq;
+#pragma unroll
+      for (int k = 0; k < 3; k++) {
+        double vp = V[k][p], vq = V[k][q];
+        V[k][p] = c * vp - s * vq;
+        V[k][q] = s * vp + c * vq;
+      }
+    }
+  }
+  int m = 0;
+  double best = A[0][0];
+  if (A[1][1] < best) { best = A[1][1]; m = 1; }
+  if (A[2][2] < best) { m = 2; }
+  n[0] = m == 0 ? V[0][0] : (m == 1 ? V[0][1] : V[0][2]);
+  n[1] = m == 0 ? V[1][0] : (m == 1 ? V[1][1] : V[1][2]);
+  n[2] = m == 0 ? V[2][0] : (m == 1 ? V[2][1] : V[2][2]);
+}
+
+// inverse of a symmetric 3x3 given as (xx,xy,xz,yy,yz,zz); result in the same packing
+__device__ __forceinline__ void sym3_inverse(const double a[6], double o[6]) {
+  double c00 = a[3] * a[5] - a[4] * a[4];
+  double c01 = a[2] * a[4] - a[1] * a[5];
+  double c02 = a[1] * a[4] - a[2] * a[3];
+  double det = a[0] * c00 + a[1] * c01 + a[2] * c02;
+  double id = 1.0 / det;
+  o[0] = c00 * id;
+  o[1] = c01 * id;
+  o[2] = c02 * id;
+  o[3] = (a[0] * a[5] - a[2] * a[2]) * id;
+  o[4] = (a[1] * a[2] - a[0] * a[4]) * id;
+  o[5] = (a[0] * a[3] - a[1] * a[1]) * id;
+}
+
+// R C R^T for symmetric C (packed) and row-major R; packed symmetric result
+__device__ __forceinline__ void rcrt(const double R[9], const double c[6], double o[6]) {
+  const double C[3][3] = {{c[0], c[1], c[2]}, {c[1], c[3], c[4]}, {c[2], c[4], c[5]}};
+  double RC[3][3];
+#pragma unroll
+  for (int i = 0; i < 3; i++)
+#pragma unroll
+    for (int j = 0; j < 3; j++) RC[i][j] = R[3 * i] * C[0][j] + R[3 * i + 1] * C[1][j] + R[3 * i + 2] * C[2][j];
+  int k = 0;
+#pragma unroll
+  for (int i = 0; i < 3; i++)
+#pragma unroll
+    for (int j = i; j < 3; j++) o[k++] = RC[i][0] * R[3 * j] + RC[i][1] * R[3 * j + 1] + RC[i][2] * R[3 * j + 2];
+}
+
+// solve (H + lambda I) x = -b, symmetric 6x6, unpivoted LDL^T
+__device__ void solve6(const double H[36], double lambda, const double b[6], double x[6]) {
+  double L[6][6], D[6];
+  for (int j = 0; j < 6; j++) {
+    double dj = H[7 * j] + lambda;
+    for (int k = 0; k < j; k++) dj -= L[j][k] * L[j][k] * D[k];
+    D[j] = dj;
+    for (int i = j + 1; i < 6; i++) {
+      double v = H[6 * i + j];
+      for (int k = 0; k < j; k++) v -= L[i][k] * L[j][k] * D[k];
+      L[i][j] = dj != 0.0 ? v / dj : 0.0;
+    }
+  }
+  double y[6];
+  for (int i = 0; i < 6; i++) {
+    double s = -b[i];
+    for (int k = 0; k < i; k++) s -= L[i][k] * y[k];
+    y[i] = s;
+  }
+  for (int i = 0; i < 6; i++) y[i] = D[i] != 0.0 ? y[i] / D[i] : 0.0;
+  for (int i = 5; i >= 0; i--) {
+    double s = y[i];
+    for (int k = i + 1; k < 6; k++) s -= L[k][i] * x[k];
+    x[i] = s;
+  }
+}
+
+// so3_exp (so3.hpp:99-118) + Quaternion::toRotationMatrix
+__device__ void so3_exp_matrix(const double w[3], double R[9]) {
+  double theta_sq = w[0] * w[0] + w[1] * w[1] + w[2] * w[2];
+  double imag, real;
+  if (theta_sq < 1e-10) {
+    double q4 = theta_sq * theta_sq;
+    imag = 0.5 - 1.0 / 48.0 * theta_sq + 1.0 / 3840.0 * q4;
+    real = 1.0 - 1.0 / 8.0 * theta_sq + 1.0 / 384.0 * q4;
+  } else {
+    double theta = sqrt(theta_sq), half = 0.5 * theta;
+    imag = sin(half) / theta;
+    real = cos(half);
+  }
+  double qw = real, qx = imag * w[0], qy = imag * w[1], qz = imag * w[2];
+  double tx = 2 * qx, ty = 2 * qy, tz = 2 * qz;
+  double twx = tx * qw, twy = ty * qw, twz = tz * qw;
+  double txx = tx * qx, txy = ty * qx, txz = tz * qx;
+  double tyy = ty * qy, tyz = tz * qy, tzz = tz * qz;
+  R[0] = 1 - (tyy + tzz); R[1] = txy - twz;       R[2] = txz + twy;
+  R[3] = txy + twz;       R[4] = 1 - (txx + tzz); R[5] = tyz - twx;
+  R[6] = txz - twy;       R[7] = tyz + twx;       R[8] = 1 - (txx + tyy);
+}
+
+__device__ bool delta_converged(const PairState* st, const GicpParamsDev& prm) {
+  double mr = 0, mt = 0;
+  for (int i = 0; i < 9; i++) mr = fmax(mr, fabs(st->dR[i] - ((i % 4) == 0 ? 1.0 : 0.0)) / prm.rotation_eps);
+  for (int i = 0; i < 3; i++) mt = fmax(mt, fabs(st->dt[i]) / prm.transformation_eps);
+  return fmax(mr, mt) < 1.0;
+}
+
+// ---------------------------------------------------------------------------------------
+// LM controller, executed by ONE thread of the last-arriving block of a pair.
+// ---------------------------------------------------------------------------------------
+__device__ void lm_prepare_trial(PairState* st) {
+  solve6(st->H, st->lambda, st->b, st->d);
+  so3_exp_matrix(st->d, st->dR);
+  st->dt[0] = st->d[3]; st->dt[1] = st->d[4]; st->dt[2] = st->d[5];
+  for (int i = 0; i < 3; i++) {
+    for (int j = 0; j < 3; j++)
+      st->Rt[3 * i + j] = st->dR[3 * i] * st->R[j] + st->dR[3 * i + 1] * st->R[3 + j] + st->dR[3 * i + 2] * st->R[6 + j];
+    st->tt[i] = st->dR[3 * i] * st->t[0] + st->dR[3 * i + 1] * st->t[1] + st->dR[3 * i + 2] * st->t[2] + st->dt[i];
+  }
+  st->phase = PH_TRIAL;
+}
+
+__device__ void lm_finish(PairState* st, int converged) {
+  st->converged = converged;
+  for (int r = 0; r < 3; r++) {
+    for (int c = 0; c < 3; c++) st->Tf[4 * r + c] = (float)st->R[3 * r + c];
+    st->Tf[4 * r + 3] = (float)st->t[r];
+  }
+  st->phase = PH_FITNESS;
+}
+
+__device__ void lm_update(PairState* st, const double* sums, const GicpParamsDev& prm, int phase, int n_src,
+                          int* done_counter) {
+  if (phase == PH_LINEARIZE) {
+    int k = 0;
+    for (int i = 0; i < 6; i++)
+      for (int j = i; j < 6; j++) {
+        st->H[6 * i + j] = sums[k];
+        st->H[6 * j + i] = sums[k];
+        k++;
+      }
+    for (int i = 0; i < 6; i++) st->b[i] = sums[21 + i];
+    st->y0 = sums[27];
+    st->n_lin++;
+    st->nr_iterations = st->outer_it;
+    if (st->lambda < 0.0) {
+      double mx = 0;
+      for (int i = 0; i < 6; i++) mx = fmax(mx, fabs(st->H[7 * i]));
+      st->lambda = prm.lm_init_lambda_factor * mx;
+    }
+    st->nu = 2.0;
+    st->inner_it = 0;
+    lm_prepare_trial(st);
+  } else if (phase == PH_TRIAL) {
+    const double yi = sums[0];
+    st->n_err++;
+    double denom = 0;
+    for (int i = 0; i < 6; i++) denom += st->d[i] * (st->lambda * st->d[i] - st->b[i]);
+    const double rho = (st->y0 - yi) / denom;
+    if (rho < 0) {
+      if (delta_converged(st, prm)) {
+        lm_finish(st, 1);  // step_lm returns true without touching x0; the caller then sees converged
+        return;
+      }
+      st->lambda = st->nu * st->lambda;
+      st->nu = 2 * st->nu;
+      st->inner_it++;
+      if (st->inner_it >= prm.lm_max_iterations) {
+        st->lm_failed = 1;  // "lm not converged!!"
+        lm_finish(st, 0);
+        return;
+      }
+      lm_prepare_trial(st);
+      return;
+    }
+    for (int i = 0; i < 9; i++) st->R[i] = st->Rt[i];
+    for (int i = 0; i < 3; i++) st->t[i] = st->tt[i];
+    const double x = 2 * rho - 1;
+    st->lambda = st->lambda * fmax(1.0 / 3.0, 1 - x * x * x);
+    if (delta_converged(st, prm)) {
+      lm_finish(st, 1);
+      return;
+    }
+    st->outer_it++;
+    if (st->outer_it >= prm.max_iterations) {
+      lm_finish(st, 0);
+      return;
+    }
+    st->phase = PH_LINEARIZE;
+  } else if (phase == PH_FITNESS) {
+    st->fitness = n_src > 0 ? sums[0] / (double)n_src : 0.0;
+    st->phase = PH_DONE;
+    atomicAdd(done_counter, 1);
+  }
+}
+
+__global__ void k_gicp_init(PairState* states, const double* guess16, int count, GicpParamsDev prm) {
+  int p = blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= count) return;
+  PairState* st = &states[p];
+  for (int i = 0; i < 3; i++) {
+    for (int j = 0; j < 3; j++) st->R[3 * i + j] = guess16 ? guess16[16 * p + 4 * i + j] : (i == j ? 1.0 : 0.0);
+    st->t[i] = guess16 ? guess16[16 * p + 4 * i + 3] : 0.0;
+  }
+  st->lambda = -1.0;
+  st->nu = 2.0;
+  st->y0 = 0.0;
+  st->fitness = 0.0;
+  st->phase = PH_LINEARIZE;
+  st->outer_it = 0;
+  st->inner_it = 0;
+  st->converged = 0;
+  st->lm_failed = 0;
+  st->n_lin = 0;
+  st->n_err = 0;
+  st->nr_iterations = 0;
+  st->arrive = 0;
+  if (prm.max_iterations <= 0) lm_finish(st, 0);
+}
+
+// ---------------------------------------------------------------------------------------
+// K2: 15-NN + covariance + PLANE regularisation (nano_gicp_impl.hpp:298-357).
+// For symmetric PSD input U diag(1,1,eps) V^T == I - (1-eps) n n^T with n the eigenvector of
+// the smallest eigenvalue, so only n is computed.
+// ---------------------------------------------------------------------------------------
+template <int K>
+__global__ void __launch_bounds__(STEP_THREADS) k_covariance(const CloudDev* clouds) {
+  const CloudDev& c = clouds[blockIdx.y];
+  const int i = blockIdx.x * STEP_THREADS + threadIdx.x;
+  if (i >= c.n) return;
+  const float4 q = c.pts[i];
+  KnnSet<K> res;
+  res.init();
+  knn_search<K>(c, q.x, q.y, q.z, res);
+  double mx = 0, my = 0, mz = 0;
+  double px[K], py[K], pz[K];
+#pragma unroll
+  for (int j = 0; j < K; j++) {
+    float4 p = res.p[j] >= 0 ? c.pts[res.p[j]] : make_float4(0.f, 0.f, 0.f, 0.f);
+    px[j] = res.p[j] >= 0 ? (double)p.x : 0.0;
+    py[j] = res.p[j] >= 0 ? (double)p.y : 0.0;
+    pz[j] = res.p[j] >= 0 ? (double)p.z : 0.0;
+    mx += px[j]; my += py[j]; mz += pz[j];
+  }
+  mx /= K; my /= K; mz /= K;
+  double cxx = 0, cxy = 0, cxz = 0, cyy = 0, cyz = 0, czz = 0;
+#pragma unroll
+  for (int j = 0; j < K; j++) {
+    if (res.p[j] < 0) continue;
+    double dx = px[j] - mx, dy = py[j] - my, dz = pz[j] - mz;
+    cxx += dx * dx; cxy += dx * dy; cxz += dx * dz; cyy += dy * dy; cyz += dy * dz; czz += dz * dz;
+  }
+  const double ik = 1.0 / K;
+  cxx *= ik; cxy *= ik; cxz *= ik; cyy *= ik; cyz *= ik; czz *= ik;
+  double n[3];
+  sym3_smallest_evec(cxx, cxy, cxz, cyy, cyz, czz, n);
+  const double w = 1.0 - 1e-3;
+  double* o = c.cov + (size_t)i * 6;
+  o[0] = 1.0 - w * n[0] * n[0];
+  o[1] = -w * n[0] * n[1];
+  o[2] = -w * n[0] * n[2];
+  o[3] = 1.0 - w * n[1] * n[1];
+  o[4] = -w * n[1] * n[2];
+  o[5] = 1.0 - w * n[2] * n[2];
+}
+
+// ---------------------------------------------------------------------------------------
+// K3/K4/K5 in one kernel, selected by the pair's phase (uniform per block):
+//   PH_LINEARIZE: q = T_f p (fp32), exact 1-NN, gate, M = (C_B + R C_A R^T)^-1, e, J,
+//                 accumulate H (21), b (6), e^T M e                      [update_correspondences + linearize]
+//   PH_TRIAL:     e^T M e at the trial pose with the stale correspondences / M      [compute_error]
+//   PH_FITNESS:   1-NN d^2 of the fp32-transformed source                           [getFitnessScore]
+// Block partials go to HBM; the last block to arrive sums them in a fixed order (deterministic,
+// SURVEY App. A.6) and runs the LM controller, so no host round trip is needed per iteration.
+// ---------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(STEP_THREADS) k_gicp_step(const PairDev* pairs, PairState* states, GicpParamsDev prm,
+                                                             int* done_counter) {
+  const PairDev& P = pairs[blockIdx.y];
+  PairState* st = &states[blockIdx.y];
+  const int N = P.src.n;
+  const int nblk = (N + STEP_THREADS - 1) / STEP_THREADS;
+  if ((int)blockIdx.x >= nblk) return;
+  const int phase = st->phase;
+  if (phase == PH_DONE) return;
+
+  __shared__ double s_T[12];
+  __shared__ float s_Tf[12];
+  __shared__ double s_red[STEP_THREADS / 32][NRED];
+  __shared__ bool s_last;
+  if (threadIdx.x < 12) {
+    const int r = threadIdx.x / 4, cc = threadIdx.x % 4;
+    double v;
+    if (phase == PH_TRIAL) v = cc < 3 ? st->Rt[3 * r + cc] : st->tt[r];
+    else v = cc < 3 ? st->R[3 * r + cc] : st->t[r];
+    s_T[threadIdx.x] = v;
+    s_Tf[threadIdx.x] = phase == PH_FITNESS ? st->Tf[threadIdx.x] : (float)v;
+  }
+  __syncthreads();
+
+  const int i = blockIdx.x * STEP_THREADS + threadIdx.x;
+  const int nred = phase == PH_LINEARIZE ? NRED : 1;
+  double v[NRED];
+#pragma unroll
+  for (int k = 0; k < NRED; k++) v[k] = 0.0;
+
+  if (i < N) {
+    const float4 p = P.src.pts[i];
+    if (phase == PH_LINEARIZE) {
+      // trans_f * p, summation order ((r0 x + r1 y) + r2 z) + t, no fma
+      const float qx = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(s_Tf[0], p.x), __fmul_rn(s_Tf[1], p.y)), __fmul_rn(s_Tf[2], p.z)), s_Tf[3]);
+      const float qy = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(s_Tf[4], p.x), __fmul_rn(s_Tf[5], p.y)), __fmul_rn(s_Tf[6], p.z)), s_Tf[7]);
+      const float qz = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(s_Tf[8], p.x), __fmul_rn(s_Tf[9], p.y)), __fmul_rn(s_Tf[10], p.z)), s_Tf[11]);
+      KnnSet<1> res;
+      res.init();
+      knn_search<1>(P.tgt, qx, qy, qz, res);
+      const int pos = ((double)res.d[0] < prm.max_corr_dist2) ? res.p[0] : -1;
+      P.corr[i] = pos;
+      P.sqd[i] = res.d[0];
+      if (pos >= 0) {
+        double R[9];
+#pragma unroll
+        for (int r = 0; r < 3; r++)
+#pragma unroll
+          for (int c = 0; c < 3; c++) R[3 * r + c] = s_T[4 * r + c];
+        double ca[6], cb[6], rcr[6], M[6];
+        const double2* pa = reinterpret_cast<const double2*>(P.src.cov + (size_t)i * 6);
+        const double2* pb = reinterpret_cast<const double2*>(P.tgt.cov + (size_t)pos * 6);
+#pragma unroll
+        for (int k = 0; k < 3; k++) {
+          double2 a = pa[k], b = __ldg(&pb[k]);
+          ca[2 * k] = a.x; ca[2 * k + 1] = a.y;
+          cb[2 * k] = b.x; cb[2 * k + 1] = b.y;
+        }
+        rcrt(R, ca, rcr);
+#pragma unroll
+        for (int k = 0; k < 6; k++) rcr[k] += cb[k];
+        sym3_inverse(rcr, M);
+        double2* pm = reinterpret_cast<double2*>(P.mahal + (size_t)i * 6);
+        pm[0] = make_double2(M[0], M[1]);
+        pm[1] = make_double2(M[2], M[3]);
+        pm[2] = make_double2(M[4], M[5]);
+        const float4 pbt = __ldg(&P.tgt.pts[pos]);
+        const double ax = p.x, ay = p.y, az = p.z;
+        const double ta[3] = {R[0] * ax + R[1] * ay + R[2] * az + s_T[3], R[3] * ax + R[4] * ay + R[5] * az + s_T[7],
+                              R[6] * ax + R[7] * ay + R[8] * az + s_T[11]};
+        const double e[3] = {(double)pbt.x - ta[0], (double)pbt.y - ta[1], (double)pbt.z - ta[2]};
+        const double Mf[3][3] = {{M[0], M[1], M[2]}, {M[1], M[3], M[4]}, {M[2], M[4], M[5]}};
+        double Me[3];
+#pragma unroll
+        for (int r = 0; r < 3; r++) Me[r] = Mf[r][0] * e[0] + Mf[r][1] * e[1] + Mf[r][2] * e[2];
+        // J = [skew(T a) | -I]
+        const double J[3][6] = {{0.0, -ta[2], ta[1], -1.0, 0.0, 0.0}, {ta[2], 0.0, -ta[0], 0.0, -1.0, 0.0}, {-ta[1], ta[0], 0.0, 0.0, 0.0, -1.0}};
+        double MJ[3][6];
+#pragma unroll
+        for (int r = 0; r < 3; r++)
+#pragma unroll
+          for (int c = 0; c < 6; c++) MJ[r][c] = Mf[r][0] * J[0][c] + Mf[r][1] * J[1][c] + Mf[r][2] * J[2][c];
+        int k = 0;
+#pragma unroll
+        for (int r = 0; r < 6; r++)
+#pragma unroll
+          for (int c = r; c < 6; c++) v[k++] = J[0][r] * MJ[0][c] + J[1][r] * MJ[1][c] + J[2][r] * MJ[2][c];
+#pragma unroll
+        for (int r = 0; r < 6; r++) v[21 + r] = J[0][r] * Me[0] + J[1][r] * Me[1] + J[2][r] * Me[2];
+        v[27] = e[0] * Me[0] + e[1] * Me[1] + e[2] * Me[2];
+      }
+    } else if (phase == PH_TRIAL) {
+      const int pos = P.corr[i];
+      if (pos >= 0) {
+        const float4 pbt = __ldg(&P.tgt.pts[pos]);
+        const double ax = p.x, ay = p.y, az = p.z;
+        const double e0 = (double)pbt.x - (s_T[0] * ax + s_T[1] * ay + s_T[2] * az + s_T[3]);
+        const double e1 = (double)pbt.y - (s_T[4] * ax + s_T[5] * ay + s_T[6] * az + s_T[7]);
+        const double e2 = (double)pbt.z - (s_T[8] * ax + s_T[9] * ay + s_T[10] * az + s_T[11]);
+        const double2* pm = reinterpret_cast<const double2*>(P.mahal + (size_t)i * 6);
+        const double2 m01 = pm[0], m23 = pm[1], m45 = pm[2];
+        const double Me0 = m01.x * e0 + m01.y * e1 + m23.x * e2;
+        const double Me1 = m01.y * e0 + m23.y * e1 + m45.x * e2;
+        const double Me2 = m23.x * e0 + m45.x * e1 + m45.y * e2;
+        v[0] = e0 * Me0 + e1 * Me1 + e2 * Me2;
+      }
+    } else {  // PH_FITNESS: pcl::transformPointCloud fp32 order x*c0 + (y*c1 + (z*c2 + c3)), then 1-NN
+      const float qx = __fadd_rn(__fmul_rn(s_Tf[0], p.x), __fadd_rn(__fmul_rn(s_Tf[1], p.y), __fadd_rn(__fmul_rn(s_Tf[2], p.z), s_Tf[3])));
+      const float qy = __fadd_rn(__fmul_rn(s_Tf[4], p.x), __fadd_rn(__fmul_rn(s_Tf[5], p.y), __fadd_rn(__fmul_rn(s_Tf[6], p.z), s_Tf[7])));
+      const float qz = __fadd_rn(__fmul_rn(s_Tf[8], p.x), __fadd_rn(__fmul_rn(s_Tf[9], p.y), __fadd_rn(__fmul_rn(s_Tf[10], p.z), s_Tf[11])));
+      KnnSet<1> res;
+      res.init();
+      knn_search<1>(P.tgt, qx, qy, qz, res);
+      v[0] = (double)res.d[0];
+    }
+  }
+
+  // warp shuffle reduction -> shared -> block partial (fixed order)
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+  for (int k = 0; k < NRED; k++) {
+    if (k < nred) {
+      double x = v[k];
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) x += __shfl_down_sync(0xffffffffu, x, o);
+      if (lane == 0) s_red[warp][k] = x;
+    }
+  }
+  __syncthreads();
+  if ((int)threadIdx.x < nred) {
+    double x = 0;
+#pragma unroll
+    for (int w = 0; w < STEP_THREADS / 32; w++) x += s_red[w][threadIdx.x];
+    P.partial[(size_t)blockIdx.x * NRED + threadIdx.x] = x;
+    __threadfence();
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const unsigned prev = atomicAdd(&st->arrive, 1u);
+    s_last = (prev == (unsigned)(nblk - 1));
+  }
+  __syncthreads();
+  if (!s_last) return;
+  __threadfence();
+  // last block: deterministic sum over blocks (4 interleaved chains, then a fixed 4-way add)
+  {
+    const int j = threadIdx.x & 31, g = threadIdx.x >> 5;
+    double x = 0;
+    if (j < nred)
+      for (int b = g; b < nblk; b += STEP_THREADS / 32) x += __ldcg(&P.partial[(size_t)b * NRED + j]);
+    __syncthreads();
+    if (j < NRED) s_red[g][j] = x;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      double sums[NRED];
+      for (int k = 0; k < nred; k++) {
+        double s = 0;
+        for (int w = 0; w < STEP_THREADS / 32; w++) s += s_red[w][k];
+        sums[k] = s;
+      }
+      st->arrive = 0;
+      lm_update(st, sums, prm, phase, N, done_counter);
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------
+// debug tap: k-NN of arbitrary queries, results as ORIGINAL indices
+// ---------------------------------------------------------------------------------------
+template <int K>
+__global__ void __launch_bounds__(STEP_THREADS) k_knn_queries(CloudDev c, const float* q, int nq, int qstride, int kout, int* idx_out,
+                                                               float* d2_out) {
+  int i = blockIdx.x * STEP_THREADS + threadIdx.x;
+  if (i >= nq) return;
+  const float* qq = q + (size_t)i * qstride;
+  KnnSet<K> res;
+  res.init();
+  knn_search<K>(c, qq[0], qq[1], qq[2], res);
+#pragma unroll
+  for (int j = 0; j < K; j++) {
+    if (j < kout) {
+      idx_out[(size_t)i * kout + j] = res.p[j] >= 0 ? __float_as_int(c.pts[res.p[j]].w) : -1;
+      d2_out[(size_t)i * kout + j] = res.d[j];
+    }
+  }
+}
+
+// output cloud: final fp32 transform in the pcl::transformPointCloud order, ORIGINAL point order
+__global__ void __launch_bounds__(256) k_transform_out(CloudDev c, const float* Tf, float* out3) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= c.n) return;
+  const float4 p = c.pts[i];
+  const int o = __float_as_int(p.w);
+#pragma unroll
+  for (int r = 0; r < 3; r++)
+    out3[(size_t)o * 3 + r] = __fadd_rn(__fmul_rn(Tf[4 * r], p.x), __fadd_rn(__fmul_rn(Tf[4 * r + 1], p.y), __fadd_rn(__fmul_rn(Tf[4 * r + 2], p.z), Tf[4 * r + 3])));
+}
+
+// ---------------------------------------------------------------------------------------
+// host launchers
+// ---------------------------------------------------------------------------------------
+int launch_covariances(const CloudDev* d_clouds, int count, int max_n, int k, cudaStream_t s) {
+  dim3 grid((max_n + STEP_THREADS - 1) / STEP_THREADS, count);
+  if (k == 15) k_covariance<15><<<grid, STEP_THREADS, 0, s>>>(d_clouds);
+  else if (k == 20) k_covariance<20><<<grid, STEP_THREADS, 0, s>>>(d_clouds);
+  else if (k == 10) k_covariance<10><<<grid, STEP_THREADS, 0, s>>>(d_clouds);
+  else return -1;
+  return 1;
+}
+
+void launch_gicp_init(PairState* states, const double* d_guess, int count, const GicpParamsDev& prm, cudaStream_t s) {
+  k_gicp_init<<<(count + 63) / 64, 64, 0, s>>>(states, d_guess, count, prm);
+}
+
+void launch_gicp_step(const PairDev* pairs, PairState* states, int count, int max_n, const GicpParamsDev& prm,
+                      int* done_counter, cudaStream_t s) {
+  dim3 grid((max_n + STEP_THREADS - 1) / STEP_THREADS, count);
+  k_gicp_step<<<grid, STEP_THREADS, 0, s>>>(pairs, states, prm, done_counter);
+}
+
+int launch_knn_queries(const CloudDev& c, const float* d_q, int nq, int qstride, int k, int* idx, float* d2, cudaStream_t s) {
+  dim3 grid((nq + STEP_THREADS - 1) / STEP_THREADS);
+  if (k == 1) k_knn_queries<1><<<grid, STEP_THREADS, 0, s>>>(c, d_q, nq, qstride, k, idx, d2);
+  else if (k <= 10) k_knn_queries<10><<<grid, STEP_THREADS, 0, s>>>(c, d_q, nq, qstride, k, idx, d2);
+  else if (k <= 15) k_knn_queries<15><<<grid, STEP_THREADS, 0, s>>>(c, d_q, nq, qstride, k, idx, d2);
+  else if (k <= 20) k_knn_queries<20><<<grid, STEP_THREADS, 0, s>>>(c, d_q, nq, qstride, k, idx, d2);
+  else return -1;
+  return 1;
+}
+
+void launch_transform_out(const CloudDev& c, const float* d_Tf, float* d_out3, cudaStream_t s) {
+  k_transform_out<<<(c.n + 255) / 256, 256, 0, s>>>(c, d_Tf, d_out3);
+}
+
+}  // namespace b200

@@ -1,0 +1,271 @@
+// index_build.cu -- batched spatial-index build (replaces the serial nanoflann kd-tree build,
+// third_party/nano_gicp/include/nano_gicp/impl/nanoflann_impl.hpp:1199-1211, 867-1012, which the
+// reference runs twice per pair plus PCL's hidden third FLANN build).
+//
+// B200-first design: instead of a top-down pointer tree, every cloud becomes a Morton-sorted
+// point array with an implicit complete binary tree of AABBs over fixed 8-point leaves
+// (one leaf = one 128-byte line).  All clouds of a batch are built together: blockIdx.y is
+// the cloud.  Steps: bbox (atomic min/max) -> 30-bit Morton keys -> stable LSD radix sort
+// (4 x 8 bit; stable => the layout, and with it every later reduction order, is deterministic)
+// -> gather into float4 (w carries the original index) -> bottom-up AABB tree with arrival flags.
+#include "internal.cuh"
+
+namespace b200 {
+
+// ------------------------------------------------------------------------------------
+__global__ void k_bbox_init(const CloudDev* clouds) {
+  const CloudDev& c = clouds[blockIdx.x];
+  if (threadIdx.x < 3) ((int*)c.bbox)[threadIdx.x] = f2ord(INFINITY);
+  else if (threadIdx.x < 6) ((int*)c.bbox)[threadIdx.x] = f2ord(-INFINITY);
+}
+
+__global__ void __launch_bounds__(256) k_bbox(const CloudDev* clouds) {
+  const CloudDev& c = clouds[blockIdx.y];
+  float mn[3] = {INFINITY, INFINITY, INFINITY}, mx[3] = {-INFINITY, -INFINITY, -INFINITY};
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < c.n; i += gridDim.x * blockDim.x) {
+    const float* p = c.raw + (size_t)i * c.raw_stride;
+#pragma unroll
+    for (int d = 0; d < 3; d++) {
+      float v = p[d];
+      mn[d] = fminf(mn[d], v);
+      mx[d] = fmaxf(mx[d], v);
+    }
+  }
+#pragma unroll
+  for (int d = 0; d < 3; d++)
+    for (int o = 16; o > 0; o >>= 1) {
+      mn[d] = fminf(mn[d], __shfl_xor_sync(0xffffffffu, mn[d], o));
+      mx[d] = fmaxf(mx[d], __shfl_xor_sync(0xffffffffu, mx[d], o));
+    }
+  if ((threadIdx.x & 31) == 0 && blockIdx.x * blockDim.x < c.n) {
+#pragma unroll
+    for (int d = 0; d < 3; d++) {
+      atomicMin(&((int*)c.bbox)[d], f2ord(mn[d]));
+      atomicMax(&((int*)c.bbox)[3 + d], f2ord(mx[d]));
+    }
+  }
+}
+
+__device__ __forceinline__ uint32_t expand10(uint32_t v) {
+  v &= 0x3FFu;
+  v = (v | (v << 16)) & 0x030000FFu;
+  v = (v | (v << 8)) & 0x0300F00Fu;
+  v = (v | (v << 4)) & 0x030C30C3u;
+  v = (v | (v << 2)) & 0x09249249u;
+  return v;
+}
+
+__global__ void __launch_bounds__(256) k_morton(const CloudDev* clouds) {
+  const CloudDev& c = clouds[blockIdx.y];
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= c.n) return;
+  const int* bb = (const int*)c.bbox;
+  float lo[3] = {ord2f(bb[0]), ord2f(bb[1]), ord2f(bb[2])};
+  float ext = fmaxf(fmaxf(ord2f(bb[3]) - lo[0], ord2f(bb[4]) - lo[1]), ord2f(bb[5]) - lo[2]);
+  float scale = ext > 0.f ? 1023.0f / ext : 0.f;  // cubic cells: one scale for all axes
+  const float* p = c.raw + (size_t)i * c.raw_stride;
+  uint32_t q[3];
+#pragma unroll
+  for (int d = 0; d < 3; d++) {
+    float f = (p[d] - lo[d]) * scale;
+    int v = (int)f;
+    q[d] = (uint32_t)min(max(v, 0), 1023);
+  }
+  c.keys[0][i] = (expand10(q[2]) << 2) | (expand10(q[1]) << 1) | expand10(q[0]);
+  c.vals[0][i] = (uint32_t)i;
+}
+
+// ---- stable LSD radix sort, one 8-bit digit per pass --------------------------------
+// pass p reads keys[p&1], writes keys[(p+1)&1].
+__global__ void __launch_bounds__(SORT_THREADS) k_sort_hist(const CloudDev* clouds, int pass) {
+  const CloudDev& c = clouds[blockIdx.y];
+  const int base = blockIdx.x * SORT_TILE;
+  if (base >= c.n) return;
+  __shared__ uint32_t h[RADIX];
+  h[threadIdx.x] = 0;
+  __syncthreads();
+  const uint32_t* keys = c.keys[pass & 1];
+  const int shift = pass * RADIX_BITS;
+#pragma unroll
+  for (int j = 0; j < SORT_ITEMS; j++) {
+    int i = base + j * SORT_THREADS + threadIdx.x;
+    if (i < c.n) atomicAdd(&h[(keys[i] >> shift) & (RADIX - 1)], 1u);
+  }
+  __syncthreads();
+  const int ntiles = (c.n + SORT_TILE - 1) / SORT_TILE;
+  c.hist[threadIdx.x * ntiles + blockIdx.x] = h[threadIdx.x];  // digit-major
+}
+
+// exclusive scan of the digit-major (digit, tile) table: one block per cloud
+__global__ void __launch_bounds__(1024) k_sort_scan(const CloudDev* clouds) {
+  const CloudDev& c = clouds[blockIdx.x];
+  const int ntiles = (c.n + SORT_TILE - 1) / SORT_TILE;
+  const int total = RADIX * ntiles;
+  __shared__ uint32_t warp_sums[32];
+  __shared__ uint32_t carry;
+  if (threadIdx.x == 0) carry = 0;
+  __syncthreads();
+  for (int base = 0; base < total; base += 1024) {
+    int i = base + threadIdx.x;
+    uint32_t v = i < total ? c.hist[i] : 0u;
+    uint32_t incl = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      uint32_t t = __shfl_up_sync(0xffffffffu, incl, o);
+      if ((threadIdx.x & 31) >= o) incl += t;
+    }
+    if ((threadIdx.x & 31) == 31) warp_sums[threadIdx.x >> 5] = incl;
+    __syncthreads();
+    if (threadIdx.x < 32) {
+      uint32_t w = warp_sums[threadIdx.x];
+      uint32_t wi = w;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        uint32_t t = __shfl_up_sync(0xffffffffu, wi, o);
+        if (threadIdx.x >= o) wi += t;
+      }
+      warp_sums[threadIdx.x] = wi - w;  // exclusive
+    }
+    __syncthreads();
+    uint32_t excl = carry + warp_sums[threadIdx.x >> 5] + incl - v;
+    if (i < total) c.hist[i] = excl;
+    __syncthreads();
+    if (threadIdx.x == 1023) carry = excl + v;
+    __syncthreads();
+  }
+}
+
+__global__ void __launch_bounds__(SORT_THREADS) k_sort_scatter(const CloudDev* clouds, int pass) {
+  const CloudDev& c = clouds[blockIdx.y];
+  const int base = blockIdx.x * SORT_TILE;
+  if (base >= c.n) return;
+  constexpr int NW = SORT_THREADS / 32;
+  __shared__ uint32_t cnt[NW][RADIX];
+  for (int j = threadIdx.x; j < NW * RADIX; j += SORT_THREADS) (&cnt[0][0])[j] = 0;
+  __syncthreads();
+  const uint32_t* keys = c.keys[pass & 1];
+  const uint32_t* vals = c.vals[pass & 1];
+  uint32_t* okeys = c.keys[(pass + 1) & 1];
+  uint32_t* ovals = c.vals[(pass + 1) & 1];
+  const int shift = pass * RADIX_BITS;
+  const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t lt = (1u << lane) - 1u;
+  // warp w owns the contiguous run [base + w*32*ITEMS, +32*ITEMS): round r, lane l -> key r*32+l,
+  // so (warp, round, lane) order == key order and the ranks below are stable.
+  uint32_t key[SORT_ITEMS], val[SORT_ITEMS], rk[SORT_ITEMS];
+#pragma unroll
+  for (int r = 0; r < SORT_ITEMS; r++) {
+    int i = base + (w * SORT_ITEMS + r) * 32 + lane;
+    bool ok = i < c.n;
+    key[r] = ok ? keys[i] : 0xFFFFFFFFu;
+    val[r] = ok ? vals[i] : 0u;
+    uint32_t dig = ok ? ((key[r] >> shift) & (RADIX - 1)) : RADIX;  // RADIX = "invalid"
+    uint32_t m = __match_any_sync(0xffffffffu, dig);
+    uint32_t old = ok ? cnt[w][dig] : 0u;
+    __syncwarp();
+    if (ok && (m & lt) == 0) cnt[w][dig] = old + __popc(m);
+    __syncwarp();
+    rk[r] = old + __popc(m & lt);
+  }
+  __syncthreads();
+  {  // per digit: exclusive prefix over warps + the global (digit, tile) offset
+    const int ntiles = (c.n + SORT_TILE - 1) / SORT_TILE;
+    uint32_t run = c.hist[threadIdx.x * ntiles + blockIdx.x];
+#pragma unroll
+    for (int ww = 0; ww < NW; ww++) {
+      uint32_t t = cnt[ww][threadIdx.x];
+      cnt[ww][threadIdx.x] = run;
+      run += t;
+    }
+  }
+  __syncthreads();
+#pragma unroll
+  for (int r = 0; r < SORT_ITEMS; r++) {
+    int i = base + (w * SORT_ITEMS + r) * 32 + lane;
+    if (i < c.n) {
+      uint32_t dig = (key[r] >> shift) & (RADIX - 1);
+      uint32_t dst = cnt[w][dig] + rk[r];
+      okeys[dst] = key[r];
+      ovals[dst] = val[r];
+    }
+  }
+}
+
+// sorted float4 array (w = original index), inverse permutation, +inf padding of the last leaf
+__global__ void __launch_bounds__(256) k_gather(const CloudDev* clouds, int final_buf) {
+  const CloudDev& c = clouds[blockIdx.y];
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  const int npad = c.nl * LEAF;
+  if (i >= npad) return;
+  if (i < c.n) {
+    uint32_t o = c.vals[final_buf][i];
+    const float* p = c.raw + (size_t)o * c.raw_stride;
+    c.pts[i] = make_float4(p[0], p[1], p[2], __int_as_float((int)o));
+    c.rank[o] = i;
+  } else {
+    c.pts[i] = make_float4(INFINITY, INFINITY, INFINITY, __int_as_float(-1));
+  }
+}
+
+// one thread per (padded) leaf: leaf AABB, then walk up; the second arrival at a parent merges.
+__global__ void __launch_bounds__(256) k_tree(const CloudDev* clouds) {
+  const CloudDev& c = clouds[blockIdx.y];
+  int l = blockIdx.x * blockDim.x + threadIdx.x;
+  if (l >= c.nlp) return;
+  float lo[3] = {INFINITY, INFINITY, INFINITY}, hi[3] = {-INFINITY, -INFINITY, -INFINITY};
+  if (l < c.nl) {
+#pragma unroll
+    for (int j = 0; j < LEAF; j++) {
+      float4 p = c.pts[l * LEAF + j];
+      if (l * LEAF + j < c.n) {
+        lo[0] = fminf(lo[0], p.x); hi[0] = fmaxf(hi[0], p.x);
+        lo[1] = fminf(lo[1], p.y); hi[1] = fmaxf(hi[1], p.y);
+        lo[2] = fminf(lo[2], p.z); hi[2] = fmaxf(hi[2], p.z);
+      }
+    }
+  }
+  int id = c.nlp + l;
+  volatile float4* vb = c.boxes;
+  for (;;) {
+    c.boxes[2 * id] = make_float4(lo[0], lo[1], lo[2], 0.f);
+    c.boxes[2 * id + 1] = make_float4(hi[0], hi[1], hi[2], 0.f);
+    if (id == 1) break;
+    __threadfence();
+    int parent = id >> 1;
+    if (atomicAdd(&c.flags[parent], 1u) == 0u) break;  // sibling not there yet
+    __threadfence();
+    int sib = id ^ 1;
+    float4 slo, shi;
+    slo.x = vb[2 * sib].x; slo.y = vb[2 * sib].y; slo.z = vb[2 * sib].z;
+    shi.x = vb[2 * sib + 1].x; shi.y = vb[2 * sib + 1].y; shi.z = vb[2 * sib + 1].z;
+    lo[0] = fminf(lo[0], slo.x); lo[1] = fminf(lo[1], slo.y); lo[2] = fminf(lo[2], slo.z);
+    hi[0] = fmaxf(hi[0], shi.x); hi[1] = fmaxf(hi[1], shi.y); hi[2] = fmaxf(hi[2], shi.z);
+    id = parent;
+  }
+}
+
+// ------------------------------------------------------------------------------------
+// host launcher: builds `count` clouds whose descriptors are already in device memory.
+// Returns the number of kernel launches issued.
+int launch_index_build(const CloudDev* d_clouds, int count, int max_n, int max_nlp, cudaStream_t s) {
+  int launches = 0;
+  k_bbox_init<<<count, 32, 0, s>>>(d_clouds); launches++;
+  {
+    int gx = min((max_n + 255) / 256, 296);
+    k_bbox<<<dim3(gx, count), 256, 0, s>>>(d_clouds); launches++;
+  }
+  k_morton<<<dim3((max_n + 255) / 256, count), 256, 0, s>>>(d_clouds); launches++;
+  const int ntiles = (max_n + SORT_TILE - 1) / SORT_TILE;
+  const int npass = 4;  // 30-bit keys
+  for (int p = 0; p < npass; p++) {
+    k_sort_hist<<<dim3(ntiles, count), SORT_THREADS, 0, s>>>(d_clouds, p);
+    k_sort_scan<<<count, 1024, 0, s>>>(d_clouds);
+    k_sort_scatter<<<dim3(ntiles, count), SORT_THREADS, 0, s>>>(d_clouds, p);
+    launches += 3;
+  }
+  k_gather<<<dim3((max_nlp * LEAF + 255) / 256, count), 256, 0, s>>>(d_clouds, npass & 1); launches++;
+  k_tree<<<dim3((max_nlp + 255) / 256, count), 256, 0, s>>>(d_clouds); launches++;
+  return launches;
+}
+
+}  // namespace b200

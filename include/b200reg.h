@@ -1,0 +1,135 @@
+/* b200reg.h -- C ABI of the B200-native loop-closure registration engine.
+ *
+ * This is the drop-in boundary for the ONE hot path of engcang/FAST-LIO-SAM-QN that
+ * this repository replaces: the registration that FastLioSamQn::loopTimerFunc
+ * (fast_lio_sam_qn/src/fast_lio_sam_qn.cpp:203-252) reaches through
+ * LoopClosure::performLoopClosure (fast_lio_sam_qn/src/loop_closure.cpp:168-205), i.e.
+ * everything behind nano_gicp::NanoGICP<PointType,PointType>
+ * (third_party/nano_gicp/include/nano_gicp/nano_gicp.hpp:58-137) and quatro<PointType>
+ * (third_party/Quatro/include/quatro/quatro_module.h:19-37).
+ *
+ * The reference has no FFI: both libraries are linked C++ templates.  The host-side
+ * facade classes in fast-lio-sam-qn_b200/host/ keep those class surfaces and call the
+ * functions below; INTEGRATION.md shows the binding.
+ *
+ * Conventions
+ *   - every function returns 0 on success, a negative B200REG_E* code otherwise; nothing
+ *     throws across this boundary;
+ *   - all 4x4 matrices are ROW-MAJOR (Eigen is column-major: the facade transposes);
+ *   - a context is bound to one CUDA device and one stream; use one context per host
+ *     thread / per GPU rank (LoopClosure itself is single-instance and not re-entrant,
+ *     fast_lio_sam_qn/src/fast_lio_sam_qn.cpp:81);
+ *   - point buffers are (x, y, z [, ...]) fp32 records `stride_bytes` apart, so
+ *     pcl::PointXYZI (32 B: x,y,z,1,intensity,pad) uploads without repacking;
+ *   - there is NO CPU fallback: if no sm_100 device is present b200reg_ctx_create fails.
+ */
+#ifndef B200REG_H
+#define B200REG_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define B200REG_OK 0
+#define B200REG_EINVAL (-1)   /* bad argument */
+#define B200REG_ECUDA (-2)    /* CUDA runtime error (see b200reg_last_error) */
+#define B200REG_ENODEV (-3)   /* no usable GPU */
+#define B200REG_ESTATE (-4)   /* call order violated (e.g. align before covariances) */
+#define B200REG_ENCCL (-5)    /* collective layer error */
+
+typedef struct b200reg_ctx b200reg_ctx;
+typedef struct b200reg_cloud b200reg_cloud;
+
+/* Mirrors NanoGICPConfig (fast_lio_sam_qn/include/loop_closure.h:25-36) + the LsqRegistration
+ * constructor defaults (third_party/nano_gicp/include/nano_gicp/impl/lsq_registration_impl.hpp:49-63). */
+typedef struct b200reg_gicp_params {
+  int32_t k_correspondences;     /* setCorrespondenceRandomness, loop_closure.cpp:10 (15)   */
+  int32_t max_iterations;        /* setMaximumIterations, loop_closure.cpp:11 (32)          */
+  double max_corr_dist;          /* setMaxCorrespondenceDistance, loop_closure.cpp:13 (52.5)*/
+  double transformation_eps;     /* setTransformationEpsilon, loop_closure.cpp:14 (0.01)    */
+  double rotation_eps;           /* lsq_registration_impl.hpp:53 (2e-3)                     */
+  int32_t lm_max_iterations;     /* lsq_registration_impl.hpp:58 (10)                       */
+  int32_t reserved;
+  double lm_init_lambda_factor;  /* lsq_registration_impl.hpp:59 (1e-9)                     */
+  double icp_score_thr;          /* validity gate, loop_closure.cpp:129 (config.yaml:21: 1.5) */
+} b200reg_gicp_params;
+
+/* RegistrationOutput (fast_lio_sam_qn/include/loop_closure.h:64-70) plus solver telemetry. */
+typedef struct b200reg_result {
+  double T[16];        /* final SE(3), fp64, row-major: maps src onto dst                      */
+  float Tf[16];        /* x0.cast<float>() -- what getFinalTransformation() returns            */
+  double fitness;      /* getFitnessScore(): mean 1-NN d^2 over ALL source points              */
+  int32_t converged;   /* hasConverged()                                                       */
+  int32_t valid;       /* converged && fitness < icp_score_thr (loop_closure.cpp:129)          */
+  int32_t iterations;  /* nr_iterations_ (index of the last outer iteration)                   */
+  int32_t n_linearize; /* number of linearize() passes (= 1-NN passes)                         */
+  int32_t n_error;     /* number of compute_error() passes                                     */
+  int32_t lm_failed;   /* "lm not converged!!" (lsq_registration_impl.hpp:105-108)             */
+  int32_t status;      /* 0 ok; <0 error for this pair                                         */
+  int32_t reserved;
+} b200reg_result;
+
+void b200reg_default_gicp_params(b200reg_gicp_params* p);
+const char* b200reg_last_error(void);
+const char* b200reg_version(void);
+
+/* ---- context ---------------------------------------------------------------------- */
+int b200reg_ctx_create(int device, b200reg_ctx** out);
+int b200reg_ctx_destroy(b200reg_ctx* ctx);
+/* Use an externally owned CUDA stream (cudaStream_t passed as void*); NULL = the context's own. */
+int b200reg_ctx_set_stream(b200reg_ctx* ctx, void* cuda_stream);
+int b200reg_ctx_synchronize(b200reg_ctx* ctx);
+/* Number of kernels this context has launched so far (bench.py reports it as gpu_launches). */
+int64_t b200reg_ctx_launch_count(const b200reg_ctx* ctx);
+
+/* ---- clouds: replaces KdTreeFLANN::setInputCloud / buildIndex
+ *      (third_party/nano_gicp/include/nano_gicp/nanoflann.hpp:131-138) ----------------- */
+/* Upload `count` clouds (host or device pointers) and build their spatial indices in one
+ * batched pass.  on_device != 0: the xyz pointers are device pointers (no H2D copy).      */
+int b200reg_clouds_create(b200reg_ctx* ctx, int count, const float* const* xyz, const size_t* n,
+                          size_t stride_bytes, int on_device, b200reg_cloud** out);
+int b200reg_cloud_destroy(b200reg_ctx* ctx, b200reg_cloud* cloud);
+size_t b200reg_cloud_size(const b200reg_cloud* cloud);
+
+/* NanoGICP::calculateSourceCovariances / calculateTargetCovariances
+ * (third_party/nano_gicp/include/nano_gicp/impl/nano_gicp_impl.hpp:151-159, 298-357), batched. */
+int b200reg_clouds_covariances(b200reg_ctx* ctx, int count, b200reg_cloud* const* clouds, int k);
+
+/* ---- registration ----------------------------------------------------------------- */
+/* pcl::Registration::align + getFitnessScore + hasConverged + getFinalTransformation for
+ * `count` (src, tgt) pairs at once (call sites fast_lio_sam_qn/src/loop_closure.cpp:124-133).
+ * guess16: count x 16 doubles row-major, or NULL for identity (the reference always uses identity).
+ * Covariances are computed on demand if a cloud has none (nano_gicp_impl.hpp:162-167).       */
+int b200reg_gicp_align(b200reg_ctx* ctx, int count, b200reg_cloud* const* src, b200reg_cloud* const* tgt,
+                       const double* guess16, const b200reg_gicp_params* params, b200reg_result* out);
+
+/* LoopClosure::icpAlignment (loop_closure.cpp:110-136) in one call, raw buffers in, results out:
+ * index build x2, covariances x2, align, fitness, validity gate -- for `count` pairs.          */
+int b200reg_icp_alignment(b200reg_ctx* ctx, int count, const float* const* src_xyz, const size_t* src_n,
+                          const float* const* tgt_xyz, const size_t* tgt_n, size_t stride_bytes, int on_device,
+                          const b200reg_gicp_params* params, b200reg_result* out);
+
+/* Output cloud of align(): final_transformation_ applied to the source in fp32
+ * (lsq_registration_impl.hpp:114).  out_xyz: n x 3 floats (host), original point order.       */
+int b200reg_transform_cloud(b200reg_ctx* ctx, const b200reg_cloud* cloud, const float* Tf16, float* out_xyz);
+
+/* ---- debug taps used by the parity tests ------------------------------------------- */
+/* exact k-NN of host queries in a cloud: KdTreeFLANN::nearestKSearch (nanoflann.hpp:140-152).
+ * idx_out/d2_out: nq x k, ascending; indices refer to the ORIGINAL point order; -1 pads k > n.   */
+int b200reg_knn(b200reg_ctx* ctx, const b200reg_cloud* cloud, const float* queries, size_t nq,
+                size_t qstride_bytes, int k, int32_t* idx_out, float* d2_out);
+/* n x 9 doubles (row-major 3x3 block of the reference's Matrix4d), original point order.          */
+int b200reg_get_covariances(b200reg_ctx* ctx, const b200reg_cloud* cloud, double* cov9_out);
+/* NanoGICP::linearize at pose T16 (nano_gicp_impl.hpp:213-270): H 6x6 row-major, b, sum of errors,
+ * per-source-point correspondence (original target index or -1) and squared distance.             */
+int b200reg_linearize(b200reg_ctx* ctx, const b200reg_cloud* src, const b200reg_cloud* tgt, const double* T16,
+                      double max_corr_dist, double* H36, double* b6, double* err, int32_t* corr_out,
+                      float* sqd_out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* B200REG_H */

@@ -1,0 +1,243 @@
+"""GPU parity tests for the Nano-GICP half of the path: CUDA (through the C ABI) vs the CPU oracle.
+
+Bars (BASELINE.json north_star): k-NN / correspondence indices bit-exact, squared distances
+bit-exact (fp32), final SE(3) within 1e-4 rad / 1e-3 m of the oracle.
+"""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+ROT_TOL = 1e-4   # rad
+TRANS_TOL = 1e-3  # m
+
+
+def _tie_ok(idx_g, d2_g, idx_o, d2_o):
+    """Indices must match except inside runs of exactly equal d2."""
+    assert np.array_equal(d2_g, d2_o), "squared distances differ"
+    bad = idx_g != idx_o
+    if not bad.any():
+        return
+    # a mismatch is only legal where the neighbouring slot holds the same d2
+    rows, cols = np.nonzero(bad)
+    for r, c in zip(rows, cols):
+        same = (c > 0 and d2_o[r, c - 1] == d2_o[r, c]) or (c + 1 < d2_o.shape[1] and d2_o[r, c + 1] == d2_o[r, c])
+        assert same, "index mismatch without a distance tie at query %d slot %d" % (r, c)
+
+
+def test_knn15_self_queries_exact(ctx, oracle, pair20k):
+    src, dst, _ = pair20k
+    cl, = ctx.create_clouds([dst])
+    idx, d2 = ctx.knn(cl, dst, 15)
+    oidx, od2 = oracle.knn(dst, dst, 15)
+    assert np.array_equal(d2, od2)
+    assert np.array_equal(idx, oidx)
+    assert (np.diff(d2, axis=1) >= 0).all()
+    assert np.array_equal(idx[:, 0], np.arange(len(dst)))  # continuous noise: every point is its own 1-NN
+    cl.destroy()
+
+
+def test_knn_against_reference_nanoflann(ctx, oracle, pair20k):
+    import os
+    if not os.path.exists(oracle.ref_so_path()):
+        pytest.skip("oracle/_ref not built")
+    src, dst, _ = pair20k
+    ref = oracle.RefNanoflann(dst)
+    cl, = ctx.create_clouds([dst])
+    for k, q in ((1, src), (15, dst[:8000]), (1, src + np.float32(3.0)), (20, src[:4000])):
+        gi, gd = ctx.knn(cl, q, k)
+        ri, rd = ref.knn(q, k)
+        _tie_ok(gi, gd, ri, rd)
+    cl.destroy()
+
+
+def test_knn1_far_queries_exact(ctx, oracle, pair20k):
+    src, dst, _ = pair20k
+    cl, = ctx.create_clouds([dst])
+    rng = np.random.default_rng(5)
+    q = (src[:, :3] + rng.normal(0, 4.0, (len(src), 3))).astype(np.float32)
+    q[:50] *= 30.0  # far outside the cloud's bounding box
+    gi, gd = ctx.knn(cl, q, 1)
+    oi, od = oracle.knn(dst, q, 1)
+    assert np.array_equal(gd, od) and np.array_equal(gi, oi)
+    cl.destroy()
+
+
+def test_knn_small_and_ragged_clouds(ctx, oracle):
+    rng = np.random.default_rng(11)
+    for n in (1, 7, 8, 9, 17, 63, 64, 65, 1000):
+        pts = rng.normal(0, 5, (n, 4)).astype(np.float32)
+        q = rng.normal(0, 6, (33, 3)).astype(np.float32)
+        cl, = ctx.create_clouds([pts])
+        for k in (1, 15):
+            gi, gd = ctx.knn(cl, q, k)
+            oi, od = oracle.knn(pts, q, k, brute=True)
+            kk = min(k, n)
+            assert np.array_equal(gi[:, :kk], oi[:, :kk]) and np.array_equal(gd[:, :kk], od[:, :kk])
+            assert (gi[:, kk:] == -1).all()
+        cl.destroy()
+
+
+def test_knn_duplicate_points_tie_rule(ctx, oracle):
+    """Exact duplicates: ties must resolve to the lower original index."""
+    rng = np.random.default_rng(3)
+    base = rng.normal(0, 3, (500, 3)).astype(np.float32)
+    pts = np.concatenate([base, base, base])[rng.permutation(1500)]
+    cl, = ctx.create_clouds([pts])
+    gi, gd = ctx.knn(cl, base, 15)
+    oi, od = oracle.knn(pts, base, 15, brute=True)
+    assert np.array_equal(gd, od) and np.array_equal(gi, oi)
+    cl.destroy()
+
+
+def test_covariances_match_oracle(ctx, oracle, pair20k):
+    src, dst, _ = pair20k
+    cl, = ctx.create_clouds([dst])
+    ctx.covariances([cl], 15)
+    g = ctx.get_covariances(cl)
+    o = oracle.covariances(dst, 15)
+    err = np.abs(g - o).reshape(len(dst), -1).max(1)
+    # plane normals are ill-conditioned where the two smallest eigenvalues coincide (edges, poles);
+    # the bulk must agree to fp64 round-off and no point may be wildly off.
+    assert np.median(err) < 1e-12
+    assert np.quantile(err, 0.999) < 1e-6
+    # structure: symmetric, eigenvalues (1, 1, 1e-3)
+    assert np.allclose(g, np.swapaxes(g, 1, 2), atol=0)
+    ev = np.linalg.eigvalsh(g[::97])
+    assert np.allclose(ev, [1e-3, 1.0, 1.0], atol=1e-9)
+    cl.destroy()
+
+
+def test_linearize_matches_oracle(ctx, oracle, synth, pair20k):
+    src, dst, _ = pair20k
+    cs, ct = ctx.create_clouds([src, dst])
+    ctx.covariances([cs, ct], 15)
+    cov_s, cov_t = ctx.get_covariances(cs), ctx.get_covariances(ct)
+    for T in (np.eye(4), synth.se3(yaw=0.02, pitch=-0.004, t=(0.3, -0.2, 0.05))):
+        g = ctx.linearize(cs, ct, T)
+        o = oracle.linearize(src, dst, cov_s, cov_t, T)  # same covariances in: isolates the linearize pass
+        assert np.array_equal(g["corr"], o["corr"]), "correspondence indices must be bit-exact"
+        assert np.array_equal(g["sqd"], o["sqd"])
+        scale = np.abs(o["H"]).max()
+        assert np.abs(g["H"] - o["H"]).max() < 1e-9 * scale
+        assert np.abs(g["b"] - o["b"]).max() < 1e-9 * max(np.abs(o["b"]).max(), 1.0)
+        assert abs(g["err"] - o["err"]) < 1e-9 * abs(o["err"])
+    # tight correspondence gate: rejected points must be -1 on both sides
+    g = ctx.linearize(cs, ct, np.eye(4), max_corr_dist=0.25)
+    o = oracle.linearize(src, dst, cov_s, cov_t, np.eye(4), max_corr_dist=0.25)
+    assert (o["corr"] < 0).any() and np.array_equal(g["corr"], o["corr"])
+    assert np.abs(g["H"] - o["H"]).max() < 1e-9 * np.abs(o["H"]).max()
+    cs.destroy(); ct.destroy()
+
+
+def _check_pair(ctx, oracle, synth, src, dst, Texp=None):
+    g = ctx.icp_alignment([src], [dst])[0]
+    o = oracle.gicp_align(src, dst)
+    rot, trans = synth.se3_error(g["T"], o["T"])
+    assert rot < ROT_TOL and trans < TRANS_TOL, (rot, trans)
+    assert g["converged"] == o["converged"]
+    assert g["n_linearize"] == o["n_linearize"] and g["n_error"] == o["n_error"]
+    assert g["iterations"] == o["iterations"]
+    assert abs(g["fitness"] - o["fitness"]) < 1e-5 * max(o["fitness"], 1e-3)
+    assert np.allclose(g["Tf"], g["T"].astype(np.float32), atol=0)
+    if Texp is not None:
+        rot, trans = synth.se3_error(g["T"], Texp)
+        assert rot < 5e-3 and trans < 5e-2, ("ground truth", rot, trans)
+    return g, o
+
+
+def test_gicp_align_matches_oracle_20k(ctx, oracle, synth, pair20k):
+    src, dst, Texp = pair20k
+    _check_pair(ctx, oracle, synth, src, dst, Texp)
+
+
+def test_gicp_align_ragged_sizes(ctx, oracle, synth, pair5k):
+    src, dst, Texp = pair5k
+    _check_pair(ctx, oracle, synth, src, dst, Texp)
+
+
+def test_gicp_align_pointxyzi_stride(ctx, oracle, synth, pair5k):
+    """pcl::PointXYZI records (32 B stride) upload without repacking."""
+    src, dst, _ = pair5k
+
+    def xyzi32(a):
+        out = np.zeros((len(a), 8), np.float32)
+        out[:, :3] = a[:, :3]
+        out[:, 3] = 1.0
+        out[:, 4] = a[:, 3]
+        return out
+    g8 = ctx.icp_alignment([xyzi32(src)], [xyzi32(dst)])[0]
+    g4 = ctx.icp_alignment([src], [dst])[0]
+    assert np.array_equal(g8["T"], g4["T"]) and g8["fitness"] == g4["fitness"]
+
+
+def test_batch_equals_single_and_is_deterministic(ctx, synth):
+    pairs = [synth.make_pair(1100 + i, 4000 + 500 * i, 5000 - 300 * i) for i in range(5)]
+    srcs = [p[0] for p in pairs]
+    dsts = [p[1] for p in pairs]
+    batch = ctx.icp_alignment(srcs, dsts)
+    again = ctx.icp_alignment(srcs, dsts)
+    for i in range(5):
+        single = ctx.icp_alignment([srcs[i]], [dsts[i]])[0]
+        for r in (batch[i], again[i]):
+            assert np.array_equal(r["T"], single["T"]), "batched result must be bit-identical to the single-pair result"
+            assert r["fitness"] == single["fitness"]
+            assert r["n_linearize"] == single["n_linearize"]
+        rot, trans = synth.se3_error(batch[i]["T"], pairs[i][2])
+        assert rot < 2e-2 and trans < 0.5  # sparse 4-6k-point scans: loose ground-truth sanity only
+
+
+def test_gicp_with_guess_and_cloud_reuse(ctx, oracle, synth, pair5k):
+    src, dst, Texp = pair5k
+    cs, ct = ctx.create_clouds([src, dst])
+    guess = synth.se3(yaw=0.01, t=(0.1, 0.05, 0.0))
+    g = ctx.gicp_align([cs], [ct], guesses=[guess])[0]
+    o = oracle.gicp_align(src, dst, guess=guess)
+    rot, trans = synth.se3_error(g["T"], o["T"])
+    assert rot < ROT_TOL and trans < TRANS_TOL
+    # aligned output cloud == oracle's fp32 transform of the source, original order
+    out = ctx.transform_cloud(cs, g["Tf"])
+    ref = oracle.transform_output(g["Tf"], src)
+    assert np.array_equal(out, ref)
+    cs.destroy(); ct.destroy()
+
+
+def test_iteration_cap_and_nonconvergence(ctx, oracle, synth, pair5k):
+    import b200reg
+    src, dst, _ = pair5k
+    prm = b200reg.default_params()
+    prm.max_iterations = 1
+    g = ctx.icp_alignment([src], [dst], params=prm)[0]
+    from oracle.oracle import GicpParams
+    op = GicpParams.default()
+    op.max_iterations = 1
+    o = oracle.gicp_align(src, dst, params=op)
+    assert g["converged"] == o["converged"] and g["n_linearize"] == o["n_linearize"] == 1
+    rot, trans = synth.se3_error(g["T"], o["T"])
+    assert rot < ROT_TOL and trans < TRANS_TOL
+
+
+def test_full_size_100k_properties(ctx, synth):
+    """BASELINE config 2 size: size-independent properties instead of an oracle run."""
+    src, dst, Texp = synth.make_pair(1000, 100000)
+    cs, ct = ctx.create_clouds([src, dst])
+    # (1) every point is its own nearest neighbour at distance 0, lists ascending
+    idx, d2 = ctx.knn(ct, dst[:30000], 15)
+    assert np.array_equal(idx[:, 0], np.arange(30000)) and (d2[:, 0] == 0).all()
+    assert (np.diff(d2, axis=1) >= 0).all()
+    # (2) k-NN distances equal a numpy recomputation from the returned indices (fp32, same order of ops)
+    nb = dst[idx[:2000, 14], :3]
+    diff = dst[:2000, :3] - nb
+    ref = (diff[:, 0] * diff[:, 0] + diff[:, 1] * diff[:, 1]) + diff[:, 2] * diff[:, 2]
+    assert np.array_equal(ref.astype(np.float32), d2[:2000, 14])
+    # (3) registration recovers the ground-truth drift correction and is run-to-run bit-identical
+    r1 = ctx.gicp_align([cs], [ct])[0]
+    r2 = ctx.gicp_align([cs], [ct])[0]
+    assert np.array_equal(r1["T"], r2["T"]) and r1["fitness"] == r2["fitness"]
+    rot, trans = synth.se3_error(r1["T"], Texp)
+    assert r1["converged"] and rot < 3e-3 and trans < 3e-2
+    # (4) fitness equals the mean 1-NN d2 of the transformed source (recomputed through the taps)
+    moved = ctx.transform_cloud(cs, r1["Tf"])
+    _, dd = ctx.knn(ct, moved, 1)
+    assert abs(dd.astype(np.float64).mean() - r1["fitness"]) < 1e-9 * max(r1["fitness"], 1e-6)
+    cs.destroy(); ct.destroy()
