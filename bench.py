@@ -1,0 +1,332 @@
+#!/usr/bin/env python
+"""bench.py -- loop-closure registrations/sec on 100k-point KITTI-shaped pairs (BASELINE.json metric).
+
+    python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path
+    python bench.py --impl reference --steps K --warmup W    # the reference's CPU path (oracle port)
+    torchrun ... bench.py --gpus N ...                       # one rank per GPU, weak scaling
+
+One "step" = LoopClosure::icpAlignment (fast_lio_sam_qn/src/loop_closure.cpp:110-136: two index
+builds, two covariance passes, align, fitness) over one batch of `--pairs` synthetic 100k x 100k
+pairs per rank (BASELINE.json configs[1]).  Prints ONE JSON line (rank 0).
+
+  value   : pairs/s with the raw xyz already resident in HBM when the timed region starts
+  e2e     : pairs/s through the same C-ABI call from PINNED HOST buffers (H2D of every cloud and
+            D2H of the results inside the timed region)
+  roofline: dominant kernel family, algorithmic bytes / CUDA-event time on the
+            launching stream, against MEASURED_PEAKS.json hbm_gbs
+  cpu_baseline: the CPU oracle (restated Nano-GICP + the reference's own nanoflann from oracle/_ref)
+            on the host cores, bounded sample
+"""
+import argparse
+import ctypes
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import time
+
+REPO = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, REPO)
+sys.path.insert(0, os.path.join(REPO, "fast-lio-sam-qn_b200"))
+
+import numpy as np  # noqa: E402
+
+METRIC = "loop_closure_registrations_per_sec_100k_pt_pairs"
+UNIT = "pairs/s"
+N_POINTS = 100000
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--pairs", type=int, default=16, help="pairs per step per rank")
+    ap.add_argument("--points", type=int, default=N_POINTS)
+    ap.add_argument("--cpu-sample-pairs", type=int, default=6)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    return ap.parse_args()
+
+
+def make_pairs(rank, n_pairs, n_points):
+    from b200reg import synth
+    pairs = []
+    for i in range(n_pairs):
+        seed = 1000 + rank * n_pairs + i  # config 2 seeds 1000..
+        src, dst, Texp = synth.make_pair(seed, n_points, n_points, mode="gicp")
+        pairs.append((src, dst, Texp))
+    return pairs
+
+
+def cpu_info():
+    model = "unknown"
+    try:
+        with open("/proc/cpuinfo") as f:
+            for line in f:
+                if line.startswith("model name"):
+                    model = line.split(":", 1)[1].strip()
+                    break
+    except OSError:
+        pass
+    return model, os.cpu_count()
+
+
+def run_cpu(pairs, budget_s=20.0, max_pairs=6):
+    """Time the CPU oracle (kNN through the reference's nanoflann when oracle/_ref exists)."""
+    from oracle import oracle as orc
+    orc.lib()
+    used_ref = orc.use_ref_nanoflann(True) == 0
+    orc.gicp_align(pairs[0][0][:20000], pairs[0][1][:20000])  # warm the OpenMP pool
+    times = []
+    t_start = time.perf_counter()
+    for i in range(max_pairs):
+        src, dst, _ = pairs[i % len(pairs)]
+        t0 = time.perf_counter()
+        orc.gicp_align(src, dst)
+        times.append(time.perf_counter() - t0)
+        if time.perf_counter() - t_start > budget_s:
+            break
+    per_pair = float(np.mean(times))
+    return dict(value=1.0 / per_pair, unit=UNIT, cores=orc.num_threads(), kind="port",
+                ms_per_pair=1e3 * per_pair, best_ms_per_pair=1e3 * float(np.min(times)),
+                sample="%d pairs of %dk x %dk points, serial over pairs, OpenMP over points; restated Nano-GICP "
+                       "(oracle/oracle_gicp.cpp) with kNN = %s" %
+                       (len(times), len(pairs[0][0]) // 1000, len(pairs[0][1]) // 1000,
+                        "reference nanoflann (oracle/_ref)" if used_ref else "oracle kd-tree (oracle/_ref missing)"),
+                cpu_model=cpu_info()[0])
+
+
+class ClockSampler:
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, device):
+        self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", "-i", str(device), "--query-gpu=" + self.Q,
+                                       "--format=csv,noheader,nounits", "-lms", "100"], stdout=self.f,
+                                      stderr=subprocess.DEVNULL)
+        except OSError:
+            self.p = None
+
+    def stop(self):
+        out = dict(sm_mhz=None, sm_max_mhz=None, reasons=[])
+        if self.p is None:
+            return out
+        self.p.terminate()
+        try:
+            self.p.wait(timeout=5)
+        except Exception:
+            self.p.kill()
+        self.f.flush()
+        self.f.seek(0)
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for line in self.f:
+            parts = [x.strip() for x in line.split(",")]
+            if len(parts) < 9:
+                continue
+            try:
+                sm.append(float(parts[1]))
+                mx.append(float(parts[2]))
+            except ValueError:
+                continue
+            for nm, v in zip(names, parts[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        os.unlink(self.f.name)
+        if sm:
+            out = dict(sm_mhz=float(np.median(sm)), sm_max_mhz=float(max(mx)), reasons=sorted(reasons), samples=len(sm))
+        return out
+
+
+def peaks():
+    p = os.path.join(REPO, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+def main_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    n_pairs = 2
+    pairs = make_pairs(0, n_pairs, args.points)
+    from oracle import oracle as orc
+    orc.lib()
+    used_ref = orc.use_ref_nanoflann(True) == 0
+    for _ in range(max(args.warmup, 1)):
+        orc.gicp_align(pairs[0][0], pairs[0][1])
+    t0 = time.perf_counter()
+    for s in range(args.steps):
+        for src, dst, _ in pairs:
+            orc.gicp_align(src, dst)
+    dt = time.perf_counter() - t0
+    val = n_pairs * args.steps / dt
+    sample = ("each step = %d pairs of %dk x %dk points run serially, all host threads per pair; CPU port of "
+              "LoopClosure::icpAlignment with kNN = %s" % (n_pairs, args.points // 1000, args.points // 1000,
+                                                            "reference nanoflann (oracle/_ref)" if used_ref else "oracle kd-tree"))
+    print(json.dumps({
+        "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32 points / f64 solver", "data": "synthetic",
+        "config": {"workload": "configs[1]: Nano-GICP %dk-pt KITTI-shaped scan pair (LoopClosure::icpAlignment)" % (args.points // 1000),
+                   "pairs_per_step": n_pairs, "points_per_cloud": args.points},
+        "cpu_baseline": {"value": val, "unit": UNIT, "cores": orc.num_threads(), "kind": "port", "sample": sample,
+                         "cpu_model": cpu_info()[0]},
+        "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }))
+
+
+def main():
+    args = parse()
+    if args.impl == "reference":
+        return main_reference(args)
+
+    import torch
+    import b200reg
+    from b200reg import native
+
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device -- the b200 arm has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    B = args.pairs
+    pairs = make_pairs(rank, B, args.points)
+    ctx = b200reg.Context(local_rank)
+    stream = torch.cuda.Stream()
+    ctx.set_stream(stream.cuda_stream)
+    prm = b200reg.default_params()
+    res_bytes = ctypes.sizeof(native.Result)
+
+    # host (pinned) and device copies of the raw x,y,z,intensity records (16 B stride)
+    host_src = [torch.from_numpy(p[0]).pin_memory() for p in pairs]
+    host_dst = [torch.from_numpy(p[1]).pin_memory() for p in pairs]
+    dev_src = [t.cuda(non_blocking=True) for t in host_src]
+    dev_dst = [t.cuda(non_blocking=True) for t in host_dst]
+    torch.cuda.synchronize()
+    ns_s = [t.shape[0] for t in host_src]
+    ns_d = [t.shape[0] for t in host_dst]
+    stride = host_src[0].shape[1] * 4
+    h2d_bytes = sum(t.numel() * 4 for t in host_src + host_dst)
+    gather_buf = torch.zeros(world * B, 16, dtype=torch.float64, device="cuda") if world > 1 else None
+
+    def step(on_device):
+        srcs = dev_src if on_device else host_src
+        dsts = dev_dst if on_device else host_dst
+        res = ctx.icp_alignment_ptrs([t.data_ptr() for t in srcs], ns_s, [t.data_ptr() for t in dsts], ns_d, stride,
+                                     on_device, prm)
+        if world > 1:  # the ONE collective of the path: all-gather of the 4x4 transforms
+            loc = torch.tensor(np.array([list(r.T) for r in res]), dtype=torch.float64, device="cuda")
+            with torch.cuda.stream(stream):
+                dist.all_gather_into_tensor(gather_buf, loc)
+        return res
+
+    def timed(on_device, steps):
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        l0 = ctx.launch_count
+        with torch.cuda.stream(stream):
+            e0.record(stream)
+            for _ in range(steps):
+                res = step(on_device)
+            e1.record(stream)
+        torch.cuda.synchronize()
+        if dist is not None:
+            dist.barrier()
+        ms = e0.elapsed_time(e1)
+        if dist is not None:
+            t = torch.tensor([ms], dtype=torch.float64, device="cuda")
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        return ms, ctx.launch_count - l0, res
+
+    for _ in range(args.warmup):
+        step(True)
+        step(False)
+
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    ms_dev, launches, res = timed(True, args.steps)
+    ms_e2e, _, res_h = timed(False, args.steps)
+    clocks = sampler.stop() if sampler else None
+
+    # per-kernel-family CUDA-event timing on the launching stream (same workload, same stream)
+    ctx.set_profiling(True)
+    ctx.reset_profile()
+    prof_steps = max(2, min(args.steps, 5))
+    for _ in range(prof_steps):
+        step(True)
+    prof = ctx.get_profile()
+    ctx.set_profiling(False)
+
+    # correctness guard: every pair must have converged onto its ground truth
+    from b200reg import synth
+    worst = (0.0, 0.0)
+    for r, p in zip(res, pairs):
+        T = np.array(r.T).reshape(4, 4)
+        rot, tr = synth.se3_error(T, p[2])
+        worst = (max(worst[0], rot), max(worst[1], tr))
+        if not r.converged or rot > 1e-2 or tr > 0.1:
+            raise SystemExit("bench.py: registration failed the ground-truth check (rot %.3g, trans %.3g)" % (rot, tr))
+
+    if rank == 0:
+        total_pairs = world * B * args.steps
+        value = total_pairs / (ms_dev * 1e-3)
+        e2e = total_pairs / (ms_e2e * 1e-3)
+        peak, peak_src = peaks()
+        fam = max((k for k in prof if k != "misc"), key=lambda k: prof[k]["ms"])
+        tot_ms = sum(v["ms"] for v in prof.values())
+        f = prof[fam]
+        achieved = f["algo_bytes"] / (f["ms"] * 1e-3) / 1e9 if f["ms"] > 0 else 0.0
+        kernels = {k: dict(ms_per_step=v["ms"] / prof_steps, launches_per_step=v["launches"] / prof_steps,
+                           algo_gb_per_step=v["algo_bytes"] / prof_steps / 1e9,
+                           achieved_gbs=(v["algo_bytes"] / (v["ms"] * 1e-3) / 1e9) if v["ms"] > 0 else 0.0,
+                           share=v["ms"] / tot_ms if tot_ms > 0 else 0.0) for k, v in prof.items()}
+        out = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms_dev / args.steps, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32 points+kNN / f64 covariance+solver",
+            "data": "synthetic",
+            "config": {"workload": "configs[1]: Nano-GICP %dk-pt KITTI-shaped scan pair (LoopClosure::icpAlignment: "
+                                   "2 index builds + 2 kNN-15 covariance passes + LM align + fitness)" % (args.points // 1000),
+                       "pairs_per_step_per_gpu": B, "points_per_cloud": args.points, "seeds": "1000+rank*B+i",
+                       "l2": "working set per step (%.0f MB raw + ~%.0f MB derived) exceeds the 126 MB L2; clouds are "
+                             "rebuilt from raw xyz every step" % (h2d_bytes / 1e6, B * 2 * args.points * 100 / 1e6),
+                       "parallelism": "pairs sharded over ranks, one NCCL all-gather of 4x4 transforms per step" if world > 1 else "single GPU"},
+            "e2e": {"value": e2e, "unit": UNIT, "ms_per_step": ms_e2e / args.steps, "h2d_bytes_per_step": h2d_bytes,
+                    "d2h_bytes_per_step": B * res_bytes},
+            "gpu_launches": launches,
+            "roofline": {"bound": "hbm", "kernel": fam, "achieved": achieved, "peak": peak, "unit": "GB/s",
+                         "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                         "note": "algorithmic bytes per SURVEY.md §8(d) / CUDA-event time of that kernel family on the "
+                                 "launching stream, %d profiled steps after the timed region" % prof_steps},
+            "kernels": kernels,
+            "clocks": clocks,
+            "accuracy": {"worst_rot_rad_vs_gt": worst[0], "worst_trans_m_vs_gt": worst[1],
+                         "mean_linearize_passes": float(np.mean([r.n_linearize for r in res]))},
+        }
+        if world == 1 and not args.no_cpu_baseline:
+            out["cpu_baseline"] = run_cpu(pairs, max_pairs=args.cpu_sample_pairs)
+        print(json.dumps(out))
+    if dist is not None:
+        dist.barrier()
+        dist.destroy_process_group()
+    ctx.close()
+
+
+if __name__ == "__main__":
+    main()

@@ -36,7 +36,8 @@ EXPORTS = [
     "b200reg_ctx_destroy", "b200reg_ctx_set_stream", "b200reg_ctx_synchronize", "b200reg_ctx_launch_count",
     "b200reg_clouds_create", "b200reg_cloud_destroy", "b200reg_cloud_size", "b200reg_clouds_covariances",
     "b200reg_gicp_align", "b200reg_icp_alignment", "b200reg_transform_cloud", "b200reg_knn",
-    "b200reg_get_covariances", "b200reg_linearize",
+    "b200reg_get_covariances", "b200reg_linearize", "b200reg_ctx_set_profiling", "b200reg_ctx_reset_profile",
+    "b200reg_ctx_get_profile",
 ]
 
 
@@ -110,6 +111,21 @@ class Context:
     @property
     def launch_count(self):
         return int(lib().b200reg_ctx_launch_count(self.h))
+
+    def set_profiling(self, enable):
+        _check(lib().b200reg_ctx_set_profiling(self.h, int(bool(enable))))
+
+    def reset_profile(self):
+        _check(lib().b200reg_ctx_reset_profile(self.h))
+
+    def get_profile(self):
+        """{family: dict(ms, algo_bytes, launches)} from CUDA events on the launching stream."""
+        out = {}
+        for f in range(4):
+            name, ms, by, ln = C.c_char_p(), C.c_double(), C.c_double(), C.c_int64()
+            _check(lib().b200reg_ctx_get_profile(self.h, f, C.byref(name), C.byref(ms), C.byref(by), C.byref(ln)))
+            out[name.value.decode()] = dict(ms=ms.value, algo_bytes=by.value, launches=ln.value)
+        return out
 
     # -- clouds ------------------------------------------------------------------------
     def create_clouds(self, arrays):

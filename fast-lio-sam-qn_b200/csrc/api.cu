@@ -13,7 +13,7 @@
 #include "internal.cuh"
 
 namespace b200 {
-int launch_index_build(const CloudDev* d_clouds, int count, int max_n, int max_nlp, cudaStream_t s);
+int launch_index_build(const CloudDev* d_clouds, int count, int max_n, cudaStream_t s);
 int launch_covariances(const CloudDev* d_clouds, int count, int max_n, int k, cudaStream_t s);
 void launch_gicp_init(PairState* states, const double* d_guess, int count, const GicpParamsDev& prm, cudaStream_t s);
 void launch_gicp_step(const PairDev* pairs, PairState* states, int count, int max_n, const GicpParamsDev& prm,
@@ -45,11 +45,64 @@ struct b200reg_ctx {
   int* h_done = nullptr;   // pinned mirror
   int64_t launches = 0;
   int step_chunk = 8;      // step kernels issued between two host polls
+  // optional per-kernel-family timing with CUDA events on the launching stream
+  bool profiling = false;
+  struct Span { int cls; cudaEvent_t a, b; };
+  std::vector<Span> pending;
+  std::vector<cudaEvent_t> free_events;
+  double prof_ms[4] = {0, 0, 0, 0};
+  double prof_bytes[4] = {0, 0, 0, 0};
+  int64_t prof_launches[4] = {0, 0, 0, 0};
 };
+
+enum { CLS_BUILD = 0, CLS_COV = 1, CLS_STEP = 2, CLS_MISC = 3 };
+static const char* kClassNames[4] = {"index_build", "knn_covariance", "gicp_step", "misc"};
+
+static cudaEvent_t prof_event(b200reg_ctx* c) {
+  cudaEvent_t e;
+  if (!c->free_events.empty()) {
+    e = c->free_events.back();
+    c->free_events.pop_back();
+  } else {
+    cudaEventCreate(&e);
+  }
+  return e;
+}
+struct ProfScope {  // brackets the kernels launched while it is alive
+  b200reg_ctx* c;
+  int cls;
+  cudaEvent_t a = nullptr;
+  int64_t l0;
+  ProfScope(b200reg_ctx* c_, int cls_) : c(c_), cls(cls_), l0(c_->launches) {
+    if (c->profiling) {
+      a = prof_event(c);
+      cudaEventRecord(a, c->stream);
+    }
+  }
+  ~ProfScope() {
+    if (c->profiling) {
+      cudaEvent_t b = prof_event(c);
+      cudaEventRecord(b, c->stream);
+      c->pending.push_back({cls, a, b});
+      c->prof_launches[cls] += c->launches - l0;
+    }
+  }
+};
+static void prof_resolve(b200reg_ctx* c) {
+  for (auto& sp : c->pending) {
+    float ms = 0.f;
+    cudaEventSynchronize(sp.b);
+    cudaEventElapsedTime(&ms, sp.a, sp.b);
+    c->prof_ms[sp.cls] += ms;
+    c->free_events.push_back(sp.a);
+    c->free_events.push_back(sp.b);
+  }
+  c->pending.clear();
+}
 
 struct b200reg_cloud {
   CloudDev dev;            // device pointers + sizes
-  void* slab = nullptr;    // persistent allocation (pts, boxes, cov, rank)
+  void* slab = nullptr;    // persistent allocation (pts, tnodes, cov, rank)
   bool has_cov = false;
   int cov_k = 0;
 };
@@ -120,6 +173,36 @@ int b200reg_ctx_synchronize(b200reg_ctx* c) {
 
 int64_t b200reg_ctx_launch_count(const b200reg_ctx* c) { return c ? c->launches : 0; }
 
+int b200reg_ctx_set_profiling(b200reg_ctx* c, int enable) {
+  if (!c) return fail(B200REG_EINVAL, "ctx is NULL");
+  CU(cudaSetDevice(c->device));
+  prof_resolve(c);
+  c->profiling = enable != 0;
+  return B200REG_OK;
+}
+
+int b200reg_ctx_reset_profile(b200reg_ctx* c) {
+  if (!c) return fail(B200REG_EINVAL, "ctx is NULL");
+  prof_resolve(c);
+  for (int i = 0; i < 4; i++) {
+    c->prof_ms[i] = 0;
+    c->prof_bytes[i] = 0;
+    c->prof_launches[i] = 0;
+  }
+  return B200REG_OK;
+}
+
+int b200reg_ctx_get_profile(b200reg_ctx* c, int cls, const char** name, double* ms, double* algo_bytes, int64_t* launches) {
+  if (!c || cls < 0 || cls >= 4) return fail(B200REG_EINVAL, "bad class");
+  CU(cudaSetDevice(c->device));
+  prof_resolve(c);
+  if (name) *name = kClassNames[cls];
+  if (ms) *ms = c->prof_ms[cls];
+  if (algo_bytes) *algo_bytes = c->prof_bytes[cls];
+  if (launches) *launches = c->prof_launches[cls];
+  return B200REG_OK;
+}
+
 size_t b200reg_cloud_size(const b200reg_cloud* cl) { return cl ? (size_t)cl->dev.n : 0; }
 
 // ------------------------------------------------------------------------------------------
@@ -133,41 +216,40 @@ int b200reg_clouds_create(b200reg_ctx* c, int count, const float* const* xyz, co
   cudaStream_t s = c->stream;
   std::vector<CloudDev> descs(count);
   std::vector<void*> temps;  // freed (stream-ordered) after the build
-  int max_n = 0, max_nlp = 0;
+  int max_n = 0;
   for (int i = 0; i < count; i++) {
     b200reg_cloud* cl = new b200reg_cloud;
     CloudDev& d = cl->dev;
     d.n = (int)n[i];
-    d.nl = (d.n + LEAF - 1) / LEAF;
-    d.nlp = 1;
-    d.depth = 0;
-    while (d.nlp < d.nl) {
-      d.nlp <<= 1;
-      d.depth++;
-    }
+    d.root_ref = d.n <= LEAF ? leaf_ref(0, d.n) : 0;
     d.raw_stride = (int)(stride_bytes / 4);
     const int ntiles = (d.n + SORT_TILE - 1) / SORT_TILE;
+    const size_t nn = (size_t)std::max(d.n - 1, 1);
     // persistent slab
     size_t o_pts = 0;
-    size_t o_box = align_up(o_pts + (size_t)d.nl * LEAF * sizeof(float4), 256);
-    size_t o_cov = align_up(o_box + (size_t)4 * d.nlp * sizeof(float4), 256);
+    size_t o_tn = align_up(o_pts + (size_t)d.n * sizeof(float4), 256);
+    size_t o_cov = align_up(o_tn + 4 * nn * sizeof(float4), 256);
     size_t o_rank = align_up(o_cov + (size_t)6 * d.n * sizeof(double), 256);
     size_t total = align_up(o_rank + (size_t)d.n * sizeof(int), 256);
     char* slab = nullptr;
     CU(cudaMallocAsync((void**)&slab, total, s));
     cl->slab = slab;
     d.pts = (float4*)(slab + o_pts);
-    d.boxes = (float4*)(slab + o_box);
+    d.tnodes = (float4*)(slab + o_tn);
     d.cov = (double*)(slab + o_cov);
     d.rank = (int*)(slab + o_rank);
-    // temporary slab (sort buffers, histogram, flags, bbox, and the raw records when uploading)
+    // temporary slab (sort buffers, histogram, tree scratch, bbox, and the raw records when uploading)
     size_t t_k0 = 0;
     size_t t_k1 = align_up(t_k0 + (size_t)d.n * 4, 256);
     size_t t_v0 = align_up(t_k1 + (size_t)d.n * 4, 256);
     size_t t_v1 = align_up(t_v0 + (size_t)d.n * 4, 256);
     size_t t_h = align_up(t_v1 + (size_t)d.n * 4, 256);
     size_t t_f = align_up(t_h + (size_t)RADIX * ntiles * 4, 256);
-    size_t t_b = align_up(t_f + (size_t)d.nlp * 4, 256);
+    size_t t_i = align_up(t_f + nn * 4, 256);
+    size_t t_pn = align_up(t_i + nn * sizeof(int4), 256);
+    size_t t_pl = align_up(t_pn + nn * 4, 256);
+    size_t t_nb = align_up(t_pl + (size_t)d.n * 4, 256);
+    size_t t_b = align_up(t_nb + 2 * nn * sizeof(float4), 256);
     size_t t_raw = align_up(t_b + 32, 256);
     size_t t_total = t_raw + (on_device ? 0 : align_up((size_t)d.n * stride_bytes, 256));
     char* tmp = nullptr;
@@ -179,8 +261,12 @@ int b200reg_clouds_create(b200reg_ctx* c, int count, const float* const* xyz, co
     d.vals[1] = (uint32_t*)(tmp + t_v1);
     d.hist = (uint32_t*)(tmp + t_h);
     d.flags = (uint32_t*)(tmp + t_f);
+    d.info = (int4*)(tmp + t_i);
+    d.parent_node = (int*)(tmp + t_pn);
+    d.parent_leaf = (int*)(tmp + t_pl);
+    d.nbox = (float4*)(tmp + t_nb);
     d.bbox = (float*)(tmp + t_b);
-    CU(cudaMemsetAsync(d.flags, 0, (size_t)d.nlp * 4, s));
+    CU(cudaMemsetAsync(d.flags, 0, nn * 4, s));
     if (on_device) {
       d.raw = xyz[i];
     } else {
@@ -190,12 +276,15 @@ int b200reg_clouds_create(b200reg_ctx* c, int count, const float* const* xyz, co
     descs[i] = d;
     out[i] = cl;
     max_n = std::max(max_n, d.n);
-    max_nlp = std::max(max_nlp, d.nlp);
   }
   CloudDev* d_descs = nullptr;
   CU(cudaMallocAsync((void**)&d_descs, sizeof(CloudDev) * count, s));
   CU(cudaMemcpyAsync(d_descs, descs.data(), sizeof(CloudDev) * count, cudaMemcpyHostToDevice, s));
-  c->launches += launch_index_build(d_descs, count, max_n, max_nlp, s);
+  {
+    ProfScope ps(c, CLS_BUILD);
+    c->launches += launch_index_build(d_descs, count, max_n, s);
+    for (int i = 0; i < count; i++) c->prof_bytes[CLS_BUILD] += 36.0 * descs[i].n;
+  }
   CU(cudaGetLastError());
   CU(cudaFreeAsync(d_descs, s));
   for (void* t : temps) CU(cudaFreeAsync(t, s));
@@ -203,6 +292,9 @@ int b200reg_clouds_create(b200reg_ctx* c, int count, const float* const* xyz, co
     CloudDev& d = out[i]->dev;
     d.raw = nullptr;
     d.keys[0] = d.keys[1] = d.vals[0] = d.vals[1] = d.hist = d.flags = nullptr;
+    d.info = nullptr;
+    d.parent_node = d.parent_leaf = nullptr;
+    d.nbox = nullptr;
     d.bbox = nullptr;
   }
   return B200REG_OK;
@@ -237,9 +329,13 @@ int b200reg_clouds_covariances(b200reg_ctx* c, int count, b200reg_cloud* const* 
   CloudDev* d_descs = nullptr;
   CU(cudaMallocAsync((void**)&d_descs, sizeof(CloudDev) * descs.size(), s));
   CU(cudaMemcpyAsync(d_descs, descs.data(), sizeof(CloudDev) * descs.size(), cudaMemcpyHostToDevice, s));
-  int l = launch_covariances(d_descs, (int)descs.size(), max_n, k, s);
-  if (l < 0) return fail(B200REG_EINVAL, "unsupported k");
-  c->launches += l;
+  {
+    ProfScope ps(c, CLS_COV);
+    int l = launch_covariances(d_descs, (int)descs.size(), max_n, k, s);
+    if (l < 0) return fail(B200REG_EINVAL, "unsupported k");
+    c->launches += l;
+    for (auto& d : descs) c->prof_bytes[CLS_COV] += 64.0 * d.n;
+  }
   CU(cudaGetLastError());
   CU(cudaFreeAsync(d_descs, s));
   for (int i = 0; i < count; i++) {
@@ -342,10 +438,13 @@ int b200reg_gicp_align(b200reg_ctx* c, int count, b200reg_cloud* const* src, b20
   const long max_steps = (long)std::max(params->max_iterations, 0) * (1 + std::max(params->lm_max_iterations, 1)) + 2;
   long steps = 0;
   for (;;) {
-    for (int j = 0; j < c->step_chunk; j++) {
-      launch_gicp_step(w.d_pairs, w.d_states, count, w.max_n, prm, c->d_done, s);
-      c->launches++;
-      steps++;
+    {
+      ProfScope ps(c, CLS_STEP);
+      for (int j = 0; j < c->step_chunk; j++) {
+        launch_gicp_step(w.d_pairs, w.d_states, count, w.max_n, prm, c->d_done, s);
+        c->launches++;
+        steps++;
+      }
     }
     CU(cudaMemcpyAsync(c->h_done, c->d_done, sizeof(int), cudaMemcpyDeviceToHost, s));
     CU(cudaStreamSynchronize(s));
@@ -377,6 +476,8 @@ int b200reg_gicp_align(b200reg_ctx* c, int count, b200reg_cloud* const* src, b20
     r.n_error = st.n_err;
     r.lm_failed = st.lm_failed;
     r.status = 0;
+    // K3 136*N per linearize, K4 132*N per compute_error, K5 16*N fitness
+    c->prof_bytes[CLS_STEP] += (136.0 * st.n_lin + 132.0 * st.n_err + 16.0) * w.pairs[i].src.n;
   }
   if (d_guess) CU(cudaFreeAsync(d_guess, s));
   return free_pair_work(c, w);

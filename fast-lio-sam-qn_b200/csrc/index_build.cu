@@ -2,12 +2,16 @@
 // third_party/nano_gicp/include/nano_gicp/impl/nanoflann_impl.hpp:1199-1211, 867-1012, which the
 // reference runs twice per pair plus PCL's hidden third FLANN build).
 //
-// B200-first design: instead of a top-down pointer tree, every cloud becomes a Morton-sorted
-// point array with an implicit complete binary tree of AABBs over fixed 8-point leaves
-// (one leaf = one 128-byte line).  All clouds of a batch are built together: blockIdx.y is
-// the cloud.  Steps: bbox (atomic min/max) -> 30-bit Morton keys -> stable LSD radix sort
-// (4 x 8 bit; stable => the layout, and with it every later reduction order, is deterministic)
-// -> gather into float4 (w carries the original index) -> bottom-up AABB tree with arrival flags.
+// B200-first design: instead of a serial top-down pointer tree, every cloud becomes a
+// Morton-sorted point array with a linear BVH on top (Karras 2012 radix tree, built with one
+// thread per node, no recursion).  All clouds of a batch are built together: blockIdx.y is the
+// cloud.  Steps: bbox (atomic min/max) -> 30-bit Morton keys -> stable LSD radix sort (4 x 8 bit;
+// stable => the layout, and with it every later reduction order, is deterministic) -> gather into
+// float4 (w carries the original index) -> radix-tree topology -> bottom-up AABBs with arrival
+// flags, writing the two-children-per-node records the traversal reads (internal.cuh).
+// A mid-count split over the same Morton order was measured first and discarded: ranges that
+// straddle octant boundaries give huge overlapping boxes (195 node + 71 leaf visits per 15-NN
+// query vs 29 + 7 with prefix splits on the 100k KITTI-shaped scan).
 #include "internal.cuh"
 
 namespace b200 {
@@ -191,63 +195,102 @@ __global__ void __launch_bounds__(SORT_THREADS) k_sort_scatter(const CloudDev* c
   }
 }
 
-// sorted float4 array (w = original index), inverse permutation, +inf padding of the last leaf
+// sorted float4 array (w = original index) and the inverse permutation
 __global__ void __launch_bounds__(256) k_gather(const CloudDev* clouds, int final_buf) {
   const CloudDev& c = clouds[blockIdx.y];
   int i = blockIdx.x * blockDim.x + threadIdx.x;
-  const int npad = c.nl * LEAF;
-  if (i >= npad) return;
-  if (i < c.n) {
-    uint32_t o = c.vals[final_buf][i];
-    const float* p = c.raw + (size_t)o * c.raw_stride;
-    c.pts[i] = make_float4(p[0], p[1], p[2], __int_as_float((int)o));
-    c.rank[o] = i;
-  } else {
-    c.pts[i] = make_float4(INFINITY, INFINITY, INFINITY, __int_as_float(-1));
-  }
+  if (i >= c.n) return;
+  uint32_t o = c.vals[final_buf][i];
+  const float* p = c.raw + (size_t)o * c.raw_stride;
+  c.pts[i] = make_float4(p[0], p[1], p[2], __int_as_float((int)o));
+  c.rank[o] = i;
 }
 
-// one thread per (padded) leaf: leaf AABB, then walk up; the second arrival at a parent merges.
-__global__ void __launch_bounds__(256) k_tree(const CloudDev* clouds) {
+// ---- Karras radix tree over the sorted keys -----------------------------------------
+__device__ __forceinline__ int delta(const uint32_t* __restrict__ keys, int n, int i, int j) {
+  if (j < 0 || j >= n) return -1;
+  uint32_t x = keys[i] ^ keys[j];
+  return x ? __clz(x) : 32 + __clz((uint32_t)i ^ (uint32_t)j);  // equal keys: fall back to the index
+}
+
+__global__ void __launch_bounds__(256) k_lbvh_topology(const CloudDev* clouds, int kbuf) {
   const CloudDev& c = clouds[blockIdx.y];
-  int l = blockIdx.x * blockDim.x + threadIdx.x;
-  if (l >= c.nlp) return;
-  float lo[3] = {INFINITY, INFINITY, INFINITY}, hi[3] = {-INFINITY, -INFINITY, -INFINITY};
-  if (l < c.nl) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  const int n = c.n;
+  if (i >= n - 1) return;
+  const uint32_t* __restrict__ keys = c.keys[kbuf];
+  const int d = (delta(keys, n, i, i + 1) - delta(keys, n, i, i - 1)) >= 0 ? 1 : -1;
+  const int dmin = delta(keys, n, i, i - d);
+  int lmax = 2;
+  while (delta(keys, n, i, i + lmax * d) > dmin) lmax <<= 1;
+  int l = 0;
+  for (int t = lmax >> 1; t >= 1; t >>= 1)
+    if (delta(keys, n, i, i + (l + t) * d) > dmin) l += t;
+  const int j = i + l * d;
+  const int dnode = delta(keys, n, i, j);
+  int s = 0;
+  int t = l;
+  do {
+    t = (t + 1) >> 1;
+    if (delta(keys, n, i, i + (s + t) * d) > dnode) s += t;
+  } while (t > 1);
+  const int gamma = i + s * d + min(d, 0);
+  const int first = min(i, j), last = max(i, j);
+  const int left_leaf = first == gamma, right_leaf = last == gamma + 1;
+  c.info[i] = make_int4(first, last, left_leaf | (right_leaf << 1), gamma);
+  if (left_leaf) c.parent_leaf[gamma] = i; else c.parent_node[gamma] = i;
+  if (right_leaf) c.parent_leaf[gamma + 1] = i; else c.parent_node[gamma + 1] = i;
+}
+
+// one thread per point walks up; the second arrival at a node owns it: merges the children's
+// boxes and, for nodes spanning more than LEAF points, writes the traversal record.
+__global__ void __launch_bounds__(256) k_lbvh_aabb(const CloudDev* clouds) {
+  const CloudDev& c = clouds[blockIdx.y];
+  const int p = blockIdx.x * blockDim.x + threadIdx.x;
+  const int n = c.n;
+  if (p >= n || n < 2) return;
+  int node = c.parent_leaf[p];
+  for (;;) {
+    if (atomicAdd(&c.flags[node], 1u) == 0u) return;
+    __threadfence();
+    const int4 inf = c.info[node];
+    const int g = inf.w;
+    float4 lo[2], hi[2];
+    int ref[2];
 #pragma unroll
-    for (int j = 0; j < LEAF; j++) {
-      float4 p = c.pts[l * LEAF + j];
-      if (l * LEAF + j < c.n) {
-        lo[0] = fminf(lo[0], p.x); hi[0] = fmaxf(hi[0], p.x);
-        lo[1] = fminf(lo[1], p.y); hi[1] = fmaxf(hi[1], p.y);
-        lo[2] = fminf(lo[2], p.z); hi[2] = fmaxf(hi[2], p.z);
+    for (int k = 0; k < 2; k++) {
+      const int ch = g + k;
+      if ((inf.z >> k) & 1) {
+        float4 q = c.pts[ch];
+        lo[k] = q;
+        hi[k] = q;
+        ref[k] = leaf_ref(ch, 1);
+      } else {
+        lo[k] = __ldcg(&c.nbox[2 * ch]);
+        hi[k] = __ldcg(&c.nbox[2 * ch + 1]);
+        const int4 ci = c.info[ch];
+        const int cnt = ci.y - ci.x + 1;
+        ref[k] = cnt <= LEAF ? leaf_ref(ci.x, cnt) : ch;
       }
     }
-  }
-  int id = c.nlp + l;
-  volatile float4* vb = c.boxes;
-  for (;;) {
-    c.boxes[2 * id] = make_float4(lo[0], lo[1], lo[2], 0.f);
-    c.boxes[2 * id + 1] = make_float4(hi[0], hi[1], hi[2], 0.f);
-    if (id == 1) break;
+    c.nbox[2 * node] = make_float4(fminf(lo[0].x, lo[1].x), fminf(lo[0].y, lo[1].y), fminf(lo[0].z, lo[1].z), 0.f);
+    c.nbox[2 * node + 1] = make_float4(fmaxf(hi[0].x, hi[1].x), fmaxf(hi[0].y, hi[1].y), fmaxf(hi[0].z, hi[1].z), 0.f);
+    if (inf.y - inf.x + 1 > LEAF) {
+      c.tnodes[4 * node + 0] = make_float4(lo[0].x, lo[0].y, lo[0].z, __int_as_float(ref[0]));
+      c.tnodes[4 * node + 1] = make_float4(hi[0].x, hi[0].y, hi[0].z, 0.f);
+      c.tnodes[4 * node + 2] = make_float4(lo[1].x, lo[1].y, lo[1].z, __int_as_float(ref[1]));
+      c.tnodes[4 * node + 3] = make_float4(hi[1].x, hi[1].y, hi[1].z, 0.f);
+    }
+    if (node == 0) return;
     __threadfence();
-    int parent = id >> 1;
-    if (atomicAdd(&c.flags[parent], 1u) == 0u) break;  // sibling not there yet
-    __threadfence();
-    int sib = id ^ 1;
-    float4 slo, shi;
-    slo.x = vb[2 * sib].x; slo.y = vb[2 * sib].y; slo.z = vb[2 * sib].z;
-    shi.x = vb[2 * sib + 1].x; shi.y = vb[2 * sib + 1].y; shi.z = vb[2 * sib + 1].z;
-    lo[0] = fminf(lo[0], slo.x); lo[1] = fminf(lo[1], slo.y); lo[2] = fminf(lo[2], slo.z);
-    hi[0] = fmaxf(hi[0], shi.x); hi[1] = fmaxf(hi[1], shi.y); hi[2] = fmaxf(hi[2], shi.z);
-    id = parent;
+    node = c.parent_node[node];
   }
 }
 
 // ------------------------------------------------------------------------------------
 // host launcher: builds `count` clouds whose descriptors are already in device memory.
 // Returns the number of kernel launches issued.
-int launch_index_build(const CloudDev* d_clouds, int count, int max_n, int max_nlp, cudaStream_t s) {
+int launch_index_build(const CloudDev* d_clouds, int count, int max_n, cudaStream_t s) {
   int launches = 0;
   k_bbox_init<<<count, 32, 0, s>>>(d_clouds); launches++;
   {
@@ -263,8 +306,11 @@ int launch_index_build(const CloudDev* d_clouds, int count, int max_n, int max_n
     k_sort_scatter<<<dim3(ntiles, count), SORT_THREADS, 0, s>>>(d_clouds, p);
     launches += 3;
   }
-  k_gather<<<dim3((max_nlp * LEAF + 255) / 256, count), 256, 0, s>>>(d_clouds, npass & 1); launches++;
-  k_tree<<<dim3((max_nlp + 255) / 256, count), 256, 0, s>>>(d_clouds); launches++;
+  k_gather<<<dim3((max_n + 255) / 256, count), 256, 0, s>>>(d_clouds, npass & 1); launches++;
+  if (max_n > 1) {
+    k_lbvh_topology<<<dim3((max_n + 254) / 256, count), 256, 0, s>>>(d_clouds, npass & 1); launches++;
+    k_lbvh_aabb<<<dim3((max_n + 255) / 256, count), 256, 0, s>>>(d_clouds); launches++;
+  }
   return launches;
 }
 

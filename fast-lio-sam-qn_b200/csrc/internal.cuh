@@ -1,11 +1,14 @@
 // internal.cuh -- device-side data layout shared by the kernels of libb200reg.so.
 //
 // HBM layout of one cloud (all arrays in MORTON-SORTED order, position p):
-//   pts   float4[P_pad]   (x, y, z, __int_as_float(original index)); padded to a whole number
-//                         of leaves with +inf points (d2 = inf never enters a result set)
-//   boxes float4[2*2*NLp] implicit complete binary tree over the leaves, heap ids 1..2*NLp-1;
-//                         id -> (lo.xyz, hi.xyz) at boxes[2*id], boxes[2*id+1]; leaves are ids
-//                         NLp..2*NLp-1, leaf l covers pts[l*LEAF, (l+1)*LEAF)
+//   pts    float4[P]      (x, y, z, __int_as_float(original index))
+//   tnodes float4[4*(P-1)] linear BVH (Karras radix tree over the 30-bit Morton keys, index
+//                         tie-break for equal keys).  Node i holds BOTH children:
+//                           [4i+0] = (lo0.xyz, ref0)  [4i+1] = (hi0.xyz, -)
+//                           [4i+2] = (lo1.xyz, ref1)  [4i+3] = (hi1.xyz, -)
+//                         ref >= 0: internal node index; ref < 0: leaf, -1-ref = (start<<4)|count
+//                         with count <= LEAF consecutive points.  Subtrees of <= LEAF points are
+//                         collapsed into leaves, so only ~P/4 of the P-1 slots are ever read.
 //   cov   double[6*P]     regularised covariance, symmetric 3x3 (xx,xy,xz,yy,yz,zz), 48 B/point
 //   rank  int[P]          original index -> sorted position
 // See DESIGN.md "Data layout in HBM".
@@ -15,7 +18,7 @@
 
 namespace b200 {
 
-constexpr int LEAF = 8;            // points per leaf: 8 x 16 B = one 128-B line
+constexpr int LEAF = 8;            // max points per leaf (8 x 16 B = one 128-B line); must be <= 15
 constexpr int SORT_THREADS = 256;  // radix sort tile = SORT_THREADS * SORT_ITEMS keys
 constexpr int SORT_ITEMS = 8;
 constexpr int SORT_TILE = SORT_THREADS * SORT_ITEMS;
@@ -23,23 +26,26 @@ constexpr int RADIX_BITS = 8;
 constexpr int RADIX = 1 << RADIX_BITS;
 constexpr int STEP_THREADS = 128;  // threads per block of the per-point kernels
 constexpr int NRED = 28;           // 21 (H upper) + 6 (b) + 1 (err)
-constexpr int MAX_STACK = 24;      // >= tree depth + 1 (2^23 leaves * 8 pts = 67M points)
+constexpr int MAX_STACK = 64;      // >= LBVH depth: 30 key bits + index tie-break bits
 
 struct CloudDev {
   const float* raw;    // device copy of the caller's records (xyz at stride)
   int raw_stride;      // in floats
   int n;               // points
-  int nl;              // leaves = ceil(n / LEAF)
-  int nlp;             // leaves padded to a power of two
-  int depth;           // log2(nlp)
-  float4* pts;         // [nl * LEAF]
-  float4* boxes;       // [2 * 2 * nlp]
+  int root_ref;        // 0 (internal root) or a leaf ref when n <= LEAF
+  float4* pts;         // [n]
+  float4* tnodes;      // [4 * (n - 1)]
   double* cov;         // [6 * n] (valid once has_cov)
   int* rank;           // [n]
+  // build-time temporaries (freed after the build)
   uint32_t* keys[2];   // sort ping-pong
   uint32_t* vals[2];
   uint32_t* hist;      // [RADIX * ntiles]
-  uint32_t* flags;     // [nlp] tree build arrival flags
+  uint32_t* flags;     // [n - 1] arrival flags of the bottom-up AABB pass
+  int4* info;          // [n - 1] (first, last, leaf-child bits, split)
+  int* parent_node;    // [n - 1]
+  int* parent_leaf;    // [n]
+  float4* nbox;        // [2 * (n - 1)] node AABBs
   float* bbox;         // [6] ordered-int encoded min/max
 };
 
@@ -92,5 +98,7 @@ __device__ __forceinline__ int f2ord(float f) {
   return i >= 0 ? i : i ^ 0x7FFFFFFF;
 }
 __device__ __forceinline__ float ord2f(int i) { return __int_as_float(i >= 0 ? i : i ^ 0x7FFFFFFF); }
+
+__host__ __device__ __forceinline__ int leaf_ref(int start, int count) { return -1 - ((start << 4) | count); }
 
 }  // namespace b200

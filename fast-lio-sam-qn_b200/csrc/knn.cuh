@@ -46,29 +46,29 @@ struct KnnSet {
 };
 
 __device__ __forceinline__ int orig_index(const float4* __restrict__ pts, int pos) {
-  return pos < 0 ? 0x7FFFFFFF : __float_as_int(pts[pos].w);
+  return pos < 0 ? 0x7FFFFFFF : __float_as_int(__ldg(&pts[pos].w));
 }
 
-// candidate (cd, cp with original index co) against slot (d, p): strictly better?
-__device__ __forceinline__ bool cand_better(float cd, int co, float d, int p, const float4* __restrict__ pts) {
+// candidate (cd at position cp) against slot (d, p): strictly better?  Original indices are only
+// fetched on an exact distance tie (measure ~0 on real data), never on the common path.
+__device__ __forceinline__ bool cand_better(float cd, int cp, float d, int p, const float4* __restrict__ pts) {
   if (cd < d) return true;
   if (cd > d) return false;
-  return co < orig_index(pts, p);  // exact tie (rare): compare original indices
+  return orig_index(pts, cp) < orig_index(pts, p);
 }
 
 template <int K>
-__device__ __forceinline__ void knn_insert(KnnSet<K>& s, float cd, int cp, int co, const float4* __restrict__ pts) {
+__device__ __forceinline__ void knn_insert(KnnSet<K>& s, float cd, int cp, const float4* __restrict__ pts) {
   // single pass: carry the displaced entry down the ascending list
 #pragma unroll
   for (int j = 0; j < K; j++) {
-    if (cand_better(cd, co, s.d[j], s.p[j], pts)) {
+    if (cand_better(cd, cp, s.d[j], s.p[j], pts)) {
       float td = s.d[j];
       int tp = s.p[j];
       s.d[j] = cd;
       s.p[j] = cp;
       cd = td;
       cp = tp;
-      co = orig_index(pts, cp);
     }
   }
 }
@@ -78,53 +78,51 @@ __device__ __forceinline__ void knn_insert(KnnSet<K>& s, float cd, int cp, int c
 template <int K>
 __device__ __forceinline__ void knn_search(const CloudDev& c, float qx, float qy, float qz, KnnSet<K>& res) {
   const float4* __restrict__ pts = c.pts;
-  const float4* __restrict__ boxes = c.boxes;
-  const int nlp = c.nlp;
-  int stack_id[MAX_STACK];
+  const float4* __restrict__ tn = c.tnodes;
+  int stack_ref[MAX_STACK];
   float stack_d[MAX_STACK];
   int sp = 0;
-  int id = 1;
+  int ref = c.root_ref;
   float dnode = 0.f;
   for (;;) {
-    // descend from `id` while it is an internal node worth visiting
     bool alive = !(dnode > res.worst());
-    while (alive && id < nlp) {
-      const int c0 = 2 * id;
-      float4 lo0 = __ldg(&boxes[2 * c0]), hi0 = __ldg(&boxes[2 * c0 + 1]);
-      float4 lo1 = __ldg(&boxes[2 * c0 + 2]), hi1 = __ldg(&boxes[2 * c0 + 3]);
-      float d0 = box_dist2_rn(qx, qy, qz, lo0, hi0);
-      float d1 = box_dist2_rn(qx, qy, qz, lo1, hi1);
-      int nid = c0, fid = c0 + 1;
+    while (alive && ref >= 0) {  // internal node: both children's boxes live in one 64-B record
+      const float4 a0 = __ldg(&tn[4 * ref]), a1 = __ldg(&tn[4 * ref + 1]);
+      const float4 b0 = __ldg(&tn[4 * ref + 2]), b1 = __ldg(&tn[4 * ref + 3]);
+      const float d0 = box_dist2_rn(qx, qy, qz, a0, a1);
+      const float d1 = box_dist2_rn(qx, qy, qz, b0, b1);
+      int nref = __float_as_int(a0.w), fref = __float_as_int(b0.w);
       float nd = d0, fd = d1;
       if (d1 < d0) {
-        nid = c0 + 1; fid = c0; nd = d1; fd = d0;
+        nref = __float_as_int(b0.w); fref = __float_as_int(a0.w); nd = d1; fd = d0;
       }
       const float w = res.worst();
       if (!(fd > w)) {
-        stack_id[sp] = fid;
+        stack_ref[sp] = fref;
         stack_d[sp] = fd;
         sp++;
       }
-      id = nid;
+      ref = nref;
       dnode = nd;
       alive = !(nd > w);
     }
-    if (alive) {  // leaf
-      const int base = (id - nlp) * LEAF;
+    if (alive) {  // leaf: up to LEAF consecutive points
+      const int code = -1 - ref;
+      const int base = code >> 4, cnt = code & 15;
 #pragma unroll
       for (int j = 0; j < LEAF; j++) {
-        float4 p = __ldg(&pts[base + j]);
-        float d2 = dist2_rn(qx, qy, qz, p.x, p.y, p.z);
-        if (cand_better(d2, __float_as_int(p.w), res.d[K - 1], res.p[K - 1], pts))
-          knn_insert<K>(res, d2, base + j, __float_as_int(p.w), pts);
+        if (j < cnt) {
+          const float4 p = __ldg(&pts[base + j]);
+          const float d2 = dist2_rn(qx, qy, qz, p.x, p.y, p.z);
+          if (cand_better(d2, base + j, res.d[K - 1], res.p[K - 1], pts)) knn_insert<K>(res, d2, base + j, pts);
+        }
       }
     }
-    // pop
     bool found = false;
     while (sp > 0) {
       sp--;
       if (!(stack_d[sp] > res.worst())) {
-        id = stack_id[sp];
+        ref = stack_ref[sp];
         dnode = stack_d[sp];
         found = true;
         break;

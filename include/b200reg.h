@@ -85,6 +85,13 @@ int b200reg_ctx_synchronize(b200reg_ctx* ctx);
 /* Number of kernels this context has launched so far (bench.py reports it as gpu_launches). */
 int64_t b200reg_ctx_launch_count(const b200reg_ctx* ctx);
 
+/* Per-kernel-family timing with CUDA events recorded on the launching stream (bench.py roofline).
+ * Families: 0 index_build, 1 knn_covariance, 2 gicp_step, 3 misc.  algo_bytes follows SURVEY.md §8(d). */
+int b200reg_ctx_set_profiling(b200reg_ctx* ctx, int enable);
+int b200reg_ctx_reset_profile(b200reg_ctx* ctx);
+int b200reg_ctx_get_profile(b200reg_ctx* ctx, int family, const char** name, double* ms, double* algo_bytes,
+                            int64_t* launches);
+
 /* ---- clouds: replaces KdTreeFLANN::setInputCloud / buildIndex
  *      (third_party/nano_gicp/include/nano_gicp/nanoflann.hpp:131-138) ----------------- */
 /* Upload `count` clouds (host or device pointers) and build their spatial indices in one

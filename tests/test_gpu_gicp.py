@@ -171,7 +171,7 @@ def test_gicp_align_pointxyzi_stride(ctx, oracle, synth, pair5k):
     assert np.array_equal(g8["T"], g4["T"]) and g8["fitness"] == g4["fitness"]
 
 
-def test_batch_equals_single_and_is_deterministic(ctx, synth):
+def test_batch_equals_single_and_is_deterministic(ctx, oracle, synth):
     pairs = [synth.make_pair(1100 + i, 4000 + 500 * i, 5000 - 300 * i) for i in range(5)]
     srcs = [p[0] for p in pairs]
     dsts = [p[1] for p in pairs]
@@ -183,8 +183,12 @@ def test_batch_equals_single_and_is_deterministic(ctx, synth):
             assert np.array_equal(r["T"], single["T"]), "batched result must be bit-identical to the single-pair result"
             assert r["fitness"] == single["fitness"]
             assert r["n_linearize"] == single["n_linearize"]
-        rot, trans = synth.se3_error(batch[i]["T"], pairs[i][2])
-        assert rot < 2e-2 and trans < 0.5  # sparse 4-6k-point scans: loose ground-truth sanity only
+        # sparse 4-6k-point scans: GICP itself may diverge (pair 4 runs all 32 iterations and ends
+        # ~1.8 rad off the ground truth) -- the bar is agreement with the oracle, including there.
+        o = oracle.gicp_align(srcs[i], dsts[i])
+        rot, trans = synth.se3_error(batch[i]["T"], o["T"])
+        assert rot < ROT_TOL and trans < TRANS_TOL
+        assert batch[i]["converged"] == o["converged"] and batch[i]["n_linearize"] == o["n_linearize"]
 
 
 def test_gicp_with_guess_and_cloud_reuse(ctx, oracle, synth, pair5k):
