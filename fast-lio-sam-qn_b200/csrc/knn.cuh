@@ -49,28 +49,51 @@ __device__ __forceinline__ int orig_index(const float4* __restrict__ pts, int po
   return pos < 0 ? 0x7FFFFFFF : __float_as_int(__ldg(&pts[pos].w));
 }
 
-// candidate (cd at position cp) against slot (d, p): strictly better?  Original indices are only
-// fetched on an exact distance tie (measure ~0 on real data), never on the common path.
-__device__ __forceinline__ bool cand_better(float cd, int cp, float d, int p, const float4* __restrict__ pts) {
-  if (cd < d) return true;
-  if (cd > d) return false;
-  return orig_index(pts, cp) < orig_index(pts, p);
+// Cold path: restore (d2, original index) order inside runs of exactly equal d2.  Kept out of
+// line so that the hot insertion chain stays small (the fully inlined tie-aware chain made
+// k_covariance<15> 82 KB of SASS and instruction-fetch bound; ncu: stall_no_instruction 14.2).
+template <int K>
+__device__ __noinline__ void knn_fix_ties(float* d, int* p, const float4* __restrict__ pts) {
+  for (int pass = 0; pass < K - 1; pass++) {
+    bool swapped = false;
+    for (int j = 0; j + 1 < K; j++) {
+      if (d[j] == d[j + 1] && p[j + 1] >= 0 && orig_index(pts, p[j + 1]) < orig_index(pts, p[j])) {
+        int t = p[j];
+        p[j] = p[j + 1];
+        p[j + 1] = t;
+        swapped = true;
+      }
+    }
+    if (!swapped) break;
+  }
 }
 
+// Insert a candidate with cd <= worst.  Hot path: strict '<' chain, branch-free selects, the
+// candidate lands AFTER entries of equal distance; any exact tie (measure ~0 on real data) is
+// repaired by knn_fix_ties.  A candidate that ties with the current worst replaces it only if
+// its original index is lower (the (d2, index) rule of SURVEY.md App. A.3).
 template <int K>
 __device__ __forceinline__ void knn_insert(KnnSet<K>& s, float cd, int cp, const float4* __restrict__ pts) {
-  // single pass: carry the displaced entry down the ascending list
+  bool tie = false;
+  if (cd == s.d[K - 1]) {  // ties with the worst entry: decide by original index
+    if (!(orig_index(pts, cp) < orig_index(pts, s.p[K - 1]))) return;
+    s.d[K - 1] = cd;
+    s.p[K - 1] = cp;
+    tie = true;
+  } else {
 #pragma unroll
-  for (int j = 0; j < K; j++) {
-    if (cand_better(cd, cp, s.d[j], s.p[j], pts)) {
-      float td = s.d[j];
-      int tp = s.p[j];
-      s.d[j] = cd;
-      s.p[j] = cp;
-      cd = td;
-      cp = tp;
+    for (int j = 0; j < K; j++) {
+      const bool lt = cd < s.d[j];
+      tie |= (cd == s.d[j]);
+      const float td = s.d[j];
+      const int tp = s.p[j];
+      s.d[j] = lt ? cd : td;
+      s.p[j] = lt ? cp : tp;
+      cd = lt ? td : cd;
+      cp = lt ? tp : cp;
     }
   }
+  if (tie) knn_fix_ties<K>(s.d, s.p, pts);
 }
 
 // Exact K-NN of (qx,qy,qz) in cloud c.  One thread per query; Morton-sorted queries keep
@@ -109,13 +132,23 @@ __device__ __forceinline__ void knn_search(const CloudDev& c, float qx, float qy
     if (alive) {  // leaf: up to LEAF consecutive points
       const int code = -1 - ref;
       const int base = code >> 4, cnt = code & 15;
+      float dl[LEAF];
+      unsigned mask = 0;
+      const float w0 = res.worst();
 #pragma unroll
       for (int j = 0; j < LEAF; j++) {
-        if (j < cnt) {
-          const float4 p = __ldg(&pts[base + j]);
-          const float d2 = dist2_rn(qx, qy, qz, p.x, p.y, p.z);
-          if (cand_better(d2, base + j, res.d[K - 1], res.p[K - 1], pts)) knn_insert<K>(res, d2, base + j, pts);
-        }
+        const float4 p = __ldg(&pts[base + (j < cnt ? j : 0)]);
+        dl[j] = dist2_rn(qx, qy, qz, p.x, p.y, p.z);
+        if (j < cnt && !(dl[j] > w0)) mask |= 1u << j;
+      }
+      // ONE insertion site per leaf: candidates are fed in slot order through a select chain
+      while (mask) {
+        const int j = __ffs(mask) - 1;
+        mask &= mask - 1;
+        float dj = dl[0];
+#pragma unroll
+        for (int t = 1; t < LEAF; t++) dj = (j == t) ? dl[t] : dj;
+        if (!(dj > res.worst())) knn_insert<K>(res, dj, base + j, pts);
       }
     }
     bool found = false;
