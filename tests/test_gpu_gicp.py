@@ -245,3 +245,30 @@ def test_full_size_100k_properties(ctx, synth):
     _, dd = ctx.knn(ct, moved, 1)
     assert abs(dd.astype(np.float64).mean() - r1["fitness"]) < 1e-9 * max(r1["fitness"], 1e-6)
     cs.destroy(); ct.destroy()
+
+
+def test_cuda_knn_equals_reference_golden(ctx):
+    """Committed answers of the reference's own kd-tree (tests/golden/make_golden.py)."""
+    import os
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "knn_ref_nanoflann.npz"))
+    cl, = ctx.create_clouds([g["cloud"]])
+    for q, k, ik, dk in ((g["q_self"], 15, "idx15", "d15"), (g["q_shift"], 1, "idx1", "d1"), (g["q_shift"][:100], 20, "idx20", "d20")):
+        gi, gd = ctx.knn(cl, q, k)
+        _tie_ok(gi, gd, g[ik], g[dk])
+    cl.destroy()
+
+
+def test_cuda_gicp_equals_oracle_golden(ctx, synth):
+    import os
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "gicp_oracle_3k.npz"))
+    cs, ct = ctx.create_clouds([g["src"], g["dst"]])
+    ctx.covariances([cs, ct], 15)
+    lin = ctx.linearize(cs, ct, np.eye(4))
+    assert np.array_equal(lin["corr"], g["corr"]) and np.array_equal(lin["sqd"], g["sqd"])
+    assert np.abs(lin["H"] - g["H"]).max() < 1e-9 * np.abs(g["H"]).max()
+    r = ctx.gicp_align([cs], [ct])[0]
+    rot, tr = synth.se3_error(r["T"], g["T"])
+    assert rot < ROT_TOL and tr < TRANS_TOL
+    assert r["n_linearize"] == int(g["n_linearize"]) and r["converged"] == bool(g["converged"])
+    assert abs(r["fitness"] - float(g["fitness"])) < 1e-6
+    cs.destroy(); ct.destroy()
