@@ -4,4 +4,5 @@ Python here is plumbing only (ctypes over the C ABI in include/b200reg.h, synthe
 torch.distributed sharding); the product is csrc/*.cu.
 """
 from . import synth  # noqa: F401
-from .native import B200RegError, Context, GicpParams, Result, default_params  # noqa: F401
+from .native import (B200RegError, Context, GicpParams, QuatroInfo, QuatroParams, Result, default_params,  # noqa: F401
+                     default_quatro_params)

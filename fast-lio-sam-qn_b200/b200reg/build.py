@@ -6,8 +6,9 @@ from concurrent.futures import ThreadPoolExecutor
 PKG = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 CSRC = os.path.join(PKG, "csrc")
 REPO = os.path.dirname(PKG)
-SOURCES = ["api.cu", "index_build.cu", "gicp.cu"]
-HEADERS = ["internal.cuh", "knn.cuh", os.path.join(REPO, "include", "b200reg.h")]
+SOURCES = ["api.cu", "index_build.cu", "gicp.cu", "quatro.cu"]
+EXTRA = {"quatro.cu": ["-fmad=false"]}  # fixed fp32 operation order for the FPFH / matcher arithmetic
+HEADERS = ["internal.cuh", "knn.cuh", "smallmath.cuh", os.path.join(REPO, "include", "b200reg.h")]
 LIB = os.path.join(CSRC, "libb200reg.so")
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-Xcompiler", "-fPIC",
@@ -28,7 +29,7 @@ def build_native(force=False, verbose=False):
 
     def cc(src):
         obj = os.path.join(CSRC, src.replace(".cu", ".o"))
-        cmd = [NVCC] + FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-c", os.path.join(CSRC, src), "-o", obj]
+        cmd = [NVCC] + FLAGS + EXTRA.get(src, []) + (["-Xptxas", "-v"] if verbose else []) + ["-c", os.path.join(CSRC, src), "-o", obj]
         r = subprocess.run(cmd, capture_output=True, text=True)
         if r.returncode != 0:
             raise RuntimeError("nvcc failed for %s:\n%s" % (src, r.stderr))

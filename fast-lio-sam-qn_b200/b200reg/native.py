@@ -31,13 +31,32 @@ class Result(C.Structure):
                     lm_failed=bool(self.lm_failed), status=self.status)
 
 
+class QuatroParams(C.Structure):
+    _fields_ = [("fpfh_normal_radius", C.c_double), ("fpfh_radius", C.c_double), ("noise_bound", C.c_double),
+                ("rot_gnc_factor", C.c_double), ("rot_cost_thr", C.c_double), ("rot_max_iter", C.c_int32),
+                ("max_corres", C.c_int32), ("distance_threshold", C.c_double), ("tuple_scale", C.c_double),
+                ("seed", C.c_uint64), ("estimate_scale", C.c_int32), ("use_optimized_matching", C.c_int32)]
+
+
+class QuatroInfo(C.Structure):
+    _fields_ = [("T", C.c_double * 16), ("valid", C.c_int32), ("n_mutual", C.c_int32), ("n_corr", C.c_int32),
+                ("clique_size", C.c_int32), ("gnc_iterations", C.c_int32), ("reserved", C.c_int32)]
+
+    def as_dict(self):
+        return dict(T=np.array(self.T).reshape(4, 4), valid=bool(self.valid), n_mutual=self.n_mutual,
+                    n_corr=self.n_corr, clique_size=self.clique_size, gnc_iterations=self.gnc_iterations)
+
+
+MAXC = 512
+
 EXPORTS = [
     "b200reg_default_gicp_params", "b200reg_last_error", "b200reg_version", "b200reg_ctx_create",
     "b200reg_ctx_destroy", "b200reg_ctx_set_stream", "b200reg_ctx_synchronize", "b200reg_ctx_launch_count",
     "b200reg_clouds_create", "b200reg_cloud_destroy", "b200reg_cloud_size", "b200reg_clouds_covariances",
     "b200reg_gicp_align", "b200reg_icp_alignment", "b200reg_transform_cloud", "b200reg_knn",
     "b200reg_get_covariances", "b200reg_linearize", "b200reg_ctx_set_profiling", "b200reg_ctx_reset_profile",
-    "b200reg_ctx_get_profile",
+    "b200reg_ctx_get_profile", "b200reg_default_quatro_params", "b200reg_clouds_fpfh", "b200reg_get_fpfh",
+    "b200reg_quatro_align", "b200reg_loop_closure",
 ]
 
 
@@ -65,6 +84,12 @@ def _check(rc):
 def default_params():
     p = GicpParams()
     lib().b200reg_default_gicp_params(C.byref(p))
+    return p
+
+
+def default_quatro_params():
+    p = QuatroParams()
+    lib().b200reg_default_quatro_params(C.byref(p))
     return p
 
 
@@ -121,7 +146,7 @@ class Context:
     def get_profile(self):
         """{family: dict(ms, algo_bytes, launches)} from CUDA events on the launching stream."""
         out = {}
-        for f in range(4):
+        for f in range(6):
             name, ms, by, ln = C.c_char_p(), C.c_double(), C.c_double(), C.c_int64()
             _check(lib().b200reg_ctx_get_profile(self.h, f, C.byref(name), C.byref(ms), C.byref(by), C.byref(ln)))
             out[name.value.decode()] = dict(ms=ms.value, algo_bytes=by.value, launches=ln.value)
@@ -199,6 +224,56 @@ class Context:
         out = np.empty((cloud.n, 3), np.float32)
         _check(lib().b200reg_transform_cloud(self.h, cloud.h, Tf.ctypes.data_as(C.c_void_p), out.ctypes.data_as(C.c_void_p)))
         return out
+
+    # -- Quatro --------------------------------------------------------------------------
+    def fpfh(self, clouds, normal_radius=0.9, fpfh_radius=1.5):
+        arr = (C.c_void_p * len(clouds))(*[c.h for c in clouds])
+        _check(lib().b200reg_clouds_fpfh(self.h, len(clouds), arr, C.c_double(normal_radius), C.c_double(fpfh_radius)))
+
+    def get_fpfh(self, cloud):
+        nrm = np.empty((cloud.n, 3), np.float32)
+        f = np.empty((cloud.n, 33), np.float32)
+        _check(lib().b200reg_get_fpfh(self.h, cloud.h, nrm.ctypes.data_as(C.c_void_p), f.ctypes.data_as(C.c_void_p)))
+        return nrm, f
+
+    def quatro_align(self, srcs, dsts, params=None, want_corr=False):
+        """quatro<T>::align for a batch of cloud handles."""
+        cnt = len(srcs)
+        prm = params or default_quatro_params()
+        sa = (C.c_void_p * cnt)(*[c.h for c in srcs])
+        da = (C.c_void_p * cnt)(*[c.h for c in dsts])
+        info = (QuatroInfo * cnt)()
+        corr = np.zeros((cnt, MAXC, 2), np.int32) if want_corr else None
+        _check(lib().b200reg_quatro_align(self.h, cnt, sa, da, C.byref(prm), info,
+                                          None if corr is None else corr.ctypes.data_as(C.c_void_p)))
+        out = [i.as_dict() for i in info]
+        if want_corr:
+            for o, cc in zip(out, corr):
+                o["corr"] = cc[:o["n_corr"]].copy()
+        return out
+
+    def loop_closure(self, src_arrays, tgt_arrays, qparams=None, gparams=None):
+        """LoopClosure::coarseToFineAlignment for a batch of host buffers -> (results, quatro infos)."""
+        srcs = [_pts(a) for a in src_arrays]
+        tgts = [_pts(a) for a in tgt_arrays]
+        cnt = len(srcs)
+        res = self.loop_closure_ptrs([a.ctypes.data for a in srcs], [len(a) for a in srcs], [a.ctypes.data for a in tgts],
+                                     [len(a) for a in tgts], srcs[0].shape[1] * 4, 0, qparams, gparams)
+        return [r.as_dict() for r in res[0]], [q.as_dict() for q in res[1]]
+
+    def loop_closure_ptrs(self, src_ptrs, src_ns, tgt_ptrs, tgt_ns, stride_bytes, on_device, qparams=None, gparams=None):
+        cnt = len(src_ptrs)
+        qp = qparams or default_quatro_params()
+        gp = gparams or default_params()
+        sp = (C.c_void_p * cnt)(*src_ptrs)
+        tp = (C.c_void_p * cnt)(*tgt_ptrs)
+        sn = (C.c_size_t * cnt)(*src_ns)
+        tn = (C.c_size_t * cnt)(*tgt_ns)
+        res = (Result * cnt)()
+        qi = (QuatroInfo * cnt)()
+        _check(lib().b200reg_loop_closure(self.h, cnt, sp, sn, tp, tn, C.c_size_t(stride_bytes), int(bool(on_device)),
+                                          C.byref(qp), C.byref(gp), res, qi))
+        return res, qi
 
     # -- debug taps ----------------------------------------------------------------------
     def knn(self, cloud, queries, k):

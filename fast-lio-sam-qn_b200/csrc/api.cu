@@ -20,6 +20,9 @@ void launch_gicp_step(const PairDev* pairs, PairState* states, int count, int ma
                       int* done_counter, cudaStream_t s);
 int launch_knn_queries(const CloudDev& c, const float* d_q, int nq, int qstride, int k, int* idx, float* d2, cudaStream_t s);
 void launch_transform_out(const CloudDev& c, const float* d_Tf, float* d_out3, cudaStream_t s);
+int launch_fpfh(const CloudDev* d_clouds, int count, int max_n, float normal_r2, float fpfh_r2, cudaStream_t s);
+int launch_quatro_match_solve(const MatchDev* d_pairs, int count, int max_ni, int max_nj, const QuatroParamsDev& prm, cudaStream_t s);
+void launch_transform_raw(const CloudDev* d_clouds, const double* d_T16s, int count, int max_n, float4* const* d_outs, cudaStream_t s);
 }  // namespace b200
 
 using namespace b200;
@@ -37,6 +40,8 @@ static int fail(int code, const std::string& msg) {
                                      std::to_string(__LINE__));                                               \
   } while (0)
 
+enum { CLS_BUILD = 0, CLS_COV = 1, CLS_STEP = 2, CLS_MISC = 3, CLS_FPFH = 4, CLS_MATCH = 5, NCLS = 6 };
+
 struct b200reg_ctx {
   int device = 0;
   cudaStream_t own_stream = nullptr;
@@ -50,13 +55,12 @@ struct b200reg_ctx {
   struct Span { int cls; cudaEvent_t a, b; };
   std::vector<Span> pending;
   std::vector<cudaEvent_t> free_events;
-  double prof_ms[4] = {0, 0, 0, 0};
-  double prof_bytes[4] = {0, 0, 0, 0};
-  int64_t prof_launches[4] = {0, 0, 0, 0};
+  double prof_ms[NCLS] = {0};
+  double prof_bytes[NCLS] = {0};
+  int64_t prof_launches[NCLS] = {0};
 };
 
-enum { CLS_BUILD = 0, CLS_COV = 1, CLS_STEP = 2, CLS_MISC = 3 };
-static const char* kClassNames[4] = {"index_build", "knn_covariance", "gicp_step", "misc"};
+static const char* kClassNames[NCLS] = {"index_build", "knn_covariance", "gicp_step", "misc", "fpfh", "quatro_match_solve"};
 
 static cudaEvent_t prof_event(b200reg_ctx* c) {
   cudaEvent_t e;
@@ -103,8 +107,11 @@ static void prof_resolve(b200reg_ctx* c) {
 struct b200reg_cloud {
   CloudDev dev;            // device pointers + sizes
   void* slab = nullptr;    // persistent allocation (pts, tnodes, cov, rank)
+  void* fslab = nullptr;   // Quatro features (nrm, spfh, fpfh), allocated on demand
   bool has_cov = false;
   int cov_k = 0;
+  bool has_fpfh = false;
+  double normal_r = 0, fpfh_r = 0;
 };
 
 static size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
@@ -184,7 +191,7 @@ int b200reg_ctx_set_profiling(b200reg_ctx* c, int enable) {
 int b200reg_ctx_reset_profile(b200reg_ctx* c) {
   if (!c) return fail(B200REG_EINVAL, "ctx is NULL");
   prof_resolve(c);
-  for (int i = 0; i < 4; i++) {
+  for (int i = 0; i < NCLS; i++) {
     c->prof_ms[i] = 0;
     c->prof_bytes[i] = 0;
     c->prof_launches[i] = 0;
@@ -193,7 +200,7 @@ int b200reg_ctx_reset_profile(b200reg_ctx* c) {
 }
 
 int b200reg_ctx_get_profile(b200reg_ctx* c, int cls, const char** name, double* ms, double* algo_bytes, int64_t* launches) {
-  if (!c || cls < 0 || cls >= 4) return fail(B200REG_EINVAL, "bad class");
+  if (!c || cls < 0 || cls >= NCLS) return fail(B200REG_EINVAL, "bad class");
   CU(cudaSetDevice(c->device));
   prof_resolve(c);
   if (name) *name = kClassNames[cls];
@@ -238,6 +245,9 @@ int b200reg_clouds_create(b200reg_ctx* c, int count, const float* const* xyz, co
     d.tnodes = (float4*)(slab + o_tn);
     d.cov = (double*)(slab + o_cov);
     d.rank = (int*)(slab + o_rank);
+    d.nrm = nullptr;
+    d.spfh = nullptr;
+    d.fpfh = nullptr;
     // temporary slab (sort buffers, histogram, tree scratch, bbox, and the raw records when uploading)
     size_t t_k0 = 0;
     size_t t_k1 = align_up(t_k0 + (size_t)d.n * 4, 256);
@@ -305,6 +315,7 @@ int b200reg_cloud_destroy(b200reg_ctx* c, b200reg_cloud* cl) {
   if (!c) return fail(B200REG_EINVAL, "ctx is NULL");
   CU(cudaSetDevice(c->device));
   if (cl->slab) CU(cudaFreeAsync(cl->slab, c->stream));
+  if (cl->fslab) CU(cudaFreeAsync(cl->fslab, c->stream));
   delete cl;
   return B200REG_OK;
 }
@@ -618,6 +629,302 @@ int b200reg_linearize(b200reg_ctx* c, const b200reg_cloud* src, const b200reg_cl
   }
   CU(cudaFreeAsync(d_guess, s));
   return free_pair_work(c, w);
+}
+
+
+// ---- Quatro ------------------------------------------------------------------------------
+void b200reg_default_quatro_params(b200reg_quatro_params* p) {
+  if (!p) return;
+  p->fpfh_normal_radius = 0.9;
+  p->fpfh_radius = 1.5;
+  p->noise_bound = 0.3;
+  p->rot_gnc_factor = 1.4;
+  p->rot_cost_thr = 1e-4;
+  p->rot_max_iter = 50;
+  p->max_corres = 200;
+  p->distance_threshold = 35.0;
+  p->tuple_scale = 0.95;
+  p->seed = 1;
+  p->estimate_scale = 0;
+  p->use_optimized_matching = 1;
+}
+
+int b200reg_clouds_fpfh(b200reg_ctx* c, int count, b200reg_cloud* const* clouds, double normal_radius, double fpfh_radius) {
+  if (!c || count <= 0 || !clouds || !(normal_radius > 0) || !(fpfh_radius > 0)) return fail(B200REG_EINVAL, "bad argument");
+  CU(cudaSetDevice(c->device));
+  cudaStream_t s = c->stream;
+  std::vector<CloudDev> descs;
+  std::vector<b200reg_cloud*> todo;
+  int max_n = 0;
+  for (int i = 0; i < count; i++) {
+    b200reg_cloud* cl = clouds[i];
+    if (!cl) return fail(B200REG_EINVAL, "NULL cloud");
+    if (cl->has_fpfh && cl->normal_r == normal_radius && cl->fpfh_r == fpfh_radius) continue;
+    if (std::find(todo.begin(), todo.end(), cl) != todo.end()) continue;
+    if (!cl->fslab) {
+      const size_t n = cl->dev.n;
+      size_t o_n = 0;
+      size_t o_s = align_up(o_n + n * sizeof(float4), 256);
+      size_t o_f = align_up(o_s + n * FPAD * sizeof(float), 256);
+      size_t total = align_up(o_f + n * FPAD * sizeof(float), 256);
+      char* fs = nullptr;
+      CU(cudaMallocAsync((void**)&fs, total, s));
+      cl->fslab = fs;
+      cl->dev.nrm = (float4*)(fs + o_n);
+      cl->dev.spfh = (float*)(fs + o_s);
+      cl->dev.fpfh = (float*)(fs + o_f);
+    }
+    todo.push_back(cl);
+    descs.push_back(cl->dev);
+    max_n = std::max(max_n, cl->dev.n);
+  }
+  if (todo.empty()) return B200REG_OK;
+  CloudDev* d_descs = nullptr;
+  CU(cudaMallocAsync((void**)&d_descs, sizeof(CloudDev) * descs.size(), s));
+  CU(cudaMemcpyAsync(d_descs, descs.data(), sizeof(CloudDev) * descs.size(), cudaMemcpyHostToDevice, s));
+  {
+    ProfScope ps(c, CLS_FPFH);
+    const float nr2 = (float)(normal_radius * normal_radius), fr2 = (float)(fpfh_radius * fpfh_radius);
+    c->launches += launch_fpfh(d_descs, (int)descs.size(), max_n, nr2, fr2, s);
+    for (auto& d : descs) c->prof_bytes[CLS_FPFH] += (32.0 + 164.0 + 280.0) * d.n;  // SURVEY §8(d) Q1+Q2+Q3
+  }
+  CU(cudaGetLastError());
+  CU(cudaFreeAsync(d_descs, s));
+  for (b200reg_cloud* cl : todo) {
+    cl->has_fpfh = true;
+    cl->normal_r = normal_radius;
+    cl->fpfh_r = fpfh_radius;
+  }
+  return B200REG_OK;
+}
+
+int b200reg_get_fpfh(b200reg_ctx* c, const b200reg_cloud* cl, float* normals_out, float* fpfh_out) {
+  if (!c || !cl) return fail(B200REG_EINVAL, "bad argument");
+  if (!cl->has_fpfh) return fail(B200REG_ESTATE, "FPFH not computed");
+  CU(cudaSetDevice(c->device));
+  cudaStream_t s = c->stream;
+  const int n = cl->dev.n;
+  std::vector<float4> pts(n), nrm(n);
+  std::vector<float> f((size_t)n * FPAD);
+  CU(cudaMemcpyAsync(pts.data(), cl->dev.pts, (size_t)n * 16, cudaMemcpyDeviceToHost, s));
+  CU(cudaMemcpyAsync(nrm.data(), cl->dev.nrm, (size_t)n * 16, cudaMemcpyDeviceToHost, s));
+  CU(cudaMemcpyAsync(f.data(), cl->dev.fpfh, (size_t)n * FPAD * 4, cudaMemcpyDeviceToHost, s));
+  CU(cudaStreamSynchronize(s));
+  for (int p = 0; p < n; p++) {
+    int o;
+    memcpy(&o, &pts[p].w, 4);
+    if (normals_out) {
+      const bool ok = nrm[p].w != 0.f;
+      normals_out[3 * (size_t)o + 0] = ok ? nrm[p].x : NAN;
+      normals_out[3 * (size_t)o + 1] = ok ? nrm[p].y : NAN;
+      normals_out[3 * (size_t)o + 2] = ok ? nrm[p].z : NAN;
+    }
+    if (fpfh_out) memcpy(&fpfh_out[(size_t)o * FDIM], &f[(size_t)p * FPAD], FDIM * sizeof(float));
+  }
+  return B200REG_OK;
+}
+
+int b200reg_quatro_align(b200reg_ctx* c, int count, b200reg_cloud* const* src, b200reg_cloud* const* dst,
+                         const b200reg_quatro_params* prm, b200reg_quatro_info* out, int32_t* corr_out) {
+  if (!c || count <= 0 || !src || !dst || !prm || !out) return fail(B200REG_EINVAL, "bad argument");
+  if (prm->estimate_scale) return fail(B200REG_EINVAL, "estimate_scale is not supported (the deployment sets it false)");
+  if (!prm->use_optimized_matching) return fail(B200REG_EINVAL, "only optimizedMatching is built");
+  if (prm->max_corres < 1 || prm->max_corres > MAXC - 3) return fail(B200REG_EINVAL, "max_corres must be in 1..509");
+  CU(cudaSetDevice(c->device));
+  cudaStream_t s = c->stream;
+  int rc;
+  {
+    std::vector<b200reg_cloud*> all;
+    for (int i = 0; i < count; i++) {
+      if (!src[i] || !dst[i]) return fail(B200REG_EINVAL, "NULL cloud");
+      all.push_back(src[i]);
+      all.push_back(dst[i]);
+    }
+    if ((rc = b200reg_clouds_fpfh(c, (int)all.size(), all.data(), prm->fpfh_normal_radius, prm->fpfh_radius))) return rc;
+  }
+  std::vector<MatchDev> pairs(count);
+  std::vector<void*> slabs;
+  int max_ni = 0, max_nj = 0;
+  for (int i = 0; i < count; i++) {
+    MatchDev& m = pairs[i];
+    const bool swapped = dst[i]->dev.n > src[i]->dev.n;  // fi = larger cloud (matcher.cc:364-369)
+    m.fi = swapped ? dst[i]->dev : src[i]->dev;
+    m.fj = swapped ? src[i]->dev : dst[i]->dev;
+    m.swapped = swapped ? 1 : 0;
+    const size_t ni = m.fi.n, nj = m.fj.n;
+    size_t o = 0;
+    auto take = [&](size_t bytes) {
+      size_t r = o;
+      o = align_up(o + bytes, 256);
+      return r;
+    };
+    const size_t o_nn = take(nj * 4), o_dis = take(nj * 4), o_fj = take(ni * 4), o_need = take(ni * 4), o_rnn = take(ni * 4);
+    const size_t o_cor = take(2 * nj * 4), o_tk = take(nj * 4), o_cnt = take(8 * 4), o_st = take(8 * 8), o_oc = take(2 * MAXC * 4), o_T = take(16 * 8);
+    char* slab = nullptr;
+    CU(cudaMallocAsync((void**)&slab, o, s));
+    slabs.push_back(slab);
+    m.nn = (int*)(slab + o_nn);
+    m.dis = (float*)(slab + o_dis);
+    m.first_j = (int*)(slab + o_fj);
+    m.need = (int*)(slab + o_need);
+    m.rnn = (int*)(slab + o_rnn);
+    m.corres = (int*)(slab + o_cor);
+    m.tkey = (unsigned*)(slab + o_tk);
+    m.counters = (int*)(slab + o_cnt);
+    m.stats = (double*)(slab + o_st);
+    m.out_corr = (int*)(slab + o_oc);
+    m.T = (double*)(slab + o_T);
+    max_ni = std::max(max_ni, (int)ni);
+    max_nj = std::max(max_nj, (int)nj);
+  }
+  MatchDev* d_pairs = nullptr;
+  CU(cudaMallocAsync((void**)&d_pairs, sizeof(MatchDev) * count, s));
+  CU(cudaMemcpyAsync(d_pairs, pairs.data(), sizeof(MatchDev) * count, cudaMemcpyHostToDevice, s));
+  QuatroParamsDev q;
+  q.normal_r2 = (float)(prm->fpfh_normal_radius * prm->fpfh_normal_radius);
+  q.fpfh_r2 = (float)(prm->fpfh_radius * prm->fpfh_radius);
+  q.thr2 = (float)prm->distance_threshold * (float)prm->distance_threshold;
+  q.tuple_scale = (float)prm->tuple_scale;
+  q.max_corres = prm->max_corres;
+  q.noise_bound = prm->noise_bound;
+  q.gnc_factor = prm->rot_gnc_factor;
+  q.cost_thr = prm->rot_cost_thr;
+  q.max_iter = prm->rot_max_iter;
+  q.seed = prm->seed;
+  {
+    ProfScope ps(c, CLS_MATCH);
+    c->launches += launch_quatro_match_solve(d_pairs, count, max_ni, max_nj, q, s);
+    for (int i = 0; i < count; i++) c->prof_bytes[CLS_MATCH] += 132.0 * (pairs[i].fi.n + pairs[i].fj.n) + 8.0 * pairs[i].fj.n;
+  }
+  CU(cudaGetLastError());
+  std::vector<int> counters(8 * (size_t)count);
+  std::vector<int> oc(corr_out ? 2 * MAXC * (size_t)count : 0);
+  for (int i = 0; i < count; i++) {
+    CU(cudaMemcpyAsync(&counters[8 * i], pairs[i].counters, 32, cudaMemcpyDeviceToHost, s));
+    CU(cudaMemcpyAsync(out[i].T, pairs[i].T, 128, cudaMemcpyDeviceToHost, s));
+    if (corr_out) CU(cudaMemcpyAsync(&corr_out[2 * MAXC * (size_t)i], pairs[i].out_corr, 2 * MAXC * 4, cudaMemcpyDeviceToHost, s));
+  }
+  CU(cudaStreamSynchronize(s));
+  for (int i = 0; i < count; i++) {
+    out[i].valid = counters[8 * i + 3];
+    out[i].n_mutual = counters[8 * i + 1];
+    out[i].n_corr = counters[8 * i + 2];
+    out[i].clique_size = counters[8 * i + 4];
+    out[i].gnc_iterations = counters[8 * i + 5];
+    out[i].reserved = 0;
+  }
+  for (void* p : slabs) CU(cudaFreeAsync(p, s));
+  CU(cudaFreeAsync(d_pairs, s));
+  return B200REG_OK;
+}
+
+int b200reg_loop_closure(b200reg_ctx* c, int count, const float* const* src_xyz, const size_t* src_n, const float* const* tgt_xyz,
+                         const size_t* tgt_n, size_t stride_bytes, int on_device, const b200reg_quatro_params* qp,
+                         const b200reg_gicp_params* gp, b200reg_result* out, b200reg_quatro_info* quatro_out) {
+  if (!c || count <= 0 || !src_xyz || !src_n || !tgt_xyz || !tgt_n || !qp || !gp || !out) return fail(B200REG_EINVAL, "bad argument");
+  CU(cudaSetDevice(c->device));
+  cudaStream_t s = c->stream;
+  std::vector<const float*> ptrs(2 * count);
+  std::vector<size_t> ns(2 * count);
+  for (int i = 0; i < count; i++) {
+    ptrs[i] = src_xyz[i];
+    ns[i] = src_n[i];
+    ptrs[count + i] = tgt_xyz[i];
+    ns[count + i] = tgt_n[i];
+  }
+  std::vector<b200reg_cloud*> clouds(2 * count, nullptr);
+  int rc = b200reg_clouds_create(c, 2 * count, ptrs.data(), ns.data(), stride_bytes, on_device, clouds.data());
+  if (rc) return rc;
+  std::vector<b200reg_quatro_info> qi(count);
+  std::vector<b200reg_cloud*> coarse;
+  std::vector<void*> raws;
+  auto cleanup = [&]() {
+    for (b200reg_cloud* cl : clouds) b200reg_cloud_destroy(c, cl);
+    for (b200reg_cloud* cl : coarse) b200reg_cloud_destroy(c, cl);
+    for (void* p : raws) cudaFreeAsync(p, s);
+  };
+  rc = b200reg_quatro_align(c, count, clouds.data(), clouds.data() + count, qp, qi.data(), nullptr);
+  if (rc) {
+    cleanup();
+    return rc;
+  }
+  if (quatro_out) memcpy(quatro_out, qi.data(), sizeof(b200reg_quatro_info) * count);
+  // pairs whose coarse stage is valid go on to icpAlignment(coarse_aligned_, dst) (loop_closure.cpp:145-156)
+  std::vector<int> vidx;
+  for (int i = 0; i < count; i++) {
+    memset(&out[i], 0, sizeof(b200reg_result));
+    for (int k = 0; k < 16; k++) {
+      out[i].T[k] = qi[i].T[k];
+      out[i].Tf[k] = (float)qi[i].T[k];
+    }
+    out[i].fitness = 1.7976931348623157e308;  // RegistrationOutput::score_ default (loop_closure.h:68)
+    if (qi[i].valid) vidx.push_back(i);
+  }
+  if (!vidx.empty()) {
+    const int nv = (int)vidx.size();
+    std::vector<CloudDev> sdesc(nv);
+    std::vector<double> Ts(16 * (size_t)nv);
+    std::vector<float4*> outs(nv);
+    std::vector<const float*> cptr(nv);
+    std::vector<size_t> cn(nv);
+    int max_n = 0;
+    for (int k = 0; k < nv; k++) {
+      const int i = vidx[k];
+      sdesc[k] = clouds[i]->dev;
+      memcpy(&Ts[16 * (size_t)k], qi[i].T, 128);
+      float4* raw = nullptr;
+      CU(cudaMallocAsync((void**)&raw, (size_t)sdesc[k].n * 16, s));
+      raws.push_back(raw);
+      outs[k] = raw;
+      cptr[k] = (const float*)raw;
+      cn[k] = sdesc[k].n;
+      max_n = std::max(max_n, sdesc[k].n);
+    }
+    CloudDev* d_desc = nullptr;
+    double* d_T = nullptr;
+    float4** d_outs = nullptr;
+    CU(cudaMallocAsync((void**)&d_desc, sizeof(CloudDev) * nv, s));
+    CU(cudaMallocAsync((void**)&d_T, 128 * (size_t)nv, s));
+    CU(cudaMallocAsync((void**)&d_outs, sizeof(float4*) * nv, s));
+    CU(cudaMemcpyAsync(d_desc, sdesc.data(), sizeof(CloudDev) * nv, cudaMemcpyHostToDevice, s));
+    CU(cudaMemcpyAsync(d_T, Ts.data(), 128 * (size_t)nv, cudaMemcpyHostToDevice, s));
+    CU(cudaMemcpyAsync(d_outs, outs.data(), sizeof(float4*) * nv, cudaMemcpyHostToDevice, s));
+    launch_transform_raw(d_desc, d_T, nv, max_n, d_outs, s);
+    c->launches++;
+    CU(cudaFreeAsync(d_desc, s));
+    CU(cudaFreeAsync(d_T, s));
+    CU(cudaFreeAsync(d_outs, s));
+    coarse.assign(nv, nullptr);
+    rc = b200reg_clouds_create(c, nv, cptr.data(), cn.data(), 16, 1, coarse.data());
+    std::vector<b200reg_cloud*> tg(nv);
+    for (int k = 0; k < nv; k++) tg[k] = clouds[count + vidx[k]];
+    std::vector<b200reg_result> gres(nv);
+    if (!rc) rc = b200reg_gicp_align(c, nv, coarse.data(), tg.data(), nullptr, gp, gres.data());
+    if (rc) {
+      cleanup();
+      return rc;
+    }
+    for (int k = 0; k < nv; k++) {
+      const int i = vidx[k];
+      b200reg_result r = gres[k];
+      // reg_output.pose_between_eig_ = fine (float -> double) * quatro_tf_  (loop_closure.cpp:156)
+      double F[16], Q[16];
+      for (int a = 0; a < 16; a++) {
+        F[a] = (double)gres[k].Tf[a];
+        Q[a] = qi[i].T[a];
+      }
+      for (int a = 0; a < 4; a++)
+        for (int b = 0; b < 4; b++) {
+          double v = 0;
+          for (int m = 0; m < 4; m++) v += F[4 * a + m] * Q[4 * m + b];
+          r.T[4 * a + b] = v;
+          r.Tf[4 * a + b] = (float)v;
+        }
+      out[i] = r;
+    }
+  }
+  cleanup();
+  return B200REG_OK;
 }
 
 }  // extern "C"

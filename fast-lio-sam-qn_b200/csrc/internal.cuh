@@ -26,6 +26,8 @@ constexpr int RADIX_BITS = 8;
 constexpr int RADIX = 1 << RADIX_BITS;
 constexpr int STEP_THREADS = 128;  // threads per block of the per-point kernels
 constexpr int NRED = 28;           // 21 (H upper) + 6 (b) + 1 (err)
+constexpr int FDIM = 33;           // FPFHSignature33
+constexpr int FPAD = 36;           // descriptor record padded to 144 B (9 x float4, TMA-bulk friendly)
 constexpr int MAX_STACK = 64;      // >= LBVH depth: 30 key bits + index tie-break bits
 
 struct CloudDev {
@@ -37,6 +39,10 @@ struct CloudDev {
   float4* tnodes;      // [4 * (n - 1)]
   double* cov;         // [6 * n] (valid once has_cov)
   int* rank;           // [n]
+  // Quatro features (allocated by b200reg_clouds_fpfh; sorted order)
+  float4* nrm;         // [n] unit normal, w = 1 valid / 0 invalid (< 3 neighbours)
+  float* spfh;         // [FPAD * n]
+  float* fpfh;         // [FPAD * n]; slot 33 = original index (int bits), slot 34 = 1.0 if the descriptor is usable
   // build-time temporaries (freed after the build)
   uint32_t* keys[2];   // sort ping-pong
   uint32_t* vals[2];
@@ -91,6 +97,36 @@ struct PairDev {
   double* mahal;   // [6 * src.n]
   double* partial; // [nblocks * NRED]
 };
+
+// ---- Quatro matcher / solver workspace ---------------------------------------------------
+// per-pair device workspace of the matcher / solver
+struct MatchDev {
+  CloudDev fi, fj;     // fi = larger cloud (base of the forward search), fj = smaller
+  int swapped;         // 1 when fi is the DESTINATION cloud (matcher.cc:364-369)
+  int* nn;             // [nj] original fi index of the 1-NN of fj point j (by ORIGINAL j), -1 if none
+  float* dis;          // [nj]
+  int* first_j;        // [ni] min original j that hit i (INT_MAX if none)
+  int* need;           // [ni] compacted original i's that need the reverse search
+  int* rnn;            // [ni] original j returned by the reverse search (by ORIGINAL i)
+  int* corres;         // [2 * nj] mutual (i, j) pairs, ascending j
+  unsigned* tkey;      // [nj] first (trial*4 + slot) at which correspondence r would be added
+  int* counters;       // [0] n_need, [1] ncorr, [2] n_out, [3] valid, [4] clique size, [5] gnc iterations
+  double* stats;       // [0..2] sum fi, [3..5] sum fj, then floats: mean fi(3) mean fj(3) scale (as float bits in doubles)
+  int* out_corr;       // [2 * (MAXC)] final (src, dst) pairs
+  double* T;           // [16] row-major result
+};
+
+struct QuatroParamsDev {
+  float normal_r2, fpfh_r2;
+  float thr2;          // distance_threshold^2 (feature space)
+  float tuple_scale;
+  int max_corres;
+  double noise_bound, gnc_factor, cost_thr;
+  int max_iter;
+  unsigned long long seed;
+};
+
+constexpr int MAXC = 512;  // capacity of the final correspondence set (max_corres + 3 <= MAXC)
 
 // ---- ordered-int encoding of floats for atomicMin/atomicMax ------------------------
 __device__ __forceinline__ int f2ord(float f) {

@@ -165,4 +165,46 @@ __device__ __forceinline__ void knn_search(const CloudDev& c, float qx, float qy
   }
 }
 
+// Fixed-radius traversal: calls f(position, d2) for every point with fp32 d2 < r2 (strict, like FLANN's
+// RadiusResultSet).  A subtree is skipped when its box bound >= r2: every point inside is then >= r2 too.
+template <typename F>
+__device__ __forceinline__ void radius_visit(const CloudDev& c, float qx, float qy, float qz, float r2, F&& f) {
+  const float4* __restrict__ pts = c.pts;
+  const float4* __restrict__ tn = c.tnodes;
+  int stack_ref[MAX_STACK];
+  int sp = 0;
+  int ref = c.root_ref;
+  for (;;) {
+    while (ref >= 0) {
+      const float4 a0 = __ldg(&tn[4 * ref]), a1 = __ldg(&tn[4 * ref + 1]);
+      const float4 b0 = __ldg(&tn[4 * ref + 2]), b1 = __ldg(&tn[4 * ref + 3]);
+      const bool in0 = box_dist2_rn(qx, qy, qz, a0, a1) < r2;
+      const bool in1 = box_dist2_rn(qx, qy, qz, b0, b1) < r2;
+      const int r0 = __float_as_int(a0.w), r1 = __float_as_int(b0.w);
+      if (in0 && in1) {
+        stack_ref[sp++] = r1;
+        ref = r0;
+      } else if (in0) {
+        ref = r0;
+      } else if (in1) {
+        ref = r1;
+      } else {
+        ref = 0x7FFFFFFF;  // dead end
+        break;
+      }
+    }
+    if (ref < 0) {
+      const int code = -1 - ref;
+      const int base = code >> 4, cnt = code & 15;
+      for (int j = 0; j < cnt; j++) {
+        const float4 p = __ldg(&pts[base + j]);
+        const float d2 = dist2_rn(qx, qy, qz, p.x, p.y, p.z);
+        if (d2 < r2) f(base + j, d2, p);
+      }
+    }
+    if (sp == 0) break;
+    ref = stack_ref[--sp];
+  }
+}
+
 }  // namespace b200

@@ -1,0 +1,984 @@
+// quatro.cu -- the Quatro half of the loop-closure path as batched GPU kernels (blockIdx.y = cloud / pair).
+// Compiled with -fmad=false: the fp32 feature arithmetic follows a fixed operation order (see the oracle).
+//
+// Reference behaviour being replaced (paths relative to /root/reference; PCL / FLANN / TEASER++ semantics per
+// SURVEY.md App. B because those libraries are not vendored):
+//   Q1 k_normals        pcl::NormalEstimation, radius 0.9, viewpoint (0,0,0)       third_party/Quatro/src/fpfh.cc:27-32
+//   Q2 k_spfh           FPFHEstimationOMP::computePointSPFHSignature                fpfh.cc:35-39
+//   Q3 k_fpfh           FPFHEstimationOMP::weightPointSPFHSignature                 fpfh.cc:35-39
+//   Q4 k_feat_nn        FLANN KDTreeSingleIndex exact 1-NN in 33-D (both directions) third_party/Quatro/src/matcher.cc:378-399, 597-636
+//      k_first_hit / k_need / k_mutual   gate + first-hit reverse search + mutual check   matcher.cc:412-455
+//      k_cloud_sum / k_cloud_scale       Matcher::normalizePoints                         matcher.cc:58-116
+//      k_tuple_trials / k_tuple_select   tuple test (<= 100 ncorr trials, stop at > max)  matcher.cc:461-538
+//   Q5 k_teaser_solve   RobustRegistrationSolver::solve, QUATRO + PMC_HEU           call site third_party/Quatro/src/quatro_module.cc:69-76
+// Deliberate definitions where the reference is seed- or race-dependent are listed in oracle/oracle_quatro.cpp.
+#include "internal.cuh"
+#include "knn.cuh"
+#include "smallmath.cuh"
+
+namespace b200 {
+
+// ------------------------------------------------------------------------------------------------
+// Q1 normals
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(STEP_THREADS) k_normals(const CloudDev* clouds, float r2) {
+  const CloudDev& c = clouds[blockIdx.y];
+  const int i = blockIdx.x * STEP_THREADS + threadIdx.x;
+  if (i >= c.n) return;
+  const float4 p = c.pts[i];
+  double m0 = 0, m1 = 0, m2 = 0, c0 = 0, c1 = 0, c2 = 0, c3 = 0, c4 = 0, c5 = 0;
+  int cnt = 0;
+  radius_visit(c, p.x, p.y, p.z, r2, [&](int, float, const float4& q) {
+    const double x = (double)q.x - (double)p.x, y = (double)q.y - (double)p.y, z = (double)q.z - (double)p.z;
+    m0 += x; m1 += y; m2 += z;
+    c0 += x * x; c1 += x * y; c2 += x * z; c3 += y * y; c4 += y * z; c5 += z * z;
+    cnt++;
+  });
+  if (cnt < 3) {
+    c.nrm[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    return;
+  }
+  const double inv = 1.0 / (double)cnt;
+  m0 *= inv; m1 *= inv; m2 *= inv;
+  double n[3];
+  sym3_smallest_evec(c0 * inv - m0 * m0, c1 * inv - m0 * m1, c2 * inv - m0 * m2, c3 * inv - m1 * m1, c4 * inv - m1 * m2,
+                     c5 * inv - m2 * m2, n);
+  float nx = (float)n[0], ny = (float)n[1], nz = (float)n[2];
+  const float cos_theta = ((0.f - p.x) * nx + (0.f - p.y) * ny) + (0.f - p.z) * nz;  // flipNormalTowardsViewpoint, vp = 0
+  if (cos_theta < 0.f) {
+    nx = -nx; ny = -ny; nz = -nz;
+  }
+  c.nrm[i] = make_float4(nx, ny, nz, 1.f);
+}
+
+// pcl::computePairFeatures in fp32 with the oracle's operation order
+__device__ __forceinline__ bool pair_features(const float4& p1, const float4& n1, const float4& p2, const float4& n2, float& f1,
+                                              float& f2, float& f3) {
+  float d0 = p2.x - p1.x, d1 = p2.y - p1.y, d2 = p2.z - p1.z;
+  const float f4 = sqrtf((d0 * d0 + d1 * d1) + d2 * d2);
+  if (f4 == 0.f) return false;
+  float a0 = n1.x, a1 = n1.y, a2 = n1.z, b0 = n2.x, b1 = n2.y, b2 = n2.z;
+  const float angle1 = ((a0 * d0 + a1 * d1) + a2 * d2) / f4;
+  const float angle2 = ((b0 * d0 + b1 * d1) + b2 * d2) / f4;
+  if (fabsf(angle1) < fabsf(angle2)) {
+    float t;
+    t = a0; a0 = b0; b0 = t;
+    t = a1; a1 = b1; b1 = t;
+    t = a2; a2 = b2; b2 = t;
+    d0 = -d0; d1 = -d1; d2 = -d2;
+    f3 = -angle2;
+  } else {
+    f3 = angle1;
+  }
+  float v0 = d1 * a2 - d2 * a1, v1 = d2 * a0 - d0 * a2, v2 = d0 * a1 - d1 * a0;
+  const float vn = sqrtf((v0 * v0 + v1 * v1) + v2 * v2);
+  if (vn == 0.f) return false;
+  v0 /= vn; v1 /= vn; v2 /= vn;
+  const float w0 = a1 * v2 - a2 * v1, w1 = a2 * v0 - a0 * v2, w2 = a0 * v1 - a1 * v0;
+  f2 = (v0 * b0 + v1 * b1) + v2 * b2;
+  f1 = atan2f((w0 * b0 + w1 * b1) + w2 * b2, (a0 * b0 + a1 * b1) + a2 * b2);
+  return true;
+}
+
+__device__ __forceinline__ int bin11(float v) {
+  const int h = (int)floorf(v);
+  return h < 0 ? 0 : (h > 10 ? 10 : h);
+}
+
+// ------------------------------------------------------------------------------------------------
+// Q2 SPFH: per-thread 33-bin integer histogram in shared memory (bin-major => conflict free)
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(STEP_THREADS) k_spfh(const CloudDev* clouds, float r2) {
+  const CloudDev& c = clouds[blockIdx.y];
+  const int i = blockIdx.x * STEP_THREADS + threadIdx.x;
+  __shared__ unsigned short hist[FDIM][STEP_THREADS];
+#pragma unroll
+  for (int k = 0; k < FDIM; k++) hist[k][threadIdx.x] = 0;
+  if (i >= c.n) return;
+  const float4 p = c.pts[i];
+  const float4 np = c.nrm[i];
+  float* out = c.spfh + (size_t)i * FPAD;
+  int cnt = 0;
+  if (np.w != 0.f) {
+    const float d_pi = 1.0f / (2.0f * 3.14159265358979323846f);
+    radius_visit(c, p.x, p.y, p.z, r2, [&](int pos, float, const float4& q) {
+      cnt++;
+      if (pos == i) return;
+      const float4 nq = __ldg(&c.nrm[pos]);
+      if (nq.w == 0.f) return;
+      float f1, f2, f3;
+      if (!pair_features(p, np, q, nq, f1, f2, f3)) return;
+      hist[bin11(11.0f * ((f1 + 3.14159265358979323846f) * d_pi))][threadIdx.x]++;
+      hist[11 + bin11(11.0f * ((f2 + 1.0f) * 0.5f))][threadIdx.x]++;
+      hist[22 + bin11(11.0f * ((f3 + 1.0f) * 0.5f))][threadIdx.x]++;
+    });
+  }
+  const float incr = cnt >= 2 ? 100.0f / (float)(cnt - 1) : 0.f;
+#pragma unroll
+  for (int k = 0; k < FDIM; k++) out[k] = (float)hist[k][threadIdx.x] * incr;
+  out[33] = 0.f; out[34] = 0.f; out[35] = 0.f;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Q3 FPFH: sum SPFH(q)/d2 over the neighbours, each 11-bin block rescaled to 100
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(STEP_THREADS) k_fpfh(const CloudDev* clouds, float r2) {
+  const CloudDev& c = clouds[blockIdx.y];
+  const int i = blockIdx.x * STEP_THREADS + threadIdx.x;
+  if (i >= c.n) return;
+  const float4 p = c.pts[i];
+  float h[FDIM];
+#pragma unroll
+  for (int k = 0; k < FDIM; k++) h[k] = 0.f;
+  float s0 = 0.f, s1 = 0.f, s2 = 0.f;
+  if (c.nrm[i].w != 0.f) {
+    radius_visit(c, p.x, p.y, p.z, r2, [&](int pos, float d2, const float4&) {
+      if (d2 == 0.f) return;
+      const float w = 1.0f / d2;
+      const float4* s4 = reinterpret_cast<const float4*>(c.spfh + (size_t)pos * FPAD);
+      float s[FPAD];
+#pragma unroll
+      for (int k = 0; k < 9; k++) {
+        const float4 v = __ldg(&s4[k]);
+        s[4 * k] = v.x; s[4 * k + 1] = v.y; s[4 * k + 2] = v.z; s[4 * k + 3] = v.w;
+      }
+#pragma unroll
+      for (int k = 0; k < 11; k++) {
+        const float v = s[k] * w;
+        s0 += v;
+        h[k] += v;
+      }
+#pragma unroll
+      for (int k = 11; k < 22; k++) {
+        const float v = s[k] * w;
+        s1 += v;
+        h[k] += v;
+      }
+#pragma unroll
+      for (int k = 22; k < 33; k++) {
+        const float v = s[k] * w;
+        s2 += v;
+        h[k] += v;
+      }
+    });
+  }
+  const float sc0 = s0 != 0.f ? 100.0f / s0 : 0.f, sc1 = s1 != 0.f ? 100.0f / s1 : 0.f, sc2 = s2 != 0.f ? 100.0f / s2 : 0.f;
+  float* out = c.fpfh + (size_t)i * FPAD;
+  bool any = false;
+#pragma unroll
+  for (int k = 0; k < FDIM; k++) {
+    const float v = h[k] * (k < 11 ? sc0 : (k < 22 ? sc1 : sc2));
+    out[k] = v;
+    any |= (v != 0.f);
+  }
+  out[33] = p.w;  // original index (int bits)
+  out[34] = any ? 1.f : 0.f;
+  out[35] = 0.f;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Q4 exact 33-D nearest neighbour, brute force with TMA-bulk staged base tiles
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned long long* bar, unsigned count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long* bar, unsigned bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, unsigned bytes, unsigned long long* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)),
+               "l"(src), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned parity) {
+  unsigned ok = 0;
+  while (!ok) {
+    asm volatile(
+        "{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}\n"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+  }
+}
+
+constexpr int NN_THREADS = 128;
+constexpr int NN_TILE = 64;  // base descriptors per smem tile: 64 * 144 B = 9216 B per cp.async.bulk
+
+// mode 0: queries = every point of fj (sorted order), base = fi; writes nn/dis by ORIGINAL j
+// mode 1: queries = fi points listed in `need` (original i), base = fj; writes rnn by ORIGINAL i
+__global__ void __launch_bounds__(NN_THREADS) k_feat_nn(const MatchDev* pairs, int mode) {
+  const MatchDev& P = pairs[blockIdx.y];
+  const CloudDev& Q = mode == 0 ? P.fj : P.fi;
+  const CloudDev& B = mode == 0 ? P.fi : P.fj;
+  const int nq = mode == 0 ? Q.n : P.counters[0];
+  const int q0 = blockIdx.x * NN_THREADS;
+  if (q0 >= nq) return;
+  __shared__ __align__(128) float tile[2][NN_TILE * FPAD];
+  __shared__ __align__(8) unsigned long long full[2];
+  const int qi = q0 + threadIdx.x;
+  const bool active = qi < nq;
+  int qpos = 0, qorig = -1;
+  if (active) {
+    if (mode == 0) {
+      qpos = qi;
+    } else {
+      qorig = P.need[qi];
+      qpos = Q.rank[qorig];
+    }
+  }
+  float q[FDIM];
+  bool qok = false;
+  if (active) {
+    const float4* q4 = reinterpret_cast<const float4*>(Q.fpfh + (size_t)qpos * FPAD);
+    float t[FPAD];
+#pragma unroll
+    for (int k = 0; k < 9; k++) {
+      const float4 v = q4[k];
+      t[4 * k] = v.x; t[4 * k + 1] = v.y; t[4 * k + 2] = v.z; t[4 * k + 3] = v.w;
+    }
+#pragma unroll
+    for (int k = 0; k < FDIM; k++) q[k] = t[k];
+    if (mode == 0) qorig = __float_as_int(t[33]);
+    qok = t[34] != 0.f;
+  } else {
+#pragma unroll
+    for (int k = 0; k < FDIM; k++) q[k] = 0.f;
+  }
+  if (threadIdx.x == 0) {
+    mbar_init(&full[0], 1);
+    mbar_init(&full[1], 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  const int nb = B.n;
+  const int ntiles = (nb + NN_TILE - 1) / NN_TILE;
+  if (threadIdx.x == 0) {
+    const unsigned bytes = (unsigned)min(NN_TILE, nb) * FPAD * 4;
+    mbar_expect_tx(&full[0], bytes);
+    bulk_g2s(tile[0], B.fpfh, bytes, &full[0]);
+  }
+  float best = 3.402823466e+38f;
+  int best_orig = -1;
+  for (int t = 0; t < ntiles; t++) {
+    if (threadIdx.x == 0 && t + 1 < ntiles) {
+      const int cntn = min(NN_TILE, nb - (t + 1) * NN_TILE);
+      const unsigned bytes = (unsigned)cntn * FPAD * 4;
+      mbar_expect_tx(&full[(t + 1) & 1], bytes);
+      bulk_g2s(tile[(t + 1) & 1], B.fpfh + (size_t)(t + 1) * NN_TILE * FPAD, bytes, &full[(t + 1) & 1]);
+    }
+    mbar_wait(&full[t & 1], (t >> 1) & 1);
+    const float* tb = tile[t & 1];
+    const int cnt = min(NN_TILE, nb - t * NN_TILE);
+    if (active && qok) {
+      for (int b = 0; b < cnt; b++) {
+        const float4* r4 = reinterpret_cast<const float4*>(tb + b * FPAD);  // all lanes read the same record: broadcast
+        float d = 0.f;
+        float4 v;
+        // sequential fp32 sum over the 33 dims (oracle's feat_d2 order); early exits only skip work
+#pragma unroll
+        for (int k = 0; k < 8; k++) {
+          v = r4[k];
+          float e;
+          e = q[4 * k] - v.x; d += e * e;
+          e = q[4 * k + 1] - v.y; d += e * e;
+          e = q[4 * k + 2] - v.z; d += e * e;
+          e = q[4 * k + 3] - v.w; d += e * e;
+          if ((k == 2 || k == 5) && d > best) break;
+        }
+        if (d > best) continue;
+        v = r4[8];
+        {
+          const float e = q[32] - v.x;
+          d += e * e;
+        }
+        if (v.z == 0.f) continue;  // unusable descriptor (invalid normal)
+        const int o = __float_as_int(v.y);
+        if (d < best || (d == best && o < best_orig)) {
+          best = d;
+          best_orig = o;
+        }
+      }
+    }
+    __syncthreads();  // everyone is done with tile[t&1] before it is refilled
+  }
+  if (active) {
+    if (mode == 0) {
+      P.nn[qorig] = best_orig;
+      P.dis[qorig] = best;
+    } else {
+      P.rnn[qorig] = best_orig;
+    }
+  }
+}
+
+__global__ void __launch_bounds__(256) k_match_init(const MatchDev* pairs) {
+  const MatchDev& P = pairs[blockIdx.y];
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < P.fi.n) {
+    P.first_j[i] = 0x7FFFFFFF;
+    P.rnn[i] = -1;
+  }
+  if (i < P.fj.n) P.tkey[i] = 0xFFFFFFFFu;
+  if (i < 8) P.counters[i] = 0;
+  if (i < 8) P.stats[i] = 0.0;
+}
+
+// gate on the FEATURE-space distance, remember the first (lowest) j that reaches each i (matcher.cc:441-447)
+__global__ void __launch_bounds__(256) k_first_hit(const MatchDev* pairs, float thr2) {
+  const MatchDev& P = pairs[blockIdx.y];
+  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= P.fj.n) return;
+  const int i = P.nn[j];
+  if (i < 0 || P.dis[j] > thr2) return;
+  atomicMin(&P.first_j[i], j);
+}
+
+__global__ void __launch_bounds__(256) k_need(const MatchDev* pairs) {
+  const MatchDev& P = pairs[blockIdx.y];
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= P.fi.n) return;
+  if (P.first_j[i] != 0x7FFFFFFF) P.need[atomicAdd(&P.counters[0], 1)] = i;  // order irrelevant: results land by index
+}
+
+// ordered compaction over ascending original j: keep (i, j) iff j was the first hit of i AND nn_j(i) == j
+__global__ void __launch_bounds__(1024) k_mutual(const MatchDev* pairs, float thr2) {
+  const MatchDev& P = pairs[blockIdx.x];
+  __shared__ int wsum[32];
+  __shared__ int carry;
+  if (threadIdx.x == 0) carry = 0;
+  __syncthreads();
+  const int nj = P.fj.n;
+  for (int base = 0; base < nj; base += 1024) {
+    const int j = base + threadIdx.x;
+    int keep = 0, i = -1;
+    if (j < nj) {
+      i = P.nn[j];
+      keep = (i >= 0 && !(P.dis[j] > thr2) && P.first_j[i] == j && P.rnn[i] == j) ? 1 : 0;
+    }
+    int incl = keep;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int t = __shfl_up_sync(0xffffffffu, incl, o);
+      if ((threadIdx.x & 31) >= o) incl += t;
+    }
+    if ((threadIdx.x & 31) == 31) wsum[threadIdx.x >> 5] = incl;
+    __syncthreads();
+    if (threadIdx.x < 32) {
+      const int w = wsum[threadIdx.x];
+      int wi = w;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const int t = __shfl_up_sync(0xffffffffu, wi, o);
+        if (threadIdx.x >= o) wi += t;
+      }
+      wsum[threadIdx.x] = wi - w;
+    }
+    __syncthreads();
+    const int pos = carry + wsum[threadIdx.x >> 5] + incl - keep;
+    if (keep) {
+      P.corres[2 * pos] = i;
+      P.corres[2 * pos + 1] = j;
+    }
+    __syncthreads();
+    if (threadIdx.x == 1023) carry = pos + keep;
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) P.counters[1] = carry;
+}
+
+// Matcher::normalizePoints: per-cloud mean (fp64 fixed-shape tree sum, cast to fp32) and the larger max radius
+__global__ void __launch_bounds__(1024) k_cloud_sum(const MatchDev* pairs) {
+  const MatchDev& P = pairs[blockIdx.y];
+  const int which = blockIdx.z;
+  const CloudDev& c = which == 0 ? P.fi : P.fj;
+  double s[3] = {0, 0, 0};
+  for (int i = threadIdx.x; i < c.n; i += 1024) {
+    const float4 p = c.pts[i];
+    s[0] += p.x; s[1] += p.y; s[2] += p.z;
+  }
+  __shared__ double red[32][3];
+#pragma unroll
+  for (int d = 0; d < 3; d++)
+    for (int o = 16; o > 0; o >>= 1) s[d] += __shfl_down_sync(0xffffffffu, s[d], o);
+  if ((threadIdx.x & 31) == 0)
+    for (int d = 0; d < 3; d++) red[threadIdx.x >> 5][d] = s[d];
+  __syncthreads();
+  if (threadIdx.x < 3) {
+    double t = 0;
+    for (int w = 0; w < 32; w++) t += red[w][threadIdx.x];
+    P.stats[3 * which + threadIdx.x] = t;
+  }
+}
+
+__global__ void __launch_bounds__(256) k_cloud_scale(const MatchDev* pairs) {
+  const MatchDev& P = pairs[blockIdx.y];
+  const int which = blockIdx.z;
+  const CloudDev& c = which == 0 ? P.fi : P.fj;
+  const float mx = (float)(P.stats[3 * which + 0] / c.n), my = (float)(P.stats[3 * which + 1] / c.n), mz = (float)(P.stats[3 * which + 2] / c.n);
+  float r = 0.f;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < c.n; i += gridDim.x * blockDim.x) {
+    const float4 p = c.pts[i];
+    const float x = p.x - mx, y = p.y - my, z = p.z - mz;
+    r = fmaxf(r, sqrtf((x * x + y * y) + z * z));
+  }
+  for (int o = 16; o > 0; o >>= 1) r = fmaxf(r, __shfl_xor_sync(0xffffffffu, r, o));
+  if ((threadIdx.x & 31) == 0) atomicMax((int*)&P.stats[6], __float_as_int(r));  // r >= 0: int order == float order
+}
+
+__device__ __forceinline__ unsigned long long splitmix64(unsigned long long x) {
+  x += 0x9E3779B97F4A7C15ull;
+  x = (x ^ (x >> 30)) * 0xBF58476D1CE4E5B9ull;
+  x = (x ^ (x >> 27)) * 0x94D049BB133111EBull;
+  return x ^ (x >> 31);
+}
+__device__ __forceinline__ int draw(unsigned long long seed, unsigned long long trial, int k, int n) {
+  return (int)(splitmix64(seed ^ splitmix64(trial * 4 + k)) % (unsigned long long)n);
+}
+
+__device__ __forceinline__ void norm_point(const CloudDev& c, int orig, float mx, float my, float mz, float scale, float o[3]) {
+  const float4 p = c.pts[c.rank[orig]];
+  o[0] = p.x - mx; o[1] = p.y - my; o[2] = p.z - mz;
+  if (scale != 1.0f) {
+    o[0] /= scale; o[1] /= scale; o[2] /= scale;
+  }
+}
+__device__ __forceinline__ float len3(const float a[3], const float b[3]) {
+  const float d0 = a[0] - b[0], d1 = a[1] - b[1], d2 = a[2] - b[2];
+  return sqrtf((d0 * d0 + d1 * d1) + d2 * d2);
+}
+
+// every trial evaluated independently (counter-based draws); a passing trial records, per correspondence,
+// the earliest (trial, slot) at which the serial loop would have added it (matcher.cc:484-536)
+__global__ void __launch_bounds__(256) k_tuple_trials(const MatchDev* pairs, QuatroParamsDev prm) {
+  const MatchDev& P = pairs[blockIdx.y];
+  const int ncorr = P.counters[1];
+  if (ncorr == 0) return;
+  const long long trials = (long long)ncorr * 100;
+  const float mxi = (float)(P.stats[0] / P.fi.n), myi = (float)(P.stats[1] / P.fi.n), mzi = (float)(P.stats[2] / P.fi.n);
+  const float mxj = (float)(P.stats[3] / P.fj.n), myj = (float)(P.stats[4] / P.fj.n), mzj = (float)(P.stats[5] / P.fj.n);
+  const float scale = __int_as_float(*(const int*)&P.stats[6]);
+  const float ts = prm.tuple_scale;
+  for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < trials; t += (long long)gridDim.x * blockDim.x) {
+    const int r0 = draw(prm.seed, t, 0, ncorr), r1 = draw(prm.seed, t, 1, ncorr);
+    float pi0[3], pi1[3], pj0[3], pj1[3];
+    norm_point(P.fi, P.corres[2 * r0], mxi, myi, mzi, scale, pi0);
+    norm_point(P.fi, P.corres[2 * r1], mxi, myi, mzi, scale, pi1);
+    norm_point(P.fj, P.corres[2 * r0 + 1], mxj, myj, mzj, scale, pj0);
+    norm_point(P.fj, P.corres[2 * r1 + 1], mxj, myj, mzj, scale, pj1);
+    const float li0 = len3(pi0, pi1), lj0 = len3(pj0, pj1);
+    if ((li0 * ts > lj0) || (lj0 > li0 / ts)) continue;
+    const int r2 = draw(prm.seed, t, 2, ncorr);
+    float pi2[3], pj2[3];
+    norm_point(P.fi, P.corres[2 * r2], mxi, myi, mzi, scale, pi2);
+    norm_point(P.fj, P.corres[2 * r2 + 1], mxj, myj, mzj, scale, pj2);
+    const float li1 = len3(pi1, pi2), li2 = len3(pi2, pi0), lj1 = len3(pj1, pj2), lj2 = len3(pj2, pj0);
+    if ((li1 * ts < lj1) && (lj1 < li1 / ts) && (li2 * ts < lj2) && (lj2 < li2 / ts)) {
+      const unsigned k = (unsigned)(t * 4);
+      atomicMin(&P.tkey[r0], k);
+      atomicMin(&P.tkey[r1], k + 1);
+      atomicMin(&P.tkey[r2], k + 2);
+    }
+  }
+}
+
+// serial semantics recovered: the loop stops after the first trial that leaves more than max_corres unique
+// correspondences; the survivors are emitted in insertion order.  One block per pair.
+__global__ void __launch_bounds__(1024) k_tuple_select(const MatchDev* pairs, QuatroParamsDev prm) {
+  const MatchDev& P = pairs[blockIdx.x];
+  const int ncorr = P.counters[1];
+  __shared__ unsigned hist[256];
+  __shared__ unsigned prefix, remaining, tstar;
+  __shared__ unsigned long long keys[1024];
+  __shared__ int nsel;
+  if (ncorr == 0) {
+    if (threadIdx.x == 0) P.counters[2] = 0;
+    return;
+  }
+  // (max_corres+1)-th smallest key by 4-pass radix select; none => keep everything
+  if (threadIdx.x == 0) {
+    prefix = 0;
+    remaining = (unsigned)prm.max_corres + 1;
+    tstar = 0xFFFFFFFFu;
+  }
+  __syncthreads();
+  bool found = true;
+  for (int pass = 3; pass >= 0 && found; pass--) {
+    if (threadIdx.x < 256) hist[threadIdx.x] = 0;
+    __syncthreads();
+    const unsigned pfx = prefix;
+    const int shift = pass * 8;
+    for (int r = threadIdx.x; r < ncorr; r += 1024) {
+      const unsigned k = P.tkey[r];
+      if (k == 0xFFFFFFFFu) continue;
+      if (pass == 3 || (k >> (shift + 8)) == (pfx >> (shift + 8))) atomicAdd(&hist[(k >> shift) & 255], 1u);
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      unsigned rem = remaining, acc = 0;
+      int b = 0;
+      for (; b < 256; b++) {
+        if (acc + hist[b] >= rem) break;
+        acc += hist[b];
+      }
+      if (b == 256) {
+        tstar = 0xFFFFFFFFu;  // fewer than max+1 unique additions in total
+        remaining = 0;
+      } else {
+        prefix = pfx | ((unsigned)b << shift);
+        remaining = rem - acc;
+        if (pass == 0) tstar = prefix >> 2;  // trial index of the (max+1)-th addition
+      }
+    }
+    __syncthreads();
+    found = remaining != 0;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) nsel = 0;
+  __syncthreads();
+  const unsigned ts = tstar;
+  for (int r = threadIdx.x; r < ncorr; r += 1024) {
+    const unsigned k = P.tkey[r];
+    if (k == 0xFFFFFFFFu) continue;
+    if (ts == 0xFFFFFFFFu || (k >> 2) <= ts) {
+      const int s = atomicAdd(&nsel, 1);
+      if (s < 1024) keys[s] = ((unsigned long long)k << 32) | (unsigned)r;
+    }
+  }
+  __syncthreads();
+  const int n = min(nsel, MAXC);
+  for (int s = threadIdx.x; s < 1024; s += 1024)
+    if (s >= nsel) keys[s] = 0xFFFFFFFFFFFFFFFFull;
+  __syncthreads();
+  for (int k = 2; k <= 1024; k <<= 1)
+    for (int j = k >> 1; j > 0; j >>= 1) {
+      const int i = threadIdx.x, l = i ^ j;
+      if (l > i) {
+        const unsigned long long a = keys[i], b = keys[l];
+        const bool up = (i & k) == 0;
+        if ((a > b) == up) {
+          keys[i] = b;
+          keys[l] = a;
+        }
+      }
+      __syncthreads();
+    }
+  if ((int)threadIdx.x < n) {
+    const int r = (int)(keys[threadIdx.x] & 0xFFFFFFFFu);
+    const int i = P.corres[2 * r], j = P.corres[2 * r + 1];
+    P.out_corr[2 * threadIdx.x] = P.swapped ? j : i;      // always (src, dst) (matcher.cc:527-535)
+    P.out_corr[2 * threadIdx.x + 1] = P.swapped ? i : j;
+  }
+  if (threadIdx.x == 0) P.counters[2] = n;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Q5 TEASER++ solve (QUATRO rotation, PMC_HEU-style clique), one block per pair
+// ------------------------------------------------------------------------------------------------
+constexpr int SV_THREADS = 256;
+constexpr int SV_WORDS = MAXC / 32;
+
+struct SolveSmem {
+  double S[MAXC][3], D[MAXC][3];
+  unsigned adj[MAXC][SV_WORDS];
+  unsigned radj[MAXC][SV_WORDS];
+  int deg[MAXC], core[MAXC], rank[MAXC], order[MAXC], csize[MAXC];
+  unsigned long long skey[MAXC];
+  int clique[MAXC];
+  double red[SV_THREADS];
+  double w[MAXC], res[MAXC];
+  double hval[2 * MAXC];
+  int hidx[2 * MAXC];
+  int m, best_r;
+  double R2[4], mu, prev_cost, t[3];
+  int stop;
+};
+
+__device__ __forceinline__ double block_sum(SolveSmem& sm, double v) {
+  sm.red[threadIdx.x] = v;
+  __syncthreads();
+  for (int o = SV_THREADS / 2; o > 0; o >>= 1) {
+    if ((int)threadIdx.x < o) sm.red[threadIdx.x] += sm.red[threadIdx.x + o];
+    __syncthreads();
+  }
+  const double r = sm.red[0];
+  __syncthreads();
+  return r;
+}
+__device__ __forceinline__ double block_max(SolveSmem& sm, double v) {
+  sm.red[threadIdx.x] = v;
+  __syncthreads();
+  for (int o = SV_THREADS / 2; o > 0; o >>= 1) {
+    if ((int)threadIdx.x < o) sm.red[threadIdx.x] = fmax(sm.red[threadIdx.x], sm.red[threadIdx.x + o]);
+    __syncthreads();
+  }
+  const double r = sm.red[0];
+  __syncthreads();
+  return r;
+}
+
+__global__ void __launch_bounds__(SV_THREADS) k_teaser_solve(const MatchDev* pairs, QuatroParamsDev prm) {
+  extern __shared__ __align__(16) unsigned char smraw[];
+  SolveSmem& sm = *reinterpret_cast<SolveSmem*>(smraw);
+  const MatchDev& P = pairs[blockIdx.x];
+  const int n = P.counters[2];
+  const int tid = threadIdx.x;
+  if (tid < 16) P.T[tid] = (tid % 5 == 0) ? 1.0 : 0.0;
+  if (tid == 0) {
+    P.counters[3] = 0;
+    P.counters[4] = 0;
+    P.counters[5] = 0;
+  }
+  if (n == 0) return;
+  const CloudDev& src = P.swapped ? P.fj : P.fi;
+  const CloudDev& dst = P.swapped ? P.fi : P.fj;
+  for (int i = tid; i < n; i += SV_THREADS) {
+    const float4 a = src.pts[src.rank[P.out_corr[2 * i]]], b = dst.pts[dst.rank[P.out_corr[2 * i + 1]]];
+    sm.S[i][0] = a.x; sm.S[i][1] = a.y; sm.S[i][2] = a.z;
+    sm.D[i][0] = b.x; sm.D[i][1] = b.y; sm.D[i][2] = b.z;
+    for (int w = 0; w < SV_WORDS; w++) {
+      sm.adj[i][w] = 0;
+      sm.radj[i][w] = 0;
+    }
+  }
+  __syncthreads();
+  // TIM scale-consistency graph: | ||b_ij|| - ||a_ij|| | <= 2 * noise_bound (cbar2 = 1, quatro_module.cc:40)
+  const double beta = 2.0 * prm.noise_bound;
+  for (int e = tid; e < n * n; e += SV_THREADS) {
+    const int i = e / n, j = e % n;
+    if (j <= i) continue;
+    double a = 0, b = 0;
+#pragma unroll
+    for (int d = 0; d < 3; d++) {
+      const double da = sm.S[j][d] - sm.S[i][d], db = sm.D[j][d] - sm.D[i][d];
+      a += da * da;
+      b += db * db;
+    }
+    if (fabs(sqrt(a) - sqrt(b)) <= beta) {
+      atomicOr(&sm.adj[i][j >> 5], 1u << (j & 31));
+      atomicOr(&sm.adj[j][i >> 5], 1u << (i & 31));
+    }
+  }
+  __syncthreads();
+  for (int i = tid; i < n; i += SV_THREADS) {
+    int d = 0;
+    for (int w = 0; w < SV_WORDS; w++) d += __popc(sm.adj[i][w]);
+    sm.deg[i] = d;
+    sm.csize[i] = d;  // csize doubles as the peeling degree
+    sm.rank[i] = 1;   // alive flag during peeling
+  }
+  __syncthreads();
+  // core numbers: peel the minimum-degree vertex (lowest index on ties); one warp, lanes own strided vertices
+  if (tid < 32) {
+    int k = 0;
+    for (int it = 0; it < n; it++) {
+      int bv = 0x7FFFFFFF, bi = -1;
+      for (int v = tid; v < n; v += 32)
+        if (sm.rank[v] && (sm.csize[v] < bv)) {
+          bv = sm.csize[v];
+          bi = v;
+        }
+      for (int o = 16; o > 0; o >>= 1) {
+        const int ov = __shfl_xor_sync(0xffffffffu, bv, o), oi = __shfl_xor_sync(0xffffffffu, bi, o);
+        if (ov < bv || (ov == bv && oi >= 0 && (bi < 0 || oi < bi))) {
+          bv = ov;
+          bi = oi;
+        }
+      }
+      k = max(k, bv);
+      if (tid == 0) {
+        sm.core[bi] = k;
+        sm.rank[bi] = 0;
+      }
+      __syncwarp();
+      for (int v = tid; v < n; v += 32)
+        if (sm.rank[v] && ((sm.adj[bi][v >> 5] >> (v & 31)) & 1u)) sm.csize[v]--;
+      __syncwarp();
+    }
+  }
+  __syncthreads();
+  // order by (core desc, degree desc, index asc): bitonic sort of packed keys
+  for (int i = tid; i < MAXC; i += SV_THREADS)
+    sm.skey[i] = i < n ? (((unsigned long long)(MAXC - sm.core[i]) << 40) | ((unsigned long long)(MAXC - sm.deg[i]) << 20) | (unsigned)i)
+                       : 0xFFFFFFFFFFFFFFFFull;
+  __syncthreads();
+  for (int k = 2; k <= MAXC; k <<= 1)
+    for (int j = k >> 1; j > 0; j >>= 1) {
+      for (int i = tid; i < MAXC; i += SV_THREADS) {
+        const int l = i ^ j;
+        if (l > i) {
+          const unsigned long long a = sm.skey[i], b = sm.skey[l];
+          const bool up = (i & k) == 0;
+          if ((a > b) == up) {
+            sm.skey[i] = b;
+            sm.skey[l] = a;
+          }
+        }
+      }
+      __syncthreads();
+    }
+  for (int r = tid; r < n; r += SV_THREADS) {
+    const int v = (int)(sm.skey[r] & 0xFFFFF);
+    sm.order[r] = v;
+    sm.rank[v] = r;
+  }
+  __syncthreads();
+  // adjacency in rank space: "first vertex of P in the global order" becomes "lowest set bit"
+  for (int v = tid; v < n; v += SV_THREADS) {
+    const int rv = sm.rank[v];
+    for (int u = 0; u < n; u++)
+      if ((sm.adj[v][u >> 5] >> (u & 31)) & 1u) {
+        const int ru = sm.rank[u];
+        sm.radj[rv][ru >> 5] |= 1u << (ru & 31);  // row rv is written by this thread only
+      }
+  }
+  __syncthreads();
+  // greedy clique from every start vertex (independent => one thread each)
+  for (int r = tid; r < n; r += SV_THREADS) {
+    unsigned Pm[SV_WORDS];
+    for (int w = 0; w < SV_WORDS; w++) Pm[w] = sm.radj[r][w];
+    int size = 1;
+    for (;;) {
+      int u = -1;
+      for (int w = 0; w < SV_WORDS; w++)
+        if (Pm[w]) {
+          u = w * 32 + __ffs(Pm[w]) - 1;
+          break;
+        }
+      if (u < 0) break;
+      size++;
+      for (int w = 0; w < SV_WORDS; w++) Pm[w] &= sm.radj[u][w];
+    }
+    sm.csize[r] = size;
+  }
+  __syncthreads();
+  if (tid == 0) {
+    int best = 0, br = 0;
+    for (int r = 0; r < n; r++)
+      if (sm.csize[r] > best) {
+        best = sm.csize[r];
+        br = r;
+      }
+    // replay the winner and list its members (ascending ORIGINAL correspondence index)
+    unsigned Pm[SV_WORDS], Cm[SV_WORDS];
+    for (int w = 0; w < SV_WORDS; w++) {
+      Pm[w] = sm.radj[br][w];
+      Cm[w] = 0;
+    }
+    {
+      const int v = sm.order[br];
+      Cm[v >> 5] |= 1u << (v & 31);
+    }
+    for (;;) {
+      int u = -1;
+      for (int w = 0; w < SV_WORDS; w++)
+        if (Pm[w]) {
+          u = w * 32 + __ffs(Pm[w]) - 1;
+          break;
+        }
+      if (u < 0) break;
+      const int v = sm.order[u];
+      Cm[v >> 5] |= 1u << (v & 31);
+      for (int w = 0; w < SV_WORDS; w++) Pm[w] &= sm.radj[u][w];
+    }
+    int m = 0;
+    for (int v = 0; v < n; v++)
+      if ((Cm[v >> 5] >> (v & 31)) & 1u) sm.clique[m++] = v;
+    sm.m = m;
+    P.counters[4] = m;
+  }
+  __syncthreads();
+  const int m = sm.m;
+  if (m <= 1) return;  // solution_.valid stays false
+  const int nt = m - 1;
+  // GNC-TLS with a weighted 2-D (yaw-only) Kabsch step on the chain TIMs
+  double nb2 = prm.noise_bound * prm.noise_bound;
+  if (nb2 < 1e-16) nb2 = 1e-2;
+  for (int k = tid; k < nt; k += SV_THREADS) sm.w[k] = 1.0;
+  if (tid == 0) {
+    sm.mu = 1.0;
+    sm.prev_cost = INFINITY;
+    sm.stop = 0;
+    sm.R2[0] = 1; sm.R2[1] = 0; sm.R2[2] = 0; sm.R2[3] = 1;
+  }
+  __syncthreads();
+  int iters = 0;
+  for (int it = 0; it < prm.max_iter; it++) {
+    iters = it + 1;
+    double h0 = 0, h1 = 0, h2 = 0, h3 = 0;
+    for (int k = tid; k < nt; k += SV_THREADS) {
+      const int c0 = sm.clique[k], c1 = sm.clique[k + 1];
+      const double ax = sm.S[c1][0] - sm.S[c0][0], ay = sm.S[c1][1] - sm.S[c0][1];
+      const double bx = sm.D[c1][0] - sm.D[c0][0], by = sm.D[c1][1] - sm.D[c0][1];
+      const double w = sm.w[k];
+      h0 += ax * w * bx; h1 += ax * w * by; h2 += ay * w * bx; h3 += ay * w * by;
+    }
+    h0 = block_sum(sm, h0); h1 = block_sum(sm, h1); h2 = block_sum(sm, h2); h3 = block_sum(sm, h3);
+    const double th = atan2(h1 - h2, h0 + h3);
+    const double cs = cos(th), sn = sin(th);
+    double mx = 0;
+    for (int k = tid; k < nt; k += SV_THREADS) {
+      const int c0 = sm.clique[k], c1 = sm.clique[k + 1];
+      const double ax = sm.S[c1][0] - sm.S[c0][0], ay = sm.S[c1][1] - sm.S[c0][1], az = sm.S[c1][2] - sm.S[c0][2];
+      const double bx = sm.D[c1][0] - sm.D[c0][0], by = sm.D[c1][1] - sm.D[c0][1], bz = sm.D[c1][2] - sm.D[c0][2];
+      const double rx = bx - (cs * ax - sn * ay), ry = by - (sn * ax + cs * ay), rz = bz - az;
+      sm.res[k] = rx * rx + ry * ry + rz * rz;
+      mx = fmax(mx, sm.res[k]);
+    }
+    mx = block_max(sm, mx);
+    if (tid == 0) {
+      sm.R2[0] = cs; sm.R2[1] = -sn; sm.R2[2] = sn; sm.R2[3] = cs;
+      if (it == 0) {
+        sm.mu = 1.0 / (2.0 * mx / nb2 - 1.0);
+        if (sm.mu <= 0) sm.stop = 1;
+      }
+    }
+    __syncthreads();
+    if (sm.stop) break;
+    const double mu = sm.mu;
+    const double th1 = (mu + 1) / mu * nb2, th2 = mu / (mu + 1) * nb2;
+    double cost = 0;
+    for (int k = tid; k < nt; k += SV_THREADS) {
+      const double r = sm.res[k];
+      cost += sm.w[k] * r;
+      sm.w[k] = r >= th1 ? 0.0 : (r <= th2 ? 1.0 : sqrt(nb2 * mu * (mu + 1) / r) - mu);
+    }
+    cost = block_sum(sm, cost);
+    if (tid == 0) {
+      const double diff = fabs(cost - sm.prev_cost);
+      sm.mu = mu * prm.gnc_factor;
+      sm.prev_cost = cost;
+      if (diff < prm.cost_thr) sm.stop = 1;
+    }
+    __syncthreads();
+    if (sm.stop) break;
+  }
+  __syncthreads();
+  // translation: per-axis TLS adaptive voting over dst_i - R src_i on the clique members
+  const double range = prm.noise_bound;
+  for (int d = 0; d < 3; d++) {
+    for (int k = tid; k < 2 * MAXC; k += SV_THREADS) {
+      sm.hval[k] = INFINITY;
+      sm.hidx[k] = 0;
+    }
+    __syncthreads();
+    for (int k = tid; k < m; k += SV_THREADS) {
+      const int c = sm.clique[k];
+      const double rs = d == 0 ? sm.R2[0] * sm.S[c][0] + sm.R2[1] * sm.S[c][1] : (d == 1 ? sm.R2[2] * sm.S[c][0] + sm.R2[3] * sm.S[c][1] : sm.S[c][2]);
+      const double x = sm.D[c][d] - rs;
+      sm.res[k] = x;
+      sm.hval[2 * k] = x - range; sm.hidx[2 * k] = k + 1;
+      sm.hval[2 * k + 1] = x + range; sm.hidx[2 * k + 1] = -k - 1;
+    }
+    __syncthreads();
+    // bitonic sort by (value, original slot) == std::stable_sort by value
+    for (int k = 2; k <= 2 * MAXC; k <<= 1)
+      for (int j = k >> 1; j > 0; j >>= 1) {
+        for (int i = tid; i < 2 * MAXC; i += SV_THREADS) {
+          const int l = i ^ j;
+          if (l > i) {
+            const double a = sm.hval[i], b = sm.hval[l];
+            const int ia = sm.hidx[i], ib = sm.hidx[l];
+            // slot order of the unsorted array: 2k for +, 2k+1 for -
+            const int sa = ia > 0 ? 2 * (ia - 1) : 2 * (-ia - 1) + 1, sb = ib > 0 ? 2 * (ib - 1) : 2 * (-ib - 1) + 1;
+            const bool gt = a > b || (a == b && (ia == 0 ? 1 << 30 : sa) > (ib == 0 ? 1 << 30 : sb));
+            const bool up = (i & k) == 0;
+            if (gt == up) {
+              sm.hval[i] = b; sm.hval[l] = a;
+              sm.hidx[i] = ib; sm.hidx[l] = ia;
+            }
+          }
+        }
+        __syncthreads();
+      }
+    if (tid == 0) {
+      const double w = 1.0 / (range * range);
+      double ris = range * m, dxw = 0, dwc = 0, sxi = 0, sxq = 0, best_cost = INFINITY, best = 0;
+      int card = 0;
+      for (int i = 0; i < 2 * m; i++) {
+        const int idx = abs(sm.hidx[i]) - 1;
+        const int eps = sm.hidx[i] > 0 ? 1 : -1;
+        const double X = sm.res[idx];
+        card += eps;
+        dwc += eps * w;
+        dxw += eps * w * X;
+        ris -= eps * range;
+        sxi += eps * X;
+        sxq += eps * X * X;
+        const double xh = dxw / dwc;
+        const double cost = (card * xh * xh + sxq - 2 * sxi * xh) + ris;
+        if (cost < best_cost) {
+          best_cost = cost;
+          best = xh;
+        }
+      }
+      sm.t[d] = best;
+    }
+    __syncthreads();
+  }
+  if (tid == 0) {
+    P.T[0] = sm.R2[0]; P.T[1] = sm.R2[1]; P.T[2] = 0; P.T[3] = sm.t[0];
+    P.T[4] = sm.R2[2]; P.T[5] = sm.R2[3]; P.T[6] = 0; P.T[7] = sm.t[1];
+    P.T[8] = 0; P.T[9] = 0; P.T[10] = 1; P.T[11] = sm.t[2];
+    P.T[12] = 0; P.T[13] = 0; P.T[14] = 0; P.T[15] = 1;
+    P.counters[3] = 1;
+    P.counters[5] = iters;
+  }
+}
+
+// coarse_aligned_ = transformPcd(src, T_quatro): double math, cast to float (utilities.hpp:164-175), ORIGINAL order,
+// emitted as (x, y, z, 1) records so that it can be fed straight back into the index build
+__global__ void __launch_bounds__(256) k_transform_raw(const CloudDev* clouds, const double* T16s, float4* const* outs) {
+  const CloudDev& src = clouds[blockIdx.y];
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= src.n) return;
+  const float4 p = src.pts[i];
+  const double* T = T16s + 16 * blockIdx.y;
+  const double x = p.x, y = p.y, z = p.z;
+  float4 o;
+  o.x = (float)(T[0] * x + T[1] * y + T[2] * z + T[3]);
+  o.y = (float)(T[4] * x + T[5] * y + T[6] * z + T[7]);
+  o.z = (float)(T[8] * x + T[9] * y + T[10] * z + T[11]);
+  o.w = 1.f;
+  outs[blockIdx.y][__float_as_int(p.w)] = o;
+}
+
+// ------------------------------------------------------------------------------------------------
+// host launchers
+// ------------------------------------------------------------------------------------------------
+int launch_fpfh(const CloudDev* d_clouds, int count, int max_n, float normal_r2, float fpfh_r2, cudaStream_t s) {
+  dim3 grid((max_n + STEP_THREADS - 1) / STEP_THREADS, count);
+  k_normals<<<grid, STEP_THREADS, 0, s>>>(d_clouds, normal_r2);
+  k_spfh<<<grid, STEP_THREADS, 0, s>>>(d_clouds, fpfh_r2);
+  k_fpfh<<<grid, STEP_THREADS, 0, s>>>(d_clouds, fpfh_r2);
+  return 3;
+}
+
+size_t solve_smem_bytes() { return sizeof(SolveSmem); }
+
+int launch_quatro_match_solve(const MatchDev* d_pairs, int count, int max_ni, int max_nj, const QuatroParamsDev& prm, cudaStream_t s) {
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaFuncSetAttribute(k_teaser_solve, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SolveSmem));
+    attr_set = true;
+  }
+  int l = 0;
+  k_match_init<<<dim3((max_ni + 255) / 256, count), 256, 0, s>>>(d_pairs); l++;
+  k_cloud_sum<<<dim3(1, count, 2), 1024, 0, s>>>(d_pairs); l++;
+  k_cloud_scale<<<dim3(64, count, 2), 256, 0, s>>>(d_pairs); l++;
+  k_feat_nn<<<dim3((max_nj + NN_THREADS - 1) / NN_THREADS, count), NN_THREADS, 0, s>>>(d_pairs, 0); l++;
+  k_first_hit<<<dim3((max_nj + 255) / 256, count), 256, 0, s>>>(d_pairs, prm.thr2); l++;
+  k_need<<<dim3((max_ni + 255) / 256, count), 256, 0, s>>>(d_pairs); l++;
+  k_feat_nn<<<dim3((max_ni + NN_THREADS - 1) / NN_THREADS, count), NN_THREADS, 0, s>>>(d_pairs, 1); l++;
+  k_mutual<<<count, 1024, 0, s>>>(d_pairs, prm.thr2); l++;
+  k_tuple_trials<<<dim3(128, count), 256, 0, s>>>(d_pairs, prm); l++;
+  k_tuple_select<<<count, 1024, 0, s>>>(d_pairs, prm); l++;
+  k_teaser_solve<<<count, SV_THREADS, sizeof(SolveSmem), s>>>(d_pairs, prm); l++;
+  return l;
+}
+
+void launch_transform_raw(const CloudDev* d_clouds, const double* d_T16s, int count, int max_n, float4* const* d_outs, cudaStream_t s) {
+  k_transform_raw<<<dim3((max_n + 255) / 256, count), 256, 0, s>>>(d_clouds, d_T16s, d_outs);
+}
+
+}  // namespace b200

@@ -72,7 +72,37 @@ typedef struct b200reg_result {
   int32_t reserved;
 } b200reg_result;
 
+/* Mirrors QuatroConfig (fast_lio_sam_qn/include/loop_closure.h:38-50) and the quatro<T> constructor arguments
+ * (third_party/Quatro/include/quatro/quatro_module.h:30-32), with the EFFECTIVE deployment values as defaults
+ * (normal radius 0.9, FPFH radius 1.5, max correspondences 200 because of the rosparam typo). */
+typedef struct b200reg_quatro_params {
+  double fpfh_normal_radius;   /* fpfh_normal_radi (0.9)                                              */
+  double fpfh_radius;          /* fpfh_radi (1.5)                                                     */
+  double noise_bound;          /* 0.3                                                                 */
+  double rot_gnc_factor;       /* 1.4                                                                 */
+  double rot_cost_thr;         /* 1e-4                                                                */
+  int32_t rot_max_iter;        /* 50                                                                  */
+  int32_t max_corres;          /* num_max_corres (200); must be <= 509                                */
+  double distance_threshold;   /* FEATURE-space gate of optimizedMatching (matcher.cc:422/444) (35)   */
+  double tuple_scale;          /* 0.95 (quatro_module.cc:61)                                          */
+  uint64_t seed;               /* replaces srand(time(NULL)) (matcher.cc:465) by a counter-based RNG  */
+  int32_t estimate_scale;      /* must be 0 (QN/config: estimating_scale false)                       */
+  int32_t use_optimized_matching; /* must be 1 (config.yaml:32); advancedMatching is not built        */
+} b200reg_quatro_params;
+
+/* Telemetry of one quatro<T>::align call. */
+typedef struct b200reg_quatro_info {
+  double T[16];          /* out_tf_ (row-major); Identity when !valid                                  */
+  int32_t valid;         /* if_valid (quatro_module.cc:63-72)                                          */
+  int32_t n_mutual;      /* correspondences after the mutual check                                     */
+  int32_t n_corr;        /* after the tuple test (<= max_corres + 3)                                   */
+  int32_t clique_size;   /* max-clique inliers                                                         */
+  int32_t gnc_iterations;
+  int32_t reserved;
+} b200reg_quatro_info;
+
 void b200reg_default_gicp_params(b200reg_gicp_params* p);
+void b200reg_default_quatro_params(b200reg_quatro_params* p);
 const char* b200reg_last_error(void);
 const char* b200reg_version(void);
 
@@ -119,6 +149,24 @@ int b200reg_icp_alignment(b200reg_ctx* ctx, int count, const float* const* src_x
                           const float* const* tgt_xyz, const size_t* tgt_n, size_t stride_bytes, int on_device,
                           const b200reg_gicp_params* params, b200reg_result* out);
 
+/* ---- Quatro (global registration) --------------------------------------------------------- */
+/* teaser::FPFHEstimation::computeFPFHFeatures (third_party/Quatro/src/fpfh.cc:14-42) for `count` clouds:
+ * normals (radius search, viewpoint (0,0,0)) -> SPFH -> FPFH, kept on the device with the cloud.     */
+int b200reg_clouds_fpfh(b200reg_ctx* ctx, int count, b200reg_cloud* const* clouds, double normal_radius,
+                        double fpfh_radius);
+/* quatro<PointType>::align (third_party/Quatro/src/quatro_module.cc:48-79) for `count` pairs: FPFH on demand,
+ * optimizedMatching (matcher.cc:358-561), TEASER++ QUATRO solve.  corr_out (optional): count x 2*512 ints,
+ * the (src, dst) ORIGINAL indices of the final correspondences of each pair.                             */
+int b200reg_quatro_align(b200reg_ctx* ctx, int count, b200reg_cloud* const* src, b200reg_cloud* const* dst,
+                         const b200reg_quatro_params* params, b200reg_quatro_info* out, int32_t* corr_out);
+/* LoopClosure::coarseToFineAlignment (fast_lio_sam_qn/src/loop_closure.cpp:138-159) for `count` pairs from raw
+ * buffers: Quatro -> transformPcd(src, T_quatro) -> icpAlignment -> T = T_gicp * T_quatro.
+ * out[i].T is the composed transform; quatro_out (optional) receives the coarse stage.                   */
+int b200reg_loop_closure(b200reg_ctx* ctx, int count, const float* const* src_xyz, const size_t* src_n,
+                         const float* const* tgt_xyz, const size_t* tgt_n, size_t stride_bytes, int on_device,
+                         const b200reg_quatro_params* qparams, const b200reg_gicp_params* gparams,
+                         b200reg_result* out, b200reg_quatro_info* quatro_out);
+
 /* Output cloud of align(): final_transformation_ applied to the source in fp32
  * (lsq_registration_impl.hpp:114).  out_xyz: n x 3 floats (host), original point order.       */
 int b200reg_transform_cloud(b200reg_ctx* ctx, const b200reg_cloud* cloud, const float* Tf16, float* out_xyz);
@@ -128,6 +176,8 @@ int b200reg_transform_cloud(b200reg_ctx* ctx, const b200reg_cloud* cloud, const 
  * idx_out/d2_out: nq x k, ascending; indices refer to the ORIGINAL point order; -1 pads k > n.   */
 int b200reg_knn(b200reg_ctx* ctx, const b200reg_cloud* cloud, const float* queries, size_t nq,
                 size_t qstride_bytes, int k, int32_t* idx_out, float* d2_out);
+/* normals (n x 3, NaN where fewer than 3 neighbours) and FPFH (n x 33), original point order.            */
+int b200reg_get_fpfh(b200reg_ctx* ctx, const b200reg_cloud* cloud, float* normals_out, float* fpfh_out);
 /* n x 9 doubles (row-major 3x3 block of the reference's Matrix4d), original point order.          */
 int b200reg_get_covariances(b200reg_ctx* ctx, const b200reg_cloud* cloud, double* cov9_out);
 /* NanoGICP::linearize at pose T16 (nano_gicp_impl.hpp:213-270): H 6x6 row-major, b, sum of errors,

@@ -177,3 +177,97 @@ def gicp_align(src, tgt, params=None, guess=None, want_aligned=False, want_trace
     if want_trace:
         out["trace"] = trace[:res.n_linearize]
     return out
+
+
+# ---------------------------------------------------------------------------------------------
+# Quatro half (oracle/oracle_quatro.cpp)
+class QuatroParams(C.Structure):
+    _fields_ = [("fpfh_normal_radius", C.c_double), ("fpfh_radius", C.c_double), ("noise_bound", C.c_double),
+                ("rot_gnc_factor", C.c_double), ("rot_cost_thr", C.c_double), ("rot_max_iter", C.c_int),
+                ("max_corres", C.c_int), ("distance_threshold", C.c_double), ("tuple_scale", C.c_double),
+                ("seed", C.c_uint64)]
+
+    @staticmethod
+    def default():
+        p = QuatroParams()
+        lib().orc_quatro_default_params(C.byref(p))
+        return p
+
+
+def fpfh(pts, normal_radius=0.9, fpfh_radius=1.5):
+    """-> (normals (n,3), spfh (n,33), fpfh (n,33)) float32; PCL NormalEstimation + FPFHEstimationOMP restated."""
+    pts = _f32(pts)
+    n = len(pts)
+    nrm = np.empty((n, 3), np.float32)
+    sp = np.empty((n, 33), np.float32)
+    fp = np.empty((n, 33), np.float32)
+    lib().orc_fpfh(_p(pts, C.c_float), n, pts.shape[1], C.c_double(normal_radius), C.c_double(fpfh_radius),
+                   _p(nrm, C.c_float), _p(sp, C.c_float), _p(fp, C.c_float))
+    return nrm, sp, fp
+
+
+def fpfh_from_normals(pts, normals, fpfh_radius=1.5):
+    pts = _f32(pts)
+    nrm = np.ascontiguousarray(normals, np.float32)
+    n = len(pts)
+    sp = np.empty((n, 33), np.float32)
+    fp = np.empty((n, 33), np.float32)
+    lib().orc_fpfh_from_normals(_p(pts, C.c_float), n, pts.shape[1], _p(nrm, C.c_float), C.c_double(fpfh_radius),
+                                _p(sp, C.c_float), _p(fp, C.c_float))
+    return sp, fp
+
+
+def match(src, dst, fsrc, fdst, params=None):
+    """Matcher::optimizedMatching -> (corr (k,2) (src,dst), mutual (m,2) (i,j) in fi/fj numbering)."""
+    src, dst = _f32(src), _f32(dst)
+    fs = np.ascontiguousarray(fsrc, np.float32)
+    fd = np.ascontiguousarray(fdst, np.float32)
+    p = params or QuatroParams.default()
+    corr = np.empty((p.max_corres + 8, 2), np.int32)
+    mut = np.empty((min(len(src), len(dst)), 2), np.int32)
+    nm = C.c_int()
+    k = lib().orc_match(_p(src, C.c_float), len(src), src.shape[1], _p(dst, C.c_float), len(dst), dst.shape[1],
+                        _p(fs, C.c_float), _p(fd, C.c_float), C.byref(p), _p(corr, C.c_int), C.byref(nm), _p(mut, C.c_int))
+    return corr[:k].copy(), mut[:nm.value].copy()
+
+
+def quatro_solve(src, dst, corr, params=None):
+    src, dst = _f32(src), _f32(dst)
+    corr = np.ascontiguousarray(corr, np.int32)
+    p = params or QuatroParams.default()
+    T = np.empty(16, np.float64)
+    clique = np.empty(max(len(corr), 1), np.int32)
+    cs, it = C.c_int(), C.c_int()
+    valid = lib().orc_quatro_solve(_p(src, C.c_float), src.shape[1], _p(dst, C.c_float), dst.shape[1], _p(corr, C.c_int),
+                                   len(corr), C.byref(p), _p(T, C.c_double), _p(clique, C.c_int), C.byref(cs), C.byref(it))
+    return dict(T=T.reshape(4, 4), valid=bool(valid), clique=clique[:cs.value].copy(), gnc_iters=it.value)
+
+
+def quatro_align(src, dst, params=None):
+    """quatro<T>::align restated (third_party/Quatro/src/quatro_module.cc:48-79)."""
+    src, dst = _f32(src), _f32(dst)
+    p = params or QuatroParams.default()
+    T = np.empty(16, np.float64)
+    nc = C.c_int()
+    t1, t2, t3 = C.c_double(), C.c_double(), C.c_double()
+    valid = lib().orc_quatro_align(_p(src, C.c_float), len(src), src.shape[1], _p(dst, C.c_float), len(dst), dst.shape[1],
+                                   C.byref(p), _p(T, C.c_double), C.byref(nc), C.byref(t1), C.byref(t2), C.byref(t3))
+    return dict(T=T.reshape(4, 4), valid=bool(valid), n_corr=nc.value, ms_fpfh=t1.value, ms_match=t2.value, ms_solve=t3.value)
+
+
+def coarse_to_fine(src, dst, qparams=None, gparams=None, quatro_T=None):
+    """LoopClosure::coarseToFineAlignment (fast_lio_sam_qn/src/loop_closure.cpp:138-159).
+
+    quatro_T: use this coarse transform instead of running the oracle's own Quatro stage (stage isolation)."""
+    q = quatro_align(src, dst, qparams) if quatro_T is None else dict(T=np.asarray(quatro_T, np.float64), valid=True)
+    out = dict(quatro=q, valid=False, T=q["T"].copy())
+    if not q["valid"]:
+        return out
+    src = _f32(src)
+    coarse = src.copy()
+    # transformPcd: Matrix4d, double math, cast to float (utilities.hpp:164-175, SURVEY App. B.2)
+    coarse[:, :3] = (src[:, :3].astype(np.float64) @ q["T"][:3, :3].T + q["T"][:3, 3]).astype(np.float32)
+    g = gicp_align(coarse, dst, gparams)
+    out.update(gicp=g, T=g["Tf"].astype(np.float64) @ q["T"], fitness=g["fitness"], converged=g["converged"],
+               valid=bool(g["converged"] and g["fitness"] < 1.5))
+    return out

@@ -1,0 +1,128 @@
+"""GPU parity tests for the Quatro half: each stage isolated against the CPU oracle, then end to end.
+
+The reference stage is nondeterministic (time-seeded rand(), racy TBB), so the bar is the oracle with a
+fixed counter-based generator; the end-to-end bar is the SE(3) AFTER the Nano-GICP refinement
+(SURVEY.md §8c iii): 1e-4 rad / 1e-3 m.
+"""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+ROT_TOL, TRANS_TOL = 1e-4, 1e-3
+
+
+@pytest.fixture(scope="module")
+def qpair(synth):
+    return synth.make_pair(2000, 8000, 9000, mode="quatro")
+
+
+def test_normals_and_fpfh_match_oracle(ctx, oracle, qpair):
+    src, dst, _ = qpair
+    cl, = ctx.create_clouds([dst])
+    ctx.fpfh([cl], 0.9, 1.5)
+    gn, gf = ctx.get_fpfh(cl)
+    on, osp, of = oracle.fpfh(dst, 0.9, 1.5)
+    assert np.array_equal(np.isnan(gn[:, 0]), np.isnan(on[:, 0]))
+    ok = ~np.isnan(on[:, 0])
+    # same flip rule on both sides: normals agree including sign, up to fp64 eigen-solver round-off; a handful of
+    # near-isotropic neighbourhoods (two equal small eigenvalues) are ill-conditioned
+    dots = np.einsum("ij,ij->i", gn[ok], on[ok])
+    assert np.quantile(dots, 0.01) > 1 - 1e-6
+    assert (dots > 0.999).mean() > 0.995
+    # FPFH: fp32 accumulation order differs (tree order vs sorted order); PCL's own float accumulation noise is ~1e-3
+    err = np.abs(gf - of).max(1)
+    assert np.median(err) < 1e-3
+    assert np.quantile(err, 0.98) < 5e-2
+    # structure: each 11-bin block sums to 100 (or the descriptor is all zero)
+    sums = gf.reshape(-1, 3, 11).sum(2)
+    nz = np.abs(gf).sum(1) > 0
+    assert np.allclose(sums[nz], 100.0, atol=2e-2)
+    # stage isolation: FPFH from the GPU's OWN normals through the oracle agrees tightly
+    _, of2 = oracle.fpfh_from_normals(dst, np.where(np.isnan(gn), np.nan, gn), 1.5)
+    err2 = np.abs(gf - of2).max(1)
+    assert np.quantile(err2, 0.99) < 5e-3, np.quantile(err2, [0.5, 0.9, 0.99, 1.0])
+    cl.destroy()
+
+
+def _gpu_stage(ctx, src, dst, prm=None):
+    cs, cd = ctx.create_clouds([src, dst])
+    info = ctx.quatro_align([cs], [cd], params=prm, want_corr=True)[0]
+    _, fs = ctx.get_fpfh(cs)
+    _, fd = ctx.get_fpfh(cd)
+    cs.destroy(); cd.destroy()
+    return info, fs, fd
+
+
+def test_matching_equals_oracle_on_same_descriptors(ctx, oracle, qpair):
+    src, dst, _ = qpair
+    info, fs, fd = _gpu_stage(ctx, src, dst)
+    corr, mutual = oracle.match(src, dst, fs, fd)  # the GPU's descriptors through the CPU matcher
+    assert info["n_mutual"] == len(mutual)
+    assert info["n_corr"] == len(corr)
+    assert np.array_equal(info["corr"], corr), "final correspondences (order included) must equal the oracle's"
+    assert 0 < len(corr) <= 203
+
+
+def test_matching_swapped_clouds(ctx, oracle, qpair):
+    """dst larger than src: fi/fj swap (matcher.cc:364-369); output pairs stay (src, dst)."""
+    src, dst, _ = qpair
+    assert len(dst) > len(src)
+    info, fs, fd = _gpu_stage(ctx, dst, src)  # now the FIRST cloud is the larger one: no swap
+    corr, _ = oracle.match(dst, src, fs, fd)
+    assert np.array_equal(info["corr"], corr)
+
+
+def test_solver_equals_oracle_on_same_correspondences(ctx, oracle, synth, qpair):
+    src, dst, Texp = qpair
+    info, _, _ = _gpu_stage(ctx, src, dst)
+    o = oracle.quatro_solve(src, dst, info["corr"])
+    assert info["valid"] == o["valid"]
+    assert info["clique_size"] == len(o["clique"])
+    assert info["gnc_iterations"] == o["gnc_iters"]
+    assert np.abs(info["T"] - o["T"]).max() < 1e-9
+    # yaw-only rotation (SURVEY A.8 viii)
+    assert info["T"][2, 2] == 1.0 and info["T"][0, 2] == 0.0 and info["T"][2, 0] == 0.0
+    rot, tr = synth.se3_error(info["T"], Texp)
+    assert rot < 0.06 and tr < 3.5  # coarse stage only: GICP absorbs the rest
+
+
+def test_coarse_to_fine_matches_oracle(ctx, oracle, synth):
+    """LoopClosure::coarseToFineAlignment.  Two statements:
+    (a) fine stage on the SAME coarse transform agrees with the oracle to the parity bar (1e-4 rad / 1e-3 m);
+    (b) the two complete pipelines (each with its own Quatro stage, whose descriptors differ by fp32 summation
+        order) land within Nano-GICP's own stopping tolerance of each other and on the ground truth."""
+    for seed in (2000, 2002):
+        src, dst, Texp = synth.make_pair(seed, 8000, 8000, mode="quatro")
+        res, qi = ctx.loop_closure([src], [dst])
+        r, q = res[0], qi[0]
+        assert q["valid"]
+        o_same = oracle.coarse_to_fine(src, dst, quatro_T=q["T"])
+        rot, tr = synth.se3_error(r["T"], o_same["T"])
+        assert rot < ROT_TOL and tr < TRANS_TOL, (seed, rot, tr)
+        assert r["converged"] == o_same["converged"] and r["n_linearize"] == o_same["gicp"]["n_linearize"]
+        assert abs(r["fitness"] - o_same["fitness"]) < 1e-5 * max(o_same["fitness"], 1e-3)
+        o = oracle.coarse_to_fine(src, dst)
+        assert o["quatro"]["valid"]
+        rot, tr = synth.se3_error(q["T"], o["quatro"]["T"])
+        assert rot < 0.05 and tr < 1.5, ("coarse stages", rot, tr)
+        rot, tr = synth.se3_error(r["T"], o["T"])
+        assert rot < 2e-3 and tr < 1e-2, ("pipelines", rot, tr)  # rotation_eps 2e-3 / transformation_eps 1e-2
+        rot, tr = synth.se3_error(r["T"], Texp)
+        assert rot < 5e-3 and tr < 5e-2
+
+
+def test_quatro_batch_equals_single_and_invalid_pairs(ctx, synth):
+    pairs = [synth.make_pair(2100 + i, 5000 + 400 * i, 6000 - 300 * i, mode="quatro") for i in range(3)]
+    # an unrelated pair of tiny random blobs: no correspondences -> invalid, Identity (quatro_module.cc:63-66)
+    rng = np.random.default_rng(0)
+    blob_a = rng.normal(0, 20, (300, 4)).astype(np.float32)
+    blob_b = rng.normal(0, 20, (280, 4)).astype(np.float32)
+    srcs = [p[0] for p in pairs] + [blob_a]
+    dsts = [p[1] for p in pairs] + [blob_b]
+    res, qi = ctx.loop_closure(srcs, dsts)
+    res2, qi2 = ctx.loop_closure(srcs, dsts)
+    for i in range(4):
+        single, qs = ctx.loop_closure([srcs[i]], [dsts[i]])
+        assert np.array_equal(res[i]["T"], single[0]["T"]) and np.array_equal(res[i]["T"], res2[i]["T"])
+        assert qi[i]["n_corr"] == qs[0]["n_corr"] == qi2[i]["n_corr"]
+    assert not qi[3]["valid"] and np.array_equal(qi[3]["T"], np.eye(4)) and not res[3]["valid"]
