@@ -32,7 +32,7 @@ sys.path.insert(0, os.path.join(REPO, "fast-lio-sam-qn_b200"))
 
 import numpy as np  # noqa: E402
 
-METRIC = "loop_closure_registrations_per_sec_100k_pt_pairs"
+METRIC = "loop_closure_registrations_per_sec_100k_pt_pairs"  # --workload quatro reports the same unit on configs[2]
 UNIT = "pairs/s"
 N_POINTS = 100000
 
@@ -44,18 +44,20 @@ def parse():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--pairs", type=int, default=16, help="pairs per step per rank")
-    ap.add_argument("--points", type=int, default=N_POINTS)
+    ap.add_argument("--points", type=int, default=None)
+    ap.add_argument("--workload", default="gicp", choices=["gicp", "quatro"],
+                    help="gicp = configs[1] (the headline); quatro = configs[2] Quatro+Nano-GICP full loop closure")
     ap.add_argument("--cpu-sample-pairs", type=int, default=6)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     return ap.parse_args()
 
 
-def make_pairs(rank, n_pairs, n_points):
+def make_pairs(rank, n_pairs, n_points, mode="gicp"):
     from b200reg import synth
     pairs = []
     for i in range(n_pairs):
-        seed = 1000 + rank * n_pairs + i  # config 2 seeds 1000..
-        src, dst, Texp = synth.make_pair(seed, n_points, n_points, mode="gicp")
+        seed = (1000 if mode == "gicp" else 2000) + rank * n_pairs + i  # config 2 seeds 1000.., config 3 2000..
+        src, dst, Texp = synth.make_pair(seed, n_points, n_points, mode=mode)
         pairs.append((src, dst, Texp))
     return pairs
 
@@ -73,27 +75,29 @@ def cpu_info():
     return model, os.cpu_count()
 
 
-def run_cpu(pairs, budget_s=20.0, max_pairs=6):
+def run_cpu(pairs, budget_s=20.0, max_pairs=6, workload="gicp"):
     """Time the CPU oracle (kNN through the reference's nanoflann when oracle/_ref exists)."""
     from oracle import oracle as orc
     orc.lib()
     used_ref = orc.use_ref_nanoflann(True) == 0
     orc.gicp_align(pairs[0][0][:20000], pairs[0][1][:20000])  # warm the OpenMP pool
+    fn = orc.gicp_align if workload == "gicp" else orc.coarse_to_fine
     times = []
     t_start = time.perf_counter()
     for i in range(max_pairs):
         src, dst, _ = pairs[i % len(pairs)]
         t0 = time.perf_counter()
-        orc.gicp_align(src, dst)
+        fn(src, dst)
         times.append(time.perf_counter() - t0)
         if time.perf_counter() - t_start > budget_s:
             break
     per_pair = float(np.mean(times))
     return dict(value=1.0 / per_pair, unit=UNIT, cores=orc.num_threads(), kind="port",
                 ms_per_pair=1e3 * per_pair, best_ms_per_pair=1e3 * float(np.min(times)),
-                sample="%d pairs of %dk x %dk points, serial over pairs, OpenMP over points; restated Nano-GICP "
-                       "(oracle/oracle_gicp.cpp) with kNN = %s" %
+                sample="%d pairs of %dk x %dk points, serial over pairs, OpenMP over points; restated %s "
+                       "(oracle/) with kNN = %s" %
                        (len(times), len(pairs[0][0]) // 1000, len(pairs[0][1]) // 1000,
+                        "Nano-GICP" if workload == "gicp" else "Quatro (FPFH + brute-force 33-D matching + QUATRO solve) + Nano-GICP",
                         "reference nanoflann (oracle/_ref)" if used_ref else "oracle kd-tree (oracle/_ref missing)"),
                 cpu_model=cpu_info()[0])
 
@@ -156,16 +160,17 @@ def main_reference(args):
     if rank != 0:
         return
     n_pairs = 2
-    pairs = make_pairs(0, n_pairs, args.points)
+    pairs = make_pairs(0, n_pairs, args.points, args.workload)
     from oracle import oracle as orc
     orc.lib()
     used_ref = orc.use_ref_nanoflann(True) == 0
+    fn = orc.gicp_align if args.workload == "gicp" else orc.coarse_to_fine
     for _ in range(max(args.warmup, 1)):
-        orc.gicp_align(pairs[0][0], pairs[0][1])
+        fn(pairs[0][0], pairs[0][1])
     t0 = time.perf_counter()
     for s in range(args.steps):
         for src, dst, _ in pairs:
-            orc.gicp_align(src, dst)
+            fn(src, dst)
     dt = time.perf_counter() - t0
     val = n_pairs * args.steps / dt
     sample = ("each step = %d pairs of %dk x %dk points run serially, all host threads per pair; CPU port of "
@@ -175,16 +180,25 @@ def main_reference(args):
         "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32 points / f64 solver", "data": "synthetic",
-        "config": {"workload": "configs[1]: Nano-GICP %dk-pt KITTI-shaped scan pair (LoopClosure::icpAlignment)" % (args.points // 1000),
-                   "pairs_per_step": n_pairs, "points_per_cloud": args.points},
+        "config": {"workload": workload_name(args), "pairs_per_step": n_pairs, "points_per_cloud": args.points},
         "cpu_baseline": {"value": val, "unit": UNIT, "cores": orc.num_threads(), "kind": "port", "sample": sample,
                          "cpu_model": cpu_info()[0]},
         "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }))
 
 
+def workload_name(args):
+    if args.workload == "gicp":
+        return ("configs[1]: Nano-GICP %dk-pt KITTI-shaped scan pair (LoopClosure::icpAlignment: 2 index builds + "
+                "2 kNN-15 covariance passes + LM align + fitness)" % (args.points // 1000))
+    return ("configs[2]: Quatro+Nano-GICP full loop closure on %dk-pt pairs (LoopClosure::coarseToFineAlignment: FPFH -> "
+            "optimizedMatching -> QUATRO solve -> transform -> GICP refine)" % (args.points // 1000))
+
+
 def main():
     args = parse()
+    if args.points is None:
+        args.points = N_POINTS if args.workload == "gicp" else 20000
     if args.impl == "reference":
         return main_reference(args)
 
@@ -204,7 +218,7 @@ def main():
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
 
     B = args.pairs
-    pairs = make_pairs(rank, B, args.points)
+    pairs = make_pairs(rank, B, args.points, args.workload)
     ctx = b200reg.Context(local_rank)
     stream = torch.cuda.Stream()
     ctx.set_stream(stream.cuda_stream)
@@ -226,8 +240,12 @@ def main():
     def step(on_device):
         srcs = dev_src if on_device else host_src
         dsts = dev_dst if on_device else host_dst
-        res = ctx.icp_alignment_ptrs([t.data_ptr() for t in srcs], ns_s, [t.data_ptr() for t in dsts], ns_d, stride,
-                                     on_device, prm)
+        if args.workload == "gicp":
+            res = ctx.icp_alignment_ptrs([t.data_ptr() for t in srcs], ns_s, [t.data_ptr() for t in dsts], ns_d, stride,
+                                         on_device, prm)
+        else:
+            res, _ = ctx.loop_closure_ptrs([t.data_ptr() for t in srcs], ns_s, [t.data_ptr() for t in dsts], ns_d, stride,
+                                           on_device, None, prm)
         if world > 1:  # the ONE collective of the path: all-gather of the 4x4 transforms
             loc = torch.tensor(np.array([list(r.T) for r in res]), dtype=torch.float64, device="cuda")
             with torch.cuda.stream(stream):
@@ -301,9 +319,7 @@ def main():
             "warmup": args.warmup, "ms_per_step": ms_dev / args.steps, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32 points+kNN / f64 covariance+solver",
             "data": "synthetic",
-            "config": {"workload": "configs[1]: Nano-GICP %dk-pt KITTI-shaped scan pair (LoopClosure::icpAlignment: "
-                                   "2 index builds + 2 kNN-15 covariance passes + LM align + fitness)" % (args.points // 1000),
-                       "pairs_per_step_per_gpu": B, "points_per_cloud": args.points, "seeds": "1000+rank*B+i",
+            "config": {"workload": workload_name(args), "pairs_per_step_per_gpu": B, "points_per_cloud": args.points, "seeds": "1000+rank*B+i",
                        "l2": "working set per step (%.0f MB raw + ~%.0f MB derived) exceeds the 126 MB L2; clouds are "
                              "rebuilt from raw xyz every step" % (h2d_bytes / 1e6, B * 2 * args.points * 100 / 1e6),
                        "parallelism": "pairs sharded over ranks, one NCCL all-gather of 4x4 transforms per step" if world > 1 else "single GPU"},
@@ -320,7 +336,7 @@ def main():
                          "mean_linearize_passes": float(np.mean([r.n_linearize for r in res]))},
         }
         if world == 1 and not args.no_cpu_baseline:
-            out["cpu_baseline"] = run_cpu(pairs, max_pairs=args.cpu_sample_pairs)
+            out["cpu_baseline"] = run_cpu(pairs, max_pairs=args.cpu_sample_pairs, workload=args.workload)
         print(json.dumps(out))
     if dist is not None:
         dist.barrier()
