@@ -75,13 +75,32 @@ def cpu_info():
     return model, os.cpu_count()
 
 
+def calibrate_threads(orc, fn, pair):
+    """Pick the OpenMP thread count that makes the CPU path FASTEST on this host (all logical CPUs is not always it:
+    on the 128-thread GPU-box Xeon the guided-schedule loops run 8x slower at 128 threads than at 32)."""
+    ncpu = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    cands = sorted({max(1, ncpu >> k) for k in range(0, 4)}, reverse=True)
+    best, best_t = cands[0], float("inf")
+    src, dst = pair[0][:30000], pair[1][:30000]
+    for n in cands:
+        orc.lib().orc_set_num_threads(n)
+        fn(src, dst)
+        t0 = time.perf_counter()
+        fn(src, dst)
+        dt = time.perf_counter() - t0
+        if dt < best_t:
+            best, best_t = n, dt
+    orc.lib().orc_set_num_threads(best)
+    return best, ncpu
+
+
 def run_cpu(pairs, budget_s=20.0, max_pairs=6, workload="gicp"):
     """Time the CPU oracle (kNN through the reference's nanoflann when oracle/_ref exists)."""
     from oracle import oracle as orc
     orc.lib()
     used_ref = orc.use_ref_nanoflann(True) == 0
-    orc.gicp_align(pairs[0][0][:20000], pairs[0][1][:20000])  # warm the OpenMP pool
     fn = orc.gicp_align if workload == "gicp" else orc.coarse_to_fine
+    threads, ncpu = calibrate_threads(orc, fn, pairs[0])
     times = []
     t_start = time.perf_counter()
     for i in range(max_pairs):
@@ -92,7 +111,7 @@ def run_cpu(pairs, budget_s=20.0, max_pairs=6, workload="gicp"):
         if time.perf_counter() - t_start > budget_s:
             break
     per_pair = float(np.mean(times))
-    return dict(value=1.0 / per_pair, unit=UNIT, cores=orc.num_threads(), kind="port",
+    return dict(value=1.0 / per_pair, unit=UNIT, cores=threads, logical_cpus=ncpu, kind="port",
                 ms_per_pair=1e3 * per_pair, best_ms_per_pair=1e3 * float(np.min(times)),
                 sample="%d pairs of %dk x %dk points, serial over pairs, OpenMP over points; restated %s "
                        "(oracle/) with kNN = %s" %
@@ -147,6 +166,18 @@ class ClockSampler:
         return out
 
 
+def ncu_traffic(kernel_family, workload):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel, from the committed
+    `ncu --set full` capture of this round (profiles/traffic.json, written by profiles/extract_traffic.py)."""
+    p = os.path.join(REPO, "profiles", "traffic.json")
+    if not os.path.exists(p):
+        return None
+    with open(p) as f:
+        t = json.load(f)
+    e = t.get(workload, {}).get(kernel_family)
+    return e
+
+
 def peaks():
     p = os.path.join(REPO, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -165,6 +196,7 @@ def main_reference(args):
     orc.lib()
     used_ref = orc.use_ref_nanoflann(True) == 0
     fn = orc.gicp_align if args.workload == "gicp" else orc.coarse_to_fine
+    threads, ncpu = calibrate_threads(orc, fn, pairs[0])
     for _ in range(max(args.warmup, 1)):
         fn(pairs[0][0], pairs[0][1])
     t0 = time.perf_counter()
@@ -181,7 +213,7 @@ def main_reference(args):
         "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32 points / f64 solver", "data": "synthetic",
         "config": {"workload": workload_name(args), "pairs_per_step": n_pairs, "points_per_cloud": args.points},
-        "cpu_baseline": {"value": val, "unit": UNIT, "cores": orc.num_threads(), "kind": "port", "sample": sample,
+        "cpu_baseline": {"value": val, "unit": UNIT, "cores": threads, "logical_cpus": ncpu, "kind": "port", "sample": sample,
                          "cpu_model": cpu_info()[0]},
         "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }))
@@ -327,7 +359,7 @@ def main():
                     "d2h_bytes_per_step": B * res_bytes},
             "gpu_launches": launches,
             "roofline": {"bound": "hbm", "kernel": fam, "achieved": achieved, "peak": peak, "unit": "GB/s",
-                         "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                         "frac": achieved / peak, "traffic": ncu_traffic(fam, args.workload), "peak_source": peak_src,
                          "note": "algorithmic bytes per SURVEY.md §8(d) / CUDA-event time of that kernel family on the "
                                  "launching stream, %d profiled steps after the timed region" % prof_steps},
             "kernels": kernels,

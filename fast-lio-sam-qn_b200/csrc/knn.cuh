@@ -49,29 +49,12 @@ __device__ __forceinline__ int orig_index(const float4* __restrict__ pts, int po
   return pos < 0 ? 0x7FFFFFFF : __float_as_int(__ldg(&pts[pos].w));
 }
 
-// Cold path: restore (d2, original index) order inside runs of exactly equal d2.  Kept out of
-// line so that the hot insertion chain stays small (the fully inlined tie-aware chain made
-// k_covariance<15> 82 KB of SASS and instruction-fetch bound; ncu: stall_no_instruction 14.2).
-template <int K>
-__device__ __noinline__ void knn_fix_ties(float* d, int* p, const float4* __restrict__ pts) {
-  for (int pass = 0; pass < K - 1; pass++) {
-    bool swapped = false;
-    for (int j = 0; j + 1 < K; j++) {
-      if (d[j] == d[j + 1] && p[j + 1] >= 0 && orig_index(pts, p[j + 1]) < orig_index(pts, p[j])) {
-        int t = p[j];
-        p[j] = p[j + 1];
-        p[j + 1] = t;
-        swapped = true;
-      }
-    }
-    if (!swapped) break;
-  }
-}
-
-// Insert a candidate with cd <= worst.  Hot path: strict '<' chain, branch-free selects, the
-// candidate lands AFTER entries of equal distance; any exact tie (measure ~0 on real data) is
-// repaired by knn_fix_ties.  A candidate that ties with the current worst replaces it only if
-// its original index is lower (the (d2, index) rule of SURVEY.md App. A.3).
+// Insert a candidate with cd <= worst.  Hot path: strict '<' chain of branch-free selects; the candidate lands
+// AFTER entries of equal distance.  Exact ties (measure ~0 on real data) are repaired by one unrolled upward bubble
+// pass in a cold branch -- written without taking the address of the arrays, so that the result set provably stays
+// in registers (an out-of-line repair taking pointers forced it into local memory: 22% of k_covariance's
+// instructions were LDL/STL).  A candidate that ties with the current worst replaces it only if its original
+// index is lower (the (d2, index) rule of SURVEY.md App. A.3).
 template <int K>
 __device__ __forceinline__ void knn_insert(KnnSet<K>& s, float cd, int cp, const float4* __restrict__ pts) {
   bool tie = false;
@@ -93,7 +76,16 @@ __device__ __forceinline__ void knn_insert(KnnSet<K>& s, float cd, int cp, const
       cp = lt ? tp : cp;
     }
   }
-  if (tie) knn_fix_ties<K>(s.d, s.p, pts);
+  if (tie) {  // cold: the new entry sits below its equal-distance peers; bubble it up by original index
+#pragma unroll
+    for (int j = K - 1; j > 0; j--) {
+      if (s.d[j] == s.d[j - 1] && s.p[j] >= 0 && orig_index(pts, s.p[j]) < orig_index(pts, s.p[j - 1])) {
+        const int t = s.p[j];
+        s.p[j] = s.p[j - 1];
+        s.p[j - 1] = t;
+      }
+    }
+  }
 }
 
 // Exact K-NN of (qx,qy,qz) in cloud c.  One thread per query; Morton-sorted queries keep
