@@ -233,7 +233,12 @@ __global__ void __launch_bounds__(STEP_THREADS) k_covariance(const CloudDev* clo
   const float4 q = c.pts[i];
   KnnSet<K> res;
   res.init();
-  knn_search<K>(c, q.x, q.y, q.z, res);
+  // seed with the K points around i in Morton order (cheap, coalesced, usually most of the true neighbours): the
+  // traversal then starts with a tight bound and only ever inserts improvements
+  int lo = max(0, i - K / 2), hi = min(c.n - 1, lo + K - 1);
+  lo = max(0, hi - (K - 1));
+  SeedLoop<K, 0>::run(res, c.pts, q.x, q.y, q.z, lo, hi);
+  knn_search<K>(c, q.x, q.y, q.z, res, lo, hi);
   double mx = 0, my = 0, mz = 0;
   double px[K], py[K], pz[K];
 #pragma unroll
@@ -284,6 +289,7 @@ __global__ void __launch_bounds__(STEP_THREADS) k_gicp_step(const PairDev* pairs
   if ((int)blockIdx.x >= nblk) return;
   const int phase = st->phase;
   if (phase == PH_DONE) return;
+  const bool seeded = st->n_lin > 0;  // P.corr holds the previous linearization's correspondences
 
   __shared__ double s_T[12];
   __shared__ float s_Tf[12];
@@ -314,6 +320,14 @@ __global__ void __launch_bounds__(STEP_THREADS) k_gicp_step(const PairDev* pairs
       const float qz = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(s_Tf[8], p.x), __fmul_rn(s_Tf[9], p.y)), __fmul_rn(s_Tf[10], p.z)), s_Tf[11]);
       KnnSet<1> res;
       res.init();
+      if (seeded) {  // last iteration's correspondence is almost always still the nearest point: start with its bound
+        const int pp = P.corr[i];
+        if (pp >= 0) {
+          const float4 t = __ldg(&P.tgt.pts[pp]);
+          res.d[0] = dist2_rn(qx, qy, qz, t.x, t.y, t.z);
+          res.p[0] = pp;
+        }
+      }
       knn_search<1>(P.tgt, qx, qy, qz, res);
       const int pos = ((double)res.d[0] < prm.max_corr_dist2) ? res.p[0] : -1;
       P.corr[i] = pos;
@@ -387,21 +401,43 @@ __global__ void __launch_bounds__(STEP_THREADS) k_gicp_step(const PairDev* pairs
       const float qz = __fadd_rn(__fmul_rn(s_Tf[8], p.x), __fadd_rn(__fmul_rn(s_Tf[9], p.y), __fadd_rn(__fmul_rn(s_Tf[10], p.z), s_Tf[11])));
       KnnSet<1> res;
       res.init();
+      if (seeded) {
+        const int pp = P.corr[i];
+        if (pp >= 0) {
+          const float4 t = __ldg(&P.tgt.pts[pp]);
+          res.d[0] = dist2_rn(qx, qy, qz, t.x, t.y, t.z);
+          res.p[0] = pp;
+        }
+      }
       knn_search<1>(P.tgt, qx, qy, qz, res);
       v[0] = (double)res.d[0];
     }
   }
 
-  // warp shuffle reduction -> shared -> block partial (fixed order)
+  // warp reduction -> shared -> block partial (fixed order).  LINEARIZE reduces 28 values at once with a
+  // transposing butterfly: at step m every lane keeps half of its values and trades the other half, so after
+  // 5 steps lane L holds the warp total of value L (31 shuffles of doubles instead of 28 * 5).
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  if (phase == PH_LINEARIZE) {
+    double w[32];
 #pragma unroll
-  for (int k = 0; k < NRED; k++) {
-    if (k < nred) {
-      double x = v[k];
+    for (int k = 0; k < 32; k++) w[k] = k < NRED ? v[k] : 0.0;
 #pragma unroll
-      for (int o = 16; o > 0; o >>= 1) x += __shfl_down_sync(0xffffffffu, x, o);
-      if (lane == 0) s_red[warp][k] = x;
+    for (int m = 16; m >= 1; m >>= 1) {
+      const bool up = (lane & m) != 0;
+#pragma unroll
+      for (int k = 0; k < m; k++) {
+        const double keep = up ? w[k + m] : w[k];
+        const double send = up ? w[k] : w[k + m];
+        w[k] = keep + __shfl_xor_sync(0xffffffffu, send, m);
+      }
     }
+    if (lane < NRED) s_red[warp][lane] = w[0];
+  } else {
+    double x = v[0];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) x += __shfl_down_sync(0xffffffffu, x, o);
+    if (lane == 0) s_red[warp][0] = x;
   }
   __syncthreads();
   if ((int)threadIdx.x < nred) {

@@ -242,14 +242,40 @@ __global__ void __launch_bounds__(256) k_lbvh_topology(const CloudDev* clouds, i
   if (right_leaf) c.parent_leaf[gamma + 1] = i; else c.parent_node[gamma + 1] = i;
 }
 
-// one thread per point walks up; the second arrival at a node owns it: merges the children's
-// boxes and, for nodes spanning more than LEAF points, writes the traversal record.
+// Bottom-up AABBs.  Work items: every point whose parent spans > LEAF points (a 1-point leaf) and every internal
+// node that is the root of a collapsed leaf (<= LEAF points, parent > LEAF): it reduces its <= 8 points directly.
+// Each item then climbs; the second arrival at a node owns it, merges the children's boxes and writes the
+// two-children traversal record.  (Starting a climb from every single point, through the tiny sub-trees, cost 2 atomics
+// per node of the full radix tree and made this the slowest build kernel.)
 __global__ void __launch_bounds__(256) k_lbvh_aabb(const CloudDev* clouds) {
   const CloudDev& c = clouds[blockIdx.y];
-  const int p = blockIdx.x * blockDim.x + threadIdx.x;
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
   const int n = c.n;
-  if (p >= n || n < 2) return;
-  int node = c.parent_leaf[p];
+  if (n <= LEAF || t >= 2 * n - 1) return;
+  int node;
+  if (t < n) {  // point t
+    node = c.parent_leaf[t];
+    const int4 pi = c.info[node];
+    if (pi.y - pi.x + 1 <= LEAF) return;  // lives inside a collapsed leaf
+  } else {      // internal node t - n
+    const int i = t - n;
+    const int4 inf = c.info[i];
+    if (i == 0 || inf.y - inf.x + 1 > LEAF) return;
+    const int par = c.parent_node[i];
+    const int4 pi = c.info[par];
+    if (pi.y - pi.x + 1 <= LEAF) return;  // an ancestor is the collapsed-leaf root
+    float lo0 = INFINITY, lo1 = INFINITY, lo2 = INFINITY, hi0 = -INFINITY, hi1 = -INFINITY, hi2 = -INFINITY;
+    for (int p = inf.x; p <= inf.y; p++) {
+      const float4 q = c.pts[p];
+      lo0 = fminf(lo0, q.x); hi0 = fmaxf(hi0, q.x);
+      lo1 = fminf(lo1, q.y); hi1 = fmaxf(hi1, q.y);
+      lo2 = fminf(lo2, q.z); hi2 = fmaxf(hi2, q.z);
+    }
+    c.nbox[2 * i] = make_float4(lo0, lo1, lo2, 0.f);
+    c.nbox[2 * i + 1] = make_float4(hi0, hi1, hi2, 0.f);
+    __threadfence();
+    node = par;
+  }
   for (;;) {
     if (atomicAdd(&c.flags[node], 1u) == 0u) return;
     __threadfence();
@@ -275,12 +301,10 @@ __global__ void __launch_bounds__(256) k_lbvh_aabb(const CloudDev* clouds) {
     }
     c.nbox[2 * node] = make_float4(fminf(lo[0].x, lo[1].x), fminf(lo[0].y, lo[1].y), fminf(lo[0].z, lo[1].z), 0.f);
     c.nbox[2 * node + 1] = make_float4(fmaxf(hi[0].x, hi[1].x), fmaxf(hi[0].y, hi[1].y), fmaxf(hi[0].z, hi[1].z), 0.f);
-    if (inf.y - inf.x + 1 > LEAF) {
-      c.tnodes[4 * node + 0] = make_float4(lo[0].x, lo[0].y, lo[0].z, __int_as_float(ref[0]));
-      c.tnodes[4 * node + 1] = make_float4(hi[0].x, hi[0].y, hi[0].z, 0.f);
-      c.tnodes[4 * node + 2] = make_float4(lo[1].x, lo[1].y, lo[1].z, __int_as_float(ref[1]));
-      c.tnodes[4 * node + 3] = make_float4(hi[1].x, hi[1].y, hi[1].z, 0.f);
-    }
+    c.tnodes[4 * node + 0] = make_float4(lo[0].x, lo[0].y, lo[0].z, __int_as_float(ref[0]));
+    c.tnodes[4 * node + 1] = make_float4(hi[0].x, hi[0].y, hi[0].z, 0.f);
+    c.tnodes[4 * node + 2] = make_float4(lo[1].x, lo[1].y, lo[1].z, __int_as_float(ref[1]));
+    c.tnodes[4 * node + 3] = make_float4(hi[1].x, hi[1].y, hi[1].z, 0.f);
     if (node == 0) return;
     __threadfence();
     node = c.parent_node[node];
@@ -309,7 +333,7 @@ int launch_index_build(const CloudDev* d_clouds, int count, int max_n, cudaStrea
   k_gather<<<dim3((max_n + 255) / 256, count), 256, 0, s>>>(d_clouds, npass & 1); launches++;
   if (max_n > 1) {
     k_lbvh_topology<<<dim3((max_n + 254) / 256, count), 256, 0, s>>>(d_clouds, npass & 1); launches++;
-    k_lbvh_aabb<<<dim3((max_n + 255) / 256, count), 256, 0, s>>>(d_clouds); launches++;
+    k_lbvh_aabb<<<dim3((2 * max_n + 254) / 256, count), 256, 0, s>>>(d_clouds); launches++;
   }
   return launches;
 }
