@@ -57,7 +57,8 @@ def make_pairs(rank, n_pairs, n_points, mode="gicp"):
     pairs = []
     for i in range(n_pairs):
         seed = (1000 if mode == "gicp" else 2000) + rank * n_pairs + i  # config 2 seeds 1000.., config 3 2000..
-        src, dst, Texp = synth.make_pair(seed, n_points, n_points, mode=mode)
+        # config 3 inputs are voxelised at 0.3 m like setSrcAndDstCloud does (loop_closure.cpp:107): --points raw returns -> ~1/4
+        src, dst, Texp = synth.make_pair(seed, n_points, n_points, mode=mode, voxel=0.3 if mode == "quatro" else None)
         pairs.append((src, dst, Texp))
     return pairs
 
@@ -223,14 +224,14 @@ def workload_name(args):
     if args.workload == "gicp":
         return ("configs[1]: Nano-GICP %dk-pt KITTI-shaped scan pair (LoopClosure::icpAlignment: 2 index builds + "
                 "2 kNN-15 covariance passes + LM align + fitness)" % (args.points // 1000))
-    return ("configs[2]: Quatro+Nano-GICP full loop closure on %dk-pt pairs (LoopClosure::coarseToFineAlignment: FPFH -> "
-            "optimizedMatching -> QUATRO solve -> transform -> GICP refine)" % (args.points // 1000))
+    return ("configs[2]: Quatro+Nano-GICP full loop closure on %dk-pt scans voxelised at 0.3 m (LoopClosure::"
+            "coarseToFineAlignment: FPFH -> optimizedMatching -> QUATRO solve -> transform -> GICP refine)" % (args.points // 1000))
 
 
 def main():
     args = parse()
     if args.points is None:
-        args.points = N_POINTS if args.workload == "gicp" else 20000
+        args.points = N_POINTS
     if args.impl == "reference":
         return main_reference(args)
 

@@ -53,7 +53,25 @@ def to_map_frame(pts, T):
     return out
 
 
-def make_pair(pair_seed, n_src, n_tgt=None, mode="gicp"):
+def voxelize(pts, leaf):
+    """pcl::VoxelGrid semantics (SURVEY.md App. B.1; utilities.hpp:38-63): centroid of ALL fields per occupied voxel,
+    output ordered by the linear voxel index i + j*dx + k*dx*dy.  numpy stand-in used to shape realistic Quatro inputs."""
+    p = np.asarray(pts, np.float32)
+    inv = np.float32(1.0 / leaf)
+    mn = np.floor(p[:, :3].min(0) * inv).astype(np.int64)
+    mx = np.floor(p[:, :3].max(0) * inv).astype(np.int64)
+    ijk = np.floor(p[:, :3] * inv).astype(np.int64) - mn
+    dims = mx - mn + 1
+    lin = ijk[:, 0] + ijk[:, 1] * dims[0] + ijk[:, 2] * dims[0] * dims[1]
+    order = np.argsort(lin, kind="stable")
+    lin_s = lin[order]
+    starts = np.flatnonzero(np.r_[True, lin_s[1:] != lin_s[:-1]])
+    counts = np.diff(np.r_[starts, len(lin_s)])
+    sums = np.add.reduceat(p[order].astype(np.float32), starts, axis=0)
+    return (sums / counts[:, None].astype(np.float32)).astype(np.float32)
+
+
+def make_pair(pair_seed, n_src, n_tgt=None, mode="gicp", voxel=None):
     """One loop-closure candidate pair in the common map frame.
 
     dst = scan at true pose A; src = scan at true pose B = A * T_gt, placed in the map with an
@@ -74,6 +92,8 @@ def make_pair(pair_seed, n_src, n_tgt=None, mode="gicp"):
         D = se3(yaw=np.deg2rad(rng.uniform(-15, 15)), t=(rng.uniform(-7, 7), rng.uniform(-7, 7), rng.uniform(-0.3, 0.3)))
     dst = to_map_frame(scan(pair_seed, 2 * pair_seed + 1, A, n_tgt), A)
     src = to_map_frame(scan(pair_seed, 2 * pair_seed + 2, B, n_src), D @ B)
+    if voxel:  # setSrcAndDstCloud voxelises both clouds (loop_closure.cpp:107, config.yaml:16 voxel_resolution 0.3)
+        src, dst = voxelize(src, voxel), voxelize(dst, voxel)
     return src, dst, np.linalg.inv(D)
 
 

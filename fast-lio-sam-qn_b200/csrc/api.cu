@@ -5,6 +5,7 @@
 
 #include <algorithm>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -46,6 +47,8 @@ struct b200reg_ctx {
   int device = 0;
   cudaStream_t own_stream = nullptr;
   cudaStream_t stream = nullptr;
+  cudaStream_t copy_stream = nullptr;  // H2D uploads of later chunks overlap the compute of earlier ones
+  int pipeline_chunks = 4;
   int* d_done = nullptr;   // device counter of finished pairs
   int* h_done = nullptr;   // pinned mirror
   int64_t launches = 0;
@@ -143,6 +146,7 @@ int b200reg_ctx_create(int device, b200reg_ctx** out) {
   b200reg_ctx* c = new b200reg_ctx;
   c->device = device;
   CU(cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking));
+  CU(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
   c->stream = c->own_stream;
   cudaMemPool_t pool;
   CU(cudaDeviceGetDefaultMemPool(&pool, device));
@@ -161,6 +165,7 @@ int b200reg_ctx_destroy(b200reg_ctx* c) {
   cudaFree(c->d_done);
   cudaFreeHost(c->h_done);
   cudaStreamDestroy(c->own_stream);
+  cudaStreamDestroy(c->copy_stream);
   delete c;
   return B200REG_OK;
 }
@@ -494,11 +499,10 @@ int b200reg_gicp_align(b200reg_ctx* c, int count, b200reg_cloud* const* src, b20
   return free_pair_work(c, w);
 }
 
-int b200reg_icp_alignment(b200reg_ctx* c, int count, const float* const* src_xyz, const size_t* src_n,
-                          const float* const* tgt_xyz, const size_t* tgt_n, size_t stride_bytes, int on_device,
-                          const b200reg_gicp_params* params, b200reg_result* out) {
-  if (!c || count <= 0 || !src_xyz || !src_n || !tgt_xyz || !tgt_n || !params || !out)
-    return fail(B200REG_EINVAL, "bad argument");
+// one chunk of pairs, raw records already on the device
+static int icp_alignment_device(b200reg_ctx* c, int count, const float* const* src_xyz, const size_t* src_n,
+                                const float* const* tgt_xyz, const size_t* tgt_n, size_t stride_bytes,
+                                const b200reg_gicp_params* params, b200reg_result* out) {
   std::vector<const float*> ptrs(2 * count);
   std::vector<size_t> ns(2 * count);
   for (int i = 0; i < count; i++) {
@@ -508,11 +512,90 @@ int b200reg_icp_alignment(b200reg_ctx* c, int count, const float* const* src_xyz
     ns[count + i] = tgt_n[i];
   }
   std::vector<b200reg_cloud*> clouds(2 * count, nullptr);
-  int rc = b200reg_clouds_create(c, 2 * count, ptrs.data(), ns.data(), stride_bytes, on_device, clouds.data());
+  int rc = b200reg_clouds_create(c, 2 * count, ptrs.data(), ns.data(), stride_bytes, 1, clouds.data());
   if (rc) return rc;
   rc = b200reg_clouds_covariances(c, 2 * count, clouds.data(), params->k_correspondences);
   if (!rc) rc = b200reg_gicp_align(c, count, clouds.data(), clouds.data() + count, nullptr, params, out);
   for (b200reg_cloud* cl : clouds) b200reg_cloud_destroy(c, cl);
+  return rc;
+}
+
+int b200reg_icp_alignment(b200reg_ctx* c, int count, const float* const* src_xyz, const size_t* src_n,
+                          const float* const* tgt_xyz, const size_t* tgt_n, size_t stride_bytes, int on_device,
+                          const b200reg_gicp_params* params, b200reg_result* out) {
+  if (!c || count <= 0 || !src_xyz || !src_n || !tgt_xyz || !tgt_n || !params || !out)
+    return fail(B200REG_EINVAL, "bad argument");
+  if (stride_bytes < 12 || stride_bytes % 4) return fail(B200REG_EINVAL, "stride_bytes must be a multiple of 4, >= 12");
+  for (int i = 0; i < count; i++)
+    if (!src_xyz[i] || !tgt_xyz[i] || src_n[i] == 0 || tgt_n[i] == 0) return fail(B200REG_EINVAL, "empty cloud");
+  CU(cudaSetDevice(c->device));
+  if (on_device) return icp_alignment_device(c, count, src_xyz, src_n, tgt_xyz, tgt_n, stride_bytes, params, out);
+  // Host buffers: all uploads are queued on the copy stream up front, chunk by chunk; the compute stream processes
+  // chunk k as soon as its records have landed, so the PCIe time of chunk k+1 hides behind the kernels of chunk k.
+  cudaStream_t s = c->stream;
+  int want = c->pipeline_chunks;
+  if (const char* e = getenv("B200REG_PIPELINE_CHUNKS")) want = atoi(e);
+  const int nchunks = std::max(1, std::min(want, count));
+  const int per = (count + nchunks - 1) / nchunks;
+  size_t total = 0;
+  std::vector<size_t> off_s(count), off_t(count);
+  for (int i = 0; i < count; i++) {
+    off_s[i] = total;
+    total += align_up(src_n[i] * stride_bytes, 256);
+    off_t[i] = total;
+    total += align_up(tgt_n[i] * stride_bytes, 256);
+  }
+  char* stage = nullptr;
+  CU(cudaMallocAsync((void**)&stage, total, s));
+  cudaEvent_t ready;
+  CU(cudaEventCreateWithFlags(&ready, cudaEventDisableTiming));
+  CU(cudaEventRecord(ready, s));
+  CU(cudaStreamWaitEvent(c->copy_stream, ready, 0));
+  std::vector<cudaEvent_t> landed;
+  for (int k0 = 0; k0 < count; k0 += per) {
+    const int k1 = std::min(count, k0 + per);
+    for (int i = k0; i < k1; i++) {
+      CU(cudaMemcpyAsync(stage + off_s[i], src_xyz[i], src_n[i] * stride_bytes, cudaMemcpyHostToDevice, c->copy_stream));
+      CU(cudaMemcpyAsync(stage + off_t[i], tgt_xyz[i], tgt_n[i] * stride_bytes, cudaMemcpyHostToDevice, c->copy_stream));
+    }
+    cudaEvent_t e;
+    CU(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    CU(cudaEventRecord(e, c->copy_stream));
+    landed.push_back(e);
+  }
+  // index build + covariances chunk by chunk (they only need that chunk's records), then ONE batched LM solve over
+  // all pairs: the host never blocks before the solve's first poll, so the GPU stays busy while later chunks land.
+  int rc = B200REG_OK;
+  int chunk = 0;
+  std::vector<b200reg_cloud*> sc(count, nullptr), tc(count, nullptr);
+  for (int k0 = 0; k0 < count && !rc; k0 += per, chunk++) {
+    const int k1 = std::min(count, k0 + per), m = k1 - k0;
+    CU(cudaStreamWaitEvent(s, landed[chunk], 0));
+    std::vector<const float*> ptrs(2 * m);
+    std::vector<size_t> ns(2 * m);
+    std::vector<b200reg_cloud*> cl(2 * m, nullptr);
+    for (int i = k0; i < k1; i++) {
+      ptrs[i - k0] = (const float*)(stage + off_s[i]);
+      ns[i - k0] = src_n[i];
+      ptrs[m + i - k0] = (const float*)(stage + off_t[i]);
+      ns[m + i - k0] = tgt_n[i];
+    }
+    rc = b200reg_clouds_create(c, 2 * m, ptrs.data(), ns.data(), stride_bytes, 1, cl.data());
+    for (int i = k0; i < k1; i++) {
+      sc[i] = cl[i - k0];
+      tc[i] = cl[m + i - k0];
+    }
+    if (!rc) rc = b200reg_clouds_covariances(c, 2 * m, cl.data(), params->k_correspondences);
+  }
+  if (!rc) rc = b200reg_gicp_align(c, count, sc.data(), tc.data(), nullptr, params, out);
+  for (int i = 0; i < count; i++) {
+    b200reg_cloud_destroy(c, sc[i]);
+    b200reg_cloud_destroy(c, tc[i]);
+  }
+  cudaStreamSynchronize(c->copy_stream);
+  for (cudaEvent_t e : landed) cudaEventDestroy(e);
+  cudaEventDestroy(ready);
+  CU(cudaFreeAsync(stage, s));
   return rc;
 }
 

@@ -226,7 +226,7 @@ __global__ void k_gicp_init(PairState* states, const double* guess16, int count,
 // the smallest eigenvalue, so only n is computed.
 // ---------------------------------------------------------------------------------------
 template <int K>
-__global__ void __launch_bounds__(STEP_THREADS) k_covariance(const CloudDev* clouds) {
+__global__ void __launch_bounds__(STEP_THREADS, (K <= 15 ? 6 : 4)) k_covariance(const CloudDev* clouds) {
   const CloudDev& c = clouds[blockIdx.y];
   const int i = blockIdx.x * STEP_THREADS + threadIdx.x;
   if (i >= c.n) return;
@@ -239,23 +239,24 @@ __global__ void __launch_bounds__(STEP_THREADS) k_covariance(const CloudDev* clo
   lo = max(0, hi - (K - 1));
   SeedLoop<K, 0>::run(res, c.pts, q.x, q.y, q.z, lo, hi);
   knn_search<K>(c, q.x, q.y, q.z, res, lo, hi);
+  // two passes over the K neighbours (second pass hits L1) instead of parking 3K doubles in registers
   double mx = 0, my = 0, mz = 0;
-  double px[K], py[K], pz[K];
 #pragma unroll
   for (int j = 0; j < K; j++) {
-    float4 p = res.p[j] >= 0 ? c.pts[res.p[j]] : make_float4(0.f, 0.f, 0.f, 0.f);
-    px[j] = res.p[j] >= 0 ? (double)p.x : 0.0;
-    py[j] = res.p[j] >= 0 ? (double)p.y : 0.0;
-    pz[j] = res.p[j] >= 0 ? (double)p.z : 0.0;
-    mx += px[j]; my += py[j]; mz += pz[j];
+    if (res.p[j] >= 0) {
+      const float4 p = __ldg(&c.pts[res.p[j]]);
+      mx += (double)p.x; my += (double)p.y; mz += (double)p.z;
+    }
   }
   mx /= K; my /= K; mz /= K;
   double cxx = 0, cxy = 0, cxz = 0, cyy = 0, cyz = 0, czz = 0;
 #pragma unroll
   for (int j = 0; j < K; j++) {
-    if (res.p[j] < 0) continue;
-    double dx = px[j] - mx, dy = py[j] - my, dz = pz[j] - mz;
-    cxx += dx * dx; cxy += dx * dy; cxz += dx * dz; cyy += dy * dy; cyz += dy * dz; czz += dz * dz;
+    if (res.p[j] >= 0) {
+      const float4 p = __ldg(&c.pts[res.p[j]]);
+      const double dx = (double)p.x - mx, dy = (double)p.y - my, dz = (double)p.z - mz;
+      cxx += dx * dx; cxy += dx * dy; cxz += dx * dz; cyy += dy * dy; cyz += dy * dz; czz += dz * dz;
+    }
   }
   const double ik = 1.0 / K;
   cxx *= ik; cxy *= ik; cxz *= ik; cyy *= ik; cyz *= ik; czz *= ik;

@@ -207,7 +207,7 @@ constexpr int NN_TILE = 64;  // base descriptors per smem tile: 64 * 144 B = 921
 
 // mode 0: queries = every point of fj (sorted order), base = fi; writes nn/dis by ORIGINAL j
 // mode 1: queries = fi points listed in `need` (original i), base = fj; writes rnn by ORIGINAL i
-__global__ void __launch_bounds__(NN_THREADS) k_feat_nn(const MatchDev* pairs, int mode) {
+__global__ void __launch_bounds__(NN_THREADS) k_feat_nn(const MatchDev* pairs, int mode, float thr2) {
   const MatchDev& P = pairs[blockIdx.y];
   const CloudDev& Q = mode == 0 ? P.fj : P.fi;
   const CloudDev& B = mode == 0 ? P.fi : P.fj;
@@ -258,7 +258,9 @@ __global__ void __launch_bounds__(NN_THREADS) k_feat_nn(const MatchDev* pairs, i
     mbar_expect_tx(&full[0], bytes);
     bulk_g2s(tile[0], B.fpfh, bytes, &full[0]);
   }
-  float best = 3.402823466e+38f;
+  // Only matches with d2 <= thr2 survive the gate (matcher.cc:422/444), in either direction, so the search starts
+  // from that bound: most base descriptors are then rejected after the first 12 of the 33 dimensions.
+  float best = __int_as_float(__float_as_int(thr2) + 1);  // nextafter(thr2, +inf): d2 == thr2 still qualifies
   int best_orig = -1;
   for (int t = 0; t < ntiles; t++) {
     if (threadIdx.x == 0 && t + 1 < ntiles) {
@@ -270,29 +272,50 @@ __global__ void __launch_bounds__(NN_THREADS) k_feat_nn(const MatchDev* pairs, i
     mbar_wait(&full[t & 1], (t >> 1) & 1);
     const float* tb = tile[t & 1];
     const int cnt = min(NN_TILE, nb - t * NN_TILE);
-    if (active && qok) {
+    {
+      const bool on = active && qok;
       for (int b = 0; b < cnt; b++) {
         const float4* r4 = reinterpret_cast<const float4*>(tb + b * FPAD);  // all lanes read the same record: broadcast
         float d = 0.f;
         float4 v;
-        // sequential fp32 sum over the 33 dims (oracle's feat_d2 order); early exits only skip work
+        // sequential fp32 sum over the 33 dims (oracle's feat_d2 order).  The partial sums only grow, so a record
+        // can be dropped as soon as EVERY lane of the warp is already above its own best (warp-uniform exit: no
+        // divergence, and skipping never changes a result).
 #pragma unroll
-        for (int k = 0; k < 8; k++) {
+        for (int k = 0; k < 3; k++) {
           v = r4[k];
           float e;
           e = q[4 * k] - v.x; d += e * e;
           e = q[4 * k + 1] - v.y; d += e * e;
           e = q[4 * k + 2] - v.z; d += e * e;
           e = q[4 * k + 3] - v.w; d += e * e;
-          if ((k == 2 || k == 5) && d > best) break;
         }
-        if (d > best) continue;
+        if (__all_sync(0xffffffffu, !on || d > best)) continue;
+#pragma unroll
+        for (int k = 3; k < 6; k++) {
+          v = r4[k];
+          float e;
+          e = q[4 * k] - v.x; d += e * e;
+          e = q[4 * k + 1] - v.y; d += e * e;
+          e = q[4 * k + 2] - v.z; d += e * e;
+          e = q[4 * k + 3] - v.w; d += e * e;
+        }
+        if (__all_sync(0xffffffffu, !on || d > best)) continue;
+#pragma unroll
+        for (int k = 6; k < 8; k++) {
+          v = r4[k];
+          float e;
+          e = q[4 * k] - v.x; d += e * e;
+          e = q[4 * k + 1] - v.y; d += e * e;
+          e = q[4 * k + 2] - v.z; d += e * e;
+          e = q[4 * k + 3] - v.w; d += e * e;
+        }
         v = r4[8];
         {
           const float e = q[32] - v.x;
           d += e * e;
         }
-        if (v.z == 0.f) continue;  // unusable descriptor (invalid normal)
+        if (!on || v.z == 0.f) continue;  // inactive lane / unusable descriptor (invalid normal)
         const int o = __float_as_int(v.y);
         if (d < best || (d == best && o < best_orig)) {
           best = d;
@@ -966,10 +989,10 @@ int launch_quatro_match_solve(const MatchDev* d_pairs, int count, int max_ni, in
   k_match_init<<<dim3((max_ni + 255) / 256, count), 256, 0, s>>>(d_pairs); l++;
   k_cloud_sum<<<dim3(1, count, 2), 1024, 0, s>>>(d_pairs); l++;
   k_cloud_scale<<<dim3(64, count, 2), 256, 0, s>>>(d_pairs); l++;
-  k_feat_nn<<<dim3((max_nj + NN_THREADS - 1) / NN_THREADS, count), NN_THREADS, 0, s>>>(d_pairs, 0); l++;
+  k_feat_nn<<<dim3((max_nj + NN_THREADS - 1) / NN_THREADS, count), NN_THREADS, 0, s>>>(d_pairs, 0, prm.thr2); l++;
   k_first_hit<<<dim3((max_nj + 255) / 256, count), 256, 0, s>>>(d_pairs, prm.thr2); l++;
   k_need<<<dim3((max_ni + 255) / 256, count), 256, 0, s>>>(d_pairs); l++;
-  k_feat_nn<<<dim3((max_ni + NN_THREADS - 1) / NN_THREADS, count), NN_THREADS, 0, s>>>(d_pairs, 1); l++;
+  k_feat_nn<<<dim3((max_ni + NN_THREADS - 1) / NN_THREADS, count), NN_THREADS, 0, s>>>(d_pairs, 1, prm.thr2); l++;
   k_mutual<<<count, 1024, 0, s>>>(d_pairs, prm.thr2); l++;
   k_tuple_trials<<<dim3(128, count), 256, 0, s>>>(d_pairs, prm); l++;
   k_tuple_select<<<count, 1024, 0, s>>>(d_pairs, prm); l++;
