@@ -327,7 +327,7 @@ int b200reg_cloud_destroy(b200reg_ctx* c, b200reg_cloud* cl) {
 
 int b200reg_clouds_covariances(b200reg_ctx* c, int count, b200reg_cloud* const* clouds, int k) {
   if (!c || count <= 0 || !clouds) return fail(B200REG_EINVAL, "bad argument");
-  if (k != 10 && k != 15 && k != 20) return fail(B200REG_EINVAL, "k_correspondences must be 10, 15 or 20 in this build");
+  if (k < 1 || k > 32) return fail(B200REG_EINVAL, "k_correspondences must be in 1..32");
   CU(cudaSetDevice(c->device));
   cudaStream_t s = c->stream;
   std::vector<CloudDev> descs;
@@ -620,8 +620,8 @@ int b200reg_transform_cloud(b200reg_ctx* c, const b200reg_cloud* cl, const float
 // ---- debug taps --------------------------------------------------------------------------
 int b200reg_knn(b200reg_ctx* c, const b200reg_cloud* cl, const float* queries, size_t nq, size_t qstride_bytes, int k,
                 int32_t* idx_out, float* d2_out) {
-  if (!c || !cl || !queries || nq == 0 || k <= 0 || k > 20 || !idx_out || !d2_out || qstride_bytes < 12 || qstride_bytes % 4)
-    return fail(B200REG_EINVAL, "bad argument (k must be 1..20)");
+  if (!c || !cl || !queries || nq == 0 || k <= 0 || k > 32 || !idx_out || !d2_out || qstride_bytes < 12 || qstride_bytes % 4)
+    return fail(B200REG_EINVAL, "bad argument (k must be 1..32)");
   CU(cudaSetDevice(c->device));
   cudaStream_t s = c->stream;
   float* d_q = nullptr;

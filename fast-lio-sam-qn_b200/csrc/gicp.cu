@@ -225,8 +225,10 @@ __global__ void k_gicp_init(PairState* states, const double* guess16, int count,
 // For symmetric PSD input U diag(1,1,eps) V^T == I - (1-eps) n n^T with n the eigenvector of
 // the smallest eigenvalue, so only n is computed.
 // ---------------------------------------------------------------------------------------
+// K is the CAPACITY of the register-resident result set; k <= K neighbours enter the covariance (the k nearest of
+// the K nearest are the k nearest), so every k in 1..32 is served by the next instantiated capacity.
 template <int K>
-__global__ void __launch_bounds__(STEP_THREADS, (K <= 15 ? 6 : 4)) k_covariance(const CloudDev* clouds) {
+__global__ void __launch_bounds__(STEP_THREADS, (K <= 16 ? 6 : 4)) k_covariance(const CloudDev* clouds, int k) {
   const CloudDev& c = clouds[blockIdx.y];
   const int i = blockIdx.x * STEP_THREADS + threadIdx.x;
   if (i >= c.n) return;
@@ -243,22 +245,22 @@ __global__ void __launch_bounds__(STEP_THREADS, (K <= 15 ? 6 : 4)) k_covariance(
   double mx = 0, my = 0, mz = 0;
 #pragma unroll
   for (int j = 0; j < K; j++) {
-    if (res.p[j] >= 0) {
+    if (j < k && res.p[j] >= 0) {
       const float4 p = __ldg(&c.pts[res.p[j]]);
       mx += (double)p.x; my += (double)p.y; mz += (double)p.z;
     }
   }
-  mx /= K; my /= K; mz /= K;
+  mx /= k; my /= k; mz /= k;
   double cxx = 0, cxy = 0, cxz = 0, cyy = 0, cyz = 0, czz = 0;
 #pragma unroll
   for (int j = 0; j < K; j++) {
-    if (res.p[j] >= 0) {
+    if (j < k && res.p[j] >= 0) {
       const float4 p = __ldg(&c.pts[res.p[j]]);
       const double dx = (double)p.x - mx, dy = (double)p.y - my, dz = (double)p.z - mz;
       cxx += dx * dx; cxy += dx * dy; cxz += dx * dz; cyy += dy * dy; cyz += dy * dz; czz += dz * dz;
     }
   }
-  const double ik = 1.0 / K;
+  const double ik = 1.0 / k;
   cxx *= ik; cxy *= ik; cxz *= ik; cyy *= ik; cyz *= ik; czz *= ik;
   double n[3];
   sym3_smallest_evec(cxx, cxy, cxz, cyy, cyz, czz, n);
@@ -515,10 +517,11 @@ __global__ void __launch_bounds__(256) k_transform_out(CloudDev c, const float* 
 // ---------------------------------------------------------------------------------------
 int launch_covariances(const CloudDev* d_clouds, int count, int max_n, int k, cudaStream_t s) {
   dim3 grid((max_n + STEP_THREADS - 1) / STEP_THREADS, count);
-  if (k == 15) k_covariance<15><<<grid, STEP_THREADS, 0, s>>>(d_clouds);
-  else if (k == 20) k_covariance<20><<<grid, STEP_THREADS, 0, s>>>(d_clouds);
-  else if (k == 10) k_covariance<10><<<grid, STEP_THREADS, 0, s>>>(d_clouds);
-  else return -1;
+  if (k < 1 || k > 32) return -1;
+  if (k <= 8) k_covariance<8><<<grid, STEP_THREADS, 0, s>>>(d_clouds, k);
+  else if (k <= 15) k_covariance<15><<<grid, STEP_THREADS, 0, s>>>(d_clouds, k);
+  else if (k <= 20) k_covariance<20><<<grid, STEP_THREADS, 0, s>>>(d_clouds, k);
+  else k_covariance<32><<<grid, STEP_THREADS, 0, s>>>(d_clouds, k);
   return 1;
 }
 
@@ -535,9 +538,10 @@ void launch_gicp_step(const PairDev* pairs, PairState* states, int count, int ma
 int launch_knn_queries(const CloudDev& c, const float* d_q, int nq, int qstride, int k, int* idx, float* d2, cudaStream_t s) {
   dim3 grid((nq + STEP_THREADS - 1) / STEP_THREADS);
   if (k == 1) k_knn_queries<1><<<grid, STEP_THREADS, 0, s>>>(c, d_q, nq, qstride, k, idx, d2);
-  else if (k <= 10) k_knn_queries<10><<<grid, STEP_THREADS, 0, s>>>(c, d_q, nq, qstride, k, idx, d2);
+  else if (k <= 8) k_knn_queries<8><<<grid, STEP_THREADS, 0, s>>>(c, d_q, nq, qstride, k, idx, d2);
   else if (k <= 15) k_knn_queries<15><<<grid, STEP_THREADS, 0, s>>>(c, d_q, nq, qstride, k, idx, d2);
   else if (k <= 20) k_knn_queries<20><<<grid, STEP_THREADS, 0, s>>>(c, d_q, nq, qstride, k, idx, d2);
+  else if (k <= 32) k_knn_queries<32><<<grid, STEP_THREADS, 0, s>>>(c, d_q, nq, qstride, k, idx, d2);
   else return -1;
   return 1;
 }

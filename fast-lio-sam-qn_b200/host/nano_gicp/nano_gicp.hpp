@@ -10,7 +10,7 @@
 //   * the class does not derive from pcl::Registration (nothing in fast_lio_sam_qn/src uses it polymorphically);
 //   * setNumThreads is accepted and ignored; RANSAC* / EuclideanFitnessEpsilon setters are stored and never read,
 //     exactly like the reference's LSQ path;
-//   * only RegularizationMethod::PLANE (the default, nano_gicp_impl.hpp:61) and k in {10,15,20} are built;
+//   * only RegularizationMethod::PLANE (the default, nano_gicp_impl.hpp:61) is built; k may be 1..32;
 //   * source_kdtree_/target_kdtree_ do not exist (the index is a device-side LBVH); covariances are materialised on
 //     the host lazily by getSource/TargetCovariances().
 #pragma once

@@ -272,3 +272,19 @@ def test_cuda_gicp_equals_oracle_golden(ctx, synth):
     assert r["n_linearize"] == int(g["n_linearize"]) and r["converged"] == bool(g["converged"])
     assert abs(r["fitness"] - float(g["fitness"])) < 1e-6
     cs.destroy(); ct.destroy()
+
+
+def test_any_k_correspondences(ctx, oracle, pair5k):
+    """setCorrespondenceRandomness(k) for k outside the tuned 15/20 (the NanoGICP default ctor uses 20)."""
+    src, dst, _ = pair5k
+    for k in (5, 12, 20, 27):
+        cl, = ctx.create_clouds([dst])
+        ctx.covariances([cl], k)
+        g = ctx.get_covariances(cl)
+        o = oracle.covariances(dst, k)
+        err = np.abs(g - o).reshape(len(dst), -1).max(1)
+        assert np.median(err) < 1e-11 and np.quantile(err, 0.995) < 1e-5, (k, np.median(err))
+        gi, gd = ctx.knn(cl, src[:500], k)
+        oi, od = oracle.knn(dst, src[:500], k)
+        assert np.array_equal(gi, oi) and np.array_equal(gd, od)
+        cl.destroy()
