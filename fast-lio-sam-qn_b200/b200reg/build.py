@@ -6,7 +6,7 @@ from concurrent.futures import ThreadPoolExecutor
 PKG = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 CSRC = os.path.join(PKG, "csrc")
 REPO = os.path.dirname(PKG)
-SOURCES = ["api.cu", "index_build.cu", "gicp.cu", "quatro.cu"]
+SOURCES = ["api.cu", "index_build.cu", "gicp.cu", "quatro.cu", "assemble.cu"]
 EXTRA = {"quatro.cu": ["-fmad=false"]}  # fixed fp32 operation order for the FPFH / matcher arithmetic
 HEADERS = ["internal.cuh", "knn.cuh", "smallmath.cuh", os.path.join(REPO, "include", "b200reg.h")]
 LIB = os.path.join(CSRC, "libb200reg.so")

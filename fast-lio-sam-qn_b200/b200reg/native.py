@@ -47,6 +47,18 @@ class QuatroInfo(C.Structure):
                     n_corr=self.n_corr, clique_size=self.clique_size, gnc_iterations=self.gnc_iterations)
 
 
+class LoopConfig(C.Structure):
+    _fields_ = [("enable_quatro", C.c_int32), ("enable_submap_matching", C.c_int32), ("num_submap_keyframes", C.c_int32),
+                ("reserved", C.c_int32), ("voxel_res", C.c_double), ("loop_detection_radius", C.c_double),
+                ("loop_detection_timediff_threshold", C.c_double), ("gicp", GicpParams), ("quatro", QuatroParams)]
+
+
+def default_loop_config():
+    cfg = LoopConfig()
+    lib().b200reg_default_loop_config(C.byref(cfg))
+    return cfg
+
+
 MAXC = 512
 
 EXPORTS = [
@@ -56,7 +68,9 @@ EXPORTS = [
     "b200reg_gicp_align", "b200reg_icp_alignment", "b200reg_transform_cloud", "b200reg_knn",
     "b200reg_get_covariances", "b200reg_linearize", "b200reg_ctx_set_profiling", "b200reg_ctx_reset_profile",
     "b200reg_ctx_get_profile", "b200reg_default_quatro_params", "b200reg_clouds_fpfh", "b200reg_get_fpfh",
-    "b200reg_quatro_align", "b200reg_loop_closure",
+    "b200reg_quatro_align", "b200reg_loop_closure", "b200reg_default_loop_config", "b200reg_keyframes_create",
+    "b200reg_keyframes_destroy", "b200reg_keyframes_add", "b200reg_keyframes_set_pose", "b200reg_keyframes_size",
+    "b200reg_fetch_closest_keyframes", "b200reg_assemble_clouds", "b200reg_cloud_points", "b200reg_perform_loop_closure",
 ]
 
 
@@ -275,6 +289,15 @@ class Context:
                                           C.byref(qp), C.byref(gp), res, qi))
         return res, qi
 
+    # -- "next" rows: keyframe store, candidate search, cloud assembly -----------------------
+    def keyframes(self):
+        return Keyframes(self)
+
+    def cloud_points(self, cloud):
+        out = np.empty((cloud.n, 3), np.float32)
+        _check(lib().b200reg_cloud_points(self.h, cloud.h, out.ctypes.data_as(C.c_void_p)))
+        return out
+
     # -- debug taps ----------------------------------------------------------------------
     def knn(self, cloud, queries, k):
         q = _pts(queries)
@@ -301,3 +324,65 @@ class Context:
                                        H.ctypes.data_as(C.c_void_p), b.ctypes.data_as(C.c_void_p), C.byref(err),
                                        corr.ctypes.data_as(C.c_void_p), sqd.ctypes.data_as(C.c_void_p)))
         return dict(H=H, b=b, err=err.value, corr=corr, sqd=sqd)
+
+
+class Keyframes:
+    """Device-resident keyframe store (PosePcd records) + batched loopTimerFunc pieces."""
+
+    def __init__(self, ctx):
+        self.ctx = ctx
+        self.h = C.c_void_p()
+        _check(lib().b200reg_keyframes_create(ctx.h, C.byref(self.h)))
+
+    def destroy(self):
+        if self.h:
+            lib().b200reg_keyframes_destroy(self.ctx.h, self.h)
+            self.h = None
+
+    def __len__(self):
+        return int(lib().b200reg_keyframes_size(self.h))
+
+    def add(self, cloud_xyzi, pose, stamp):
+        a = np.ascontiguousarray(cloud_xyzi, np.float32)
+        assert a.ndim == 2 and a.shape[1] >= 4
+        T = np.ascontiguousarray(pose, np.float64).reshape(16)
+        rc = lib().b200reg_keyframes_add(self.ctx.h, self.h, a.ctypes.data_as(C.c_void_p), C.c_size_t(len(a)),
+                                         C.c_size_t(a.shape[1] * 4), T.ctypes.data_as(C.c_void_p), C.c_double(stamp))
+        if rc < 0:
+            _check(rc)
+        return rc
+
+    def set_pose(self, idx, pose):
+        T = np.ascontiguousarray(pose, np.float64).reshape(16)
+        _check(lib().b200reg_keyframes_set_pose(self.ctx.h, self.h, int(idx), T.ctypes.data_as(C.c_void_p)))
+
+    def fetch_closest(self, queries, radius=35.0, tdiff=30.0):
+        q = np.ascontiguousarray(queries, np.int32)
+        out = np.empty(len(q), np.int32)
+        _check(lib().b200reg_fetch_closest_keyframes(self.ctx.h, self.h, len(q), q.ctypes.data_as(C.c_void_p), C.c_double(radius),
+                                                     C.c_double(tdiff), out.ctypes.data_as(C.c_void_p)))
+        return out
+
+    def assemble(self, src_idx, dst_idx, cfg=None, n_keyframes=0):
+        cfg = cfg or default_loop_config()
+        s = np.ascontiguousarray(src_idx, np.int32)
+        d = np.ascontiguousarray(dst_idx, np.int32)
+        cnt = len(s)
+        so, do = (C.c_void_p * cnt)(), (C.c_void_p * cnt)()
+        _check(lib().b200reg_assemble_clouds(self.ctx.h, self.h, cnt, s.ctypes.data_as(C.c_void_p), d.ctypes.data_as(C.c_void_p),
+                                             C.byref(cfg), int(n_keyframes), so, do))
+        mk = lambda h: Cloud(self.ctx, C.c_void_p(h), int(lib().b200reg_cloud_size(C.c_void_p(h))))
+        return [mk(so[i]) for i in range(cnt)], [mk(do[i]) for i in range(cnt)]
+
+    def perform_loop_closure(self, query_idx, closest_idx, cfg=None, raw=False):
+        cfg = cfg or default_loop_config()
+        q = np.ascontiguousarray(query_idx, np.int32)
+        cidx = np.ascontiguousarray(closest_idx, np.int32)
+        cnt = len(q)
+        res = (Result * cnt)()
+        qi = (QuatroInfo * cnt)()
+        _check(lib().b200reg_perform_loop_closure(self.ctx.h, self.h, cnt, q.ctypes.data_as(C.c_void_p), cidx.ctypes.data_as(C.c_void_p),
+                                                  C.byref(cfg), res, qi))
+        if raw:
+            return res, qi
+        return [r.as_dict() for r in res], [x.as_dict() for x in qi]

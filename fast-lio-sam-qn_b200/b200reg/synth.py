@@ -102,3 +102,37 @@ def se3_error(T_est, T_ref):
     E = np.linalg.inv(T_ref) @ T_est
     c = np.clip((np.trace(E[:3, :3]) - 1.0) / 2.0, -1.0, 1.0)
     return float(np.arccos(c)), float(np.linalg.norm(E[:3, 3]))
+
+
+def make_sequence(seed, n_keyframes, pts_per_keyframe=30000, spacing=0.8, speed=8.0, drift_xy=0.01, drift_yaw_deg=0.01):
+    """KITTI-05-shaped keyframe sequence: laps of a two-lane street (U-turns at both ends,
+    411 m per lap) so that every place is revisited after > 30 s; one scan per keyframe in the LiDAR frame; odometry
+    poses = true poses with a slow random-walk drift.  Returns dict(clouds, poses (n,4,4), true_poses, stamps)."""
+    rng = np.random.default_rng(seed)
+    half, r = 100.0, 1.8
+    lap = 4 * half + 2 * np.pi * r
+
+    def pose_at(sarc):
+        u = sarc % lap
+        if u < 2 * half:                      # +x lane
+            x, y, yaw = -half + u, -r, 0.0
+        elif u < 2 * half + np.pi * r:        # U-turn at x = +half
+            a = (u - 2 * half) / r
+            x, y, yaw = half + r * np.sin(a), -r * np.cos(a), a
+        elif u < 4 * half + np.pi * r:        # -x lane
+            x, y, yaw = half - (u - 2 * half - np.pi * r), r, np.pi
+        else:                                 # U-turn at x = -half
+            a = (u - 4 * half - np.pi * r) / r
+            x, y, yaw = -half - r * np.sin(a), r * np.cos(a), np.pi + a
+        return se3(yaw=yaw, t=(x, y, 1.73))
+
+    clouds, poses, true_poses, stamps = [], [], [], []
+    D = np.eye(4)
+    for k in range(n_keyframes):
+        Tt = pose_at(k * spacing)
+        D = D @ se3(yaw=np.deg2rad(rng.normal(0, drift_yaw_deg)), t=(rng.normal(0, drift_xy), rng.normal(0, drift_xy), rng.normal(0, drift_xy * 0.1)))
+        clouds.append(scan(seed, 7919 * seed + k, Tt, pts_per_keyframe))
+        true_poses.append(Tt)
+        poses.append(D @ Tt)
+        stamps.append(k * spacing / speed)
+    return dict(clouds=clouds, poses=np.array(poses), true_poses=np.array(true_poses), stamps=np.array(stamps))

@@ -24,6 +24,10 @@ void launch_transform_out(const CloudDev& c, const float* d_Tf, float* d_out3, c
 int launch_fpfh(const CloudDev* d_clouds, int count, int max_n, float normal_r2, float fpfh_r2, cudaStream_t s);
 int launch_quatro_match_solve(const MatchDev* d_pairs, int count, int max_ni, int max_nj, const QuatroParamsDev& prm, cudaStream_t s);
 void launch_transform_raw(const CloudDev* d_clouds, const double* d_T16s, int count, int max_n, float4* const* d_outs, cudaStream_t s);
+int launch_fetch_closest(const double* d_pos, const double* d_stamp, const int* d_queries, int count, double radius, double tdiff,
+                         int* d_out, cudaStream_t s);
+int launch_assemble_voxelize(const AssembleJob* d_jobs, const CloudDev* d_sort, int count, int max_total, const KeyframeDev* d_kfs,
+                             const double* d_poses, float inv_leaf, cudaStream_t s);
 }  // namespace b200
 
 using namespace b200;
@@ -901,36 +905,20 @@ int b200reg_quatro_align(b200reg_ctx* c, int count, b200reg_cloud* const* src, b
   return B200REG_OK;
 }
 
-int b200reg_loop_closure(b200reg_ctx* c, int count, const float* const* src_xyz, const size_t* src_n, const float* const* tgt_xyz,
-                         const size_t* tgt_n, size_t stride_bytes, int on_device, const b200reg_quatro_params* qp,
-                         const b200reg_gicp_params* gp, b200reg_result* out, b200reg_quatro_info* quatro_out) {
-  if (!c || count <= 0 || !src_xyz || !src_n || !tgt_xyz || !tgt_n || !qp || !gp || !out) return fail(B200REG_EINVAL, "bad argument");
-  CU(cudaSetDevice(c->device));
+// LoopClosure::coarseToFineAlignment on cloud handles (loop_closure.cpp:138-159)
+static int coarse_to_fine_on_clouds(b200reg_ctx* c, int count, b200reg_cloud* const* src, b200reg_cloud* const* dst,
+                                    const b200reg_quatro_params* qp, const b200reg_gicp_params* gp, b200reg_result* out,
+                                    b200reg_quatro_info* quatro_out) {
   cudaStream_t s = c->stream;
-  std::vector<const float*> ptrs(2 * count);
-  std::vector<size_t> ns(2 * count);
-  for (int i = 0; i < count; i++) {
-    ptrs[i] = src_xyz[i];
-    ns[i] = src_n[i];
-    ptrs[count + i] = tgt_xyz[i];
-    ns[count + i] = tgt_n[i];
-  }
-  std::vector<b200reg_cloud*> clouds(2 * count, nullptr);
-  int rc = b200reg_clouds_create(c, 2 * count, ptrs.data(), ns.data(), stride_bytes, on_device, clouds.data());
-  if (rc) return rc;
   std::vector<b200reg_quatro_info> qi(count);
   std::vector<b200reg_cloud*> coarse;
   std::vector<void*> raws;
   auto cleanup = [&]() {
-    for (b200reg_cloud* cl : clouds) b200reg_cloud_destroy(c, cl);
     for (b200reg_cloud* cl : coarse) b200reg_cloud_destroy(c, cl);
     for (void* p : raws) cudaFreeAsync(p, s);
   };
-  rc = b200reg_quatro_align(c, count, clouds.data(), clouds.data() + count, qp, qi.data(), nullptr);
-  if (rc) {
-    cleanup();
-    return rc;
-  }
+  int rc = b200reg_quatro_align(c, count, src, dst, qp, qi.data(), nullptr);
+  if (rc) return rc;
   if (quatro_out) memcpy(quatro_out, qi.data(), sizeof(b200reg_quatro_info) * count);
   // pairs whose coarse stage is valid go on to icpAlignment(coarse_aligned_, dst) (loop_closure.cpp:145-156)
   std::vector<int> vidx;
@@ -953,7 +941,7 @@ int b200reg_loop_closure(b200reg_ctx* c, int count, const float* const* src_xyz,
     int max_n = 0;
     for (int k = 0; k < nv; k++) {
       const int i = vidx[k];
-      sdesc[k] = clouds[i]->dev;
+      sdesc[k] = src[i]->dev;
       memcpy(&Ts[16 * (size_t)k], qi[i].T, 128);
       float4* raw = nullptr;
       CU(cudaMallocAsync((void**)&raw, (size_t)sdesc[k].n * 16, s));
@@ -980,7 +968,7 @@ int b200reg_loop_closure(b200reg_ctx* c, int count, const float* const* src_xyz,
     coarse.assign(nv, nullptr);
     rc = b200reg_clouds_create(c, nv, cptr.data(), cn.data(), 16, 1, coarse.data());
     std::vector<b200reg_cloud*> tg(nv);
-    for (int k = 0; k < nv; k++) tg[k] = clouds[count + vidx[k]];
+    for (int k = 0; k < nv; k++) tg[k] = dst[vidx[k]];
     std::vector<b200reg_result> gres(nv);
     if (!rc) rc = b200reg_gicp_align(c, nv, coarse.data(), tg.data(), nullptr, gp, gres.data());
     if (rc) {
@@ -1008,6 +996,292 @@ int b200reg_loop_closure(b200reg_ctx* c, int count, const float* const* src_xyz,
   }
   cleanup();
   return B200REG_OK;
+}
+
+int b200reg_loop_closure(b200reg_ctx* c, int count, const float* const* src_xyz, const size_t* src_n, const float* const* tgt_xyz,
+                         const size_t* tgt_n, size_t stride_bytes, int on_device, const b200reg_quatro_params* qp,
+                         const b200reg_gicp_params* gp, b200reg_result* out, b200reg_quatro_info* quatro_out) {
+  if (!c || count <= 0 || !src_xyz || !src_n || !tgt_xyz || !tgt_n || !qp || !gp || !out) return fail(B200REG_EINVAL, "bad argument");
+  CU(cudaSetDevice(c->device));
+  std::vector<const float*> ptrs(2 * count);
+  std::vector<size_t> ns(2 * count);
+  for (int i = 0; i < count; i++) {
+    ptrs[i] = src_xyz[i];
+    ns[i] = src_n[i];
+    ptrs[count + i] = tgt_xyz[i];
+    ns[count + i] = tgt_n[i];
+  }
+  std::vector<b200reg_cloud*> clouds(2 * count, nullptr);
+  int rc = b200reg_clouds_create(c, 2 * count, ptrs.data(), ns.data(), stride_bytes, on_device, clouds.data());
+  if (!rc) rc = coarse_to_fine_on_clouds(c, count, clouds.data(), clouds.data() + count, qp, gp, out, quatro_out);
+  for (b200reg_cloud* cl : clouds) b200reg_cloud_destroy(c, cl);
+  return rc;
+}
+
+// ---- "next" rows: keyframe store, candidate search, cloud assembly ----------------------------
+struct b200reg_keyframes {
+  std::vector<float4*> pts;
+  std::vector<int> n;
+  std::vector<double> poses;   // 16 per keyframe, row-major
+  std::vector<double> stamps;
+};
+
+void b200reg_default_loop_config(b200reg_loop_config* cfg) {
+  if (!cfg) return;
+  cfg->enable_quatro = 1;
+  cfg->enable_submap_matching = 0;
+  cfg->num_submap_keyframes = 5;
+  cfg->reserved = 0;
+  cfg->voxel_res = 0.3;
+  cfg->loop_detection_radius = 35.0;
+  cfg->loop_detection_timediff_threshold = 30.0;
+  b200reg_default_gicp_params(&cfg->gicp);
+  b200reg_default_quatro_params(&cfg->quatro);
+}
+
+int b200reg_keyframes_create(b200reg_ctx* c, b200reg_keyframes** out) {
+  if (!c || !out) return fail(B200REG_EINVAL, "bad argument");
+  *out = new b200reg_keyframes;
+  return B200REG_OK;
+}
+
+int b200reg_keyframes_destroy(b200reg_ctx* c, b200reg_keyframes* kf) {
+  if (!kf) return B200REG_OK;
+  if (!c) return fail(B200REG_EINVAL, "ctx is NULL");
+  CU(cudaSetDevice(c->device));
+  for (float4* p : kf->pts) CU(cudaFreeAsync(p, c->stream));
+  delete kf;
+  return B200REG_OK;
+}
+
+int b200reg_keyframes_size(const b200reg_keyframes* kf) { return kf ? (int)kf->pts.size() : 0; }
+
+int b200reg_keyframes_add(b200reg_ctx* c, b200reg_keyframes* kf, const float* xyzi, size_t n, size_t stride_bytes, const double* pose16,
+                          double timestamp) {
+  if (!c || !kf || !xyzi || n == 0 || !pose16 || stride_bytes < 16 || stride_bytes % 4) return fail(B200REG_EINVAL, "bad argument");
+  CU(cudaSetDevice(c->device));
+  float4* d = nullptr;
+  CU(cudaMallocAsync((void**)&d, n * 16, c->stream));
+  CU(cudaMemcpy2DAsync(d, 16, xyzi, stride_bytes, 16, n, cudaMemcpyHostToDevice, c->stream));
+  kf->pts.push_back(d);
+  kf->n.push_back((int)n);
+  kf->poses.insert(kf->poses.end(), pose16, pose16 + 16);
+  kf->stamps.push_back(timestamp);
+  return (int)kf->pts.size() - 1;
+}
+
+int b200reg_keyframes_set_pose(b200reg_ctx* c, b200reg_keyframes* kf, int idx, const double* pose16) {
+  if (!c || !kf || !pose16 || idx < 0 || idx >= (int)kf->pts.size()) return fail(B200REG_EINVAL, "bad argument");
+  memcpy(&kf->poses[16 * (size_t)idx], pose16, 128);
+  return B200REG_OK;
+}
+
+int b200reg_fetch_closest_keyframes(b200reg_ctx* c, b200reg_keyframes* kf, int count, const int32_t* query_idx, double radius,
+                                    double tdiff, int32_t* closest_out) {
+  if (!c || !kf || count <= 0 || !query_idx || !closest_out) return fail(B200REG_EINVAL, "bad argument");
+  const int nk = (int)kf->pts.size();
+  for (int i = 0; i < count; i++)
+    if (query_idx[i] < 0 || query_idx[i] >= nk) return fail(B200REG_EINVAL, "query index out of range");
+  CU(cudaSetDevice(c->device));
+  cudaStream_t s = c->stream;
+  std::vector<double> pos(3 * (size_t)nk);
+  for (int i = 0; i < nk; i++)
+    for (int d = 0; d < 3; d++) pos[3 * (size_t)i + d] = kf->poses[16 * (size_t)i + 4 * d + 3];
+  double *d_pos = nullptr, *d_st = nullptr;
+  int *d_q = nullptr, *d_o = nullptr;
+  CU(cudaMallocAsync((void**)&d_pos, pos.size() * 8, s));
+  CU(cudaMallocAsync((void**)&d_st, (size_t)nk * 8, s));
+  CU(cudaMallocAsync((void**)&d_q, (size_t)count * 4, s));
+  CU(cudaMallocAsync((void**)&d_o, (size_t)count * 4, s));
+  CU(cudaMemcpyAsync(d_pos, pos.data(), pos.size() * 8, cudaMemcpyHostToDevice, s));
+  CU(cudaMemcpyAsync(d_st, kf->stamps.data(), (size_t)nk * 8, cudaMemcpyHostToDevice, s));
+  CU(cudaMemcpyAsync(d_q, query_idx, (size_t)count * 4, cudaMemcpyHostToDevice, s));
+  c->launches += launch_fetch_closest(d_pos, d_st, d_q, count, radius, tdiff, d_o, s);
+  CU(cudaMemcpyAsync(closest_out, d_o, (size_t)count * 4, cudaMemcpyDeviceToHost, s));
+  CU(cudaStreamSynchronize(s));
+  CU(cudaFreeAsync(d_pos, s));
+  CU(cudaFreeAsync(d_st, s));
+  CU(cudaFreeAsync(d_q, s));
+  CU(cudaFreeAsync(d_o, s));
+  return B200REG_OK;
+}
+
+int b200reg_assemble_clouds(b200reg_ctx* c, b200reg_keyframes* kf, int count, const int32_t* src_idx, const int32_t* dst_idx,
+                            const b200reg_loop_config* cfg, int n_keyframes, b200reg_cloud** src_out, b200reg_cloud** dst_out) {
+  if (!c || !kf || count <= 0 || !src_idx || !dst_idx || !cfg || !src_out || !dst_out) return fail(B200REG_EINVAL, "bad argument");
+  const int nk = n_keyframes > 0 ? n_keyframes : (int)kf->pts.size();
+  if (nk > (int)kf->pts.size()) return fail(B200REG_EINVAL, "n_keyframes exceeds the store");
+  const int range = cfg->num_submap_keyframes;
+  if (2 * range + 1 > MAXSEG) return fail(B200REG_EINVAL, "num_submap_keyframes too large");
+  if (!(cfg->voxel_res > 0)) return fail(B200REG_EINVAL, "voxel_res must be positive");
+  CU(cudaSetDevice(c->device));
+  cudaStream_t s = c->stream;
+  const int njobs = 2 * count;  // jobs [0,count) = src clouds, [count, 2 count) = dst clouds
+  std::vector<AssembleJob> jobs(njobs);
+  std::vector<CloudDev> sorts(njobs);
+  std::vector<void*> slabs;
+  int max_total = 0;
+  for (int j = 0; j < njobs; j++) {
+    const bool is_src = j < count;
+    const int centre = is_src ? src_idx[j] : dst_idx[j - count];
+    if (centre < 0 || centre >= nk) return fail(B200REG_EINVAL, "keyframe index out of range");
+    AssembleJob& J = jobs[j];
+    memset(&J, 0, sizeof(J));
+    // loop_closure.cpp:68-105: which keyframes are merged
+    const bool merged = cfg->enable_submap_matching || (!is_src && !cfg->enable_quatro);
+    J.nseg = 0;
+    J.seg_off[0] = 0;
+    if (merged) {
+      for (int i = centre - range; i < centre + range + 1; i++)
+        if (i >= 0 && i < nk - 1) {  // the reference excludes the last keyframe (loop_closure.cpp:72,79,100)
+          J.seg_kf[J.nseg] = i;
+          J.seg_off[J.nseg + 1] = J.seg_off[J.nseg] + kf->n[i];
+          J.nseg++;
+        }
+    } else {
+      J.seg_kf[0] = centre;
+      J.seg_off[1] = kf->n[centre];
+      J.nseg = 1;
+    }
+    J.total = J.seg_off[J.nseg];
+    if (J.total <= 0) return fail(B200REG_EINVAL, "empty merged cloud");
+    const size_t n = J.total;
+    const int ntiles = (J.total + SORT_TILE - 1) / SORT_TILE;
+    size_t o = 0;
+    auto take = [&](size_t bytes) {
+      size_t r = o;
+      o = align_up(o + bytes, 256);
+      return r;
+    };
+    const size_t o_m = take(n * 16), o_o = take(n * 16), o_h = take(n * 4), o_b = take(32), o_c = take(16);
+    const size_t o_k0 = take(n * 4), o_k1 = take(n * 4), o_v0 = take(n * 4), o_v1 = take(n * 4), o_hist = take((size_t)RADIX * ntiles * 4);
+    char* slab = nullptr;
+    CU(cudaMallocAsync((void**)&slab, o, s));
+    slabs.push_back(slab);
+    J.merged = (float4*)(slab + o_m);
+    J.out = (float4*)(slab + o_o);
+    J.heads = (int*)(slab + o_h);
+    J.bbox = (int*)(slab + o_b);
+    J.counters = (int*)(slab + o_c);
+    J.sort.keys[0] = (uint32_t*)(slab + o_k0);
+    J.sort.keys[1] = (uint32_t*)(slab + o_k1);
+    J.sort.vals[0] = (uint32_t*)(slab + o_v0);
+    J.sort.vals[1] = (uint32_t*)(slab + o_v1);
+    J.sort.hist = (uint32_t*)(slab + o_hist);
+    CloudDev& sd = sorts[j];
+    memset(&sd, 0, sizeof(sd));
+    sd.n = J.total;
+    sd.keys[0] = J.sort.keys[0];
+    sd.keys[1] = J.sort.keys[1];
+    sd.vals[0] = J.sort.vals[0];
+    sd.vals[1] = J.sort.vals[1];
+    sd.hist = J.sort.hist;
+    max_total = std::max(max_total, J.total);
+  }
+  const int nkall = (int)kf->pts.size();
+  std::vector<KeyframeDev> kd(nkall);
+  for (int i = 0; i < nkall; i++) kd[i] = KeyframeDev{kf->pts[i], kf->n[i], 0};
+  AssembleJob* d_jobs = nullptr;
+  CloudDev* d_sorts = nullptr;
+  KeyframeDev* d_kf = nullptr;
+  double* d_poses = nullptr;
+  CU(cudaMallocAsync((void**)&d_jobs, sizeof(AssembleJob) * njobs, s));
+  CU(cudaMallocAsync((void**)&d_sorts, sizeof(CloudDev) * njobs, s));
+  CU(cudaMallocAsync((void**)&d_kf, sizeof(KeyframeDev) * nkall, s));
+  CU(cudaMallocAsync((void**)&d_poses, 128 * (size_t)nkall, s));
+  CU(cudaMemcpyAsync(d_jobs, jobs.data(), sizeof(AssembleJob) * njobs, cudaMemcpyHostToDevice, s));
+  CU(cudaMemcpyAsync(d_sorts, sorts.data(), sizeof(CloudDev) * njobs, cudaMemcpyHostToDevice, s));
+  CU(cudaMemcpyAsync(d_kf, kd.data(), sizeof(KeyframeDev) * nkall, cudaMemcpyHostToDevice, s));
+  CU(cudaMemcpyAsync(d_poses, kf->poses.data(), 128 * (size_t)nkall, cudaMemcpyHostToDevice, s));
+  {
+    ProfScope ps(c, CLS_MISC);
+    const float inv_leaf = 1.0f / (float)cfg->voxel_res;
+    c->launches += launch_assemble_voxelize(d_jobs, d_sorts, njobs, max_total, d_kf, d_poses, inv_leaf, s);
+    for (int j = 0; j < njobs; j++) c->prof_bytes[CLS_MISC] += 68.0 * jobs[j].total;  // 16 in + 16 merged + 36 sort/centroid
+  }
+  CU(cudaGetLastError());
+  std::vector<int> counters(4 * (size_t)njobs);
+  for (int j = 0; j < njobs; j++) CU(cudaMemcpyAsync(&counters[4 * j], jobs[j].counters, 8, cudaMemcpyDeviceToHost, s));
+  CU(cudaStreamSynchronize(s));
+  // index the voxelised clouds (records are (x, y, z, intensity), 16-byte stride, already on the device)
+  std::vector<const float*> ptrs(njobs);
+  std::vector<size_t> ns(njobs);
+  for (int j = 0; j < njobs; j++) {
+    const bool overflow = counters[4 * j + 1] != 0;  // PCL returns the input unchanged in that case
+    ptrs[j] = (const float*)(overflow ? jobs[j].merged : jobs[j].out);
+    ns[j] = overflow ? (size_t)jobs[j].total : (size_t)counters[4 * j];
+  }
+  std::vector<b200reg_cloud*> clouds(njobs, nullptr);
+  int rc = b200reg_clouds_create(c, njobs, ptrs.data(), ns.data(), 16, 1, clouds.data());
+  for (int i = 0; i < count && !rc; i++) {
+    src_out[i] = clouds[i];
+    dst_out[i] = clouds[count + i];
+  }
+  for (void* p : slabs) CU(cudaFreeAsync(p, s));
+  CU(cudaFreeAsync(d_jobs, s));
+  CU(cudaFreeAsync(d_sorts, s));
+  CU(cudaFreeAsync(d_kf, s));
+  CU(cudaFreeAsync(d_poses, s));
+  return rc;
+}
+
+int b200reg_cloud_points(b200reg_ctx* c, const b200reg_cloud* cl, float* xyz_out) {
+  if (!c || !cl || !xyz_out) return fail(B200REG_EINVAL, "bad argument");
+  CU(cudaSetDevice(c->device));
+  const int n = cl->dev.n;
+  std::vector<float4> pts(n);
+  CU(cudaMemcpyAsync(pts.data(), cl->dev.pts, (size_t)n * 16, cudaMemcpyDeviceToHost, c->stream));
+  CU(cudaStreamSynchronize(c->stream));
+  for (int p = 0; p < n; p++) {
+    int o;
+    memcpy(&o, &pts[p].w, 4);
+    xyz_out[3 * (size_t)o] = pts[p].x;
+    xyz_out[3 * (size_t)o + 1] = pts[p].y;
+    xyz_out[3 * (size_t)o + 2] = pts[p].z;
+  }
+  return B200REG_OK;
+}
+
+int b200reg_perform_loop_closure(b200reg_ctx* c, b200reg_keyframes* kf, int count, const int32_t* query_idx, const int32_t* closest_idx,
+                                 const b200reg_loop_config* cfg, b200reg_result* out, b200reg_quatro_info* quatro_out) {
+  if (!c || !kf || count <= 0 || !query_idx || !closest_idx || !cfg || !out) return fail(B200REG_EINVAL, "bad argument");
+  std::vector<int32_t> qs, cs;
+  std::vector<int> where;
+  for (int i = 0; i < count; i++) {
+    memset(&out[i], 0, sizeof(b200reg_result));  // dummy output whose is_valid is false (loop_closure.cpp:201-204)
+    out[i].T[0] = out[i].T[5] = out[i].T[10] = out[i].T[15] = 1.0;
+    out[i].Tf[0] = out[i].Tf[5] = out[i].Tf[10] = out[i].Tf[15] = 1.f;
+    out[i].fitness = 1.7976931348623157e308;
+    if (quatro_out) memset(&quatro_out[i], 0, sizeof(b200reg_quatro_info));
+    if (closest_idx[i] >= 0) {
+      qs.push_back(query_idx[i]);
+      cs.push_back(closest_idx[i]);
+      where.push_back(i);
+    }
+  }
+  if (qs.empty()) return B200REG_OK;
+  const int m = (int)qs.size();
+  // at the time query q was the latest keyframe the vector held q + 1 keyframes (fast_lio_sam_qn.cpp:205-219); a batch
+  // replays several ticks, so the "size" the submap bounds see is taken per batch from the largest query
+  int nk = 0;
+  for (int q : qs) nk = std::max(nk, q + 1);
+  std::vector<b200reg_cloud*> sc(m, nullptr), dc(m, nullptr);
+  int rc = b200reg_assemble_clouds(c, kf, m, qs.data(), cs.data(), cfg, nk, sc.data(), dc.data());
+  std::vector<b200reg_result> res(m);
+  std::vector<b200reg_quatro_info> qi(m);
+  if (!rc) {
+    if (cfg->enable_quatro) rc = coarse_to_fine_on_clouds(c, m, sc.data(), dc.data(), &cfg->quatro, &cfg->gicp, res.data(), qi.data());
+    else rc = b200reg_gicp_align(c, m, sc.data(), dc.data(), nullptr, &cfg->gicp, res.data());
+  }
+  for (int k = 0; k < m && !rc; k++) {
+    out[where[k]] = res[k];
+    if (quatro_out && cfg->enable_quatro) quatro_out[where[k]] = qi[k];
+  }
+  for (int k = 0; k < m; k++) {
+    b200reg_cloud_destroy(c, sc[k]);
+    b200reg_cloud_destroy(c, dc[k]);
+  }
+  return rc;
 }
 
 }  // extern "C"

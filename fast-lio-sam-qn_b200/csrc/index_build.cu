@@ -311,6 +311,18 @@ __global__ void __launch_bounds__(256) k_lbvh_aabb(const CloudDev* clouds) {
   }
 }
 
+// stable LSD radix sort of (keys[0], vals[0]) of every descriptor; result in keys[npass & 1] / vals[npass & 1].
+// Only the n / keys / vals / hist fields of the descriptors are used (also by the voxel grid, assemble.cu).
+int launch_radix_sort(const CloudDev* d_clouds, int count, int max_n, int npass, cudaStream_t s) {
+  const int ntiles = (max_n + SORT_TILE - 1) / SORT_TILE;
+  for (int p = 0; p < npass; p++) {
+    k_sort_hist<<<dim3(ntiles, count), SORT_THREADS, 0, s>>>(d_clouds, p);
+    k_sort_scan<<<count, 1024, 0, s>>>(d_clouds);
+    k_sort_scatter<<<dim3(ntiles, count), SORT_THREADS, 0, s>>>(d_clouds, p);
+  }
+  return 3 * npass;
+}
+
 // ------------------------------------------------------------------------------------
 // host launcher: builds `count` clouds whose descriptors are already in device memory.
 // Returns the number of kernel launches issued.
@@ -322,14 +334,8 @@ int launch_index_build(const CloudDev* d_clouds, int count, int max_n, cudaStrea
     k_bbox<<<dim3(gx, count), 256, 0, s>>>(d_clouds); launches++;
   }
   k_morton<<<dim3((max_n + 255) / 256, count), 256, 0, s>>>(d_clouds); launches++;
-  const int ntiles = (max_n + SORT_TILE - 1) / SORT_TILE;
   const int npass = 4;  // 30-bit keys
-  for (int p = 0; p < npass; p++) {
-    k_sort_hist<<<dim3(ntiles, count), SORT_THREADS, 0, s>>>(d_clouds, p);
-    k_sort_scan<<<count, 1024, 0, s>>>(d_clouds);
-    k_sort_scatter<<<dim3(ntiles, count), SORT_THREADS, 0, s>>>(d_clouds, p);
-    launches += 3;
-  }
+  launches += launch_radix_sort(d_clouds, count, max_n, npass, s);
   k_gather<<<dim3((max_n + 255) / 256, count), 256, 0, s>>>(d_clouds, npass & 1); launches++;
   if (max_n > 1) {
     k_lbvh_topology<<<dim3((max_n + 254) / 256, count), 256, 0, s>>>(d_clouds, npass & 1); launches++;

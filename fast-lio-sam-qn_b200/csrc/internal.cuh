@@ -98,6 +98,30 @@ struct PairDev {
   double* partial; // [nblocks * NRED]
 };
 
+// ---- keyframe store / cloud assembly -------------------------------------------
+constexpr int MAXSEG = 32;  // keyframes merged into one cloud: 2 * submap_range + 1 <= MAXSEG
+struct KeyframeDev {
+  const float4* pts;  // (x, y, z, intensity), LiDAR frame, original order
+  int n;
+  int pad;
+};
+struct SortBufs {  // what the radix sort needs (mirrors the CloudDev fields it reads)
+  uint32_t* keys[2];
+  uint32_t* vals[2];
+  uint32_t* hist;
+};
+struct AssembleJob {  // one output cloud of setSrcAndDstCloud
+  int nseg, total;
+  int seg_kf[MAXSEG];
+  int seg_off[MAXSEG + 1];
+  float4* merged;   // [total] transformed, merged points
+  float4* out;      // [total] voxel centroids (counters[0] of them)
+  int* heads;       // [total]
+  int* bbox;        // [6] ordered-int min/max
+  int* counters;    // [0] voxels, [1] int32-overflow flag
+  SortBufs sort;
+};
+
 // ---- Quatro matcher / solver workspace ---------------------------------------------------
 // per-pair device workspace of the matcher / solver
 struct MatchDev {

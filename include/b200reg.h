@@ -167,6 +167,51 @@ int b200reg_loop_closure(b200reg_ctx* ctx, int count, const float* const* src_xy
                          const b200reg_quatro_params* qparams, const b200reg_gicp_params* gparams,
                          b200reg_result* out, b200reg_quatro_info* quatro_out);
 
+/* ---- "next" rows: device-resident keyframes, candidate search, cloud assembly ---------- */
+typedef struct b200reg_keyframes b200reg_keyframes;
+
+/* Mirrors LoopClosureConfig (fast_lio_sam_qn/include/loop_closure.h:52-62) with the EFFECTIVE deployment values
+ * (num_submap_keyframes 5 because of the rosparam typo). */
+typedef struct b200reg_loop_config {
+  int32_t enable_quatro;            /* config.yaml:29 (1)                                   */
+  int32_t enable_submap_matching;   /* config.yaml:9 (0)                                    */
+  int32_t num_submap_keyframes;     /* submap_range (5)                                     */
+  int32_t reserved;
+  double voxel_res;                 /* config.yaml:16 (0.3)                                 */
+  double loop_detection_radius;     /* config.yaml:13 (35.0)                                */
+  double loop_detection_timediff_threshold; /* config.yaml:14 (30.0)                        */
+  b200reg_gicp_params gicp;
+  b200reg_quatro_params quatro;
+} b200reg_loop_config;
+void b200reg_default_loop_config(b200reg_loop_config* cfg);
+
+int b200reg_keyframes_create(b200reg_ctx* ctx, b200reg_keyframes** out);
+int b200reg_keyframes_destroy(b200reg_ctx* ctx, b200reg_keyframes* kf);
+/* PosePcd (fast_lio_sam_qn/include/pose_pcd.hpp:7-43): cloud in the LiDAR frame as (x, y, z, intensity) records
+ * `stride_bytes` apart (host memory), its corrected pose (row-major 4x4) and timestamp.  Returns the index.   */
+int b200reg_keyframes_add(b200reg_ctx* ctx, b200reg_keyframes* kf, const float* xyzi, size_t n, size_t stride_bytes,
+                          const double* pose16, double timestamp);
+/* pose_corrected_eig_ rewrite after an accepted loop (fast_lio_sam_qn/src/fast_lio_sam_qn.cpp:180-188).     */
+int b200reg_keyframes_set_pose(b200reg_ctx* ctx, b200reg_keyframes* kf, int idx, const double* pose16);
+int b200reg_keyframes_size(const b200reg_keyframes* kf);
+/* LoopClosure::fetchClosestKeyframeIdx (loop_closure.cpp:34-56) for `count` query keyframes at once; each query
+ * is treated as the latest keyframe at its time, so its candidates are the indices below it. -1 = none.       */
+int b200reg_fetch_closest_keyframes(b200reg_ctx* ctx, b200reg_keyframes* kf, int count, const int32_t* query_idx,
+                                    double radius, double timediff_threshold, int32_t* closest_out);
+/* LoopClosure::setSrcAndDstCloud (loop_closure.cpp:58-108) for `count` (src, dst) keyframe index pairs:
+ * transformPcd by the corrected poses, +-submap merge, pcl::VoxelGrid at voxel_res; the resulting clouds are
+ * indexed and stay on the device.  n_keyframes = size of the keyframe vector at the time (0 = current size).  */
+int b200reg_assemble_clouds(b200reg_ctx* ctx, b200reg_keyframes* kf, int count, const int32_t* src_idx,
+                            const int32_t* dst_idx, const b200reg_loop_config* cfg, int n_keyframes,
+                            b200reg_cloud** src_out, b200reg_cloud** dst_out);
+/* Points of a cloud in their ORIGINAL order as (x, y, z) (debug tap for the assembled / voxelised clouds).    */
+int b200reg_cloud_points(b200reg_ctx* ctx, const b200reg_cloud* cloud, float* xyz_out);
+/* LoopClosure::performLoopClosure (loop_closure.cpp:168-205) for `count` query keyframes with given closest
+ * indices (-1 = no candidate -> invalid dummy output): assemble, then coarse-to-fine (enable_quatro) or GICP only. */
+int b200reg_perform_loop_closure(b200reg_ctx* ctx, b200reg_keyframes* kf, int count, const int32_t* query_idx,
+                                 const int32_t* closest_idx, const b200reg_loop_config* cfg, b200reg_result* out,
+                                 b200reg_quatro_info* quatro_out);
+
 /* Output cloud of align(): final_transformation_ applied to the source in fp32
  * (lsq_registration_impl.hpp:114).  out_xyz: n x 3 floats (host), original point order.       */
 int b200reg_transform_cloud(b200reg_ctx* ctx, const b200reg_cloud* cloud, const float* Tf16, float* out_xyz);

@@ -271,3 +271,45 @@ def coarse_to_fine(src, dst, qparams=None, gparams=None, quatro_T=None):
     out.update(gicp=g, T=g["Tf"].astype(np.float64) @ q["T"], fitness=g["fitness"], converged=g["converged"],
                valid=bool(g["converged"] and g["fitness"] < 1.5))
     return out
+
+
+# ---------------------------------------------------------------------------------------------
+# "next" rows: cloud assembly and candidate search
+def transform_pcd(pts, T):
+    pts = np.ascontiguousarray(pts, np.float32)
+    T = np.ascontiguousarray(T, np.float64)
+    out = np.empty_like(pts)
+    lib().orc_transform_pcd(_p(pts, C.c_float), len(pts), pts.shape[1], _p(T, C.c_double), _p(out, C.c_float))
+    return out
+
+
+def voxelize(pts, leaf):
+    """pcl::VoxelGrid restated; pts (n,4) x,y,z,intensity -> (m,4) centroids in voxel-index order."""
+    pts = np.ascontiguousarray(pts, np.float32)
+    assert pts.shape[1] == 4
+    out = np.empty_like(pts)
+    m = lib().orc_voxelize(_p(pts, C.c_float), len(pts), C.c_float(leaf), _p(out, C.c_float))
+    return pts.copy() if m < 0 else out[:m].copy()
+
+
+def fetch_closest(pos, stamps, q, radius=35.0, tdiff=30.0):
+    pos = np.ascontiguousarray(pos, np.float64)
+    st = np.ascontiguousarray(stamps, np.float64)
+    return lib().orc_fetch_closest(_p(pos, C.c_double), _p(st, C.c_double), int(q), C.c_double(radius), C.c_double(tdiff))
+
+
+def set_src_and_dst_cloud(kf_clouds, kf_poses, src_idx, dst_idx, submap_range=5, voxel_res=0.3, enable_quatro=True,
+                          enable_submap_matching=False, n_keyframes=None):
+    """LoopClosure::setSrcAndDstCloud (fast_lio_sam_qn/src/loop_closure.cpp:58-108)."""
+    nk = n_keyframes if n_keyframes is not None else len(kf_clouds)
+
+    def merged(center):
+        parts = [transform_pcd(kf_clouds[i], kf_poses[i]) for i in range(center - submap_range, center + submap_range + 1)
+                 if 0 <= i < nk - 1]
+        return np.concatenate(parts) if parts else np.zeros((0, 4), np.float32)
+    if enable_submap_matching:
+        src, dst = merged(src_idx), merged(dst_idx)
+    else:
+        src = transform_pcd(kf_clouds[src_idx], kf_poses[src_idx])
+        dst = transform_pcd(kf_clouds[dst_idx], kf_poses[dst_idx]) if enable_quatro else merged(dst_idx)
+    return voxelize(src, voxel_res), voxelize(dst, voxel_res)

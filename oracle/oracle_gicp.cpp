@@ -618,3 +618,86 @@ int orc_gicp_align(const float* src, int N, int sstride, const float* tgt, int M
 }
 
 }  // extern "C"
+
+// ===========================================================================================
+// "Next" rows of SURVEY.md §8(f): the steps either side of the registration path.
+// ===========================================================================================
+extern "C" {
+
+// transformPcd (fast_lio_sam_qn/include/utilities.hpp:164-175): pcl::transformPointCloud with a Matrix4d --
+// per point double math, result cast to float; other fields (intensity) copied.
+void orc_transform_pcd(const float* in, int n, int stride, const double* T16, float* out /* n x stride */) {
+  for (int i = 0; i < n; i++) {
+    const float* p = &in[(size_t)i * stride];
+    float* o = &out[(size_t)i * stride];
+    const double x = p[0], y = p[1], z = p[2];
+    for (int d = 3; d < stride; d++) o[d] = p[d];
+    for (int r = 0; r < 3; r++) o[r] = (float)(T16[4 * r] * x + T16[4 * r + 1] * y + T16[4 * r + 2] * z + T16[4 * r + 3]);
+  }
+}
+
+// voxelizePcd (utilities.hpp:38-63) = pcl::VoxelGrid, leaf L on all axes, downsample_all_data:
+// fp32 min/max -> min_b = floor(min * (1/L)); ijk = floor(p * (1/L)) - float(min_b); idx = i + j*dx + k*dx*dy;
+// sort by idx; per occupied voxel the centroid of x, y, z, intensity (fp32 running sums) in idx order.
+// Within a voxel PCL's std::sort leaves the order unspecified; ascending point index is used here.
+// in/out records: (x, y, z, intensity).  Returns the number of voxels, or -1 when dx*dy*dz overflows int32
+// (PCL then warns and returns the input unchanged).
+int orc_voxelize(const float* in, int n, float leaf, float* out /* up to n x 4 */) {
+  if (n <= 0) return 0;
+  const float inv = 1.0f / leaf;
+  float mn[3] = {INFINITY, INFINITY, INFINITY}, mx[3] = {-INFINITY, -INFINITY, -INFINITY};
+  for (int i = 0; i < n; i++)
+    for (int d = 0; d < 3; d++) {
+      mn[d] = std::min(mn[d], in[4 * (size_t)i + d]);
+      mx[d] = std::max(mx[d], in[4 * (size_t)i + d]);
+    }
+  long long dd[3];
+  int min_b[3], div_b[3];
+  for (int d = 0; d < 3; d++) {
+    dd[d] = (long long)((mx[d] - mn[d]) * inv) + 1;
+    min_b[d] = (int)std::floor(mn[d] * inv);
+    div_b[d] = (int)std::floor(mx[d] * inv) - min_b[d] + 1;
+  }
+  if (dd[0] * dd[1] * dd[2] > (long long)std::numeric_limits<int>::max()) return -1;
+  std::vector<std::pair<int, int>> iv(n);
+  for (int i = 0; i < n; i++) {
+    int ijk[3];
+    for (int d = 0; d < 3; d++) ijk[d] = (int)(std::floor(in[4 * (size_t)i + d] * inv) - (float)min_b[d]);
+    iv[i] = {ijk[0] + ijk[1] * div_b[0] + ijk[2] * div_b[0] * div_b[1], i};
+  }
+  std::sort(iv.begin(), iv.end());
+  int nv = 0;
+  for (int a = 0; a < n;) {
+    int b = a;
+    float s[4] = {0.f, 0.f, 0.f, 0.f};
+    while (b < n && iv[b].first == iv[a].first) {
+      for (int d = 0; d < 4; d++) s[d] += in[4 * (size_t)iv[b].second + d];
+      b++;
+    }
+    for (int d = 0; d < 4; d++) out[4 * (size_t)nv + d] = s[d] / (float)(b - a);
+    nv++;
+    a = b;
+  }
+  return nv;
+}
+
+// LoopClosure::fetchClosestKeyframeIdx (fast_lio_sam_qn/src/loop_closure.cpp:34-56) for the query keyframe q being
+// the LATEST one: candidates are idx < q (keyframes.size() - 1 == q), position distance < radius, time gap > thr,
+// strictly-closer wins so the lowest index survives ties.  pos: n x 3 doubles; returns -1 when none.
+int orc_fetch_closest(const double* pos, const double* stamp, int q, double radius, double tdiff_thr) {
+  double shortest = radius * 3.0;
+  int closest = -1;
+  for (int idx = 0; idx < q; idx++) {
+    const double dx = pos[3 * idx] - pos[3 * q], dy = pos[3 * idx + 1] - pos[3 * q + 1], dz = pos[3 * idx + 2] - pos[3 * q + 2];
+    const double dist = std::sqrt(dx * dx + dy * dy + dz * dz);
+    if (radius > dist && tdiff_thr < (stamp[q] - stamp[idx])) {
+      if (dist < shortest) {
+        shortest = dist;
+        closest = idx;
+      }
+    }
+  }
+  return closest;
+}
+
+}  // extern "C"

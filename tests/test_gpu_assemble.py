@@ -1,0 +1,87 @@
+"""GPU parity for the "next" rows: candidate search, cloud assembly (transformPcd + submap merge +
+pcl::VoxelGrid) and the batched performLoopClosure driver, against the CPU oracle."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def seq(synth):
+    return synth.make_sequence(7, 140, pts_per_keyframe=6000, spacing=3.0, speed=8.0)
+
+
+@pytest.fixture(scope="module")
+def store(ctx, seq):
+    kf = ctx.keyframes()
+    for c, T, t in zip(seq["clouds"], seq["poses"], seq["stamps"]):
+        kf.add(c, T, t)
+    yield kf
+    kf.destroy()
+
+
+def test_fetch_closest_equals_oracle(store, oracle, seq):
+    pos = seq["poses"][:, :3, 3]
+    queries = np.arange(len(pos), dtype=np.int32)
+    got = store.fetch_closest(queries, 35.0, 30.0)
+    want = np.array([oracle.fetch_closest(pos, seq["stamps"], q, 35.0, 30.0) for q in queries])
+    assert np.array_equal(got, want)
+    assert (want >= 0).sum() > 10 and (want < 0).sum() > 10
+
+
+def _sorted_rows(a):
+    return a[np.lexsort((a[:, 2], a[:, 1], a[:, 0]))]
+
+
+def test_assemble_quatro_and_submap_modes(ctx, store, oracle, seq):
+    import b200reg
+    pairs = [(137, 3), (139, 70), (120, 55)]
+    src_idx = [p[0] for p in pairs]
+    dst_idx = [p[1] for p in pairs]
+    for quatro, submap in ((1, 0), (0, 0), (1, 1)):
+        cfg = b200reg.default_loop_config()
+        cfg.enable_quatro, cfg.enable_submap_matching = quatro, submap
+        sc, dc = store.assemble(src_idx, dst_idx, cfg, n_keyframes=140)
+        for k, (si, di) in enumerate(pairs):
+            os_, od_ = oracle.set_src_and_dst_cloud(seq["clouds"], seq["poses"], si, di, submap_range=5, voxel_res=0.3,
+                                                    enable_quatro=bool(quatro), enable_submap_matching=bool(submap), n_keyframes=140)
+            for cloud, want in ((sc[k], os_), (dc[k], od_)):
+                got = ctx.cloud_points(cloud)
+                assert got.shape[0] == want.shape[0], "voxel count must match pcl::VoxelGrid's"
+                # same voxel order (linear voxel index); centroids agree to fp32 summation-order noise
+                assert np.abs(got - want[:, :3]).max() < 2e-4
+        for c in sc + dc:
+            c.destroy()
+
+
+def test_perform_loop_closure_matches_oracle(ctx, store, oracle, synth, seq):
+    import b200reg
+    queries = np.array([137, 139, 20, 118], np.int32)
+    closest = store.fetch_closest(queries)
+    assert closest[2] == -1 and (closest[[0, 1, 3]] >= 0).all()
+    res, qi = store.perform_loop_closure(queries, closest)
+    assert not res[2]["valid"] and np.array_equal(res[2]["T"], np.eye(4))  # dummy output (loop_closure.cpp:201-204)
+    for k in (0, 1, 3):
+        q, c = int(queries[k]), int(closest[k])
+        src, dst = oracle.set_src_and_dst_cloud(seq["clouds"], seq["poses"], q, c, n_keyframes=q + 1)
+        if qi[k]["valid"]:
+            o = oracle.coarse_to_fine(src, dst, quatro_T=qi[k]["T"])
+            rot, tr = synth.se3_error(res[k]["T"], o["T"])
+            assert rot < 3e-4 and tr < 3e-3, (k, rot, tr)  # inputs differ by the voxel-centroid fp32 noise (2e-4 m)
+            # the loop closure undoes the accumulated odometry drift between the two keyframes
+            drift = seq["true_poses"][c] @ np.linalg.inv(seq["poses"][c]) @ seq["poses"][q] @ np.linalg.inv(seq["true_poses"][q])
+            # T maps src (map frame by odom) onto dst: T ~= D_c * inv(D_q) with D = odom * inv(true)
+            Dq = seq["poses"][q] @ np.linalg.inv(seq["true_poses"][q])
+            Dc = seq["poses"][c] @ np.linalg.inv(seq["true_poses"][c])
+            rot, tr = synth.se3_error(res[k]["T"], Dc @ np.linalg.inv(Dq))
+            assert rot < 2e-2 and tr < 0.3, ("ground truth", k, rot, tr)
+    # GICP-only mode (scan-to-submap, loop_closure.cpp:94-105)
+    cfg = b200reg.default_loop_config()
+    cfg.enable_quatro = 0
+    res2, _ = store.perform_loop_closure(queries[:2], closest[:2], cfg)
+    for k in range(2):
+        q, c = int(queries[k]), int(closest[k])
+        src, dst = oracle.set_src_and_dst_cloud(seq["clouds"], seq["poses"], q, c, enable_quatro=False, n_keyframes=int(queries[:2].max()) + 1)
+        o = oracle.gicp_align(src, dst)
+        rot, tr = synth.se3_error(res2[k]["T"], o["T"])
+        assert rot < 3e-4 and tr < 3e-3, (k, rot, tr)
