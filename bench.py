@@ -45,8 +45,10 @@ def parse():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--pairs", type=int, default=16, help="pairs per step per rank")
     ap.add_argument("--points", type=int, default=None)
-    ap.add_argument("--workload", default="gicp", choices=["gicp", "quatro"],
-                    help="gicp = configs[1] (the headline); quatro = configs[2] Quatro+Nano-GICP full loop closure")
+    ap.add_argument("--workload", default="gicp", choices=["gicp", "quatro", "sequence"],
+                    help="gicp = configs[1] (the headline); quatro = configs[2] Quatro+Nano-GICP full loop closure; "
+                         "sequence = configs[4] loopTimerFunc over a KITTI-05-shaped keyframe sequence held on the device")
+    ap.add_argument("--keyframes", type=int, default=600, help="sequence workload: keyframes generated (KITTI 05: 2761)")
     ap.add_argument("--cpu-sample-pairs", type=int, default=6)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     return ap.parse_args()
@@ -228,8 +230,123 @@ def workload_name(args):
             "coarseToFineAlignment: FPFH -> optimizedMatching -> QUATRO solve -> transform -> GICP refine)" % (args.points // 1000))
 
 
+def main_sequence(args):
+    """configs[4]: every keyframe with a loop candidate goes through fetchClosestKeyframeIdx + setSrcAndDstCloud +
+    coarse-to-fine registration, all from device-resident keyframes (fast_lio_sam_qn.cpp:203-252)."""
+    import torch
+    import b200reg
+    from b200reg import synth
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device -- the b200 arm has no CPU fallback")
+    torch.cuda.set_device(0)
+    B = args.pairs
+    pts = 30000 if args.points is None else args.points  # ~120k returns / 4 (kitti.launch:7)
+    seq = synth.make_sequence(5, args.keyframes, pts_per_keyframe=pts)
+    ctx = b200reg.Context(0)
+    stream = torch.cuda.Stream()
+    ctx.set_stream(stream.cuda_stream)
+    kf = ctx.keyframes()
+    for c, T, t in zip(seq["clouds"], seq["poses"], seq["stamps"]):
+        kf.add(c, T, t)
+    ctx.synchronize()
+    cfg = b200reg.default_loop_config()
+    allq = np.arange(args.keyframes, dtype=np.int32)
+    closest_all = kf.fetch_closest(allq, cfg.loop_detection_radius, cfg.loop_detection_timediff_threshold)
+    cand = allq[closest_all >= 0]
+    if len(cand) < B:
+        raise SystemExit("bench.py: sequence too short for loop candidates (%d)" % len(cand))
+    batches = [cand[i:i + B] for i in range(0, len(cand) - B + 1, B)]
+    pinned = [torch.from_numpy(seq["clouds"][q]).pin_memory() for q in cand[:B]]
+
+    def step(i, ingest):
+        q = batches[i % len(batches)]
+        if ingest:  # e2e: the step's query keyframes arrive from the host first (odomPcdCallback -> keyframe store)
+            for j, qq in enumerate(q):
+                kf.add(pinned[j % len(pinned)].numpy(), seq["poses"][qq], seq["stamps"][qq])
+        cl = kf.fetch_closest(q, cfg.loop_detection_radius, cfg.loop_detection_timediff_threshold)
+        return kf.perform_loop_closure(q, cl, cfg, raw=True)
+
+    def timed(ingest, steps):
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        l0 = ctx.launch_count
+        with torch.cuda.stream(stream):
+            e0.record(stream)
+            for i in range(steps):
+                out = step(i, ingest)
+            e1.record(stream)
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1), ctx.launch_count - l0, out
+
+    sampler = ClockSampler(0)
+    for i in range(args.warmup):
+        step(i, False)
+    steps = min(args.steps, 4 * len(batches))
+    ms_dev, launches, out = timed(False, steps)
+    ms_e2e, _, _ = timed(True, steps)
+    clocks = sampler.stop()
+    ctx.set_profiling(True)
+    ctx.reset_profile()
+    prof_steps = min(3, steps)
+    for i in range(prof_steps):
+        step(i, False)
+    prof = ctx.get_profile()
+    ctx.set_profiling(False)
+    n_valid = sum(1 for r in out[0] if r.valid)
+    peak, peak_src = peaks()
+    fam = max((k for k in prof), key=lambda k: prof[k]["ms"])
+    tot_ms = sum(v["ms"] for v in prof.values())
+    f = prof[fam]
+    achieved = f["algo_bytes"] / (f["ms"] * 1e-3) / 1e9 if f["ms"] > 0 else 0.0
+    res = {
+        "metric": "loop_closure_attempts_per_sec_kitti05_shaped_sequence", "value": B * steps / (ms_dev * 1e-3), "unit": UNIT,
+        "n_gpus": 1, "steps": steps, "warmup": args.warmup, "ms_per_step": ms_dev / steps, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32 points+kNN+features / f64 covariance+solver", "data": "synthetic",
+        "config": {"workload": "configs[4]: loopTimerFunc over a synthetic KITTI-05-shaped sequence of %d keyframes x %dk points kept "
+                               "on the device: fetchClosestKeyframeIdx + setSrcAndDstCloud (transform, voxel 0.3 m) + Quatro + Nano-GICP"
+                               % (args.keyframes, pts // 1000), "attempts_per_step": B, "candidates": int(len(cand)),
+                   "l2": "each step touches %d distinct keyframe pairs (%.0f MB of points) and rebuilds all derived data"
+                         % (B, 2 * B * pts * 16 / 1e6)},
+        "e2e": {"value": B * steps / (ms_e2e * 1e-3), "unit": UNIT, "ms_per_step": ms_e2e / steps,
+                "h2d_bytes_per_step": B * pts * 16, "d2h_bytes_per_step": B * ctypes.sizeof(b200reg.Result)},
+        "gpu_launches": launches,
+        "roofline": {"bound": "hbm", "kernel": fam, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                     "traffic": None, "peak_source": peak_src},
+        "kernels": {k: dict(ms_per_step=v["ms"] / prof_steps, share=v["ms"] / tot_ms if tot_ms else 0.0) for k, v in prof.items()},
+        "clocks": clocks, "accuracy": {"valid_in_last_batch": n_valid, "batch": B},
+    }
+    if not args.no_cpu_baseline:
+        from oracle import oracle as orc
+        orc.lib()
+        orc.use_ref_nanoflann(True)
+        q0 = batches[0]
+        c0 = kf.fetch_closest(q0)
+
+        def cpu_one(src_dst):
+            return orc.coarse_to_fine(src_dst[0], src_dst[1])
+        pair0 = orc.set_src_and_dst_cloud(seq["clouds"], seq["poses"], int(q0[0]), int(c0[0]), n_keyframes=int(q0[0]) + 1)
+        threads, ncpu = calibrate_threads(orc, lambda a, b: orc.coarse_to_fine(a, b), pair0)
+        t0 = time.perf_counter()
+        nrun = 0
+        for qq, cc in zip(q0[:6], c0[:6]):
+            pos = seq["poses"][:int(qq) + 1, :3, 3]
+            orc.fetch_closest(pos, seq["stamps"], int(qq))
+            s_, d_ = orc.set_src_and_dst_cloud(seq["clouds"], seq["poses"], int(qq), int(cc), n_keyframes=int(qq) + 1)
+            orc.coarse_to_fine(s_, d_)
+            nrun += 1
+        dt = time.perf_counter() - t0
+        res["cpu_baseline"] = {"value": nrun / dt, "unit": UNIT, "cores": threads, "logical_cpus": ncpu, "kind": "port",
+                               "sample": "%d loop attempts (candidate search + assembly + Quatro + GICP), CPU oracle" % nrun,
+                               "cpu_model": cpu_info()[0]}
+    print(json.dumps(res))
+    kf.destroy()
+    ctx.close()
+
+
 def main():
     args = parse()
+    if args.workload == "sequence" and args.impl == "b200":
+        return main_sequence(args)
     if args.points is None:
         args.points = N_POINTS
     if args.impl == "reference":
