@@ -257,6 +257,7 @@ int b200reg_clouds_create(b200reg_ctx* c, int count, const float* const* xyz, co
     d.nrm = nullptr;
     d.spfh = nullptr;
     d.fpfh = nullptr;
+    d.fnorm = nullptr;
     // temporary slab (sort buffers, histogram, tree scratch, bbox, and the raw records when uploading)
     size_t t_k0 = 0;
     size_t t_k1 = align_up(t_k0 + (size_t)d.n * 4, 256);
@@ -753,13 +754,15 @@ int b200reg_clouds_fpfh(b200reg_ctx* c, int count, b200reg_cloud* const* clouds,
       size_t o_n = 0;
       size_t o_s = align_up(o_n + n * sizeof(float4), 256);
       size_t o_f = align_up(o_s + n * FPAD * sizeof(float), 256);
-      size_t total = align_up(o_f + n * FPAD * sizeof(float), 256);
+      size_t o_fn = align_up(o_f + n * FPAD * sizeof(float), 256);
+      size_t total = align_up(o_fn + n * sizeof(float4), 256);
       char* fs = nullptr;
       CU(cudaMallocAsync((void**)&fs, total, s));
       cl->fslab = fs;
       cl->dev.nrm = (float4*)(fs + o_n);
       cl->dev.spfh = (float*)(fs + o_s);
       cl->dev.fpfh = (float*)(fs + o_f);
+      cl->dev.fnorm = (float4*)(fs + o_fn);
     }
     todo.push_back(cl);
     descs.push_back(cl->dev);

@@ -43,6 +43,7 @@ struct CloudDev {
   float4* nrm;         // [n] unit normal, w = 1 valid / 0 invalid (< 3 neighbours)
   float* spfh;         // [FPAD * n]
   float* fpfh;         // [FPAD * n]; slot 33 = original index (int bits), slot 34 = 1.0 if the descriptor is usable
+  float4* fnorm;       // [n] L2 norms of the three 11-bin blocks (x, y, z): lower bound ||a-b||^2 >= sum_k (|a_k| - |b_k|)^2
   // build-time temporaries (freed after the build)
   uint32_t* keys[2];   // sort ping-pong
   uint32_t* vals[2];
