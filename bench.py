@@ -84,10 +84,10 @@ def calibrate_threads(orc, fn, pair):
     ncpu = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
     cands = sorted({max(1, ncpu >> k) for k in range(0, 4)}, reverse=True)
     best, best_t = cands[0], float("inf")
-    src, dst = pair[0][:30000], pair[1][:30000]
+    src, dst = pair[0], pair[1]  # the full-size pair: the best thread count depends on the problem size
     for n in cands:
         orc.lib().orc_set_num_threads(n)
-        fn(src, dst)
+        fn(src[:20000], dst[:20000])  # spin the pool up at this width
         t0 = time.perf_counter()
         fn(src, dst)
         dt = time.perf_counter() - t0

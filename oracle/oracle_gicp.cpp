@@ -10,7 +10,7 @@
 // and PCL/Eigen are absent so the reference itself cannot be run here.  The one
 // piece of the reference that DOES compile here is its kd-tree
 // (NG/impl/nanoflann_impl.hpp): oracle/ref_nanoflann_shim.cpp wraps it into
-// oracle/_ref/libref_nanoflann.so and tests/test_oracle_knn.py pins this
+// oracle/_ref/libref_nanoflann.so and tests/test_oracle.py pins this
 // file's kNN against it index-for-index.  Everything after the kNN (covariance,
 // Mahalanobis, LM) is "parity unpinned" by reference outputs and is instead
 // pinned by (i) closed-form known-answer tests and (ii) ground-truth SE(3)
