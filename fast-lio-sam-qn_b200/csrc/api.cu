@@ -52,6 +52,7 @@ struct b200reg_ctx {
   cudaStream_t own_stream = nullptr;
   cudaStream_t stream = nullptr;
   cudaStream_t copy_stream = nullptr;  // H2D uploads of later chunks overlap the compute of earlier ones
+  cudaMemPool_t pool = nullptr;        // per-context pool: reuse never adds dependencies on another context's streams
   int pipeline_chunks = 4;
   int* d_done = nullptr;   // device counter of finished pairs
   int* h_done = nullptr;   // pinned mirror
@@ -152,10 +153,14 @@ int b200reg_ctx_create(int device, b200reg_ctx** out) {
   CU(cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking));
   CU(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
   c->stream = c->own_stream;
-  cudaMemPool_t pool;
-  CU(cudaDeviceGetDefaultMemPool(&pool, device));
+  cudaMemPoolProps props = {};
+  props.allocType = cudaMemAllocationTypePinned;
+  props.handleTypes = cudaMemHandleTypeNone;
+  props.location.type = cudaMemLocationTypeDevice;
+  props.location.id = device;
+  CU(cudaMemPoolCreate(&c->pool, &props));
   uint64_t thr = UINT64_MAX;
-  CU(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr));
+  CU(cudaMemPoolSetAttribute(c->pool, cudaMemPoolAttrReleaseThreshold, &thr));
   CU(cudaMalloc(&c->d_done, sizeof(int)));
   CU(cudaMallocHost(&c->h_done, sizeof(int)));
   *out = c;
@@ -170,6 +175,7 @@ int b200reg_ctx_destroy(b200reg_ctx* c) {
   cudaFreeHost(c->h_done);
   cudaStreamDestroy(c->own_stream);
   cudaStreamDestroy(c->copy_stream);
+  if (c->pool) cudaMemPoolDestroy(c->pool);
   delete c;
   return B200REG_OK;
 }
@@ -248,7 +254,7 @@ int b200reg_clouds_create(b200reg_ctx* c, int count, const float* const* xyz, co
     size_t o_rank = align_up(o_cov + (size_t)6 * d.n * sizeof(double), 256);
     size_t total = align_up(o_rank + (size_t)d.n * sizeof(int), 256);
     char* slab = nullptr;
-    CU(cudaMallocAsync((void**)&slab, total, s));
+    CU(cudaMallocFromPoolAsync((void**)&slab, total, c->pool, s));
     cl->slab = slab;
     d.pts = (float4*)(slab + o_pts);
     d.tnodes = (float4*)(slab + o_tn);
@@ -273,7 +279,7 @@ int b200reg_clouds_create(b200reg_ctx* c, int count, const float* const* xyz, co
     size_t t_raw = align_up(t_b + 32, 256);
     size_t t_total = t_raw + (on_device ? 0 : align_up((size_t)d.n * stride_bytes, 256));
     char* tmp = nullptr;
-    CU(cudaMallocAsync((void**)&tmp, t_total, s));
+    CU(cudaMallocFromPoolAsync((void**)&tmp, t_total, c->pool, s));
     temps.push_back(tmp);
     d.keys[0] = (uint32_t*)(tmp + t_k0);
     d.keys[1] = (uint32_t*)(tmp + t_k1);
@@ -298,7 +304,7 @@ int b200reg_clouds_create(b200reg_ctx* c, int count, const float* const* xyz, co
     max_n = std::max(max_n, d.n);
   }
   CloudDev* d_descs = nullptr;
-  CU(cudaMallocAsync((void**)&d_descs, sizeof(CloudDev) * count, s));
+  CU(cudaMallocFromPoolAsync((void**)&d_descs, sizeof(CloudDev) * count, c->pool, s));
   CU(cudaMemcpyAsync(d_descs, descs.data(), sizeof(CloudDev) * count, cudaMemcpyHostToDevice, s));
   {
     ProfScope ps(c, CLS_BUILD);
@@ -348,7 +354,7 @@ int b200reg_clouds_covariances(b200reg_ctx* c, int count, b200reg_cloud* const* 
   }
   if (descs.empty()) return B200REG_OK;
   CloudDev* d_descs = nullptr;
-  CU(cudaMallocAsync((void**)&d_descs, sizeof(CloudDev) * descs.size(), s));
+  CU(cudaMallocFromPoolAsync((void**)&d_descs, sizeof(CloudDev) * descs.size(), c->pool, s));
   CU(cudaMemcpyAsync(d_descs, descs.data(), sizeof(CloudDev) * descs.size(), cudaMemcpyHostToDevice, s));
   {
     ProfScope ps(c, CLS_COV);
@@ -402,7 +408,7 @@ static int make_pair_work(b200reg_ctx* c, int count, b200reg_cloud* const* src, 
     size_t o_par = align_up(o_mah + (size_t)N * 6 * 8, 256);
     size_t total = align_up(o_par + (size_t)nblk * NRED * 8, 256);
     char* slab = nullptr;
-    CU(cudaMallocAsync((void**)&slab, total, s));
+    CU(cudaMallocFromPoolAsync((void**)&slab, total, c->pool, s));
     w.slabs.push_back(slab);
     p.corr = (int*)(slab + o_corr);
     p.sqd = (float*)(slab + o_sqd);
@@ -410,8 +416,8 @@ static int make_pair_work(b200reg_ctx* c, int count, b200reg_cloud* const* src, 
     p.partial = (double*)(slab + o_par);
     w.max_n = std::max(w.max_n, N);
   }
-  CU(cudaMallocAsync((void**)&w.d_pairs, sizeof(PairDev) * count, s));
-  CU(cudaMallocAsync((void**)&w.d_states, sizeof(PairState) * count, s));
+  CU(cudaMallocFromPoolAsync((void**)&w.d_pairs, sizeof(PairDev) * count, c->pool, s));
+  CU(cudaMallocFromPoolAsync((void**)&w.d_states, sizeof(PairState) * count, c->pool, s));
   CU(cudaMemcpyAsync(w.d_pairs, w.pairs.data(), sizeof(PairDev) * count, cudaMemcpyHostToDevice, s));
   return B200REG_OK;
 }
@@ -449,7 +455,7 @@ int b200reg_gicp_align(b200reg_ctx* c, int count, b200reg_cloud* const* src, b20
   const GicpParamsDev prm = to_dev(*params);
   double* d_guess = nullptr;
   if (guess16) {
-    CU(cudaMallocAsync((void**)&d_guess, sizeof(double) * 16 * count, s));
+    CU(cudaMallocFromPoolAsync((void**)&d_guess, sizeof(double) * 16 * count, c->pool, s));
     CU(cudaMemcpyAsync(d_guess, guess16, sizeof(double) * 16 * count, cudaMemcpyHostToDevice, s));
   }
   CU(cudaMemsetAsync(c->d_done, 0, sizeof(int), s));
@@ -551,7 +557,7 @@ int b200reg_icp_alignment(b200reg_ctx* c, int count, const float* const* src_xyz
     total += align_up(tgt_n[i] * stride_bytes, 256);
   }
   char* stage = nullptr;
-  CU(cudaMallocAsync((void**)&stage, total, s));
+  CU(cudaMallocFromPoolAsync((void**)&stage, total, c->pool, s));
   cudaEvent_t ready;
   CU(cudaEventCreateWithFlags(&ready, cudaEventDisableTiming));
   CU(cudaEventRecord(ready, s));
@@ -610,8 +616,8 @@ int b200reg_transform_cloud(b200reg_ctx* c, const b200reg_cloud* cl, const float
   cudaStream_t s = c->stream;
   float* d_T = nullptr;
   float* d_out = nullptr;
-  CU(cudaMallocAsync((void**)&d_T, 64, s));
-  CU(cudaMallocAsync((void**)&d_out, (size_t)cl->dev.n * 12, s));
+  CU(cudaMallocFromPoolAsync((void**)&d_T, 64, c->pool, s));
+  CU(cudaMallocFromPoolAsync((void**)&d_out, (size_t)cl->dev.n * 12, c->pool, s));
   CU(cudaMemcpyAsync(d_T, Tf16, 64, cudaMemcpyHostToDevice, s));
   launch_transform_out(cl->dev, d_T, d_out, s);
   c->launches++;
@@ -632,9 +638,9 @@ int b200reg_knn(b200reg_ctx* c, const b200reg_cloud* cl, const float* queries, s
   float* d_q = nullptr;
   int* d_idx = nullptr;
   float* d_d2 = nullptr;
-  CU(cudaMallocAsync((void**)&d_q, nq * qstride_bytes, s));
-  CU(cudaMallocAsync((void**)&d_idx, nq * k * 4, s));
-  CU(cudaMallocAsync((void**)&d_d2, nq * k * 4, s));
+  CU(cudaMallocFromPoolAsync((void**)&d_q, nq * qstride_bytes, c->pool, s));
+  CU(cudaMallocFromPoolAsync((void**)&d_idx, nq * k * 4, c->pool, s));
+  CU(cudaMallocFromPoolAsync((void**)&d_d2, nq * k * 4, c->pool, s));
   CU(cudaMemcpyAsync(d_q, queries, nq * qstride_bytes, cudaMemcpyHostToDevice, s));
   if (launch_knn_queries(cl->dev, d_q, (int)nq, (int)(qstride_bytes / 4), k, d_idx, d_d2, s) < 0)
     return fail(B200REG_EINVAL, "unsupported k");
@@ -688,7 +694,7 @@ int b200reg_linearize(b200reg_ctx* c, const b200reg_cloud* src, const b200reg_cl
   p.max_corr_dist = max_corr_dist;
   const GicpParamsDev prm = to_dev(p);
   double* d_guess = nullptr;
-  CU(cudaMallocAsync((void**)&d_guess, sizeof(double) * 16, s));
+  CU(cudaMallocFromPoolAsync((void**)&d_guess, sizeof(double) * 16, c->pool, s));
   CU(cudaMemcpyAsync(d_guess, T16, sizeof(double) * 16, cudaMemcpyHostToDevice, s));
   CU(cudaMemsetAsync(c->d_done, 0, sizeof(int), s));
   launch_gicp_init(w.d_states, d_guess, 1, prm, s);
@@ -757,7 +763,7 @@ int b200reg_clouds_fpfh(b200reg_ctx* c, int count, b200reg_cloud* const* clouds,
       size_t o_fn = align_up(o_f + n * FPAD * sizeof(float), 256);
       size_t total = align_up(o_fn + n * sizeof(float4), 256);
       char* fs = nullptr;
-      CU(cudaMallocAsync((void**)&fs, total, s));
+      CU(cudaMallocFromPoolAsync((void**)&fs, total, c->pool, s));
       cl->fslab = fs;
       cl->dev.nrm = (float4*)(fs + o_n);
       cl->dev.spfh = (float*)(fs + o_s);
@@ -770,7 +776,7 @@ int b200reg_clouds_fpfh(b200reg_ctx* c, int count, b200reg_cloud* const* clouds,
   }
   if (todo.empty()) return B200REG_OK;
   CloudDev* d_descs = nullptr;
-  CU(cudaMallocAsync((void**)&d_descs, sizeof(CloudDev) * descs.size(), s));
+  CU(cudaMallocFromPoolAsync((void**)&d_descs, sizeof(CloudDev) * descs.size(), c->pool, s));
   CU(cudaMemcpyAsync(d_descs, descs.data(), sizeof(CloudDev) * descs.size(), cudaMemcpyHostToDevice, s));
   {
     ProfScope ps(c, CLS_FPFH);
@@ -851,7 +857,7 @@ int b200reg_quatro_align(b200reg_ctx* c, int count, b200reg_cloud* const* src, b
     const size_t o_nn = take(nj * 4), o_dis = take(nj * 4), o_fj = take(ni * 4), o_need = take(ni * 4), o_rnn = take(ni * 4);
     const size_t o_cor = take(2 * nj * 4), o_tk = take(nj * 4), o_cnt = take(8 * 4), o_st = take(8 * 8), o_oc = take(2 * MAXC * 4), o_T = take(16 * 8);
     char* slab = nullptr;
-    CU(cudaMallocAsync((void**)&slab, o, s));
+    CU(cudaMallocFromPoolAsync((void**)&slab, o, c->pool, s));
     slabs.push_back(slab);
     m.nn = (int*)(slab + o_nn);
     m.dis = (float*)(slab + o_dis);
@@ -868,7 +874,7 @@ int b200reg_quatro_align(b200reg_ctx* c, int count, b200reg_cloud* const* src, b
     max_nj = std::max(max_nj, (int)nj);
   }
   MatchDev* d_pairs = nullptr;
-  CU(cudaMallocAsync((void**)&d_pairs, sizeof(MatchDev) * count, s));
+  CU(cudaMallocFromPoolAsync((void**)&d_pairs, sizeof(MatchDev) * count, c->pool, s));
   CU(cudaMemcpyAsync(d_pairs, pairs.data(), sizeof(MatchDev) * count, cudaMemcpyHostToDevice, s));
   QuatroParamsDev q;
   q.normal_r2 = (float)(prm->fpfh_normal_radius * prm->fpfh_normal_radius);
@@ -947,7 +953,7 @@ static int coarse_to_fine_on_clouds(b200reg_ctx* c, int count, b200reg_cloud* co
       sdesc[k] = src[i]->dev;
       memcpy(&Ts[16 * (size_t)k], qi[i].T, 128);
       float4* raw = nullptr;
-      CU(cudaMallocAsync((void**)&raw, (size_t)sdesc[k].n * 16, s));
+      CU(cudaMallocFromPoolAsync((void**)&raw, (size_t)sdesc[k].n * 16, c->pool, s));
       raws.push_back(raw);
       outs[k] = raw;
       cptr[k] = (const float*)raw;
@@ -957,9 +963,9 @@ static int coarse_to_fine_on_clouds(b200reg_ctx* c, int count, b200reg_cloud* co
     CloudDev* d_desc = nullptr;
     double* d_T = nullptr;
     float4** d_outs = nullptr;
-    CU(cudaMallocAsync((void**)&d_desc, sizeof(CloudDev) * nv, s));
-    CU(cudaMallocAsync((void**)&d_T, 128 * (size_t)nv, s));
-    CU(cudaMallocAsync((void**)&d_outs, sizeof(float4*) * nv, s));
+    CU(cudaMallocFromPoolAsync((void**)&d_desc, sizeof(CloudDev) * nv, c->pool, s));
+    CU(cudaMallocFromPoolAsync((void**)&d_T, 128 * (size_t)nv, c->pool, s));
+    CU(cudaMallocFromPoolAsync((void**)&d_outs, sizeof(float4*) * nv, c->pool, s));
     CU(cudaMemcpyAsync(d_desc, sdesc.data(), sizeof(CloudDev) * nv, cudaMemcpyHostToDevice, s));
     CU(cudaMemcpyAsync(d_T, Ts.data(), 128 * (size_t)nv, cudaMemcpyHostToDevice, s));
     CU(cudaMemcpyAsync(d_outs, outs.data(), sizeof(float4*) * nv, cudaMemcpyHostToDevice, s));
@@ -1064,7 +1070,7 @@ int b200reg_keyframes_add(b200reg_ctx* c, b200reg_keyframes* kf, const float* xy
   if (!c || !kf || !xyzi || n == 0 || !pose16 || stride_bytes < 16 || stride_bytes % 4) return fail(B200REG_EINVAL, "bad argument");
   CU(cudaSetDevice(c->device));
   float4* d = nullptr;
-  CU(cudaMallocAsync((void**)&d, n * 16, c->stream));
+  CU(cudaMallocFromPoolAsync((void**)&d, n * 16, c->pool, c->stream));
   CU(cudaMemcpy2DAsync(d, 16, xyzi, stride_bytes, 16, n, cudaMemcpyHostToDevice, c->stream));
   kf->pts.push_back(d);
   kf->n.push_back((int)n);
@@ -1092,10 +1098,10 @@ int b200reg_fetch_closest_keyframes(b200reg_ctx* c, b200reg_keyframes* kf, int c
     for (int d = 0; d < 3; d++) pos[3 * (size_t)i + d] = kf->poses[16 * (size_t)i + 4 * d + 3];
   double *d_pos = nullptr, *d_st = nullptr;
   int *d_q = nullptr, *d_o = nullptr;
-  CU(cudaMallocAsync((void**)&d_pos, pos.size() * 8, s));
-  CU(cudaMallocAsync((void**)&d_st, (size_t)nk * 8, s));
-  CU(cudaMallocAsync((void**)&d_q, (size_t)count * 4, s));
-  CU(cudaMallocAsync((void**)&d_o, (size_t)count * 4, s));
+  CU(cudaMallocFromPoolAsync((void**)&d_pos, pos.size() * 8, c->pool, s));
+  CU(cudaMallocFromPoolAsync((void**)&d_st, (size_t)nk * 8, c->pool, s));
+  CU(cudaMallocFromPoolAsync((void**)&d_q, (size_t)count * 4, c->pool, s));
+  CU(cudaMallocFromPoolAsync((void**)&d_o, (size_t)count * 4, c->pool, s));
   CU(cudaMemcpyAsync(d_pos, pos.data(), pos.size() * 8, cudaMemcpyHostToDevice, s));
   CU(cudaMemcpyAsync(d_st, kf->stamps.data(), (size_t)nk * 8, cudaMemcpyHostToDevice, s));
   CU(cudaMemcpyAsync(d_q, query_idx, (size_t)count * 4, cudaMemcpyHostToDevice, s));
@@ -1159,7 +1165,7 @@ int b200reg_assemble_clouds(b200reg_ctx* c, b200reg_keyframes* kf, int count, co
     const size_t o_m = take(n * 16), o_o = take(n * 16), o_h = take(n * 4), o_b = take(32), o_c = take(16);
     const size_t o_k0 = take(n * 4), o_k1 = take(n * 4), o_v0 = take(n * 4), o_v1 = take(n * 4), o_hist = take((size_t)RADIX * ntiles * 4);
     char* slab = nullptr;
-    CU(cudaMallocAsync((void**)&slab, o, s));
+    CU(cudaMallocFromPoolAsync((void**)&slab, o, c->pool, s));
     slabs.push_back(slab);
     J.merged = (float4*)(slab + o_m);
     J.out = (float4*)(slab + o_o);
@@ -1188,10 +1194,10 @@ int b200reg_assemble_clouds(b200reg_ctx* c, b200reg_keyframes* kf, int count, co
   CloudDev* d_sorts = nullptr;
   KeyframeDev* d_kf = nullptr;
   double* d_poses = nullptr;
-  CU(cudaMallocAsync((void**)&d_jobs, sizeof(AssembleJob) * njobs, s));
-  CU(cudaMallocAsync((void**)&d_sorts, sizeof(CloudDev) * njobs, s));
-  CU(cudaMallocAsync((void**)&d_kf, sizeof(KeyframeDev) * nkall, s));
-  CU(cudaMallocAsync((void**)&d_poses, 128 * (size_t)nkall, s));
+  CU(cudaMallocFromPoolAsync((void**)&d_jobs, sizeof(AssembleJob) * njobs, c->pool, s));
+  CU(cudaMallocFromPoolAsync((void**)&d_sorts, sizeof(CloudDev) * njobs, c->pool, s));
+  CU(cudaMallocFromPoolAsync((void**)&d_kf, sizeof(KeyframeDev) * nkall, c->pool, s));
+  CU(cudaMallocFromPoolAsync((void**)&d_poses, 128 * (size_t)nkall, c->pool, s));
   CU(cudaMemcpyAsync(d_jobs, jobs.data(), sizeof(AssembleJob) * njobs, cudaMemcpyHostToDevice, s));
   CU(cudaMemcpyAsync(d_sorts, sorts.data(), sizeof(CloudDev) * njobs, cudaMemcpyHostToDevice, s));
   CU(cudaMemcpyAsync(d_kf, kd.data(), sizeof(KeyframeDev) * nkall, cudaMemcpyHostToDevice, s));
