@@ -439,13 +439,13 @@ def main():
             ms = float(t.item())
         return ms, ctx.launch_count - l0, res
 
-    # e2e: the package's double-buffered driver -- two contexts on two host threads take alternate steps, so one
-    # step's H2D + polling hide behind the other's kernels (b200reg/pipeline.py).  Every step still uploads all of
-    # its inputs from pinned host memory and reads its results back.
+    # Both timed arms go through the package's double-buffered driver -- two contexts on two host threads take alternate
+    # steps, so one step's H2D + polling hide behind the other's kernels (b200reg/pipeline.py).  In the e2e arm every
+    # step still uploads all of its inputs from pinned host memory and reads its results back.
     from b200reg.pipeline import PipelinedRegistrar
     pipe = PipelinedRegistrar(local_rank, depth=2) if args.workload == "gicp" else None
 
-    def e2e_pipelined(steps):
+    def run_pipelined(steps, on_device):
         if dist is not None:
             dist.barrier()
         torch.cuda.synchronize()
@@ -453,7 +453,10 @@ def main():
         ends = [torch.cuda.Event(enable_timing=True) for _ in pipe.ctxs]
         e0.record(stream)
         stream.synchronize()
-        futs = [pipe.icp_alignment_ptrs([t.data_ptr() for t in host_src], ns_s, [t.data_ptr() for t in host_dst], ns_d, stride, 0, prm)
+        srcs = dev_src if on_device else host_src
+        dsts = dev_dst if on_device else host_dst
+        l0 = pipe.launch_count
+        futs = [pipe.icp_alignment_ptrs([t.data_ptr() for t in srcs], ns_s, [t.data_ptr() for t in dsts], ns_d, stride, int(on_device), prm)
                 for _ in range(steps)]
         outs = [pipe.wait(f) for f in futs]
         if world > 1:  # the step results of this rank, gathered once per step like the device arm
@@ -475,19 +478,21 @@ def main():
             t = torch.tensor([ms], dtype=torch.float64, device="cuda")
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
             ms = float(t.item())
-        return ms, outs[-1]
+        return ms, pipe.launch_count - l0, outs[-1]
 
     sampler = ClockSampler(local_rank) if rank == 0 else None  # samples from the warm-up on: same load as the timed region
     for _ in range(args.warmup):
         step(True)
         step(False)
     if pipe is not None:
-        e2e_pipelined(max(2, args.warmup))
+        run_pipelined(max(2, args.warmup), True)
+        run_pipelined(max(2, args.warmup), False)
 
-    ms_dev, launches, res = timed(True, args.steps)
-    if pipe is not None:
-        ms_e2e, res_h = e2e_pipelined(args.steps)
+    if pipe is not None:  # both arms through the same double-buffered driver
+        ms_dev, launches, res = run_pipelined(args.steps, True)
+        ms_e2e, _, res_h = run_pipelined(args.steps, False)
     else:
+        ms_dev, launches, res = timed(True, args.steps)
         ms_e2e, _, res_h = timed(False, args.steps)
     clocks = sampler.stop() if sampler else None
 
@@ -531,7 +536,9 @@ def main():
             "config": {"workload": workload_name(args), "pairs_per_step_per_gpu": B, "points_per_cloud": args.points, "seeds": "1000+rank*B+i",
                        "l2": "working set per step (%.0f MB raw + ~%.0f MB derived) exceeds the 126 MB L2; clouds are "
                              "rebuilt from raw xyz every step" % (h2d_bytes / 1e6, B * 2 * args.points * 100 / 1e6),
-                       "parallelism": "pairs sharded over ranks, one NCCL all-gather of 4x4 transforms per step" if world > 1 else "single GPU"},
+                       "parallelism": "pairs sharded over ranks, one NCCL all-gather of 4x4 transforms per step" if world > 1 else "single GPU",
+                       "driver": "b200reg.pipeline.PipelinedRegistrar(depth=2): two contexts / host threads take alternate steps"
+                                 if pipe is not None else "single context"},
             "e2e": {"value": e2e, "unit": UNIT, "ms_per_step": ms_e2e / args.steps, "h2d_bytes_per_step": h2d_bytes,
                     "d2h_bytes_per_step": B * res_bytes,
                     "driver": "b200reg.pipeline.PipelinedRegistrar(depth=2): two contexts / host threads take alternate steps"
