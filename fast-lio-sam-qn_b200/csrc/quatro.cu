@@ -748,6 +748,7 @@ __global__ void __launch_bounds__(SV_THREADS) k_teaser_solve(const MatchDev* pai
         }
       }
       k = max(k, bv);
+      __syncwarp();  // every lane has finished reading the alive flags of this round before lane 0 clears one
       if (tid == 0) {
         sm.core[bi] = k;
         sm.rank[bi] = 0;

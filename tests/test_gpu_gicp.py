@@ -288,3 +288,38 @@ def test_any_k_correspondences(ctx, oracle, pair5k):
         oi, od = oracle.knn(dst, src[:500], k)
         assert np.array_equal(gi, oi) and np.array_equal(gd, od)
         cl.destroy()
+
+
+def test_error_paths_return_codes(ctx):
+    """Nothing throws across the ABI; bad input is a negative status + message (include/b200reg.h conventions)."""
+    import ctypes as C
+    import b200reg
+    from b200reg import native
+    lib = native.lib()
+    prm = b200reg.default_params()
+    res = (native.Result * 1)()
+    pts = np.zeros((10, 4), np.float32)
+    ptr = (C.c_void_p * 1)(pts.ctypes.data)
+    n0 = (C.c_size_t * 1)(0)
+    n10 = (C.c_size_t * 1)(10)
+    out = (C.c_void_p * 1)()
+    assert lib.b200reg_clouds_create(ctx.h, 1, ptr, n0, C.c_size_t(16), 0, out) == -1            # empty cloud
+    assert lib.b200reg_clouds_create(ctx.h, 1, ptr, n10, C.c_size_t(10), 0, out) == -1           # stride not a multiple of 4
+    assert lib.b200reg_clouds_create(None, 1, ptr, n10, C.c_size_t(16), 0, out) == -1            # NULL context
+    assert b"stride" in lib.b200reg_last_error() or b"bad" in lib.b200reg_last_error()
+    cl, = ctx.create_clouds([np.random.default_rng(0).normal(size=(50, 3)).astype(np.float32)])
+    arr = (C.c_void_p * 1)(cl.h)
+    assert lib.b200reg_clouds_covariances(ctx.h, 1, arr, 0) == -1                                 # k out of range
+    assert lib.b200reg_clouds_covariances(ctx.h, 1, arr, 33) == -1
+    cov = np.empty((50, 9))
+    assert lib.b200reg_get_covariances(ctx.h, cl.h, cov.ctypes.data_as(C.c_void_p)) == -4        # ESTATE: not computed yet
+    qp = b200reg.default_quatro_params()
+    qp.estimate_scale = 1
+    info = (native.QuatroInfo * 1)()
+    assert lib.b200reg_quatro_align(ctx.h, 1, arr, arr, C.byref(qp), info, None) == -1            # unsupported mode, loudly
+    qp = b200reg.default_quatro_params()
+    qp.max_corres = 10000
+    assert lib.b200reg_quatro_align(ctx.h, 1, arr, arr, C.byref(qp), info, None) == -1
+    cl.destroy()
+    with pytest.raises(b200reg.B200RegError):
+        b200reg.Context(99)                                                                       # no such device: ENODEV
