@@ -228,7 +228,7 @@ __global__ void k_gicp_init(PairState* states, const double* guess16, int count,
 // K is the CAPACITY of the register-resident result set; k <= K neighbours enter the covariance (the k nearest of
 // the K nearest are the k nearest), so every k in 1..32 is served by the next instantiated capacity.
 template <int K>
-__global__ void __launch_bounds__(STEP_THREADS, (K <= 16 ? 6 : 4)) k_covariance(const CloudDev* clouds, int k) {
+__global__ void __launch_bounds__(STEP_THREADS, (K <= 16 ? 8 : 4)) k_covariance(const CloudDev* clouds, int k) {
   const CloudDev& c = clouds[blockIdx.y];
   const int i = blockIdx.x * STEP_THREADS + threadIdx.x;
   if (i >= c.n) return;
@@ -283,7 +283,7 @@ __global__ void __launch_bounds__(STEP_THREADS, (K <= 16 ? 6 : 4)) k_covariance(
 // Block partials go to HBM; the last block to arrive sums them in a fixed order (deterministic,
 // SURVEY App. A.6) and runs the LM controller, so no host round trip is needed per iteration.
 // ---------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(STEP_THREADS) k_gicp_step(const PairDev* pairs, PairState* states, GicpParamsDev prm,
+__global__ void __launch_bounds__(STEP_THREADS, 8) k_gicp_step(const PairDev* pairs, PairState* states, GicpParamsDev prm,
                                                              int* done_counter) {
   const PairDev& P = pairs[blockIdx.y];
   PairState* st = &states[blockIdx.y];
