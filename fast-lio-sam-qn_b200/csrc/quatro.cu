@@ -267,7 +267,14 @@ __global__ void __launch_bounds__(NN_THREADS) k_feat_nn(const MatchDev* pairs, i
     float4 qn = active ? Q.fnorm[qpos] : make_float4(0.f, 0.f, 0.f, 0.f);
     qn.w = qok ? 1.f : 0.f;
     sqn[warp][lane] = qn;
-    sbest[warp][lane] = ((unsigned long long)__float_as_uint(lim) << 32) | 0xFFFFFFFFull;
+    // reverse search: i was reached from j0 = first_j[i] at distance dis[j0], and the metric is symmetric, so that
+    // very pair is a valid starting candidate -- the filter is tight from the first tile on
+    unsigned long long init = ((unsigned long long)__float_as_uint(lim) << 32) | 0xFFFFFFFFull;
+    if (mode == 1 && active) {
+      const int j0 = P.first_j[qorig];
+      init = ((unsigned long long)__float_as_uint(P.dis[j0]) << 32) | (unsigned)j0;
+    }
+    sbest[warp][lane] = init;
   }
   if (threadIdx.x == 0) {
     mbar_init(&full[0], 1);
