@@ -64,10 +64,13 @@ __device__ __forceinline__ void knn_insert(KnnSet<K>& s, float cd, int cp, const
     s.p[K - 1] = cp;
     tie = true;
   } else {
+    bool placed = false;  // once the candidate is in, everything below simply shifts down by one (a carried entry must
+                          // never leapfrog its equal-distance peers: it is the lowest index of its run)
 #pragma unroll
     for (int j = 0; j < K; j++) {
-      const bool lt = cd < s.d[j];
-      tie |= (cd == s.d[j]);
+      const bool lt = placed || cd < s.d[j];
+      tie |= (!placed && cd == s.d[j]);
+      placed = lt;
       const float td = s.d[j];
       const int tp = s.p[j];
       s.d[j] = lt ? cd : td;
@@ -92,11 +95,12 @@ __device__ __forceinline__ void knn_insert(KnnSet<K>& s, float cd, int cp, const
 // look at slots 0..S, so filling K seeds costs K^2/2 compare-selects instead of K^2.
 template <int K, int S>
 __device__ __forceinline__ void knn_insert_prefix(KnnSet<K>& s, float cd, int cp, const float4* __restrict__ pts) {
-  bool tie = false;
+  bool tie = false, placed = false;
 #pragma unroll
   for (int j = 0; j <= S; j++) {
-    const bool lt = cd < s.d[j];
-    tie |= (cd == s.d[j]);
+    const bool lt = placed || cd < s.d[j];
+    tie |= (!placed && cd == s.d[j]);
+    placed = lt;
     const float td = s.d[j];
     const int tp = s.p[j];
     s.d[j] = lt ? cd : td;

@@ -323,3 +323,45 @@ def test_error_paths_return_codes(ctx):
     cl.destroy()
     with pytest.raises(b200reg.B200RegError):
         b200reg.Context(99)                                                                       # no such device: ENODEV
+
+
+def test_knn_degenerate_geometries_tie_rule(ctx, oracle):
+    """Regular lattices (masses of exactly equal distances), identical points, collinear points, huge offsets:
+    the (d2, lower original index) rule must hold everywhere."""
+    rng = np.random.default_rng(42)
+    g = np.stack(np.meshgrid(np.arange(18), np.arange(18), np.arange(18), indexing="ij"), -1).reshape(-1, 3).astype(np.float32)
+    lattice = g[rng.permutation(len(g))] * np.float32(0.5)
+    same = np.tile(np.array([[1.5, -2.0, 0.25]], np.float32), (300, 1))
+    line = np.c_[np.linspace(0, 50, 2000), np.zeros(2000), np.zeros(2000)].astype(np.float32)
+    far = (rng.normal(0, 3, (3000, 3)) + np.array([25000.0, -18000.0, 900.0])).astype(np.float32)
+    plane = np.c_[rng.uniform(-20, 20, (4000, 2)), np.zeros(4000)].astype(np.float32)
+    for name, pts in (("lattice", lattice), ("identical", same), ("line", line), ("far", far), ("plane", plane)):
+        cl, = ctx.create_clouds([pts])
+        q = np.concatenate([pts[:400], pts[:200] + np.float32(0.25)])
+        for k in (1, 15):
+            gi, gd = ctx.knn(cl, q, k)
+            oi, od = oracle.knn(pts, q, k, brute=True)
+            kk = min(k, len(pts))
+            assert np.array_equal(gd[:, :kk], od[:, :kk]), name
+            assert np.array_equal(gi[:, :kk], oi[:, :kk]), name
+        # covariances stay finite and symmetric even where the neighbourhood is rank deficient
+        ctx.covariances([cl], 15)
+        c = ctx.get_covariances(cl)
+        assert np.isfinite(c).all(), name
+        ev = np.linalg.eigvalsh(c[::37])
+        assert np.allclose(ev, [1e-3, 1.0, 1.0], atol=1e-6), name
+        cl.destroy()
+
+
+def test_gicp_lattice_pair_with_ties(ctx, oracle, synth):
+    """Registration of a lattice against a shifted copy: correspondence ties everywhere, results must still agree."""
+    rng = np.random.default_rng(1)
+    g = np.stack(np.meshgrid(np.arange(30), np.arange(30), np.arange(4), indexing="ij"), -1).reshape(-1, 3).astype(np.float32)
+    dst = (g * np.float32(0.4) + rng.normal(0, 0.01, g.shape).astype(np.float32)).astype(np.float32)
+    T = synth.se3(yaw=0.01, t=(0.05, -0.03, 0.01))
+    src = synth.to_map_frame(np.c_[dst, np.zeros(len(dst), np.float32)], np.linalg.inv(T))[:, :3]
+    r = ctx.icp_alignment([src], [dst])[0]
+    o = oracle.gicp_align(src, dst)
+    rot, tr = synth.se3_error(r["T"], o["T"])
+    assert rot < ROT_TOL and tr < TRANS_TOL
+    assert r["n_linearize"] == o["n_linearize"] and r["converged"] == o["converged"]
