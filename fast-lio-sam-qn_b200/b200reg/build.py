@@ -7,7 +7,8 @@ PKG = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 CSRC = os.path.join(PKG, "csrc")
 REPO = os.path.dirname(PKG)
 SOURCES = ["api.cu", "index_build.cu", "gicp.cu", "quatro.cu", "assemble.cu"]
-EXTRA = {"quatro.cu": ["-fmad=false"]}  # fixed fp32 operation order for the FPFH / matcher arithmetic
+EXTRA = {"quatro.cu": ["-fmad=false"],    # fixed fp32 operation order for the FPFH / matcher arithmetic
+         "assemble.cu": ["-fmad=false"]}  # transformPcd / VoxelGrid / candidate distances as the (FMA-free) reference computes them
 HEADERS = ["internal.cuh", "knn.cuh", "smallmath.cuh", os.path.join(REPO, "include", "b200reg.h")]
 LIB = os.path.join(CSRC, "libb200reg.so")
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")

@@ -365,3 +365,31 @@ def test_gicp_lattice_pair_with_ties(ctx, oracle, synth):
     rot, tr = synth.se3_error(r["T"], o["T"])
     assert rot < ROT_TOL and tr < TRANS_TOL
     assert r["n_linearize"] == o["n_linearize"] and r["converged"] == o["converged"]
+
+
+def test_lm_corner_cases_match_oracle(ctx, oracle, synth, pair5k):
+    """State-machine corners: nothing within the correspondence gate (H = 0, zero step, 'converged' like the reference),
+    clouds smaller than k, and a single-point target (ill-posed: flags only)."""
+    import b200reg
+    from oracle.oracle import GicpParams
+    src, dst, _ = pair5k
+    prm = b200reg.default_params()
+    prm.max_corr_dist = 1e-4
+    op = GicpParams.default()
+    op.max_corr_dist = 1e-4
+    g = ctx.icp_alignment([src], [dst], params=prm)[0]
+    o = oracle.gicp_align(src, dst, params=op)
+    assert np.allclose(g["T"], np.eye(4)) and np.allclose(o["T"], np.eye(4))
+    assert g["converged"] == o["converged"] and g["n_linearize"] == o["n_linearize"] and g["n_error"] == o["n_error"]
+    assert abs(g["fitness"] - o["fitness"]) < 1e-6 * o["fitness"]
+    # n < k: the k-NN list is short, the mean still divides by k (nano_gicp_impl.hpp:320-321)
+    tiny = dst[:7]
+    cl, = ctx.create_clouds([tiny])
+    ctx.covariances([cl], 15)
+    assert np.abs(ctx.get_covariances(cl) - oracle.covariances(tiny, 15)).max() < 1e-9
+    cl.destroy()
+    # (a single-point target makes the rotation unobservable: the LM answer is then dominated by round-off on both
+    # sides, so that case is only required to terminate with matching flags)
+    g = ctx.icp_alignment([src[:500]], [dst[:1]])[0]
+    o = oracle.gicp_align(src[:500], dst[:1])
+    assert np.isfinite(g["T"]).all() and g["converged"] == o["converged"]
