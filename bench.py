@@ -443,7 +443,8 @@ def main():
     # steps, so one step's H2D + polling hide behind the other's kernels (b200reg/pipeline.py).  In the e2e arm every
     # step still uploads all of its inputs from pinned host memory and reads its results back.
     from b200reg.pipeline import PipelinedRegistrar
-    pipe = PipelinedRegistrar(local_rank, depth=2) if args.workload == "gicp" else None
+    depth = int(os.environ.get("B200REG_PIPE_DEPTH", "3"))
+    pipe = PipelinedRegistrar(local_rank, depth=depth) if args.workload == "gicp" else None
 
     def run_pipelined(steps, on_device):
         if dist is not None:
@@ -537,12 +538,11 @@ def main():
                        "l2": "working set per step (%.0f MB raw + ~%.0f MB derived) exceeds the 126 MB L2; clouds are "
                              "rebuilt from raw xyz every step" % (h2d_bytes / 1e6, B * 2 * args.points * 100 / 1e6),
                        "parallelism": "pairs sharded over ranks, one NCCL all-gather of 4x4 transforms per step" if world > 1 else "single GPU",
-                       "driver": "b200reg.pipeline.PipelinedRegistrar(depth=2): two contexts / host threads take alternate steps"
+                       "driver": ("b200reg.pipeline.PipelinedRegistrar(depth=%d): contexts on separate host threads take alternate steps" % depth)
                                  if pipe is not None else "single context"},
             "e2e": {"value": e2e, "unit": UNIT, "ms_per_step": ms_e2e / args.steps, "h2d_bytes_per_step": h2d_bytes,
                     "d2h_bytes_per_step": B * res_bytes,
-                    "driver": "b200reg.pipeline.PipelinedRegistrar(depth=2): two contexts / host threads take alternate steps"
-                              if pipe is not None else "single context"},
+                    "driver": ("b200reg.pipeline.PipelinedRegistrar(depth=%d)" % depth) if pipe is not None else "single context"},
             "gpu_launches": launches,
             "roofline": {"bound": "hbm", "kernel": fam, "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak, "traffic": ncu_traffic(fam, args.workload), "peak_source": peak_src,
