@@ -70,7 +70,7 @@ EXPORTS = [
     "b200reg_ctx_get_profile", "b200reg_default_quatro_params", "b200reg_clouds_fpfh", "b200reg_get_fpfh",
     "b200reg_quatro_align", "b200reg_loop_closure", "b200reg_default_loop_config", "b200reg_keyframes_create",
     "b200reg_keyframes_destroy", "b200reg_keyframes_add", "b200reg_keyframes_set_pose", "b200reg_keyframes_size",
-    "b200reg_fetch_closest_keyframes", "b200reg_assemble_clouds", "b200reg_cloud_points", "b200reg_perform_loop_closure",
+    "b200reg_knn_bruteforce", "b200reg_fetch_closest_keyframes", "b200reg_assemble_clouds", "b200reg_cloud_points", "b200reg_perform_loop_closure",
 ]
 
 
@@ -299,11 +299,12 @@ class Context:
         return out
 
     # -- debug taps ----------------------------------------------------------------------
-    def knn(self, cloud, queries, k):
+    def knn(self, cloud, queries, k, brute=False):
         q = _pts(queries)
         idx = np.empty((len(q), k), np.int32)
         d2 = np.empty((len(q), k), np.float32)
-        _check(lib().b200reg_knn(self.h, cloud.h, q.ctypes.data_as(C.c_void_p), C.c_size_t(len(q)),
+        fn = lib().b200reg_knn_bruteforce if brute else lib().b200reg_knn
+        _check(fn(self.h, cloud.h, q.ctypes.data_as(C.c_void_p), C.c_size_t(len(q)),
                                  C.c_size_t(q.shape[1] * 4), int(k), idx.ctypes.data_as(C.c_void_p),
                                  d2.ctypes.data_as(C.c_void_p)))
         return idx, d2

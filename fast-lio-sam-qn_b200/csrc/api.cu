@@ -19,7 +19,7 @@ int launch_covariances(const CloudDev* d_clouds, int count, int max_n, int k, cu
 void launch_gicp_init(PairState* states, const double* d_guess, int count, const GicpParamsDev& prm, cudaStream_t s);
 void launch_gicp_step(const PairDev* pairs, PairState* states, int count, int max_n, const GicpParamsDev& prm,
                       int* done_counter, cudaStream_t s);
-int launch_knn_queries(const CloudDev& c, const float* d_q, int nq, int qstride, int k, int* idx, float* d2, cudaStream_t s);
+int launch_knn_queries(const CloudDev& c, const float* d_q, int nq, int qstride, int k, int* idx, float* d2, cudaStream_t s, int brute);
 void launch_transform_out(const CloudDev& c, const float* d_Tf, float* d_out3, cudaStream_t s);
 int launch_fpfh(const CloudDev* d_clouds, int count, int max_n, float normal_r2, float fpfh_r2, cudaStream_t s);
 int launch_quatro_match_solve(const MatchDev* d_pairs, int count, int max_ni, int max_nj, const QuatroParamsDev& prm, cudaStream_t s);
@@ -629,8 +629,21 @@ int b200reg_transform_cloud(b200reg_ctx* c, const b200reg_cloud* cl, const float
 }
 
 // ---- debug taps --------------------------------------------------------------------------
+static int knn_impl(b200reg_ctx* c, const b200reg_cloud* cl, const float* queries, size_t nq, size_t qstride_bytes, int k,
+                    int32_t* idx_out, float* d2_out, int brute);
+
 int b200reg_knn(b200reg_ctx* c, const b200reg_cloud* cl, const float* queries, size_t nq, size_t qstride_bytes, int k,
                 int32_t* idx_out, float* d2_out) {
+  return knn_impl(c, cl, queries, nq, qstride_bytes, k, idx_out, d2_out, 0);
+}
+
+int b200reg_knn_bruteforce(b200reg_ctx* c, const b200reg_cloud* cl, const float* queries, size_t nq, size_t qstride_bytes, int k,
+                           int32_t* idx_out, float* d2_out) {
+  return knn_impl(c, cl, queries, nq, qstride_bytes, k, idx_out, d2_out, 1);
+}
+
+static int knn_impl(b200reg_ctx* c, const b200reg_cloud* cl, const float* queries, size_t nq, size_t qstride_bytes, int k,
+                    int32_t* idx_out, float* d2_out, int brute) {
   if (!c || !cl || !queries || nq == 0 || k <= 0 || k > 32 || !idx_out || !d2_out || qstride_bytes < 12 || qstride_bytes % 4)
     return fail(B200REG_EINVAL, "bad argument (k must be 1..32)");
   CU(cudaSetDevice(c->device));
@@ -642,7 +655,7 @@ int b200reg_knn(b200reg_ctx* c, const b200reg_cloud* cl, const float* queries, s
   CU(cudaMallocFromPoolAsync((void**)&d_idx, nq * k * 4, c->pool, s));
   CU(cudaMallocFromPoolAsync((void**)&d_d2, nq * k * 4, c->pool, s));
   CU(cudaMemcpyAsync(d_q, queries, nq * qstride_bytes, cudaMemcpyHostToDevice, s));
-  if (launch_knn_queries(cl->dev, d_q, (int)nq, (int)(qstride_bytes / 4), k, d_idx, d_d2, s) < 0)
+  if (launch_knn_queries(cl->dev, d_q, (int)nq, (int)(qstride_bytes / 4), k, d_idx, d_d2, s, brute) < 0)
     return fail(B200REG_EINVAL, "unsupported k");
   c->launches++;
   CU(cudaGetLastError());

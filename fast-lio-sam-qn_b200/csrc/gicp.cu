@@ -501,6 +501,70 @@ __global__ void __launch_bounds__(STEP_THREADS) k_knn_queries(CloudDev c, const 
   }
 }
 
+// ---------------------------------------------------------------------------------------
+// debug tap: brute-force exact k-NN, the on-GPU anchor the LBVH traversal is checked against at full size
+// (SURVEY.md §7 step 4a).  One query per thread; the cloud streams through shared memory in 8 KB tiles staged by
+// TMA bulk copies (mbarrier double buffer); all lanes read the same staged point (broadcast, conflict free).
+// ---------------------------------------------------------------------------------------
+constexpr int BF_TILE = 512;
+
+__device__ __forceinline__ unsigned bf_smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+
+template <int K>
+__global__ void __launch_bounds__(STEP_THREADS) k_knn_brute(CloudDev c, const float* q, int nq, int qstride, int kout, int* idx_out,
+                                                            float* d2_out) {
+  __shared__ __align__(128) float4 tile[2][BF_TILE];
+  __shared__ __align__(8) unsigned long long full[2];
+  const int i = blockIdx.x * STEP_THREADS + threadIdx.x;
+  const bool active = i < nq;
+  const float* qq = q + (size_t)(active ? i : 0) * qstride;
+  const float qx = qq[0], qy = qq[1], qz = qq[2];
+  KnnSet<K> res;
+  res.init();
+  if (threadIdx.x == 0) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bf_smem_u32(&full[0])), "r"(1));
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bf_smem_u32(&full[1])), "r"(1));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  const int ntiles = (c.n + BF_TILE - 1) / BF_TILE;
+  auto issue = [&](int t) {
+    const unsigned bytes = (unsigned)min(BF_TILE, c.n - t * BF_TILE) * 16u;
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bf_smem_u32(&full[t & 1])), "r"(bytes) : "memory");
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(bf_smem_u32(tile[t & 1])),
+                 "l"(c.pts + (size_t)t * BF_TILE), "r"(bytes), "r"(bf_smem_u32(&full[t & 1]))
+                 : "memory");
+  };
+  if (threadIdx.x == 0) issue(0);
+  for (int t = 0; t < ntiles; t++) {
+    if (threadIdx.x == 0 && t + 1 < ntiles) issue(t + 1);
+    unsigned ok = 0;
+    while (!ok)
+      asm volatile("{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}\n"
+                   : "=r"(ok)
+                   : "r"(bf_smem_u32(&full[t & 1])), "r"((unsigned)((t >> 1) & 1))
+                   : "memory");
+    const int cnt = min(BF_TILE, c.n - t * BF_TILE);
+    if (active) {
+      for (int j = 0; j < cnt; j++) {
+        const float4 p = tile[t & 1][j];
+        const float d2 = dist2_rn(qx, qy, qz, p.x, p.y, p.z);
+        if (!(d2 > res.worst())) knn_insert<K>(res, d2, t * BF_TILE + j, c.pts);
+      }
+    }
+    __syncthreads();
+  }
+  if (active) {
+#pragma unroll
+    for (int j = 0; j < K; j++) {
+      if (j < kout) {
+        idx_out[(size_t)i * kout + j] = res.p[j] >= 0 ? __float_as_int(c.pts[res.p[j]].w) : -1;
+        d2_out[(size_t)i * kout + j] = res.d[j];
+      }
+    }
+  }
+}
+
 // output cloud: final fp32 transform in the pcl::transformPointCloud order, ORIGINAL point order
 __global__ void __launch_bounds__(256) k_transform_out(CloudDev c, const float* Tf, float* out3) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -535,8 +599,15 @@ void launch_gicp_step(const PairDev* pairs, PairState* states, int count, int ma
   k_gicp_step<<<grid, STEP_THREADS, 0, s>>>(pairs, states, prm, done_counter);
 }
 
-int launch_knn_queries(const CloudDev& c, const float* d_q, int nq, int qstride, int k, int* idx, float* d2, cudaStream_t s) {
+int launch_knn_queries(const CloudDev& c, const float* d_q, int nq, int qstride, int k, int* idx, float* d2, cudaStream_t s, int brute) {
   dim3 grid((nq + STEP_THREADS - 1) / STEP_THREADS);
+  if (brute) {
+    if (k == 1) k_knn_brute<1><<<grid, STEP_THREADS, 0, s>>>(c, d_q, nq, qstride, k, idx, d2);
+    else if (k <= 15) k_knn_brute<15><<<grid, STEP_THREADS, 0, s>>>(c, d_q, nq, qstride, k, idx, d2);
+    else if (k <= 32) k_knn_brute<32><<<grid, STEP_THREADS, 0, s>>>(c, d_q, nq, qstride, k, idx, d2);
+    else return -1;
+    return 1;
+  }
   if (k == 1) k_knn_queries<1><<<grid, STEP_THREADS, 0, s>>>(c, d_q, nq, qstride, k, idx, d2);
   else if (k <= 8) k_knn_queries<8><<<grid, STEP_THREADS, 0, s>>>(c, d_q, nq, qstride, k, idx, d2);
   else if (k <= 15) k_knn_queries<15><<<grid, STEP_THREADS, 0, s>>>(c, d_q, nq, qstride, k, idx, d2);

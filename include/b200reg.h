@@ -221,6 +221,10 @@ int b200reg_transform_cloud(b200reg_ctx* ctx, const b200reg_cloud* cloud, const 
  * idx_out/d2_out: nq x k, ascending; indices refer to the ORIGINAL point order; -1 pads k > n.   */
 int b200reg_knn(b200reg_ctx* ctx, const b200reg_cloud* cloud, const float* queries, size_t nq,
                 size_t qstride_bytes, int k, int32_t* idx_out, float* d2_out);
+/* Same answer by brute force (every point tested, tiles staged into shared memory by TMA bulk copies): the on-GPU
+ * anchor the tree traversal is verified against at full size (100k x 100k).                               */
+int b200reg_knn_bruteforce(b200reg_ctx* ctx, const b200reg_cloud* cloud, const float* queries, size_t nq,
+                           size_t qstride_bytes, int k, int32_t* idx_out, float* d2_out);
 /* normals (n x 3, NaN where fewer than 3 neighbours) and FPFH (n x 33), original point order.            */
 int b200reg_get_fpfh(b200reg_ctx* ctx, const b200reg_cloud* cloud, float* normals_out, float* fpfh_out);
 /* n x 9 doubles (row-major 3x3 block of the reference's Matrix4d), original point order.          */

@@ -221,6 +221,20 @@ def test_iteration_cap_and_nonconvergence(ctx, oracle, synth, pair5k):
     assert rot < ROT_TOL and trans < TRANS_TOL
 
 
+def test_full_size_100k_tree_equals_bruteforce(ctx, synth):
+    """BASELINE config 2 size, no oracle needed: the LBVH traversal must return exactly what the TMA-tiled brute-force
+    kernel returns (every one of the 100k points tested for every query) -- indices and fp32 distances bit for bit."""
+    src, dst, _ = synth.make_pair(1003, 100000)
+    cl, = ctx.create_clouds([dst])
+    rng = np.random.default_rng(0)
+    far = (src[:3000, :3] + rng.normal(0, 6.0, (3000, 3))).astype(np.float32)
+    for q, k in ((dst[::5], 15), (src, 1), (far, 15), (far * np.float32(4.0), 1)):
+        ti, td = ctx.knn(cl, q, k)
+        bi, bd = ctx.knn(cl, q, k, brute=True)
+        assert np.array_equal(td, bd) and np.array_equal(ti, bi)
+    cl.destroy()
+
+
 def test_full_size_100k_properties(ctx, synth):
     """BASELINE config 2 size: size-independent properties instead of an oracle run."""
     src, dst, Texp = synth.make_pair(1000, 100000)
