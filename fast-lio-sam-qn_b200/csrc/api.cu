@@ -112,6 +112,24 @@ static void prof_resolve(b200reg_ctx* c) {
   c->pending.clear();
 }
 
+// Stream-ordered scratch memory with scope lifetime: everything allocated through it is returned to the context's
+// pool when the scope ends -- on every path, including the early error returns of the CU() macro.
+struct Scratch {
+  b200reg_ctx* c;
+  std::vector<void*> ptrs;
+  explicit Scratch(b200reg_ctx* c_) : c(c_) {}
+  Scratch(const Scratch&) = delete;
+  Scratch& operator=(const Scratch&) = delete;
+  cudaError_t alloc(void** p, size_t bytes) {
+    cudaError_t e = cudaMallocFromPoolAsync(p, bytes ? bytes : 16, c->pool, c->stream);
+    if (e == cudaSuccess) ptrs.push_back(*p);
+    return e;
+  }
+  ~Scratch() {
+    for (void* p : ptrs) cudaFreeAsync(p, c->stream);
+  }
+};
+
 struct b200reg_cloud {
   CloudDev dev;            // device pointers + sizes
   void* slab = nullptr;    // persistent allocation (pts, tnodes, cov, rank)
@@ -236,11 +254,29 @@ int b200reg_clouds_create(b200reg_ctx* c, int count, const float* const* xyz, co
     if (!xyz[i] || n[i] == 0 || n[i] > (size_t)(1u << 26)) return fail(B200REG_EINVAL, "empty or oversized cloud");
   CU(cudaSetDevice(c->device));
   cudaStream_t s = c->stream;
+  Scratch scratch(c);
   std::vector<CloudDev> descs(count);
-  std::vector<void*> temps;  // freed (stream-ordered) after the build
   int max_n = 0;
+  for (int i = 0; i < count; i++) out[i] = nullptr;
+  struct Guard {  // a failure half way must not leak the clouds already created
+    b200reg_ctx* c;
+    b200reg_cloud** out;
+    int count;
+    bool ok = false;
+    ~Guard() {
+      if (ok) return;
+      for (int i = 0; i < count; i++) {
+        if (out[i]) {
+          if (out[i]->slab) cudaFreeAsync(out[i]->slab, c->stream);
+          delete out[i];
+          out[i] = nullptr;
+        }
+      }
+    }
+  } guard{c, out, count};
   for (int i = 0; i < count; i++) {
     b200reg_cloud* cl = new b200reg_cloud;
+    out[i] = cl;
     CloudDev& d = cl->dev;
     d.n = (int)n[i];
     d.root_ref = d.n <= LEAF ? leaf_ref(0, d.n) : 0;
@@ -279,8 +315,7 @@ int b200reg_clouds_create(b200reg_ctx* c, int count, const float* const* xyz, co
     size_t t_raw = align_up(t_b + 32, 256);
     size_t t_total = t_raw + (on_device ? 0 : align_up((size_t)d.n * stride_bytes, 256));
     char* tmp = nullptr;
-    CU(cudaMallocFromPoolAsync((void**)&tmp, t_total, c->pool, s));
-    temps.push_back(tmp);
+    CU(scratch.alloc((void**)&tmp, t_total));
     d.keys[0] = (uint32_t*)(tmp + t_k0);
     d.keys[1] = (uint32_t*)(tmp + t_k1);
     d.vals[0] = (uint32_t*)(tmp + t_v0);
@@ -304,7 +339,7 @@ int b200reg_clouds_create(b200reg_ctx* c, int count, const float* const* xyz, co
     max_n = std::max(max_n, d.n);
   }
   CloudDev* d_descs = nullptr;
-  CU(cudaMallocFromPoolAsync((void**)&d_descs, sizeof(CloudDev) * count, c->pool, s));
+  CU(scratch.alloc((void**)&d_descs, sizeof(CloudDev) * count));
   CU(cudaMemcpyAsync(d_descs, descs.data(), sizeof(CloudDev) * count, cudaMemcpyHostToDevice, s));
   {
     ProfScope ps(c, CLS_BUILD);
@@ -312,8 +347,6 @@ int b200reg_clouds_create(b200reg_ctx* c, int count, const float* const* xyz, co
     for (int i = 0; i < count; i++) c->prof_bytes[CLS_BUILD] += 36.0 * descs[i].n;
   }
   CU(cudaGetLastError());
-  CU(cudaFreeAsync(d_descs, s));
-  for (void* t : temps) CU(cudaFreeAsync(t, s));
   for (int i = 0; i < count; i++) {  // the temporaries are gone once the build has run
     CloudDev& d = out[i]->dev;
     d.raw = nullptr;
@@ -323,6 +356,7 @@ int b200reg_clouds_create(b200reg_ctx* c, int count, const float* const* xyz, co
     d.nbox = nullptr;
     d.bbox = nullptr;
   }
+  guard.ok = true;
   return B200REG_OK;
 }
 
@@ -341,6 +375,7 @@ int b200reg_clouds_covariances(b200reg_ctx* c, int count, b200reg_cloud* const* 
   if (k < 1 || k > 32) return fail(B200REG_EINVAL, "k_correspondences must be in 1..32");
   CU(cudaSetDevice(c->device));
   cudaStream_t s = c->stream;
+  Scratch scratch(c);
   std::vector<CloudDev> descs;
   int max_n = 0;
   for (int i = 0; i < count; i++) {
@@ -354,7 +389,7 @@ int b200reg_clouds_covariances(b200reg_ctx* c, int count, b200reg_cloud* const* 
   }
   if (descs.empty()) return B200REG_OK;
   CloudDev* d_descs = nullptr;
-  CU(cudaMallocFromPoolAsync((void**)&d_descs, sizeof(CloudDev) * descs.size(), c->pool, s));
+  CU(scratch.alloc((void**)&d_descs, sizeof(CloudDev) * descs.size()));
   CU(cudaMemcpyAsync(d_descs, descs.data(), sizeof(CloudDev) * descs.size(), cudaMemcpyHostToDevice, s));
   {
     ProfScope ps(c, CLS_COV);
@@ -364,7 +399,6 @@ int b200reg_clouds_covariances(b200reg_ctx* c, int count, b200reg_cloud* const* 
     for (auto& d : descs) c->prof_bytes[CLS_COV] += 64.0 * d.n;
   }
   CU(cudaGetLastError());
-  CU(cudaFreeAsync(d_descs, s));
   for (int i = 0; i < count; i++) {
     clouds[i]->has_cov = true;
     clouds[i]->cov_k = k;
@@ -385,15 +419,14 @@ static GicpParamsDev to_dev(const b200reg_gicp_params& p) {
   return d;
 }
 
-struct PairWork {
+struct PairWork {  // device memory comes from the caller's Scratch and goes back with it
   std::vector<PairDev> pairs;
-  std::vector<void*> slabs;
   PairDev* d_pairs = nullptr;
   PairState* d_states = nullptr;
   int max_n = 0;
 };
 
-static int make_pair_work(b200reg_ctx* c, int count, b200reg_cloud* const* src, b200reg_cloud* const* tgt, PairWork& w) {
+static int make_pair_work(b200reg_ctx* c, int count, b200reg_cloud* const* src, b200reg_cloud* const* tgt, PairWork& w, Scratch& scratch) {
   cudaStream_t s = c->stream;
   w.pairs.resize(count);
   for (int i = 0; i < count; i++) {
@@ -408,28 +441,16 @@ static int make_pair_work(b200reg_ctx* c, int count, b200reg_cloud* const* src, 
     size_t o_par = align_up(o_mah + (size_t)N * 6 * 8, 256);
     size_t total = align_up(o_par + (size_t)nblk * NRED * 8, 256);
     char* slab = nullptr;
-    CU(cudaMallocFromPoolAsync((void**)&slab, total, c->pool, s));
-    w.slabs.push_back(slab);
+    CU(scratch.alloc((void**)&slab, total));
     p.corr = (int*)(slab + o_corr);
     p.sqd = (float*)(slab + o_sqd);
     p.mahal = (double*)(slab + o_mah);
     p.partial = (double*)(slab + o_par);
     w.max_n = std::max(w.max_n, N);
   }
-  CU(cudaMallocFromPoolAsync((void**)&w.d_pairs, sizeof(PairDev) * count, c->pool, s));
-  CU(cudaMallocFromPoolAsync((void**)&w.d_states, sizeof(PairState) * count, c->pool, s));
+  CU(scratch.alloc((void**)&w.d_pairs, sizeof(PairDev) * count));
+  CU(scratch.alloc((void**)&w.d_states, sizeof(PairState) * count));
   CU(cudaMemcpyAsync(w.d_pairs, w.pairs.data(), sizeof(PairDev) * count, cudaMemcpyHostToDevice, s));
-  return B200REG_OK;
-}
-
-static int free_pair_work(b200reg_ctx* c, PairWork& w) {
-  cudaStream_t s = c->stream;
-  for (void* p : w.slabs) CU(cudaFreeAsync(p, s));
-  if (w.d_pairs) CU(cudaFreeAsync(w.d_pairs, s));
-  if (w.d_states) CU(cudaFreeAsync(w.d_states, s));
-  w.slabs.clear();
-  w.d_pairs = nullptr;
-  w.d_states = nullptr;
   return B200REG_OK;
 }
 
@@ -438,6 +459,7 @@ int b200reg_gicp_align(b200reg_ctx* c, int count, b200reg_cloud* const* src, b20
   if (!c || count <= 0 || !src || !tgt || !params || !out) return fail(B200REG_EINVAL, "bad argument");
   CU(cudaSetDevice(c->device));
   cudaStream_t s = c->stream;
+  Scratch scratch(c);
   int rc;
   // covariances on demand (nano_gicp_impl.hpp:162-167)
   {
@@ -451,11 +473,11 @@ int b200reg_gicp_align(b200reg_ctx* c, int count, b200reg_cloud* const* src, b20
       return rc;
   }
   PairWork w;
-  if ((rc = make_pair_work(c, count, src, tgt, w))) return rc;
+  if ((rc = make_pair_work(c, count, src, tgt, w, scratch))) return rc;
   const GicpParamsDev prm = to_dev(*params);
   double* d_guess = nullptr;
   if (guess16) {
-    CU(cudaMallocFromPoolAsync((void**)&d_guess, sizeof(double) * 16 * count, c->pool, s));
+    CU(scratch.alloc((void**)&d_guess, sizeof(double) * 16 * count));
     CU(cudaMemcpyAsync(d_guess, guess16, sizeof(double) * 16 * count, cudaMemcpyHostToDevice, s));
   }
   CU(cudaMemsetAsync(c->d_done, 0, sizeof(int), s));
@@ -476,10 +498,7 @@ int b200reg_gicp_align(b200reg_ctx* c, int count, b200reg_cloud* const* src, b20
     CU(cudaMemcpyAsync(c->h_done, c->d_done, sizeof(int), cudaMemcpyDeviceToHost, s));
     CU(cudaStreamSynchronize(s));
     if (*c->h_done >= count) break;
-    if (steps > max_steps) {
-      free_pair_work(c, w);
-      return fail(B200REG_ESTATE, "LM state machine did not terminate");
-    }
+    if (steps > max_steps) return fail(B200REG_ESTATE, "LM state machine did not terminate");
   }
   std::vector<PairState> states(count);
   CU(cudaMemcpyAsync(states.data(), w.d_states, sizeof(PairState) * count, cudaMemcpyDeviceToHost, s));
@@ -506,8 +525,7 @@ int b200reg_gicp_align(b200reg_ctx* c, int count, b200reg_cloud* const* src, b20
     // K3 136*N per linearize, K4 132*N per compute_error, K5 16*N fitness
     c->prof_bytes[CLS_STEP] += (136.0 * st.n_lin + 132.0 * st.n_err + 16.0) * w.pairs[i].src.n;
   }
-  if (d_guess) CU(cudaFreeAsync(d_guess, s));
-  return free_pair_work(c, w);
+  return B200REG_OK;
 }
 
 // one chunk of pairs, raw records already on the device
@@ -544,6 +562,7 @@ int b200reg_icp_alignment(b200reg_ctx* c, int count, const float* const* src_xyz
   // Host buffers: all uploads are queued on the copy stream up front, chunk by chunk; the compute stream processes
   // chunk k as soon as its records have landed, so the PCIe time of chunk k+1 hides behind the kernels of chunk k.
   cudaStream_t s = c->stream;
+  Scratch scratch(c);
   int want = c->pipeline_chunks;
   if (const char* e = getenv("B200REG_PIPELINE_CHUNKS")) want = atoi(e);
   const int nchunks = std::max(1, std::min(want, count));
@@ -557,7 +576,7 @@ int b200reg_icp_alignment(b200reg_ctx* c, int count, const float* const* src_xyz
     total += align_up(tgt_n[i] * stride_bytes, 256);
   }
   char* stage = nullptr;
-  CU(cudaMallocFromPoolAsync((void**)&stage, total, c->pool, s));
+  CU(scratch.alloc((void**)&stage, total));
   cudaEvent_t ready;
   CU(cudaEventCreateWithFlags(&ready, cudaEventDisableTiming));
   CU(cudaEventRecord(ready, s));
@@ -606,7 +625,6 @@ int b200reg_icp_alignment(b200reg_ctx* c, int count, const float* const* src_xyz
   cudaStreamSynchronize(c->copy_stream);
   for (cudaEvent_t e : landed) cudaEventDestroy(e);
   cudaEventDestroy(ready);
-  CU(cudaFreeAsync(stage, s));
   return rc;
 }
 
@@ -614,17 +632,16 @@ int b200reg_transform_cloud(b200reg_ctx* c, const b200reg_cloud* cl, const float
   if (!c || !cl || !Tf16 || !out_xyz) return fail(B200REG_EINVAL, "bad argument");
   CU(cudaSetDevice(c->device));
   cudaStream_t s = c->stream;
+  Scratch scratch(c);
   float* d_T = nullptr;
   float* d_out = nullptr;
-  CU(cudaMallocFromPoolAsync((void**)&d_T, 64, c->pool, s));
-  CU(cudaMallocFromPoolAsync((void**)&d_out, (size_t)cl->dev.n * 12, c->pool, s));
+  CU(scratch.alloc((void**)&d_T, 64));
+  CU(scratch.alloc((void**)&d_out, (size_t)cl->dev.n * 12));
   CU(cudaMemcpyAsync(d_T, Tf16, 64, cudaMemcpyHostToDevice, s));
   launch_transform_out(cl->dev, d_T, d_out, s);
   c->launches++;
   CU(cudaMemcpyAsync(out_xyz, d_out, (size_t)cl->dev.n * 12, cudaMemcpyDeviceToHost, s));
   CU(cudaStreamSynchronize(s));
-  CU(cudaFreeAsync(d_T, s));
-  CU(cudaFreeAsync(d_out, s));
   return B200REG_OK;
 }
 
@@ -648,12 +665,13 @@ static int knn_impl(b200reg_ctx* c, const b200reg_cloud* cl, const float* querie
     return fail(B200REG_EINVAL, "bad argument (k must be 1..32)");
   CU(cudaSetDevice(c->device));
   cudaStream_t s = c->stream;
+  Scratch scratch(c);
   float* d_q = nullptr;
   int* d_idx = nullptr;
   float* d_d2 = nullptr;
-  CU(cudaMallocFromPoolAsync((void**)&d_q, nq * qstride_bytes, c->pool, s));
-  CU(cudaMallocFromPoolAsync((void**)&d_idx, nq * k * 4, c->pool, s));
-  CU(cudaMallocFromPoolAsync((void**)&d_d2, nq * k * 4, c->pool, s));
+  CU(scratch.alloc((void**)&d_q, nq * qstride_bytes));
+  CU(scratch.alloc((void**)&d_idx, nq * k * 4));
+  CU(scratch.alloc((void**)&d_d2, nq * k * 4));
   CU(cudaMemcpyAsync(d_q, queries, nq * qstride_bytes, cudaMemcpyHostToDevice, s));
   if (launch_knn_queries(cl->dev, d_q, (int)nq, (int)(qstride_bytes / 4), k, d_idx, d_d2, s, brute) < 0)
     return fail(B200REG_EINVAL, "unsupported k");
@@ -662,9 +680,6 @@ static int knn_impl(b200reg_ctx* c, const b200reg_cloud* cl, const float* querie
   CU(cudaMemcpyAsync(idx_out, d_idx, nq * k * 4, cudaMemcpyDeviceToHost, s));
   CU(cudaMemcpyAsync(d2_out, d_d2, nq * k * 4, cudaMemcpyDeviceToHost, s));
   CU(cudaStreamSynchronize(s));
-  CU(cudaFreeAsync(d_q, s));
-  CU(cudaFreeAsync(d_idx, s));
-  CU(cudaFreeAsync(d_d2, s));
   return B200REG_OK;
 }
 
@@ -697,17 +712,18 @@ int b200reg_linearize(b200reg_ctx* c, const b200reg_cloud* src, const b200reg_cl
   if (!src->has_cov || !tgt->has_cov) return fail(B200REG_ESTATE, "covariances not computed");
   CU(cudaSetDevice(c->device));
   cudaStream_t s = c->stream;
+  Scratch scratch(c);
   PairWork w;
   b200reg_cloud* sp = const_cast<b200reg_cloud*>(src);
   b200reg_cloud* tp = const_cast<b200reg_cloud*>(tgt);
   int rc;
-  if ((rc = make_pair_work(c, 1, &sp, &tp, w))) return rc;
+  if ((rc = make_pair_work(c, 1, &sp, &tp, w, scratch))) return rc;
   b200reg_gicp_params p;
   b200reg_default_gicp_params(&p);
   p.max_corr_dist = max_corr_dist;
   const GicpParamsDev prm = to_dev(p);
   double* d_guess = nullptr;
-  CU(cudaMallocFromPoolAsync((void**)&d_guess, sizeof(double) * 16, c->pool, s));
+  CU(scratch.alloc((void**)&d_guess, sizeof(double) * 16));
   CU(cudaMemcpyAsync(d_guess, T16, sizeof(double) * 16, cudaMemcpyHostToDevice, s));
   CU(cudaMemsetAsync(c->d_done, 0, sizeof(int), s));
   launch_gicp_init(w.d_states, d_guess, 1, prm, s);
@@ -734,8 +750,7 @@ int b200reg_linearize(b200reg_ctx* c, const b200reg_cloud* src, const b200reg_cl
     if (corr_out) corr_out[o] = to;
     if (sqd_out) sqd_out[o] = sqd[p_];
   }
-  CU(cudaFreeAsync(d_guess, s));
-  return free_pair_work(c, w);
+  return B200REG_OK;
 }
 
 
@@ -760,6 +775,7 @@ int b200reg_clouds_fpfh(b200reg_ctx* c, int count, b200reg_cloud* const* clouds,
   if (!c || count <= 0 || !clouds || !(normal_radius > 0) || !(fpfh_radius > 0)) return fail(B200REG_EINVAL, "bad argument");
   CU(cudaSetDevice(c->device));
   cudaStream_t s = c->stream;
+  Scratch scratch(c);
   std::vector<CloudDev> descs;
   std::vector<b200reg_cloud*> todo;
   int max_n = 0;
@@ -789,7 +805,7 @@ int b200reg_clouds_fpfh(b200reg_ctx* c, int count, b200reg_cloud* const* clouds,
   }
   if (todo.empty()) return B200REG_OK;
   CloudDev* d_descs = nullptr;
-  CU(cudaMallocFromPoolAsync((void**)&d_descs, sizeof(CloudDev) * descs.size(), c->pool, s));
+  CU(scratch.alloc((void**)&d_descs, sizeof(CloudDev) * descs.size()));
   CU(cudaMemcpyAsync(d_descs, descs.data(), sizeof(CloudDev) * descs.size(), cudaMemcpyHostToDevice, s));
   {
     ProfScope ps(c, CLS_FPFH);
@@ -798,7 +814,6 @@ int b200reg_clouds_fpfh(b200reg_ctx* c, int count, b200reg_cloud* const* clouds,
     for (auto& d : descs) c->prof_bytes[CLS_FPFH] += (32.0 + 164.0 + 280.0) * d.n;  // SURVEY §8(d) Q1+Q2+Q3
   }
   CU(cudaGetLastError());
-  CU(cudaFreeAsync(d_descs, s));
   for (b200reg_cloud* cl : todo) {
     cl->has_fpfh = true;
     cl->normal_r = normal_radius;
@@ -841,6 +856,7 @@ int b200reg_quatro_align(b200reg_ctx* c, int count, b200reg_cloud* const* src, b
   if (prm->max_corres < 1 || prm->max_corres > MAXC - 3) return fail(B200REG_EINVAL, "max_corres must be in 1..509");
   CU(cudaSetDevice(c->device));
   cudaStream_t s = c->stream;
+  Scratch scratch(c);
   int rc;
   {
     std::vector<b200reg_cloud*> all;
@@ -852,7 +868,6 @@ int b200reg_quatro_align(b200reg_ctx* c, int count, b200reg_cloud* const* src, b
     if ((rc = b200reg_clouds_fpfh(c, (int)all.size(), all.data(), prm->fpfh_normal_radius, prm->fpfh_radius))) return rc;
   }
   std::vector<MatchDev> pairs(count);
-  std::vector<void*> slabs;
   int max_ni = 0, max_nj = 0;
   for (int i = 0; i < count; i++) {
     MatchDev& m = pairs[i];
@@ -870,8 +885,7 @@ int b200reg_quatro_align(b200reg_ctx* c, int count, b200reg_cloud* const* src, b
     const size_t o_nn = take(nj * 4), o_dis = take(nj * 4), o_fj = take(ni * 4), o_need = take(ni * 4), o_rnn = take(ni * 4);
     const size_t o_cor = take(2 * nj * 4), o_tk = take(nj * 4), o_cnt = take(8 * 4), o_st = take(8 * 8), o_oc = take(2 * MAXC * 4), o_T = take(16 * 8);
     char* slab = nullptr;
-    CU(cudaMallocFromPoolAsync((void**)&slab, o, c->pool, s));
-    slabs.push_back(slab);
+    CU(scratch.alloc((void**)&slab, o));
     m.nn = (int*)(slab + o_nn);
     m.dis = (float*)(slab + o_dis);
     m.first_j = (int*)(slab + o_fj);
@@ -887,7 +901,7 @@ int b200reg_quatro_align(b200reg_ctx* c, int count, b200reg_cloud* const* src, b
     max_nj = std::max(max_nj, (int)nj);
   }
   MatchDev* d_pairs = nullptr;
-  CU(cudaMallocFromPoolAsync((void**)&d_pairs, sizeof(MatchDev) * count, c->pool, s));
+  CU(scratch.alloc((void**)&d_pairs, sizeof(MatchDev) * count));
   CU(cudaMemcpyAsync(d_pairs, pairs.data(), sizeof(MatchDev) * count, cudaMemcpyHostToDevice, s));
   QuatroParamsDev q;
   q.normal_r2 = (float)(prm->fpfh_normal_radius * prm->fpfh_normal_radius);
@@ -922,8 +936,6 @@ int b200reg_quatro_align(b200reg_ctx* c, int count, b200reg_cloud* const* src, b
     out[i].gnc_iterations = counters[8 * i + 5];
     out[i].reserved = 0;
   }
-  for (void* p : slabs) CU(cudaFreeAsync(p, s));
-  CU(cudaFreeAsync(d_pairs, s));
   return B200REG_OK;
 }
 
@@ -932,12 +944,11 @@ static int coarse_to_fine_on_clouds(b200reg_ctx* c, int count, b200reg_cloud* co
                                     const b200reg_quatro_params* qp, const b200reg_gicp_params* gp, b200reg_result* out,
                                     b200reg_quatro_info* quatro_out) {
   cudaStream_t s = c->stream;
+  Scratch scratch(c);
   std::vector<b200reg_quatro_info> qi(count);
   std::vector<b200reg_cloud*> coarse;
-  std::vector<void*> raws;
   auto cleanup = [&]() {
     for (b200reg_cloud* cl : coarse) b200reg_cloud_destroy(c, cl);
-    for (void* p : raws) cudaFreeAsync(p, s);
   };
   int rc = b200reg_quatro_align(c, count, src, dst, qp, qi.data(), nullptr);
   if (rc) return rc;
@@ -966,8 +977,7 @@ static int coarse_to_fine_on_clouds(b200reg_ctx* c, int count, b200reg_cloud* co
       sdesc[k] = src[i]->dev;
       memcpy(&Ts[16 * (size_t)k], qi[i].T, 128);
       float4* raw = nullptr;
-      CU(cudaMallocFromPoolAsync((void**)&raw, (size_t)sdesc[k].n * 16, c->pool, s));
-      raws.push_back(raw);
+      CU(scratch.alloc((void**)&raw, (size_t)sdesc[k].n * 16));
       outs[k] = raw;
       cptr[k] = (const float*)raw;
       cn[k] = sdesc[k].n;
@@ -976,17 +986,14 @@ static int coarse_to_fine_on_clouds(b200reg_ctx* c, int count, b200reg_cloud* co
     CloudDev* d_desc = nullptr;
     double* d_T = nullptr;
     float4** d_outs = nullptr;
-    CU(cudaMallocFromPoolAsync((void**)&d_desc, sizeof(CloudDev) * nv, c->pool, s));
-    CU(cudaMallocFromPoolAsync((void**)&d_T, 128 * (size_t)nv, c->pool, s));
-    CU(cudaMallocFromPoolAsync((void**)&d_outs, sizeof(float4*) * nv, c->pool, s));
+    CU(scratch.alloc((void**)&d_desc, sizeof(CloudDev) * nv));
+    CU(scratch.alloc((void**)&d_T, 128 * (size_t)nv));
+    CU(scratch.alloc((void**)&d_outs, sizeof(float4*) * nv));
     CU(cudaMemcpyAsync(d_desc, sdesc.data(), sizeof(CloudDev) * nv, cudaMemcpyHostToDevice, s));
     CU(cudaMemcpyAsync(d_T, Ts.data(), 128 * (size_t)nv, cudaMemcpyHostToDevice, s));
     CU(cudaMemcpyAsync(d_outs, outs.data(), sizeof(float4*) * nv, cudaMemcpyHostToDevice, s));
     launch_transform_raw(d_desc, d_T, nv, max_n, d_outs, s);
     c->launches++;
-    CU(cudaFreeAsync(d_desc, s));
-    CU(cudaFreeAsync(d_T, s));
-    CU(cudaFreeAsync(d_outs, s));
     coarse.assign(nv, nullptr);
     rc = b200reg_clouds_create(c, nv, cptr.data(), cn.data(), 16, 1, coarse.data());
     std::vector<b200reg_cloud*> tg(nv);
@@ -1106,25 +1113,22 @@ int b200reg_fetch_closest_keyframes(b200reg_ctx* c, b200reg_keyframes* kf, int c
     if (query_idx[i] < 0 || query_idx[i] >= nk) return fail(B200REG_EINVAL, "query index out of range");
   CU(cudaSetDevice(c->device));
   cudaStream_t s = c->stream;
+  Scratch scratch(c);
   std::vector<double> pos(3 * (size_t)nk);
   for (int i = 0; i < nk; i++)
     for (int d = 0; d < 3; d++) pos[3 * (size_t)i + d] = kf->poses[16 * (size_t)i + 4 * d + 3];
   double *d_pos = nullptr, *d_st = nullptr;
   int *d_q = nullptr, *d_o = nullptr;
-  CU(cudaMallocFromPoolAsync((void**)&d_pos, pos.size() * 8, c->pool, s));
-  CU(cudaMallocFromPoolAsync((void**)&d_st, (size_t)nk * 8, c->pool, s));
-  CU(cudaMallocFromPoolAsync((void**)&d_q, (size_t)count * 4, c->pool, s));
-  CU(cudaMallocFromPoolAsync((void**)&d_o, (size_t)count * 4, c->pool, s));
+  CU(scratch.alloc((void**)&d_pos, pos.size() * 8));
+  CU(scratch.alloc((void**)&d_st, (size_t)nk * 8));
+  CU(scratch.alloc((void**)&d_q, (size_t)count * 4));
+  CU(scratch.alloc((void**)&d_o, (size_t)count * 4));
   CU(cudaMemcpyAsync(d_pos, pos.data(), pos.size() * 8, cudaMemcpyHostToDevice, s));
   CU(cudaMemcpyAsync(d_st, kf->stamps.data(), (size_t)nk * 8, cudaMemcpyHostToDevice, s));
   CU(cudaMemcpyAsync(d_q, query_idx, (size_t)count * 4, cudaMemcpyHostToDevice, s));
   c->launches += launch_fetch_closest(d_pos, d_st, d_q, count, radius, tdiff, d_o, s);
   CU(cudaMemcpyAsync(closest_out, d_o, (size_t)count * 4, cudaMemcpyDeviceToHost, s));
   CU(cudaStreamSynchronize(s));
-  CU(cudaFreeAsync(d_pos, s));
-  CU(cudaFreeAsync(d_st, s));
-  CU(cudaFreeAsync(d_q, s));
-  CU(cudaFreeAsync(d_o, s));
   return B200REG_OK;
 }
 
@@ -1138,10 +1142,10 @@ int b200reg_assemble_clouds(b200reg_ctx* c, b200reg_keyframes* kf, int count, co
   if (!(cfg->voxel_res > 0)) return fail(B200REG_EINVAL, "voxel_res must be positive");
   CU(cudaSetDevice(c->device));
   cudaStream_t s = c->stream;
+  Scratch scratch(c);
   const int njobs = 2 * count;  // jobs [0,count) = src clouds, [count, 2 count) = dst clouds
   std::vector<AssembleJob> jobs(njobs);
   std::vector<CloudDev> sorts(njobs);
-  std::vector<void*> slabs;
   int max_total = 0;
   for (int j = 0; j < njobs; j++) {
     const bool is_src = j < count;
@@ -1178,8 +1182,7 @@ int b200reg_assemble_clouds(b200reg_ctx* c, b200reg_keyframes* kf, int count, co
     const size_t o_m = take(n * 16), o_o = take(n * 16), o_h = take(n * 4), o_b = take(32), o_c = take(16);
     const size_t o_k0 = take(n * 4), o_k1 = take(n * 4), o_v0 = take(n * 4), o_v1 = take(n * 4), o_hist = take((size_t)RADIX * ntiles * 4);
     char* slab = nullptr;
-    CU(cudaMallocFromPoolAsync((void**)&slab, o, c->pool, s));
-    slabs.push_back(slab);
+    CU(scratch.alloc((void**)&slab, o));
     J.merged = (float4*)(slab + o_m);
     J.out = (float4*)(slab + o_o);
     J.heads = (int*)(slab + o_h);
@@ -1207,10 +1210,10 @@ int b200reg_assemble_clouds(b200reg_ctx* c, b200reg_keyframes* kf, int count, co
   CloudDev* d_sorts = nullptr;
   KeyframeDev* d_kf = nullptr;
   double* d_poses = nullptr;
-  CU(cudaMallocFromPoolAsync((void**)&d_jobs, sizeof(AssembleJob) * njobs, c->pool, s));
-  CU(cudaMallocFromPoolAsync((void**)&d_sorts, sizeof(CloudDev) * njobs, c->pool, s));
-  CU(cudaMallocFromPoolAsync((void**)&d_kf, sizeof(KeyframeDev) * nkall, c->pool, s));
-  CU(cudaMallocFromPoolAsync((void**)&d_poses, 128 * (size_t)nkall, c->pool, s));
+  CU(scratch.alloc((void**)&d_jobs, sizeof(AssembleJob) * njobs));
+  CU(scratch.alloc((void**)&d_sorts, sizeof(CloudDev) * njobs));
+  CU(scratch.alloc((void**)&d_kf, sizeof(KeyframeDev) * nkall));
+  CU(scratch.alloc((void**)&d_poses, 128 * (size_t)nkall));
   CU(cudaMemcpyAsync(d_jobs, jobs.data(), sizeof(AssembleJob) * njobs, cudaMemcpyHostToDevice, s));
   CU(cudaMemcpyAsync(d_sorts, sorts.data(), sizeof(CloudDev) * njobs, cudaMemcpyHostToDevice, s));
   CU(cudaMemcpyAsync(d_kf, kd.data(), sizeof(KeyframeDev) * nkall, cudaMemcpyHostToDevice, s));
@@ -1239,11 +1242,6 @@ int b200reg_assemble_clouds(b200reg_ctx* c, b200reg_keyframes* kf, int count, co
     src_out[i] = clouds[i];
     dst_out[i] = clouds[count + i];
   }
-  for (void* p : slabs) CU(cudaFreeAsync(p, s));
-  CU(cudaFreeAsync(d_jobs, s));
-  CU(cudaFreeAsync(d_sorts, s));
-  CU(cudaFreeAsync(d_kf, s));
-  CU(cudaFreeAsync(d_poses, s));
   return rc;
 }
 
