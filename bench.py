@@ -485,9 +485,10 @@ def main():
     for _ in range(args.warmup):
         step(True)
         step(False)
-    if pipe is not None:
-        run_pipelined(max(2, args.warmup), True)
-        run_pipelined(max(2, args.warmup), False)
+    if pipe is not None:  # every context of the pipeline must see both arms at least twice before anything is timed
+        run_pipelined(max(2 * depth, args.warmup), True)
+        run_pipelined(max(2 * depth, args.warmup), False)
+        run_pipelined(depth, True)
 
     if pipe is not None:  # both arms through the same double-buffered driver
         ms_dev, launches, res = run_pipelined(args.steps, True)
