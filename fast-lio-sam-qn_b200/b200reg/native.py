@@ -16,7 +16,7 @@ _lib = None
 class GicpParams(C.Structure):
     _fields_ = [("k_correspondences", C.c_int32), ("max_iterations", C.c_int32), ("max_corr_dist", C.c_double),
                 ("transformation_eps", C.c_double), ("rotation_eps", C.c_double), ("lm_max_iterations", C.c_int32),
-                ("reserved", C.c_int32), ("lm_init_lambda_factor", C.c_double), ("icp_score_thr", C.c_double)]
+                ("regularization", C.c_int32), ("lm_init_lambda_factor", C.c_double), ("icp_score_thr", C.c_double)]
 
 
 class Result(C.Structure):
@@ -64,7 +64,7 @@ MAXC = 512
 EXPORTS = [
     "b200reg_default_gicp_params", "b200reg_last_error", "b200reg_version", "b200reg_ctx_create",
     "b200reg_ctx_destroy", "b200reg_ctx_set_stream", "b200reg_ctx_synchronize", "b200reg_ctx_launch_count",
-    "b200reg_clouds_create", "b200reg_cloud_destroy", "b200reg_cloud_size", "b200reg_clouds_covariances",
+    "b200reg_clouds_create", "b200reg_cloud_destroy", "b200reg_cloud_size", "b200reg_clouds_covariances", "b200reg_clouds_covariances_ex",
     "b200reg_gicp_align", "b200reg_icp_alignment", "b200reg_transform_cloud", "b200reg_knn",
     "b200reg_get_covariances", "b200reg_linearize", "b200reg_ctx_set_profiling", "b200reg_ctx_reset_profile",
     "b200reg_ctx_get_profile", "b200reg_default_quatro_params", "b200reg_clouds_fpfh", "b200reg_get_fpfh",
@@ -187,9 +187,9 @@ class Context:
         _check(lib().b200reg_clouds_create(self.h, cnt, ptrs, nsa, C.c_size_t(stride_bytes), 1, outs))
         return [Cloud(self, C.c_void_p(outs[i]), ns[i]) for i in range(cnt)]
 
-    def covariances(self, clouds, k=15):
+    def covariances(self, clouds, k=15, method=3):
         arr = (C.c_void_p * len(clouds))(*[c.h for c in clouds])
-        _check(lib().b200reg_clouds_covariances(self.h, len(clouds), arr, int(k)))
+        _check(lib().b200reg_clouds_covariances_ex(self.h, len(clouds), arr, int(k), int(method)))
 
     # -- registration ------------------------------------------------------------------
     def gicp_align(self, srcs, tgts, params=None, guesses=None):

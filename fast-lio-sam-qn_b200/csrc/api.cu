@@ -15,7 +15,7 @@
 
 namespace b200 {
 int launch_index_build(const CloudDev* d_clouds, int count, int max_n, cudaStream_t s);
-int launch_covariances(const CloudDev* d_clouds, int count, int max_n, int k, cudaStream_t s);
+int launch_covariances(const CloudDev* d_clouds, int count, int max_n, int k, int method, cudaStream_t s);
 void launch_gicp_init(PairState* states, const double* d_guess, int count, const GicpParamsDev& prm, cudaStream_t s);
 void launch_gicp_step(const PairDev* pairs, PairState* states, int count, int max_n, const GicpParamsDev& prm,
                       int* done_counter, cudaStream_t s);
@@ -136,6 +136,7 @@ struct b200reg_cloud {
   void* fslab = nullptr;   // Quatro features (nrm, spfh, fpfh), allocated on demand
   bool has_cov = false;
   int cov_k = 0;
+  int cov_method = 3;
   bool has_fpfh = false;
   double normal_r = 0, fpfh_r = 0;
 };
@@ -152,7 +153,7 @@ void b200reg_default_gicp_params(b200reg_gicp_params* p) {
   p->transformation_eps = 0.01;
   p->rotation_eps = 2e-3;
   p->lm_max_iterations = 10;
-  p->reserved = 0;
+  p->regularization = 3;  // PLANE
   p->lm_init_lambda_factor = 1e-9;
   p->icp_score_thr = 1.5;
 }
@@ -371,7 +372,12 @@ int b200reg_cloud_destroy(b200reg_ctx* c, b200reg_cloud* cl) {
 }
 
 int b200reg_clouds_covariances(b200reg_ctx* c, int count, b200reg_cloud* const* clouds, int k) {
+  return b200reg_clouds_covariances_ex(c, count, clouds, k, 3);
+}
+
+int b200reg_clouds_covariances_ex(b200reg_ctx* c, int count, b200reg_cloud* const* clouds, int k, int method) {
   if (!c || count <= 0 || !clouds) return fail(B200REG_EINVAL, "bad argument");
+  if (method < 0 || method > 4) return fail(B200REG_EINVAL, "regularization must be 0..4 (NONE, MIN_EIG, NORMALIZED_MIN_EIG, PLANE, FROBENIUS)");
   if (k < 1 || k > 32) return fail(B200REG_EINVAL, "k_correspondences must be in 1..32");
   CU(cudaSetDevice(c->device));
   cudaStream_t s = c->stream;
@@ -380,7 +386,7 @@ int b200reg_clouds_covariances(b200reg_ctx* c, int count, b200reg_cloud* const* 
   int max_n = 0;
   for (int i = 0; i < count; i++) {
     if (!clouds[i]) return fail(B200REG_EINVAL, "NULL cloud");
-    if (clouds[i]->has_cov && clouds[i]->cov_k == k) continue;
+    if (clouds[i]->has_cov && clouds[i]->cov_k == k && clouds[i]->cov_method == method) continue;
     bool dup = false;
     for (int j = 0; j < i; j++) dup |= clouds[j] == clouds[i];
     if (dup) continue;
@@ -393,7 +399,7 @@ int b200reg_clouds_covariances(b200reg_ctx* c, int count, b200reg_cloud* const* 
   CU(cudaMemcpyAsync(d_descs, descs.data(), sizeof(CloudDev) * descs.size(), cudaMemcpyHostToDevice, s));
   {
     ProfScope ps(c, CLS_COV);
-    int l = launch_covariances(d_descs, (int)descs.size(), max_n, k, s);
+    int l = launch_covariances(d_descs, (int)descs.size(), max_n, k, method, s);
     if (l < 0) return fail(B200REG_EINVAL, "unsupported k");
     c->launches += l;
     for (auto& d : descs) c->prof_bytes[CLS_COV] += 64.0 * d.n;
@@ -402,6 +408,7 @@ int b200reg_clouds_covariances(b200reg_ctx* c, int count, b200reg_cloud* const* 
   for (int i = 0; i < count; i++) {
     clouds[i]->has_cov = true;
     clouds[i]->cov_k = k;
+    clouds[i]->cov_method = method;
   }
   return B200REG_OK;
 }
@@ -466,10 +473,12 @@ int b200reg_gicp_align(b200reg_ctx* c, int count, b200reg_cloud* const* src, b20
     std::vector<b200reg_cloud*> need;
     for (int i = 0; i < count; i++) {
       if (!src[i] || !tgt[i]) return fail(B200REG_EINVAL, "NULL cloud");
-      if (!src[i]->has_cov || src[i]->cov_k != params->k_correspondences) need.push_back(src[i]);
-      if (!tgt[i]->has_cov || tgt[i]->cov_k != params->k_correspondences) need.push_back(tgt[i]);
+      const int m = params->regularization;
+      if (!src[i]->has_cov || src[i]->cov_k != params->k_correspondences || src[i]->cov_method != m) need.push_back(src[i]);
+      if (!tgt[i]->has_cov || tgt[i]->cov_k != params->k_correspondences || tgt[i]->cov_method != m) need.push_back(tgt[i]);
     }
-    if (!need.empty() && (rc = b200reg_clouds_covariances(c, (int)need.size(), need.data(), params->k_correspondences)))
+    if (!need.empty() &&
+        (rc = b200reg_clouds_covariances_ex(c, (int)need.size(), need.data(), params->k_correspondences, params->regularization)))
       return rc;
   }
   PairWork w;
@@ -543,7 +552,7 @@ static int icp_alignment_device(b200reg_ctx* c, int count, const float* const* s
   std::vector<b200reg_cloud*> clouds(2 * count, nullptr);
   int rc = b200reg_clouds_create(c, 2 * count, ptrs.data(), ns.data(), stride_bytes, 1, clouds.data());
   if (rc) return rc;
-  rc = b200reg_clouds_covariances(c, 2 * count, clouds.data(), params->k_correspondences);
+  rc = b200reg_clouds_covariances_ex(c, 2 * count, clouds.data(), params->k_correspondences, params->regularization);
   if (!rc) rc = b200reg_gicp_align(c, count, clouds.data(), clouds.data() + count, nullptr, params, out);
   for (b200reg_cloud* cl : clouds) b200reg_cloud_destroy(c, cl);
   return rc;
@@ -615,7 +624,7 @@ int b200reg_icp_alignment(b200reg_ctx* c, int count, const float* const* src_xyz
       sc[i] = cl[i - k0];
       tc[i] = cl[m + i - k0];
     }
-    if (!rc) rc = b200reg_clouds_covariances(c, 2 * m, cl.data(), params->k_correspondences);
+    if (!rc) rc = b200reg_clouds_covariances_ex(c, 2 * m, cl.data(), params->k_correspondences, params->regularization);
   }
   if (!rc) rc = b200reg_gicp_align(c, count, sc.data(), tc.data(), nullptr, params, out);
   for (int i = 0; i < count; i++) {

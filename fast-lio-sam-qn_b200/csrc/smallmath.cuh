@@ -62,4 +62,37 @@ __device__ __forceinline__ void sym3_smallest_evec(double a00, double a01, doubl
   n[0] = vx * inv; n[1] = vy * inv; n[2] = vz * inv;
 }
 
+// Full eigen-decomposition of a symmetric 3x3 by cyclic Jacobi (fp64): eigenvalues in w (unsorted), eigenvectors in
+// the columns of V.  Only the non-default regularisation methods need it (cold path).
+static __device__ __noinline__ void sym3_eigen_jacobi(const double a[6], double w[3], double V[3][3]) {
+  double A[3][3] = {{a[0], a[1], a[2]}, {a[1], a[3], a[4]}, {a[2], a[4], a[5]}};
+  for (int i = 0; i < 3; i++)
+    for (int j = 0; j < 3; j++) V[i][j] = i == j ? 1.0 : 0.0;
+  for (int sweep = 0; sweep < 16; sweep++) {
+    const double off = A[0][1] * A[0][1] + A[0][2] * A[0][2] + A[1][2] * A[1][2];
+    const double dg = A[0][0] * A[0][0] + A[1][1] * A[1][1] + A[2][2] * A[2][2];
+    if (off == 0.0 || off <= 1e-34 * dg) break;
+    for (int pq = 0; pq < 3; pq++) {
+      const int p = pq == 2 ? 1 : 0, q = pq == 0 ? 1 : 2, r = 3 - p - q;
+      const double apq = A[p][q];
+      if (apq == 0.0) continue;
+      const double theta = (A[q][q] - A[p][p]) / (2.0 * apq);
+      const double t = (theta >= 0 ? 1.0 : -1.0) / (fabs(theta) + sqrt(theta * theta + 1.0));
+      const double c = 1.0 / sqrt(t * t + 1.0), s = t * c;
+      A[p][p] -= t * apq;
+      A[q][q] += t * apq;
+      A[p][q] = A[q][p] = 0.0;
+      const double arp = A[r][p], arq = A[r][q];
+      A[r][p] = A[p][r] = c * arp - s * arq;
+      A[r][q] = A[q][r] = s * arp + c * arq;
+      for (int k = 0; k < 3; k++) {
+        const double vp = V[k][p], vq = V[k][q];
+        V[k][p] = c * vp - s * vq;
+        V[k][q] = s * vp + c * vq;
+      }
+    }
+  }
+  w[0] = A[0][0]; w[1] = A[1][1]; w[2] = A[2][2];
+}
+
 }  // namespace b200

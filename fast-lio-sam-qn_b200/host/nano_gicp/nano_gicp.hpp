@@ -64,7 +64,10 @@ class NanoGICP {
     }
   }
   void setRegularizationMethod(RegularizationMethod m) {
-    if (m != RegularizationMethod::PLANE) std::fprintf(stderr, "b200reg: only RegularizationMethod::PLANE is built; keeping PLANE\n");
+    if (static_cast<int>(m) != prm_.regularization) {
+      prm_.regularization = static_cast<int>(m);  // same enumerator order as gicp/gicp_settings.hpp:47
+      src_cov_ok_ = tgt_cov_ok_ = false;
+    }
   }
   // ---- pcl::Registration setters (loop_closure.cpp:11-16)
   void setMaximumIterations(int n) { prm_.max_iterations = n; }
@@ -197,7 +200,7 @@ class NanoGICP {
   bool covariances(b200reg_cloud* cl, bool* ok) {
     if (!cl) return false;
     b200reg_cloud* a[1] = {cl};
-    const int rc = b200reg_clouds_covariances(b200reg_host::context(), 1, a, prm_.k_correspondences);
+    const int rc = b200reg_clouds_covariances_ex(b200reg_host::context(), 1, a, prm_.k_correspondences, prm_.regularization);
     if (rc != 0) std::fprintf(stderr, "b200reg: covariances failed (%d): %s\n", rc, b200reg_last_error());
     *ok = rc == 0;
     return true;  // the reference returns true unconditionally (nano_gicp_impl.hpp:356)

@@ -52,7 +52,8 @@ typedef struct b200reg_gicp_params {
   double transformation_eps;     /* setTransformationEpsilon, loop_closure.cpp:14 (0.01)    */
   double rotation_eps;           /* lsq_registration_impl.hpp:53 (2e-3)                     */
   int32_t lm_max_iterations;     /* lsq_registration_impl.hpp:58 (10)                       */
-  int32_t reserved;
+  int32_t regularization;        /* RegularizationMethod (gicp/gicp_settings.hpp:47): 0 NONE, 1 MIN_EIG,
+                                    2 NORMALIZED_MIN_EIG, 3 PLANE (default, nano_gicp_impl.hpp:61), 4 FROBENIUS */
   double lm_init_lambda_factor;  /* lsq_registration_impl.hpp:59 (1e-9)                     */
   double icp_score_thr;          /* validity gate, loop_closure.cpp:129 (config.yaml:21: 1.5) */
 } b200reg_gicp_params;
@@ -134,6 +135,8 @@ size_t b200reg_cloud_size(const b200reg_cloud* cloud);
 /* NanoGICP::calculateSourceCovariances / calculateTargetCovariances
  * (third_party/nano_gicp/include/nano_gicp/impl/nano_gicp_impl.hpp:151-159, 298-357), batched. */
 int b200reg_clouds_covariances(b200reg_ctx* ctx, int count, b200reg_cloud* const* clouds, int k);
+/* Same with an explicit RegularizationMethod (setRegularizationMethod, nano_gicp.hpp:84); the plain call uses PLANE. */
+int b200reg_clouds_covariances_ex(b200reg_ctx* ctx, int count, b200reg_cloud* const* clouds, int k, int method);
 
 /* ---- registration ----------------------------------------------------------------- */
 /* pcl::Registration::align + getFitnessScore + hasConverged + getFinalTransformation for

@@ -113,6 +113,14 @@ class RefNanoflann:
             pass
 
 
+def covariances_ex(pts, k=15, method=3):
+    """RegularizationMethod: 0 NONE, 1 MIN_EIG, 2 NORMALIZED_MIN_EIG, 3 PLANE, 4 FROBENIUS (nano_gicp_impl.hpp:323-353)."""
+    pts = _f32(pts)
+    cov = np.empty((len(pts), 3, 3), np.float64)
+    lib().orc_covariances_ex(_p(pts, C.c_float), len(pts), pts.shape[1], k, int(method), _p(cov, C.c_double))
+    return cov
+
+
 def covariances(pts, k=15, return_knn=False):
     pts = _f32(pts)
     cov = np.empty((len(pts), 3, 3), np.float64)

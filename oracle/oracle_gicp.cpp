@@ -204,7 +204,7 @@ static double now_ms() {
 // k-NN (self included) -> mean-subtracted 3xk -> cov = X X^T / k -> SVD ->
 // U diag(1,1,1e-3) V^T.  Row/col 3 of the reference's 4x4 is identically zero
 //  so only the 3x3 block is produced.
-static void covariances(const float* xyz, int n, int stride, const Index& index, int k, double* cov9, int* knn_idx_out) {
+static void covariances(const float* xyz, int n, int stride, const Index& index, int k, double* cov9, int* knn_idx_out, int method = 3) {
 #pragma omp parallel for schedule(guided, 8)
   for (int i = 0; i < n; i++) {
     std::vector<int> idx(k);
@@ -230,17 +230,38 @@ static void covariances(const float* xyz, int n, int stride, const Index& index,
         for (int b = 0; b < 3; b++) cov(a, b) += v[a] * v[b];
     }
     for (int a = 0; a < 9; a++) cov.m[a] /= k;  // (:321)
-    M3 U, V;
-    double s[3];
-    m3_svd(cov, U, s, V);
-    const double vals[3] = {1.0, 1.0, 1e-3};  // PLANE (:341-343)
+    // RegularizationMethod (gicp/gicp_settings.hpp:47): 0 NONE, 1 MIN_EIG, 2 NORMALIZED_MIN_EIG, 3 PLANE, 4 FROBENIUS
     M3 C = m3_zero();
-    for (int a = 0; a < 3; a++)
-      for (int b = 0; b < 3; b++) {
-        double acc = 0;
-        for (int c = 0; c < 3; c++) acc += U(a, c) * vals[c] * V(b, c);
-        C(a, b) = acc;
+    if (method == 0) {  // NONE (:323-324)
+      C = cov;
+    } else if (method == 4) {  // FROBENIUS (:325-330): ((C+1e-3 I)^-1 / ||.||_F)^-1
+      M3 Cl = cov;
+      for (int a = 0; a < 3; a++) Cl(a, a) += 1e-3;
+      M3 Ci = m3_inverse(Cl);
+      double nrm = 0;
+      for (int a = 0; a < 9; a++) nrm += Ci.m[a] * Ci.m[a];
+      nrm = std::sqrt(nrm);
+      M3 Cn;
+      for (int a = 0; a < 9; a++) Cn.m[a] = Ci.m[a] / nrm;
+      C = m3_inverse(Cn);
+    } else {
+      M3 U, V;
+      double s[3];
+      m3_svd(cov, U, s, V);
+      double vals[3] = {1.0, 1.0, 1e-3};  // PLANE (:341-343)
+      if (method == 1) {                  // MIN_EIG (:344-346)
+        for (int a = 0; a < 3; a++) vals[a] = std::max(s[a], 1e-3);
+      } else if (method == 2) {           // NORMALIZED_MIN_EIG (:347-350)
+        const double mx = std::max(s[0], std::max(s[1], s[2]));
+        for (int a = 0; a < 3; a++) vals[a] = std::max(s[a] / mx, 1e-3);
       }
+      for (int a = 0; a < 3; a++)
+        for (int b = 0; b < 3; b++) {
+          double acc = 0;
+          for (int c = 0; c < 3; c++) acc += U(a, c) * vals[c] * V(b, c);
+          C(a, b) = acc;
+        }
+    }
     std::memcpy(&cov9[(size_t)i * 9], C.m, sizeof(double) * 9);
   }
 }
@@ -453,6 +474,12 @@ void orc_covariances(const float* xyz, int n, int stride, int k, double* cov9, i
   Index index;
   index.build(xyz, n, stride);
   covariances(xyz, n, stride, index, k, cov9, knn_idx_out);
+}
+
+void orc_covariances_ex(const float* xyz, int n, int stride, int k, int method, double* cov9) {
+  Index index;
+  index.build(xyz, n, stride);
+  covariances(xyz, n, stride, index, k, cov9, nullptr, method);
 }
 
 void orc_transform_queries(const double* T16, const float* xyz, int n, int stride, float* out3) {

@@ -39,6 +39,7 @@ def test_no_gpu_means_loud_failure_not_fallback():
 def test_struct_layouts_match_header():
     from b200reg import native
     assert ctypes.sizeof(native.GicpParams) == 56
+    assert native.default_params().regularization == 3  # PLANE
     assert ctypes.sizeof(native.Result) == 16 * 8 + 16 * 4 + 8 + 8 * 4
     p = native.default_params()
     assert (p.k_correspondences, p.max_iterations, p.lm_max_iterations) == (15, 32, 10)

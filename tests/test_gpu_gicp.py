@@ -407,3 +407,28 @@ def test_lm_corner_cases_match_oracle(ctx, oracle, synth, pair5k):
     g = ctx.icp_alignment([src[:500]], [dst[:1]])[0]
     o = oracle.gicp_align(src[:500], dst[:1])
     assert np.isfinite(g["T"]).all() and g["converged"] == o["converged"]
+
+
+def test_all_regularization_methods(ctx, oracle, synth, pair5k):
+    """setRegularizationMethod: NONE, MIN_EIG, NORMALIZED_MIN_EIG, PLANE, FROBENIUS (nano_gicp_impl.hpp:323-353)."""
+    import b200reg
+    from oracle.oracle import GicpParams
+    src, dst, Texp = pair5k
+    cl, = ctx.create_clouds([dst])
+    for method in (0, 1, 2, 3, 4):
+        ctx.covariances([cl], 15, method)
+        g = ctx.get_covariances(cl)
+        o = oracle.covariances_ex(dst, 15, method)
+        scale = np.abs(o).reshape(len(o), -1).max(1) + 1e-12
+        err = np.abs(g - o).reshape(len(o), -1).max(1) / scale
+        assert np.median(err) < 1e-10 and np.quantile(err, 0.995) < 1e-5, (method, np.median(err), np.quantile(err, 0.995))
+    cl.destroy()
+    # the registration honours the method end to end (MIN_EIG here)
+    prm = b200reg.default_params()
+    prm.regularization = 1
+    g = ctx.icp_alignment([src], [dst], params=prm)[0]
+    assert g["converged"]
+    p3 = ctx.icp_alignment([src], [dst])[0]
+    assert not np.array_equal(g["T"], p3["T"])  # a different weighting gives a (slightly) different optimum
+    rot, tr = synth.se3_error(g["T"], Texp)
+    assert rot < 2e-2 and tr < 0.3  # still lands on the ground truth
