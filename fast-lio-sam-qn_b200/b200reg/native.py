@@ -59,7 +59,8 @@ def default_loop_config():
     return cfg
 
 
-MAXC = 512
+MAXC = 512       # B200REG_CORR_CAPACITY
+ADV_MAXC = 8192  # B200REG_ADV_CORR_CAPACITY
 
 EXPORTS = [
     "b200reg_default_gicp_params", "b200reg_last_error", "b200reg_version", "b200reg_ctx_create",
@@ -257,7 +258,7 @@ class Context:
         sa = (C.c_void_p * cnt)(*[c.h for c in srcs])
         da = (C.c_void_p * cnt)(*[c.h for c in dsts])
         info = (QuatroInfo * cnt)()
-        corr = np.zeros((cnt, MAXC, 2), np.int32) if want_corr else None
+        corr = np.zeros((cnt, MAXC if prm.use_optimized_matching else ADV_MAXC, 2), np.int32) if want_corr else None
         _check(lib().b200reg_quatro_align(self.h, cnt, sa, da, C.byref(prm), info,
                                           None if corr is None else corr.ctypes.data_as(C.c_void_p)))
         out = [i.as_dict() for i in info]

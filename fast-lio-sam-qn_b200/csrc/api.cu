@@ -861,8 +861,9 @@ int b200reg_quatro_align(b200reg_ctx* c, int count, b200reg_cloud* const* src, b
                          const b200reg_quatro_params* prm, b200reg_quatro_info* out, int32_t* corr_out) {
   if (!c || count <= 0 || !src || !dst || !prm || !out) return fail(B200REG_EINVAL, "bad argument");
   if (prm->estimate_scale) return fail(B200REG_EINVAL, "estimate_scale is not supported (the deployment sets it false)");
-  if (!prm->use_optimized_matching) return fail(B200REG_EINVAL, "only optimizedMatching is built");
-  if (prm->max_corres < 1 || prm->max_corres > MAXC - 3) return fail(B200REG_EINVAL, "max_corres must be in 1..509");
+  const bool advanced = !prm->use_optimized_matching;  // Matcher::advancedMatching (matcher.cc:118-356)
+  if (!advanced && (prm->max_corres < 1 || prm->max_corres > MAXC - 3)) return fail(B200REG_EINVAL, "max_corres must be in 1..509");
+  const int corr_stride = advanced ? BIGC : MAXC;  // B200REG_ADV_CORR_CAPACITY / B200REG_CORR_CAPACITY
   CU(cudaSetDevice(c->device));
   cudaStream_t s = c->stream;
   Scratch scratch(c);
@@ -877,6 +878,8 @@ int b200reg_quatro_align(b200reg_ctx* c, int count, b200reg_cloud* const* src, b
     if ((rc = b200reg_clouds_fpfh(c, (int)all.size(), all.data(), prm->fpfh_normal_radius, prm->fpfh_radius))) return rc;
   }
   std::vector<MatchDev> pairs(count);
+  std::vector<BigSolveWs> big_host;
+  big_host.reserve(count);  // addresses stay valid for the async copies below
   int max_ni = 0, max_nj = 0;
   for (int i = 0; i < count; i++) {
     MatchDev& m = pairs[i];
@@ -892,7 +895,27 @@ int b200reg_quatro_align(b200reg_ctx* c, int count, b200reg_cloud* const* src, b
       return r;
     };
     const size_t o_nn = take(nj * 4), o_dis = take(nj * 4), o_fj = take(ni * 4), o_need = take(ni * 4), o_rnn = take(ni * 4);
-    const size_t o_cor = take(2 * nj * 4), o_tk = take(nj * 4), o_cnt = take(8 * 4), o_st = take(8 * 8), o_oc = take(2 * MAXC * 4), o_T = take(16 * 8);
+    // advancedMatching: the cross-checked set has at most nj members; the solver workspace is sized for the next
+    // power of two (>= 1024, <= BIGC)
+    int cap = 1024;
+    while (advanced && cap < (int)nj && cap < BIGC) cap <<= 1;
+    const size_t o_cor = take(2 * nj * 4), o_tk = take(nj * 4), o_cnt = take(8 * 4), o_st = take(8 * 8),
+                 o_oc = take(2 * (size_t)(advanced ? cap : MAXC) * 4), o_T = take(16 * 8);
+    const size_t words = cap / 32;
+    size_t o_big = 0, o_S = 0, o_D = 0, o_adj = 0, o_radj = 0, o_int = 0, o_skey = 0, o_w = 0, o_res = 0, o_hval = 0, o_hidx = 0;
+    if (advanced) {
+      o_big = take(sizeof(BigSolveWs));
+      o_S = take((size_t)cap * 24);
+      o_D = take((size_t)cap * 24);
+      o_adj = take((size_t)cap * words * 4);
+      o_radj = take((size_t)cap * words * 4);
+      o_int = take((size_t)cap * 4 * 9);
+      o_skey = take((size_t)cap * 8);
+      o_w = take((size_t)cap * 8);
+      o_res = take((size_t)cap * 8);
+      o_hval = take((size_t)cap * 16);
+      o_hidx = take((size_t)cap * 8);
+    }
     char* slab = nullptr;
     CU(scratch.alloc((void**)&slab, o));
     m.nn = (int*)(slab + o_nn);
@@ -906,6 +929,27 @@ int b200reg_quatro_align(b200reg_ctx* c, int count, b200reg_cloud* const* src, b
     m.stats = (double*)(slab + o_st);
     m.out_corr = (int*)(slab + o_oc);
     m.T = (double*)(slab + o_T);
+    m.big = nullptr;
+    if (advanced) {
+      BigSolveWs w;
+      w.cap = cap;
+      w.words = (int)words;
+      w.S = (double*)(slab + o_S);
+      w.D = (double*)(slab + o_D);
+      w.adj = (unsigned*)(slab + o_adj);
+      w.radj = (unsigned*)(slab + o_radj);
+      int* ip = (int*)(slab + o_int);
+      w.deg = ip; w.pdeg = ip + cap; w.core = ip + 2 * (size_t)cap; w.alive = ip + 3 * (size_t)cap; w.rank = ip + 4 * (size_t)cap;
+      w.order = ip + 5 * (size_t)cap; w.csize = ip + 6 * (size_t)cap; w.clique = ip + 7 * (size_t)cap; w.list = ip + 8 * (size_t)cap;
+      w.skey = (unsigned long long*)(slab + o_skey);
+      w.w = (double*)(slab + o_w);
+      w.res = (double*)(slab + o_res);
+      w.hval = (double*)(slab + o_hval);
+      w.hidx = (int*)(slab + o_hidx);
+      m.big = (BigSolveWs*)(slab + o_big);
+      big_host.push_back(w);
+      CU(cudaMemcpyAsync(m.big, &big_host.back(), sizeof(BigSolveWs), cudaMemcpyHostToDevice, s));
+    }
     max_ni = std::max(max_ni, (int)ni);
     max_nj = std::max(max_nj, (int)nj);
   }
@@ -915,7 +959,9 @@ int b200reg_quatro_align(b200reg_ctx* c, int count, b200reg_cloud* const* src, b
   QuatroParamsDev q;
   q.normal_r2 = (float)(prm->fpfh_normal_radius * prm->fpfh_normal_radius);
   q.fpfh_r2 = (float)(prm->fpfh_radius * prm->fpfh_radius);
-  q.thr2 = (float)prm->distance_threshold * (float)prm->distance_threshold;
+  // advancedMatching searches without a distance gate: FLT_MAX makes every finite distance qualify
+  q.thr2 = advanced ? 3.402823466e38f : (float)prm->distance_threshold * (float)prm->distance_threshold;
+  q.advanced = advanced ? 1 : 0;
   q.tuple_scale = (float)prm->tuple_scale;
   q.max_corres = prm->max_corres;
   q.noise_bound = prm->noise_bound;
@@ -930,13 +976,22 @@ int b200reg_quatro_align(b200reg_ctx* c, int count, b200reg_cloud* const* src, b
   }
   CU(cudaGetLastError());
   std::vector<int> counters(8 * (size_t)count);
-  std::vector<int> oc(corr_out ? 2 * MAXC * (size_t)count : 0);
   for (int i = 0; i < count; i++) {
     CU(cudaMemcpyAsync(&counters[8 * i], pairs[i].counters, 32, cudaMemcpyDeviceToHost, s));
     CU(cudaMemcpyAsync(out[i].T, pairs[i].T, 128, cudaMemcpyDeviceToHost, s));
-    if (corr_out) CU(cudaMemcpyAsync(&corr_out[2 * MAXC * (size_t)i], pairs[i].out_corr, 2 * MAXC * 4, cudaMemcpyDeviceToHost, s));
+    if (corr_out) {
+      const size_t have = advanced ? (size_t)big_host[i].cap : (size_t)MAXC;  // what this pair's buffer holds
+      CU(cudaMemcpyAsync(&corr_out[2 * (size_t)corr_stride * i], pairs[i].out_corr, 2 * have * 4, cudaMemcpyDeviceToHost, s));
+    }
   }
   CU(cudaStreamSynchronize(s));
+  for (int i = 0; i < count; i++)
+    if (counters[8 * i + 6] > 0) {
+      char msg[160];
+      snprintf(msg, sizeof msg, "advancedMatching kept %d correspondences for pair %d; the solver workspace holds %d", counters[8 * i + 6], i,
+               big_host[i].cap);
+      return fail(B200REG_ESTATE, msg);
+    }
   for (int i = 0; i < count; i++) {
     out[i].valid = counters[8 * i + 3];
     out[i].n_mutual = counters[8 * i + 1];

@@ -137,8 +137,24 @@ struct MatchDev {
   unsigned* tkey;      // [nj] first (trial*4 + slot) at which correspondence r would be added
   int* counters;       // [0] n_need, [1] ncorr, [2] n_out, [3] valid, [4] clique size, [5] gnc iterations
   double* stats;       // [0..2] sum fi, [3..5] sum fj, then floats: mean fi(3) mean fj(3) scale (as float bits in doubles)
-  int* out_corr;       // [2 * (MAXC)] final (src, dst) pairs
+  int* out_corr;       // [2 * corr_cap] final (src, dst) pairs (corr_cap = MAXC, or BigSolveWs::cap for advancedMatching)
   double* T;           // [16] row-major result
+  struct BigSolveWs* big;  // global-memory solver workspace (advancedMatching only; nullptr otherwise)
+};
+
+// Global-memory workspace of the multi-kernel TEASER++ solve used when the correspondence set is not capped at MAXC
+// (Matcher::advancedMatching, matcher.cc:118-356).  cap is a multiple of 1024, words = cap / 32.
+struct BigSolveWs {
+  int cap, words;
+  double* S;                 // [cap * 3] source points of the correspondences
+  double* D;                 // [cap * 3]
+  unsigned* adj;             // [cap * words] TIM consistency graph, bit j of row i
+  unsigned* radj;            // [cap * words] same graph with vertices renamed by their rank in the clique order
+  int *deg, *pdeg, *core, *alive, *rank, *order, *csize, *clique, *list;  // [cap] each
+  unsigned long long* skey;  // [cap]
+  double *w, *res;           // [cap]
+  double* hval;              // [2 * cap]
+  int* hidx;                 // [2 * cap]
 };
 
 struct QuatroParamsDev {
@@ -149,9 +165,11 @@ struct QuatroParamsDev {
   double noise_bound, gnc_factor, cost_thr;
   int max_iter;
   unsigned long long seed;
+  int advanced;        // 1: Matcher::advancedMatching (cross check, 3-edge tuple test, no cap); 0: optimizedMatching
 };
 
 constexpr int MAXC = 512;  // capacity of the final correspondence set (max_corres + 3 <= MAXC)
+constexpr int BIGC = 8192; // capacity of the advancedMatching correspondence set (B200REG_ADV_CORR_CAPACITY)
 
 // ---- ordered-int encoding of floats for atomicMin/atomicMax ------------------------
 __device__ __forceinline__ int f2ord(float f) {

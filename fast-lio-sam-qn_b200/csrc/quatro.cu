@@ -410,8 +410,9 @@ __global__ void __launch_bounds__(256) k_need(const MatchDev* pairs) {
   if (P.first_j[i] != 0x7FFFFFFF) P.need[atomicAdd(&P.counters[0], 1)] = i;  // order irrelevant: results land by index
 }
 
-// ordered compaction over ascending original j: keep (i, j) iff j was the first hit of i AND nn_j(i) == j
-__global__ void __launch_bounds__(1024) k_mutual(const MatchDev* pairs, float thr2) {
+// ordered compaction over ascending original j: keep (i, j) iff j was the first hit of i AND nn_j(i) == j.
+// advanced != 0 (Matcher::advancedMatching, TBB branch, matcher.cc:160-188): no gate, keep (nn(j), j) iff nn_j(nn(j)) == j.
+__global__ void __launch_bounds__(1024) k_mutual(const MatchDev* pairs, float thr2, int advanced) {
   const MatchDev& P = pairs[blockIdx.x];
   __shared__ int wsum[32];
   __shared__ int carry;
@@ -423,7 +424,7 @@ __global__ void __launch_bounds__(1024) k_mutual(const MatchDev* pairs, float th
     int keep = 0, i = -1;
     if (j < nj) {
       i = P.nn[j];
-      keep = (i >= 0 && !(P.dis[j] > thr2) && P.first_j[i] == j && P.rnn[i] == j) ? 1 : 0;
+      keep = (i >= 0 && !(P.dis[j] > thr2) && (advanced || P.first_j[i] == j) && P.rnn[i] == j) ? 1 : 0;
     }
     int incl = keep;
 #pragma unroll
@@ -536,7 +537,7 @@ __global__ void __launch_bounds__(256) k_tuple_trials(const MatchDev* pairs, Qua
     norm_point(P.fj, P.corres[2 * r0 + 1], mxj, myj, mzj, scale, pj0);
     norm_point(P.fj, P.corres[2 * r1 + 1], mxj, myj, mzj, scale, pj1);
     const float li0 = len3(pi0, pi1), lj0 = len3(pj0, pj1);
-    if ((li0 * ts > lj0) || (lj0 > li0 / ts)) continue;
+    if (prm.advanced ? !((li0 * ts < lj0) && (lj0 < li0 / ts)) : ((li0 * ts > lj0) || (lj0 > li0 / ts))) continue;  // matcher.cc:314 / :509
     const int r2 = draw(prm.seed, t, 2, ncorr);
     float pi2[3], pj2[3];
     norm_point(P.fi, P.corres[2 * r2], mxi, myi, mzi, scale, pi2);
@@ -996,6 +997,487 @@ __global__ void __launch_bounds__(SV_THREADS) k_teaser_solve(const MatchDev* pai
   }
 }
 
+// ------------------------------------------------------------------------------------------------
+// Matcher::advancedMatching tail + the TEASER++ solve for correspondence sets beyond MAXC: the same algorithm as
+// k_teaser_solve, restated as a short chain of kernels over a global-memory workspace (BigSolveWs) so that a set of
+// several thousand correspondences (8 MB of adjacency bits) is spread over the whole GPU.
+// ------------------------------------------------------------------------------------------------
+// every member of a passing triplet survives (matcher.cc:314-320); (src, dst) ordering, sort, unique (:338-355).
+// The cross-checked pairs are unique already, so "unique" is a no-op; the sort is a bitonic sort of packed keys.
+__global__ void __launch_bounds__(1024) k_adv_select(const MatchDev* pairs, QuatroParamsDev prm) {
+  extern __shared__ __align__(16) unsigned long long akeys[];  // [BIGC]
+  const MatchDev& P = pairs[blockIdx.x];
+  const int ncorr = P.counters[1];
+  const int cap = P.big->cap;
+  __shared__ int nsel;
+  if (threadIdx.x == 0) nsel = 0;
+  __syncthreads();
+  const bool keepall = prm.tuple_scale == 0.f;  // "use_tuple_test && tuple_scale != 0" (matcher.cc:272)
+  for (int r = threadIdx.x; r < ncorr; r += 1024) {
+    if (!keepall && P.tkey[r] == 0xFFFFFFFFu) continue;
+    const int s = atomicAdd(&nsel, 1);
+    if (s < cap) {
+      const int i = P.corres[2 * r], j = P.corres[2 * r + 1];
+      akeys[s] = ((unsigned long long)(unsigned)(P.swapped ? j : i) << 32) | (unsigned)(P.swapped ? i : j);
+    }
+  }
+  __syncthreads();
+  const int total = nsel;
+  if (total > cap) {  // reported as B200REG_ESTATE by the host; nothing is solved
+    if (threadIdx.x == 0) {
+      P.counters[2] = 0;
+      P.counters[6] = total;
+    }
+    return;
+  }
+  int n2 = 2;
+  while (n2 < total) n2 <<= 1;
+  for (int i = total + threadIdx.x; i < n2; i += 1024) akeys[i] = 0xFFFFFFFFFFFFFFFFull;
+  __syncthreads();
+  for (int k = 2; k <= n2; k <<= 1)
+    for (int j = k >> 1; j > 0; j >>= 1) {
+      for (int i = threadIdx.x; i < n2; i += 1024) {
+        const int l = i ^ j;
+        if (l > i) {
+          const unsigned long long a = akeys[i], b = akeys[l];
+          if ((a > b) == ((i & k) == 0)) {
+            akeys[i] = b;
+            akeys[l] = a;
+          }
+        }
+      }
+      __syncthreads();
+    }
+  for (int i = threadIdx.x; i < total; i += 1024) {
+    P.out_corr[2 * i] = (int)(akeys[i] >> 32);
+    P.out_corr[2 * i + 1] = (int)(akeys[i] & 0xFFFFFFFFull);
+  }
+  if (threadIdx.x == 0) P.counters[2] = total;
+}
+
+__global__ void __launch_bounds__(256) k_big_gather(const MatchDev* pairs) {
+  const MatchDev& P = pairs[blockIdx.y];
+  const BigSolveWs& W = *P.big;
+  const int n = P.counters[2];
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < 16) P.T[i] = (i % 5 == 0) ? 1.0 : 0.0;
+  if (i == 0) {
+    P.counters[3] = 0;
+    P.counters[4] = 0;
+    P.counters[5] = 0;
+  }
+  if (i >= n) return;
+  const CloudDev& src = P.swapped ? P.fj : P.fi;
+  const CloudDev& dst = P.swapped ? P.fi : P.fj;
+  const float4 a = src.pts[src.rank[P.out_corr[2 * i]]], b = dst.pts[dst.rank[P.out_corr[2 * i + 1]]];
+  W.S[3 * i] = a.x; W.S[3 * i + 1] = a.y; W.S[3 * i + 2] = a.z;
+  W.D[3 * i] = b.x; W.D[3 * i + 1] = b.y; W.D[3 * i + 2] = b.z;
+  W.deg[i] = 0;
+}
+
+// one thread per (vertex i, 32-vertex word w) of the TIM consistency graph: no atomics on the bit matrix; the test is
+// symmetric bit for bit ((x - y)^2 == (y - x)^2), so row i and row j agree without communicating
+__global__ void __launch_bounds__(256) k_big_tim(const MatchDev* pairs, QuatroParamsDev prm) {
+  const MatchDev& P = pairs[blockIdx.y];
+  const BigSolveWs& W = *P.big;
+  const int n = P.counters[2];
+  const int wn = (n + 31) >> 5;
+  const double beta = 2.0 * prm.noise_bound;
+  for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < (long long)n * wn; idx += (long long)gridDim.x * blockDim.x) {
+    const int i = (int)(idx / wn), w = (int)(idx % wn);
+    const double sx = W.S[3 * i], sy = W.S[3 * i + 1], sz = W.S[3 * i + 2];
+    const double dx = W.D[3 * i], dy = W.D[3 * i + 1], dz = W.D[3 * i + 2];
+    unsigned bits = 0;
+    const int jend = min(32, n - w * 32);
+    for (int b = 0; b < jend; b++) {
+      const int j = w * 32 + b;
+      if (j == i) continue;
+      double a = 0, c = 0, t;
+      t = W.S[3 * j] - sx; a += t * t;
+      t = W.S[3 * j + 1] - sy; a += t * t;
+      t = W.S[3 * j + 2] - sz; a += t * t;
+      t = W.D[3 * j] - dx; c += t * t;
+      t = W.D[3 * j + 1] - dy; c += t * t;
+      t = W.D[3 * j + 2] - dz; c += t * t;
+      if (fabs(sqrt(a) - sqrt(c)) <= beta) bits |= 1u << b;
+    }
+    W.adj[(size_t)i * W.words + w] = bits;
+    if (bits) atomicAdd(&W.deg[i], __popc(bits));
+  }
+}
+
+__device__ __forceinline__ int block_min_i(int v, int* red) {
+  for (int o = 16; o > 0; o >>= 1) v = min(v, __shfl_xor_sync(0xffffffffu, v, o));
+  __syncthreads();  // red may still be read from the previous call
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v;
+  __syncthreads();
+  int r = red[threadIdx.x & 31];
+  for (int o = 16; o > 0; o >>= 1) r = min(r, __shfl_xor_sync(0xffffffffu, r, o));
+  return r;
+}
+
+// core numbers by level-synchronous peeling (every vertex whose remaining degree is <= the current level leaves in
+// the same round); core numbers do not depend on the peeling order, so this equals the one-at-a-time peel of
+// k_teaser_solve / the oracle.  Then the clique order (core desc, degree desc, index asc).  One block per pair.
+__global__ void __launch_bounds__(1024) k_big_core(const MatchDev* pairs) {
+  const MatchDev& P = pairs[blockIdx.x];
+  const BigSolveWs& W = *P.big;
+  const int n = P.counters[2];
+  if (n == 0) return;
+  const int wn = (n + 31) >> 5;
+  const int tid = threadIdx.x;
+  __shared__ int red[32];
+  __shared__ int nf;
+  for (int v = tid; v < n; v += 1024) {
+    W.pdeg[v] = W.deg[v];
+    W.alive[v] = 1;
+  }
+  __syncthreads();
+  int remaining = n, k = 0;
+  while (remaining > 0) {
+    int mn = 0x7FFFFFFF;
+    for (int v = tid; v < n; v += 1024)
+      if (W.alive[v]) mn = min(mn, W.pdeg[v]);
+    mn = block_min_i(mn, red);
+    k = max(k, mn);
+    if (tid == 0) nf = 0;
+    __syncthreads();
+    for (int v = tid; v < n; v += 1024)
+      if (W.alive[v] && W.pdeg[v] <= k) {
+        W.alive[v] = 0;
+        W.core[v] = k;
+        W.list[atomicAdd(&nf, 1)] = v;
+      }
+    __syncthreads();
+    const int f = nf;
+    for (int idx = tid; idx < f * wn; idx += 1024) {
+      const int fv = W.list[idx / wn], w = idx % wn;
+      unsigned bits = W.adj[(size_t)fv * W.words + w];
+      while (bits) {
+        const int u = w * 32 + __ffs(bits) - 1;
+        bits &= bits - 1;
+        if (W.alive[u]) atomicSub(&W.pdeg[u], 1);
+      }
+    }
+    __syncthreads();
+    remaining -= f;
+  }
+  int n2 = 2;
+  while (n2 < n) n2 <<= 1;
+  for (int i = tid; i < n2; i += 1024)
+    W.skey[i] = i < n ? (((unsigned long long)(BIGC - W.core[i]) << 40) | ((unsigned long long)(BIGC - W.deg[i]) << 20) | (unsigned)i)
+                      : 0xFFFFFFFFFFFFFFFFull;
+  __syncthreads();
+  for (int kk = 2; kk <= n2; kk <<= 1)
+    for (int j = kk >> 1; j > 0; j >>= 1) {
+      for (int i = tid; i < n2; i += 1024) {
+        const int l = i ^ j;
+        if (l > i) {
+          const unsigned long long a = W.skey[i], b = W.skey[l];
+          if ((a > b) == ((i & kk) == 0)) {
+            W.skey[i] = b;
+            W.skey[l] = a;
+          }
+        }
+      }
+      __syncthreads();
+    }
+  for (int r = tid; r < n; r += 1024) {
+    const int v = (int)(W.skey[r] & 0xFFFFF);
+    W.order[r] = v;
+    W.rank[v] = r;
+  }
+}
+
+// adjacency in rank space, one thread per (rank row, word)
+__global__ void __launch_bounds__(256) k_big_radj(const MatchDev* pairs) {
+  const MatchDev& P = pairs[blockIdx.y];
+  const BigSolveWs& W = *P.big;
+  const int n = P.counters[2];
+  const int wn = (n + 31) >> 5;
+  for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < (long long)n * wn; idx += (long long)gridDim.x * blockDim.x) {
+    const int rv = (int)(idx / wn), w = (int)(idx % wn);
+    const unsigned* row = W.adj + (size_t)W.order[rv] * W.words;
+    unsigned bits = 0;
+    const int end = min(32, n - w * 32);
+    for (int b = 0; b < end; b++) {
+      const int u = W.order[w * 32 + b];
+      bits |= ((row[u >> 5] >> (u & 31)) & 1u) << b;
+    }
+    W.radj[(size_t)rv * W.words + w] = bits;
+  }
+}
+
+constexpr int BIG_WPL = BIGC / 32 / 32;  // candidate-set words per lane
+
+// the greedy clique grown from start vertex `r` by one warp: the candidate set lives in registers, word w in lane
+// w % 32; "first candidate in the global order" is a warp-wide minimum over bit positions.  mark != nullptr lists
+// the members (by original correspondence index) as flags.
+__device__ __forceinline__ int warp_greedy_clique(const BigSolveWs& W, int wn, int r, int* mark) {
+  const int lane = threadIdx.x & 31;
+  unsigned Pm[BIG_WPL];
+#pragma unroll
+  for (int s = 0; s < BIG_WPL; s++) {
+    const int w = s * 32 + lane;
+    Pm[s] = w < wn ? W.radj[(size_t)r * W.words + w] : 0u;
+  }
+  if (mark && lane == 0) mark[W.order[r]] = 1;
+  int size = 1;
+  for (;;) {
+    unsigned pos = 0xFFFFFFFFu;
+#pragma unroll
+    for (int s = 0; s < BIG_WPL; s++)
+      if (pos == 0xFFFFFFFFu && Pm[s]) pos = (unsigned)((s * 32 + lane) * 32 + __ffs(Pm[s]) - 1);
+    pos = __reduce_min_sync(0xffffffffu, pos);
+    if (pos == 0xFFFFFFFFu) break;
+    size++;
+    if (mark && lane == 0) mark[W.order[pos]] = 1;
+#pragma unroll
+    for (int s = 0; s < BIG_WPL; s++) {
+      const int w = s * 32 + lane;
+      if (w < wn) Pm[s] &= W.radj[(size_t)pos * W.words + w];
+    }
+  }
+  return size;
+}
+
+__global__ void __launch_bounds__(256) k_big_greedy(const MatchDev* pairs) {
+  const MatchDev& P = pairs[blockIdx.y];
+  const BigSolveWs& W = *P.big;
+  const int n = P.counters[2];
+  const int wn = (n + 31) >> 5;
+  const int nwarps = gridDim.x * (blockDim.x >> 5);
+  for (int r = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); r < n; r += nwarps) {
+    const int size = warp_greedy_clique(W, wn, r, nullptr);
+    if ((threadIdx.x & 31) == 0) W.csize[r] = size;
+  }
+}
+
+__device__ __forceinline__ double block_sum_d(double v, double* red) {
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  __syncthreads();
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v;
+  __syncthreads();
+  double r = red[threadIdx.x & 31];
+  for (int o = 16; o > 0; o >>= 1) r += __shfl_xor_sync(0xffffffffu, r, o);
+  return r;
+}
+__device__ __forceinline__ double block_max_d(double v, double* red) {
+  for (int o = 16; o > 0; o >>= 1) v = fmax(v, __shfl_xor_sync(0xffffffffu, v, o));
+  __syncthreads();
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v;
+  __syncthreads();
+  double r = red[threadIdx.x & 31];
+  for (int o = 16; o > 0; o >>= 1) r = fmax(r, __shfl_xor_sync(0xffffffffu, r, o));
+  return r;
+}
+
+// pick the largest clique (lowest rank on ties), list it, GNC-TLS yaw rotation, TLS translation.  One block per pair.
+__global__ void __launch_bounds__(1024) k_big_finish(const MatchDev* pairs, QuatroParamsDev prm) {
+  const MatchDev& P = pairs[blockIdx.x];
+  const BigSolveWs& W = *P.big;
+  const int n = P.counters[2];
+  if (n == 0) return;
+  const int wn = (n + 31) >> 5;
+  const int tid = threadIdx.x;
+  __shared__ double red[32];
+  __shared__ unsigned long long kred[32];
+  __shared__ int wsum[32];
+  __shared__ int carry, stop;
+  __shared__ double s_mu, s_prev, s_R2[4], s_t[3];
+  constexpr int SWEEP = 2048;
+  __shared__ double cX[SWEEP];
+  __shared__ int cE[SWEEP];
+  {
+    unsigned long long key = 0;
+    for (int r = tid; r < n; r += 1024) key = max(key, ((unsigned long long)W.csize[r] << 32) | (unsigned)(0xFFFFFFFFu - (unsigned)r));
+    for (int o = 16; o > 0; o >>= 1) key = max(key, __shfl_xor_sync(0xffffffffu, key, o));
+    if ((tid & 31) == 0) kred[tid >> 5] = key;
+    __syncthreads();
+    key = kred[tid & 31];
+    for (int o = 16; o > 0; o >>= 1) key = max(key, __shfl_xor_sync(0xffffffffu, key, o));
+    const int br = (int)(0xFFFFFFFFu - (unsigned)(key & 0xFFFFFFFFull));
+    for (int v = tid; v < n; v += 1024) W.alive[v] = 0;  // member flags
+    __syncthreads();
+    if (tid < 32) warp_greedy_clique(W, wn, br, W.alive);
+    if (tid == 0) carry = 0;
+    __syncthreads();
+  }
+  // members in ascending ORIGINAL correspondence index: ordered block compaction
+  for (int base = 0; base < n; base += 1024) {
+    const int v = base + tid;
+    const int keep = (v < n && W.alive[v]) ? 1 : 0;
+    int incl = keep;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int t = __shfl_up_sync(0xffffffffu, incl, o);
+      if ((tid & 31) >= o) incl += t;
+    }
+    if ((tid & 31) == 31) wsum[tid >> 5] = incl;
+    __syncthreads();
+    if (tid < 32) {
+      const int w = wsum[tid];
+      int wi = w;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const int t = __shfl_up_sync(0xffffffffu, wi, o);
+        if (tid >= o) wi += t;
+      }
+      wsum[tid] = wi - w;
+    }
+    __syncthreads();
+    const int pos = carry + wsum[tid >> 5] + incl - keep;
+    if (keep) W.clique[pos] = v;
+    __syncthreads();
+    if (tid == 1023) carry = pos + keep;
+    __syncthreads();
+  }
+  const int m = carry;
+  if (tid == 0) P.counters[4] = m;
+  if (m <= 1) return;  // solution_.valid stays false
+  const int nt = m - 1;
+  double nb2 = prm.noise_bound * prm.noise_bound;
+  if (nb2 < 1e-16) nb2 = 1e-2;
+  for (int k = tid; k < nt; k += 1024) W.w[k] = 1.0;
+  if (tid == 0) {
+    s_mu = 1.0;
+    s_prev = INFINITY;
+    stop = 0;
+    s_R2[0] = 1; s_R2[1] = 0; s_R2[2] = 0; s_R2[3] = 1;
+  }
+  __syncthreads();
+  int iters = 0;
+  for (int it = 0; it < prm.max_iter; it++) {
+    iters = it + 1;
+    double h0 = 0, h1 = 0, h2 = 0, h3 = 0;
+    for (int k = tid; k < nt; k += 1024) {
+      const int c0 = W.clique[k], c1 = W.clique[k + 1];
+      const double ax = W.S[3 * c1] - W.S[3 * c0], ay = W.S[3 * c1 + 1] - W.S[3 * c0 + 1];
+      const double bx = W.D[3 * c1] - W.D[3 * c0], by = W.D[3 * c1 + 1] - W.D[3 * c0 + 1];
+      const double w = W.w[k];
+      h0 += ax * w * bx; h1 += ax * w * by; h2 += ay * w * bx; h3 += ay * w * by;
+    }
+    h0 = block_sum_d(h0, red); h1 = block_sum_d(h1, red); h2 = block_sum_d(h2, red); h3 = block_sum_d(h3, red);
+    const double th = atan2(h1 - h2, h0 + h3);
+    const double cs = cos(th), sn = sin(th);
+    double mx = 0;
+    for (int k = tid; k < nt; k += 1024) {
+      const int c0 = W.clique[k], c1 = W.clique[k + 1];
+      const double ax = W.S[3 * c1] - W.S[3 * c0], ay = W.S[3 * c1 + 1] - W.S[3 * c0 + 1], az = W.S[3 * c1 + 2] - W.S[3 * c0 + 2];
+      const double bx = W.D[3 * c1] - W.D[3 * c0], by = W.D[3 * c1 + 1] - W.D[3 * c0 + 1], bz = W.D[3 * c1 + 2] - W.D[3 * c0 + 2];
+      const double rx = bx - (cs * ax - sn * ay), ry = by - (sn * ax + cs * ay), rz = bz - az;
+      const double r = rx * rx + ry * ry + rz * rz;
+      W.res[k] = r;
+      mx = fmax(mx, r);
+    }
+    mx = block_max_d(mx, red);
+    if (tid == 0) {
+      s_R2[0] = cs; s_R2[1] = -sn; s_R2[2] = sn; s_R2[3] = cs;
+      if (it == 0) {
+        s_mu = 1.0 / (2.0 * mx / nb2 - 1.0);
+        if (s_mu <= 0) stop = 1;
+      }
+    }
+    __syncthreads();
+    if (stop) break;
+    const double mu = s_mu;
+    const double th1 = (mu + 1) / mu * nb2, th2 = mu / (mu + 1) * nb2;
+    double cost = 0;
+    for (int k = tid; k < nt; k += 1024) {
+      const double r = W.res[k];
+      cost += W.w[k] * r;
+      W.w[k] = r >= th1 ? 0.0 : (r <= th2 ? 1.0 : sqrt(nb2 * mu * (mu + 1) / r) - mu);
+    }
+    cost = block_sum_d(cost, red);
+    if (tid == 0) {
+      const double diff = fabs(cost - s_prev);
+      s_mu = mu * prm.gnc_factor;
+      s_prev = cost;
+      if (diff < prm.cost_thr) stop = 1;
+    }
+    __syncthreads();
+    if (stop) break;
+  }
+  __syncthreads();
+  const double range = prm.noise_bound;
+  int n2 = 2;
+  while (n2 < 2 * m) n2 <<= 1;
+  for (int d = 0; d < 3; d++) {
+    for (int k = tid; k < n2; k += 1024) {
+      W.hval[k] = INFINITY;
+      W.hidx[k] = 0;
+    }
+    __syncthreads();
+    for (int k = tid; k < m; k += 1024) {
+      const int c = W.clique[k];
+      const double rs = d == 0 ? s_R2[0] * W.S[3 * c] + s_R2[1] * W.S[3 * c + 1] : (d == 1 ? s_R2[2] * W.S[3 * c] + s_R2[3] * W.S[3 * c + 1] : W.S[3 * c + 2]);
+      const double x = W.D[3 * c + d] - rs;
+      W.res[k] = x;
+      W.hval[2 * k] = x - range; W.hidx[2 * k] = k + 1;
+      W.hval[2 * k + 1] = x + range; W.hidx[2 * k + 1] = -k - 1;
+    }
+    __syncthreads();
+    for (int k = 2; k <= n2; k <<= 1)
+      for (int j = k >> 1; j > 0; j >>= 1) {
+        for (int i = tid; i < n2; i += 1024) {
+          const int l = i ^ j;
+          if (l > i) {
+            const double a = W.hval[i], b = W.hval[l];
+            const int ia = W.hidx[i], ib = W.hidx[l];
+            const int sa = ia > 0 ? 2 * (ia - 1) : 2 * (-ia - 1) + 1, sb = ib > 0 ? 2 * (ib - 1) : 2 * (-ib - 1) + 1;
+            const bool gt = a > b || (a == b && (ia == 0 ? 1 << 30 : sa) > (ib == 0 ? 1 << 30 : sb));
+            if (gt == ((i & k) == 0)) {
+              W.hval[i] = b; W.hval[l] = a;
+              W.hidx[i] = ib; W.hidx[l] = ia;
+            }
+          }
+        }
+        __syncthreads();
+      }
+    // serial consensus sweep by one thread, fed from shared memory in chunks
+    const double w = 1.0 / (range * range);
+    double ris = range * m, dxw = 0, dwc = 0, sxi = 0, sxq = 0, best_cost = INFINITY, best = 0;
+    int card = 0;
+    for (int base = 0; base < 2 * m; base += SWEEP) {
+      const int cnt = min(SWEEP, 2 * m - base);
+      for (int i = tid; i < cnt; i += 1024) {
+        const int h = W.hidx[base + i];
+        cE[i] = h > 0 ? 1 : -1;
+        cX[i] = W.res[abs(h) - 1];
+      }
+      __syncthreads();
+      if (tid == 0)
+        for (int i = 0; i < cnt; i++) {
+          const int eps = cE[i];
+          const double X = cX[i];
+          card += eps;
+          dwc += eps * w;
+          dxw += eps * w * X;
+          ris -= eps * range;
+          sxi += eps * X;
+          sxq += eps * X * X;
+          const double xh = dxw / dwc;
+          const double cost = (card * xh * xh + sxq - 2 * sxi * xh) + ris;
+          if (cost < best_cost) {
+            best_cost = cost;
+            best = xh;
+          }
+        }
+      __syncthreads();
+    }
+    if (tid == 0) s_t[d] = best;
+    __syncthreads();
+  }
+  if (tid == 0) {
+    P.T[0] = s_R2[0]; P.T[1] = s_R2[1]; P.T[2] = 0; P.T[3] = s_t[0];
+    P.T[4] = s_R2[2]; P.T[5] = s_R2[3]; P.T[6] = 0; P.T[7] = s_t[1];
+    P.T[8] = 0; P.T[9] = 0; P.T[10] = 1; P.T[11] = s_t[2];
+    P.T[12] = 0; P.T[13] = 0; P.T[14] = 0; P.T[15] = 1;
+    P.counters[3] = 1;
+    P.counters[5] = iters;
+  }
+}
+
 // coarse_aligned_ = transformPcd(src, T_quatro): double math, cast to float (utilities.hpp:164-175), ORIGINAL order,
 // emitted as (x, y, z, 1) records so that it can be fed straight back into the index build
 __global__ void __launch_bounds__(256) k_transform_raw(const CloudDev* clouds, const double* T16s, float4* const* outs) {
@@ -1025,11 +1507,13 @@ int launch_fpfh(const CloudDev* d_clouds, int count, int max_n, float normal_r2,
 }
 
 size_t solve_smem_bytes() { return sizeof(SolveSmem); }
+int launch_big_solve(const MatchDev* d_pairs, int count, const QuatroParamsDev& prm, cudaStream_t s);
 
 int launch_quatro_match_solve(const MatchDev* d_pairs, int count, int max_ni, int max_nj, const QuatroParamsDev& prm, cudaStream_t s) {
   static bool attr_set = false;
   if (!attr_set) {
     cudaFuncSetAttribute(k_teaser_solve, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SolveSmem));
+    cudaFuncSetAttribute(k_adv_select, cudaFuncAttributeMaxDynamicSharedMemorySize, BIGC * 8);
     attr_set = true;
   }
   int l = 0;
@@ -1040,10 +1524,27 @@ int launch_quatro_match_solve(const MatchDev* d_pairs, int count, int max_ni, in
   k_first_hit<<<dim3((max_nj + 255) / 256, count), 256, 0, s>>>(d_pairs, prm.thr2); l++;
   k_need<<<dim3((max_ni + 255) / 256, count), 256, 0, s>>>(d_pairs); l++;
   k_feat_nn<<<dim3((max_ni + NN_THREADS - 1) / NN_THREADS, count), NN_THREADS, 0, s>>>(d_pairs, 1, prm.thr2); l++;
-  k_mutual<<<count, 1024, 0, s>>>(d_pairs, prm.thr2); l++;
+  k_mutual<<<count, 1024, 0, s>>>(d_pairs, prm.thr2, prm.advanced); l++;
   k_tuple_trials<<<dim3(128, count), 256, 0, s>>>(d_pairs, prm); l++;
-  k_tuple_select<<<count, 1024, 0, s>>>(d_pairs, prm); l++;
-  k_teaser_solve<<<count, SV_THREADS, sizeof(SolveSmem), s>>>(d_pairs, prm); l++;
+  if (!prm.advanced) {
+    k_tuple_select<<<count, 1024, 0, s>>>(d_pairs, prm); l++;
+    k_teaser_solve<<<count, SV_THREADS, sizeof(SolveSmem), s>>>(d_pairs, prm); l++;
+    return l;
+  }
+  k_adv_select<<<count, 1024, BIGC * 8, s>>>(d_pairs, prm); l++;
+  return l + launch_big_solve(d_pairs, count, prm, s);
+}
+
+// TEASER++ solve over the global-memory workspace (correspondences already in out_corr / counters[2])
+int launch_big_solve(const MatchDev* d_pairs, int count, const QuatroParamsDev& prm, cudaStream_t s) {
+  int l = 0;
+  const int wide = 592 / count > 0 ? 592 / count : 1;  // ~4 CTAs per SM over the batch
+  k_big_gather<<<dim3(BIGC / 256, count), 256, 0, s>>>(d_pairs); l++;
+  k_big_tim<<<dim3(wide, count), 256, 0, s>>>(d_pairs, prm); l++;
+  k_big_core<<<count, 1024, 0, s>>>(d_pairs); l++;
+  k_big_radj<<<dim3(wide, count), 256, 0, s>>>(d_pairs); l++;
+  k_big_greedy<<<dim3(wide, count), 256, 0, s>>>(d_pairs); l++;
+  k_big_finish<<<count, 1024, 0, s>>>(d_pairs, prm); l++;
   return l;
 }
 

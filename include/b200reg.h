@@ -88,7 +88,7 @@ typedef struct b200reg_quatro_params {
   double tuple_scale;          /* 0.95 (quatro_module.cc:61)                                          */
   uint64_t seed;               /* replaces srand(time(NULL)) (matcher.cc:465) by a counter-based RNG  */
   int32_t estimate_scale;      /* must be 0 (QN/config: estimating_scale false)                       */
-  int32_t use_optimized_matching; /* must be 1 (config.yaml:32); advancedMatching is not built        */
+  int32_t use_optimized_matching; /* 1 (config.yaml:32): optimizedMatching; 0: advancedMatching       */
 } b200reg_quatro_params;
 
 /* Telemetry of one quatro<T>::align call. */
@@ -158,8 +158,13 @@ int b200reg_icp_alignment(b200reg_ctx* ctx, int count, const float* const* src_x
 int b200reg_clouds_fpfh(b200reg_ctx* ctx, int count, b200reg_cloud* const* clouds, double normal_radius,
                         double fpfh_radius);
 /* quatro<PointType>::align (third_party/Quatro/src/quatro_module.cc:48-79) for `count` pairs: FPFH on demand,
- * optimizedMatching (matcher.cc:358-561), TEASER++ QUATRO solve.  corr_out (optional): count x 2*512 ints,
- * the (src, dst) ORIGINAL indices of the final correspondences of each pair.                             */
+ * optimizedMatching (matcher.cc:358-561) or, with use_optimized_matching = 0, advancedMatching (matcher.cc:118-356:
+ * ungated forward / reverse 1-NN, cross check, three-edge tuple test, sort + unique), then the TEASER++ QUATRO solve.
+ * corr_out (optional): count x 2*CAP ints, the (src, dst) ORIGINAL indices of the final correspondences of each
+ * pair, CAP = B200REG_CORR_CAPACITY (optimized) or B200REG_ADV_CORR_CAPACITY (advanced).  An advancedMatching set
+ * larger than B200REG_ADV_CORR_CAPACITY fails the call with B200REG_ESTATE (nothing is truncated silently).     */
+#define B200REG_CORR_CAPACITY 512
+#define B200REG_ADV_CORR_CAPACITY 8192
 int b200reg_quatro_align(b200reg_ctx* ctx, int count, b200reg_cloud* const* src, b200reg_cloud* const* dst,
                          const b200reg_quatro_params* params, b200reg_quatro_info* out, int32_t* corr_out);
 /* LoopClosure::coarseToFineAlignment (fast_lio_sam_qn/src/loop_closure.cpp:138-159) for `count` pairs from raw

@@ -193,7 +193,7 @@ class QuatroParams(C.Structure):
     _fields_ = [("fpfh_normal_radius", C.c_double), ("fpfh_radius", C.c_double), ("noise_bound", C.c_double),
                 ("rot_gnc_factor", C.c_double), ("rot_cost_thr", C.c_double), ("rot_max_iter", C.c_int),
                 ("max_corres", C.c_int), ("distance_threshold", C.c_double), ("tuple_scale", C.c_double),
-                ("seed", C.c_uint64)]
+                ("seed", C.c_uint64), ("use_optimized_matching", C.c_int), ("pad_", C.c_int)]
 
     @staticmethod
     def default():
@@ -237,6 +237,20 @@ def match(src, dst, fsrc, fdst, params=None):
     k = lib().orc_match(_p(src, C.c_float), len(src), src.shape[1], _p(dst, C.c_float), len(dst), dst.shape[1],
                         _p(fs, C.c_float), _p(fd, C.c_float), C.byref(p), _p(corr, C.c_int), C.byref(nm), _p(mut, C.c_int))
     return corr[:k].copy(), mut[:nm.value].copy()
+
+
+def match_advanced(src, dst, fsrc, fdst, params=None, crosscheck=True, tuple_test=True):
+    """Matcher::advancedMatching (matcher.cc:118-356) -> (k, 2) sorted unique (src, dst) pairs."""
+    src, dst = _f32(src), _f32(dst)
+    fs = np.ascontiguousarray(fsrc, np.float32)
+    fd = np.ascontiguousarray(fdst, np.float32)
+    p = params or QuatroParams.default()
+    cap = 2 * (len(src) + len(dst))
+    corr = np.empty((cap, 2), np.int32)
+    k = lib().orc_match_advanced(_p(src, C.c_float), len(src), src.shape[1], _p(dst, C.c_float), len(dst), dst.shape[1],
+                                 _p(fs, C.c_float), _p(fd, C.c_float), C.byref(p), int(crosscheck), int(tuple_test),
+                                 _p(corr, C.c_int), cap)
+    return corr[:min(k, cap)].copy()
 
 
 def quatro_solve(src, dst, corr, params=None):

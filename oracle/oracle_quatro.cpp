@@ -427,6 +427,116 @@ static std::vector<Corr> optimized_matching(const float* src, int N, int sstride
   return out;
 }
 
+// Matcher::advancedMatching (matcher.cc:118-356): forward 1-NN of every fj feature in fi (no distance gate), reverse
+// 1-NN for every i that was hit, cross check (keep (i, j) iff j = nn_j(i) and nn_i(j) = i; the TBB branch :160-188
+// lists them by ascending j, which fixes the index space of the random triplets), tuple test with ALL three edge
+// ratios on 100*ncorr random triplets (every member of a passing triplet is kept, no cap), (src, dst) ordering,
+// sort + unique.  use_crosscheck = false exists only in the non-TBB branch (:215-218).
+static std::vector<Corr> advanced_matching(const float* src, int N, int sstride, const float* dst, int M, int dstride, const float* fsrc,
+                                           const float* fdst, bool use_crosscheck, bool use_tuple_test, float tuple_scale,
+                                           uint64_t seed) {
+  const bool swapped = M > N;
+  const float* P[2] = {src, dst};
+  const int np[2] = {N, M}, st[2] = {sstride, dstride};
+  const float* F[2] = {fsrc, fdst};
+  const int fi = swapped ? 1 : 0, fj = swapped ? 0 : 1;
+  const int nPti = np[fi], nPtj = np[fj];
+  // normalizePoints, as in optimized_matching
+  std::vector<float> pc[2];
+  float scale = 0.f;
+  for (int c = 0; c < 2; c++) {
+    pc[c].resize((size_t)np[c] * 3);
+    float mean[3] = {0.f, 0.f, 0.f};
+    for (int i = 0; i < np[c]; i++)
+      for (int d = 0; d < 3; d++) mean[d] = mean[d] + P[c][(size_t)i * st[c] + d];
+    for (int d = 0; d < 3; d++) mean[d] = mean[d] / np[c];
+    float mx = 0.f;
+    for (int i = 0; i < np[c]; i++) {
+      float v[3];
+      for (int d = 0; d < 3; d++) v[d] = pc[c][(size_t)i * 3 + d] = P[c][(size_t)i * st[c] + d] - mean[d];
+      float nrm = std::sqrt((v[0] * v[0] + v[1] * v[1]) + v[2] * v[2]);
+      if (nrm > mx) mx = nrm;
+    }
+    if (mx > scale) scale = mx;
+  }
+  if (scale != 1.0f)
+    for (int c = 0; c < 2; c++)
+      for (auto& v : pc[c]) v /= scale;
+  std::vector<unsigned char> ok[2];
+  for (int c = 0; c < 2; c++) {
+    ok[c].assign(np[c], 0);
+    for (int i = 0; i < np[c]; i++)
+      for (int k = 0; k < 33; k++)
+        if (F[c][(size_t)i * 33 + k] != 0.f) {
+          ok[c][i] = 1;
+          break;
+        }
+  }
+  std::vector<int> nn(nPtj);
+  std::vector<float> dis(nPtj);
+  feature_nn(F[fj], nPtj, F[fi], nPti, ok[fi].data(), nn.data(), dis.data());
+  std::vector<int> need;
+  std::vector<unsigned char> hit(nPti, 0);
+  for (int j = 0; j < nPtj; j++) {
+    if (!ok[fj][j] || nn[j] < 0) continue;
+    if (!hit[nn[j]]) {
+      hit[nn[j]] = 1;
+      need.push_back(nn[j]);
+    }
+  }
+  std::vector<float> qf((size_t)need.size() * 33);
+  for (size_t k = 0; k < need.size(); k++) std::memcpy(&qf[k * 33], &F[fi][(size_t)need[k] * 33], 33 * sizeof(float));
+  std::vector<int> rnn(need.size());
+  std::vector<float> rd(need.size());
+  feature_nn(qf.data(), (int)need.size(), F[fj], nPtj, ok[fj].data(), rnn.data(), rd.data());
+  std::vector<int> i_to_j(nPti, -1);
+  for (size_t k = 0; k < need.size(); k++) i_to_j[need[k]] = rnn[k];
+  std::vector<std::pair<int, int>> corres;  // (i, j)
+  if (use_crosscheck) {
+    for (int j = 0; j < nPtj; j++)  // ascending j (matcher.cc:181-186)
+      if (ok[fj][j] && nn[j] >= 0 && i_to_j[nn[j]] == j) corres.emplace_back(nn[j], j);
+  } else {  // corres_ij followed by corres_ji (matcher.cc:215-218)
+    for (int i = 0; i < nPti; i++)
+      if (i_to_j[i] != -1) corres.emplace_back(i, i_to_j[i]);
+    for (int j = 0; j < nPtj; j++)
+      if (ok[fj][j] && nn[j] >= 0) corres.emplace_back(nn[j], j);
+  }
+  const int ncorr = (int)corres.size();
+  std::vector<std::pair<int, int>> kept;
+  if (use_tuple_test && tuple_scale != 0.f && ncorr > 0) {
+    std::vector<unsigned char> inc(ncorr, 0);
+    auto len = [&](int c, int a, int b) {
+      const float* pa = &pc[c][(size_t)a * 3];
+      const float* pb = &pc[c][(size_t)b * 3];
+      const float d0 = pa[0] - pb[0], d1 = pa[1] - pb[1], d2 = pa[2] - pb[2];
+      return std::sqrt((d0 * d0 + d1 * d1) + d2 * d2);
+    };
+    const long trials = (long)ncorr * 100;
+    for (long t = 0; t < trials; t++) {
+      const int r0 = draw(seed, t, 0, ncorr), r1 = draw(seed, t, 1, ncorr), r2 = draw(seed, t, 2, ncorr);
+      const float li0 = len(fi, corres[r0].first, corres[r1].first), li1 = len(fi, corres[r1].first, corres[r2].first),
+                  li2 = len(fi, corres[r2].first, corres[r0].first);
+      const float lj0 = len(fj, corres[r0].second, corres[r1].second), lj1 = len(fj, corres[r1].second, corres[r2].second),
+                  lj2 = len(fj, corres[r2].second, corres[r0].second);
+      if ((li0 * tuple_scale < lj0) && (lj0 < li0 / tuple_scale) && (li1 * tuple_scale < lj1) && (lj1 < li1 / tuple_scale) &&
+          (li2 * tuple_scale < lj2) && (lj2 < li2 / tuple_scale)) {
+        inc[r0] = inc[r1] = inc[r2] = 1;
+      }
+    }
+    for (int r = 0; r < ncorr; r++)
+      if (inc[r]) kept.push_back(corres[r]);
+  } else {
+    kept = corres;
+  }
+  std::vector<std::pair<int, int>> outp;
+  for (auto& c : kept) outp.emplace_back(swapped ? c.second : c.first, swapped ? c.first : c.second);
+  std::sort(outp.begin(), outp.end());
+  outp.erase(std::unique(outp.begin(), outp.end()), outp.end());
+  std::vector<Corr> out;
+  for (auto& c : outp) out.push_back({c.first, c.second});
+  return out;
+}
+
 // ---- TEASER++ solve in QUATRO / PMC_HEU mode ---------------------------------
 struct SolveOut {
   double R[9], t[3];
@@ -640,6 +750,8 @@ struct orc_quatro_params {
   double distance_threshold;  // feature-space gate (35 in the deployment; class default 30)
   double tuple_scale;         // 0.95 (quatro_module.cc:61)
   uint64_t seed;              // replaces srand(time(NULL))
+  int use_optimized_matching; // config.yaml:32 (true); 0 = Matcher::advancedMatching
+  int pad_;
 };
 
 void orc_quatro_default_params(orc_quatro_params* p) {
@@ -653,6 +765,8 @@ void orc_quatro_default_params(orc_quatro_params* p) {
   p->distance_threshold = 35.0;
   p->tuple_scale = 0.95;
   p->seed = 1;
+  p->use_optimized_matching = 1;
+  p->pad_ = 0;
 }
 
 // normals (n x 3) and FPFH (n x 33) of one cloud
@@ -697,6 +811,19 @@ int orc_match(const float* src, int N, int sstride, const float* dst, int M, int
   return (int)c.size();
 }
 
+// advancedMatching from GIVEN descriptors; corr_out must hold 2 * min(N, M) * 2 ints in the worst case (no cross check)
+int orc_match_advanced(const float* src, int N, int sstride, const float* dst, int M, int dstride, const float* fsrc, const float* fdst,
+                       const orc_quatro_params* p, int use_crosscheck, int use_tuple_test, int* corr_out, int cap) {
+  std::vector<Corr> c = advanced_matching(src, N, sstride, dst, M, dstride, fsrc, fdst, use_crosscheck != 0, use_tuple_test != 0,
+                                          (float)p->tuple_scale, p->seed);
+  const int n = std::min((int)c.size(), cap);
+  for (int i = 0; i < n; i++) {
+    corr_out[2 * i] = c[i].s;
+    corr_out[2 * i + 1] = c[i].d;
+  }
+  return (int)c.size();
+}
+
 // TEASER++ QUATRO solve from GIVEN correspondences.  T16 row-major.  Returns valid.
 int orc_quatro_solve(const float* src, int sstride, const float* dst, int dstride, const int* corr, int ncorr,
                      const orc_quatro_params* p, double* T16, int* clique_out, int* clique_size, int* gnc_iters) {
@@ -724,8 +851,10 @@ int orc_quatro_align(const float* src, int N, int sstride, const float* dst, int
   orc_fpfh(src, N, sstride, p->fpfh_normal_radius, p->fpfh_radius, nullptr, nullptr, fs.data());
   orc_fpfh(dst, M, dstride, p->fpfh_normal_radius, p->fpfh_radius, nullptr, nullptr, fd.data());
   const double t1 = now();
-  std::vector<int> corr(2 * (size_t)(p->max_corres + 8));
-  const int nc = orc_match(src, N, sstride, dst, M, dstride, fs.data(), fd.data(), p, corr.data(), nullptr, nullptr);
+  std::vector<int> corr(2 * (size_t)(p->use_optimized_matching ? p->max_corres + 8 : std::min(N, M)));
+  const int nc = p->use_optimized_matching
+                     ? orc_match(src, N, sstride, dst, M, dstride, fs.data(), fd.data(), p, corr.data(), nullptr, nullptr)
+                     : orc_match_advanced(src, N, sstride, dst, M, dstride, fs.data(), fd.data(), p, 1, 1, corr.data(), std::min(N, M));
   const double t2 = now();
   for (int i = 0; i < 16; i++) T16[i] = (i % 5 == 0) ? 1.0 : 0.0;
   int valid = 0;

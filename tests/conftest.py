@@ -26,6 +26,12 @@ def synth():
 
 
 @pytest.fixture(scope="session")
+def native():
+    from b200reg import native as n
+    return n
+
+
+@pytest.fixture(scope="session")
 def ctx():
     import b200reg
     c = b200reg.Context(0)

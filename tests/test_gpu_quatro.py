@@ -86,6 +86,57 @@ def test_solver_equals_oracle_on_same_correspondences(ctx, oracle, synth, qpair)
     assert rot < 0.06 and tr < 3.5  # coarse stage only: GICP absorbs the rest
 
 
+def _adv_params(native):
+    prm = native.default_quatro_params()
+    prm.use_optimized_matching = 0
+    return prm
+
+
+@pytest.mark.parametrize("case", ["small", "small_swapped", "beyond_512", "thousands"])
+def test_advanced_matching_and_big_solver_equal_oracle(ctx, oracle, synth, native, qpair, case):
+    """Matcher::advancedMatching (matcher.cc:118-356) + the global-memory TEASER++ solve: the final correspondence
+    list is bit-identical to the oracle's on the same descriptors (below and above the 512-entry shared-memory
+    solver's capacity), clique size / GNC iterations equal, T to 1e-9."""
+    if case == "small":
+        src, dst, Texp = qpair
+    elif case == "small_swapped":
+        dst, src, Texp = qpair  # first cloud smaller: fi/fj swap inside the matcher (matcher.cc:125-130)
+        Texp = np.linalg.inv(Texp)
+    elif case == "beyond_512":
+        src, dst, Texp = synth.make_pair(2002, 100000, 100000, mode="quatro", voxel=0.2)
+    else:
+        src, dst, Texp = synth.make_pair(2003, 100000, 100000, mode="quatro", voxel=0.1)
+    info, fs, fd = _gpu_stage(ctx, src, dst, _adv_params(native))
+    corr = oracle.match_advanced(src, dst, fs, fd)
+    assert info["n_corr"] == len(corr)
+    assert np.array_equal(info["corr"], corr)
+    if case == "beyond_512":
+        assert len(corr) > 512
+    if case == "thousands":
+        assert len(corr) > 1500
+    assert np.all(np.diff(corr[:, 0].astype(np.int64) * (1 << 32) + corr[:, 1]) > 0), "sorted, unique (matcher.cc:353-355)"
+    o = oracle.quatro_solve(src, dst, corr)
+    assert info["valid"] == o["valid"]
+    assert info["clique_size"] == len(o["clique"])
+    assert info["gnc_iterations"] == o["gnc_iters"]
+    assert np.abs(info["T"] - o["T"]).max() < 1e-9
+    rot, tr = synth.se3_error(info["T"], Texp)
+    assert rot < 0.06 and tr < 3.5
+
+
+def test_advanced_matching_batch_and_loop_closure(ctx, synth, native):
+    """advancedMatching through the batched entry points: batch == single, and coarse-to-fine lands on the truth."""
+    pairs = [synth.make_pair(2010 + i, 30000, 30000, mode="quatro", voxel=0.3) for i in range(3)]
+    prm = _adv_params(native)
+    res, qi = ctx.loop_closure([p[0] for p in pairs], [p[1] for p in pairs], qparams=prm)
+    for i, (s, d, T) in enumerate(pairs):
+        r1, q1 = ctx.loop_closure([s], [d], qparams=prm)
+        assert np.array_equal(res[i]["T"], r1[0]["T"]) and qi[i]["n_corr"] == q1[0]["n_corr"]
+        assert qi[i]["valid"] and res[i]["converged"]
+        rot, tr = synth.se3_error(res[i]["T"], T)
+        assert rot < 5e-3 and tr < 5e-2, (i, rot, tr)
+
+
 def test_coarse_to_fine_matches_oracle(ctx, oracle, synth):
     """LoopClosure::coarseToFineAlignment.  Two statements:
     (a) fine stage on the SAME coarse transform agrees with the oracle to the parity bar (1e-4 rad / 1e-3 m);
