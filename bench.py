@@ -48,6 +48,8 @@ def parse():
     ap.add_argument("--workload", default="gicp", choices=["gicp", "quatro", "sequence"],
                     help="gicp = configs[1] (the headline); quatro = configs[2] Quatro+Nano-GICP full loop closure; "
                          "sequence = configs[4] loopTimerFunc over a KITTI-05-shaped keyframe sequence held on the device")
+    ap.add_argument("--matching", default="optimized", choices=["optimized", "advanced"],
+                    help="quatro workload: Matcher::optimizedMatching (config.yaml:32) or advancedMatching (matcher.cc:118)")
     ap.add_argument("--keyframes", type=int, default=600, help="sequence workload: keyframes generated (KITTI 05: 2761)")
     ap.add_argument("--cpu-sample-pairs", type=int, default=6)
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -97,12 +99,22 @@ def calibrate_threads(orc, fn, pair):
     return best, ncpu
 
 
-def run_cpu(pairs, budget_s=20.0, max_pairs=6, workload="gicp"):
+def oracle_fn(orc, workload, matching="optimized"):
+    if workload == "gicp":
+        return orc.gicp_align
+    if matching == "optimized":
+        return orc.coarse_to_fine
+    qp = orc.QuatroParams.default()
+    qp.use_optimized_matching = 0
+    return lambda s, d: orc.coarse_to_fine(s, d, qparams=qp)
+
+
+def run_cpu(pairs, budget_s=20.0, max_pairs=6, workload="gicp", matching="optimized"):
     """Time the CPU oracle (kNN through the reference's nanoflann when oracle/_ref exists)."""
     from oracle import oracle as orc
     orc.lib()
     used_ref = orc.use_ref_nanoflann(True) == 0
-    fn = orc.gicp_align if workload == "gicp" else orc.coarse_to_fine
+    fn = oracle_fn(orc, workload, matching)
     threads, ncpu = calibrate_threads(orc, fn, pairs[0])
     times = []
     t_start = time.perf_counter()
@@ -198,7 +210,7 @@ def main_reference(args):
     from oracle import oracle as orc
     orc.lib()
     used_ref = orc.use_ref_nanoflann(True) == 0
-    fn = orc.gicp_align if args.workload == "gicp" else orc.coarse_to_fine
+    fn = oracle_fn(orc, args.workload, args.matching)
     threads, ncpu = calibrate_threads(orc, fn, pairs[0])
     for _ in range(max(args.warmup, 1)):
         fn(pairs[0][0], pairs[0][1])
@@ -227,7 +239,7 @@ def workload_name(args):
         return ("configs[1]: Nano-GICP %dk-pt KITTI-shaped scan pair (LoopClosure::icpAlignment: 2 index builds + "
                 "2 kNN-15 covariance passes + LM align + fitness)" % (args.points // 1000))
     return ("configs[2]: Quatro+Nano-GICP full loop closure on %dk-pt scans voxelised at 0.3 m (LoopClosure::"
-            "coarseToFineAlignment: FPFH -> optimizedMatching -> QUATRO solve -> transform -> GICP refine)" % (args.points // 1000))
+            "coarseToFineAlignment: FPFH -> %sMatching -> QUATRO solve -> transform -> GICP refine)" % (args.points // 1000, args.matching))
 
 
 def main_sequence(args):
@@ -399,6 +411,8 @@ def main():
     stream = torch.cuda.Stream()
     ctx.set_stream(stream.cuda_stream)
     prm = b200reg.default_params()
+    qprm = native.default_quatro_params()
+    qprm.use_optimized_matching = 1 if args.matching == "optimized" else 0
     res_bytes = ctypes.sizeof(native.Result)
 
     # host (pinned) and device copies of the raw x,y,z,intensity records (16 B stride)
@@ -423,7 +437,7 @@ def main():
                                          on_device, prm)
         else:
             res, _ = ctx.loop_closure_ptrs([t.data_ptr() for t in srcs], ns_s, [t.data_ptr() for t in dsts], ns_d, stride,
-                                           on_device, None, prm)
+                                           on_device, qprm, prm)
         if world > 1:  # the ONE collective of the path: all-gather of the 4x4 transforms
             rec = np.frombuffer(res, dtype=np.uint8).reshape(B, res_bytes)[:, :128]  # Result.T = first 16 doubles
             stage_h.numpy()[:] = np.ascontiguousarray(rec).view(np.float64)
@@ -576,7 +590,7 @@ def main():
                          "mean_linearize_passes": float(np.mean([r.n_linearize for r in res]))},
         }
         if world == 1 and not args.no_cpu_baseline:
-            out["cpu_baseline"] = run_cpu(pairs, max_pairs=args.cpu_sample_pairs, workload=args.workload)
+            out["cpu_baseline"] = run_cpu(pairs, max_pairs=args.cpu_sample_pairs, workload=args.workload, matching=args.matching)
         print(json.dumps(out))
     if pipe is not None:
         pipe.close()

@@ -24,6 +24,10 @@ def main():
     cs.destroy(); cd.destroy()
     qs, qd, _ = synth.make_pair(2000, 20000, 20000, mode="quatro", voxel=0.3)
     res, qi = ctx.loop_closure([qs, qs[:50]], [qd, qd[:40]])       # quatro path incl. an invalid pair
+    from b200reg import native
+    adv = native.default_quatro_params()
+    adv.use_optimized_matching = 0                                  # advancedMatching + the global-memory solver
+    res, qi = ctx.loop_closure([qs, qs[:50], qd], [qd, qd[:40], qs], qparams=adv)
     seq = synth.make_sequence(7, 60, pts_per_keyframe=2500, spacing=7.0)
     kf = ctx.keyframes()
     for c, T, t in zip(seq["clouds"], seq["poses"], seq["stamps"]):
