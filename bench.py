@@ -472,7 +472,7 @@ def main():
     # step still uploads all of its inputs from pinned host memory and reads its results back.
     from b200reg.pipeline import PipelinedRegistrar
     depth = int(os.environ.get("B200REG_PIPE_DEPTH", "3"))
-    pipe = PipelinedRegistrar(local_rank, depth=depth) if args.workload == "gicp" else None
+    pipe = PipelinedRegistrar(local_rank, depth=depth)
 
     def run_pipelined(steps, on_device):
         if dist is not None:
@@ -485,8 +485,11 @@ def main():
         srcs = dev_src if on_device else host_src
         dsts = dev_dst if on_device else host_dst
         l0 = pipe.launch_count
-        futs = [pipe.icp_alignment_ptrs([t.data_ptr() for t in srcs], ns_s, [t.data_ptr() for t in dsts], ns_d, stride, int(on_device), prm)
-                for _ in range(steps)]
+        sp, tp = [t.data_ptr() for t in srcs], [t.data_ptr() for t in dsts]
+        if args.workload == "gicp":
+            futs = [pipe.icp_alignment_ptrs(sp, ns_s, tp, ns_d, stride, int(on_device), prm) for _ in range(steps)]
+        else:
+            futs = [pipe.loop_closure_ptrs(sp, ns_s, tp, ns_d, stride, int(on_device), qprm, prm) for _ in range(steps)]
         outs = [pipe.wait(f) for f in futs]
         if world > 1:  # the step results of this rank, gathered once per step like the device arm
             for r_ in outs:

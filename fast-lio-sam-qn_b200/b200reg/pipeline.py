@@ -49,6 +49,10 @@ class PipelinedRegistrar:
     def icp_alignment_ptrs(self, *args, **kw):
         return self.submit(lambda ctx: ctx.icp_alignment_ptrs(*args, **kw))
 
+    def loop_closure_ptrs(self, *args, **kw):
+        """LoopClosure::coarseToFineAlignment batches; the future resolves to the Result array."""
+        return self.submit(lambda ctx: ctx.loop_closure_ptrs(*args, **kw)[0])
+
     def synchronize(self):
         for c in self.ctxs:
             c.synchronize()

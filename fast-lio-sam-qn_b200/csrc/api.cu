@@ -301,6 +301,10 @@ int b200reg_clouds_create(b200reg_ctx* c, int count, const float* const* xyz, co
     d.spfh = nullptr;
     d.fpfh = nullptr;
     d.fnorm = nullptr;
+    d.fpfh_s = nullptr;
+    d.fnorm_s = nullptr;
+    d.ftile = nullptr;
+    d.fcode_s = nullptr;
     // temporary slab (sort buffers, histogram, tree scratch, bbox, and the raw records when uploading)
     size_t t_k0 = 0;
     size_t t_k1 = align_up(t_k0 + (size_t)d.n * 4, 256);
@@ -799,7 +803,10 @@ int b200reg_clouds_fpfh(b200reg_ctx* c, int count, b200reg_cloud* const* clouds,
       size_t o_s = align_up(o_n + n * sizeof(float4), 256);
       size_t o_f = align_up(o_s + n * FPAD * sizeof(float), 256);
       size_t o_fn = align_up(o_f + n * FPAD * sizeof(float), 256);
-      size_t total = align_up(o_fn + n * sizeof(float4), 256);
+      size_t o_fns = align_up(o_fn + n * sizeof(float4), 256);
+      size_t o_ft = align_up(o_fns + n * sizeof(float4), 256);
+      size_t o_fc = align_up(o_ft + 2 * ((n + 63) / 64) * sizeof(float4), 256);
+      size_t total = align_up(o_fc + n * sizeof(uint32_t), 256);
       char* fs = nullptr;
       CU(cudaMallocFromPoolAsync((void**)&fs, total, c->pool, s));
       cl->fslab = fs;
@@ -807,9 +814,25 @@ int b200reg_clouds_fpfh(b200reg_ctx* c, int count, b200reg_cloud* const* clouds,
       cl->dev.spfh = (float*)(fs + o_s);
       cl->dev.fpfh = (float*)(fs + o_f);
       cl->dev.fnorm = (float4*)(fs + o_fn);
+      cl->dev.fpfh_s = cl->dev.spfh;  // the SPFH table is dead once k_fpfh has consumed it
+      cl->dev.fnorm_s = (float4*)(fs + o_fns);
+      cl->dev.ftile = (float4*)(fs + o_ft);
+      cl->dev.fcode_s = (uint32_t*)(fs + o_fc);
     }
     todo.push_back(cl);
     descs.push_back(cl->dev);
+    {  // sort buffers of the norm-code ordering (scratch: only this call uses them)
+      CloudDev& d = descs.back();
+      const size_t n = d.n, nt = (n + SORT_TILE - 1) / SORT_TILE;
+      const size_t s_k = align_up(n * 4, 256);
+      char* sb = nullptr;
+      CU(scratch.alloc((void**)&sb, 4 * s_k + align_up((size_t)RADIX * nt * 4, 256)));
+      d.keys[0] = (uint32_t*)sb;
+      d.keys[1] = (uint32_t*)(sb + s_k);
+      d.vals[0] = (uint32_t*)(sb + 2 * s_k);
+      d.vals[1] = (uint32_t*)(sb + 3 * s_k);
+      d.hist = (uint32_t*)(sb + 4 * s_k);
+    }
     max_n = std::max(max_n, cl->dev.n);
   }
   if (todo.empty()) return B200REG_OK;

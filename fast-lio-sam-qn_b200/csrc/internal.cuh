@@ -44,6 +44,12 @@ struct CloudDev {
   float* spfh;         // [FPAD * n]
   float* fpfh;         // [FPAD * n]; slot 33 = original index (int bits), slot 34 = 1.0 if the descriptor is usable
   float4* fnorm;       // [n] L2 norms of the three 11-bin blocks (x, y, z): lower bound ||a-b||^2 >= sum_k (|a_k| - |b_k|)^2
+  // the matcher's view of the descriptors: records re-ordered by the Morton code of their three block norms, so that a
+  // tile of 64 consecutive records is a small box in norm space and whole tiles can be skipped per query
+  float* fpfh_s;       // [FPAD * n] (aliases spfh, which is dead once k_fpfh has run); unusable records last
+  float4* fnorm_s;     // [n]
+  float4* ftile;       // [2 * ceil(n / 64)] per tile: (min norms, #usable) and (max norms, -)
+  uint32_t* fcode_s;   // [n] sorted norm codes (0x3FFFFFFF+ for unusable records)
   // build-time temporaries (freed after the build)
   uint32_t* keys[2];   // sort ping-pong
   uint32_t* vals[2];

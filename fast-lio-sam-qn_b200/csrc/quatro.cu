@@ -88,31 +88,35 @@ __device__ __forceinline__ int bin11(float v) {
 // ------------------------------------------------------------------------------------------------
 // Q2 SPFH: per-thread 33-bin integer histogram in shared memory (bin-major => conflict free)
 // ------------------------------------------------------------------------------------------------
+constexpr int RV_BUF = 16;  // deferred-neighbour buffer per thread (radius_visit_batched)
+
 __global__ void __launch_bounds__(STEP_THREADS) k_spfh(const CloudDev* clouds, float r2) {
   const CloudDev& c = clouds[blockIdx.y];
   const int i = blockIdx.x * STEP_THREADS + threadIdx.x;
   __shared__ unsigned short hist[FDIM][STEP_THREADS];
+  __shared__ int spos[RV_BUF * STEP_THREADS];
+  __shared__ float sd2[RV_BUF * STEP_THREADS];
 #pragma unroll
   for (int k = 0; k < FDIM; k++) hist[k][threadIdx.x] = 0;
-  if (i >= c.n) return;
-  const float4 p = c.pts[i];
-  const float4 np = c.nrm[i];
-  float* out = c.spfh + (size_t)i * FPAD;
+  const bool inrange = i < c.n;
+  const float4 p = inrange ? c.pts[i] : make_float4(0.f, 0.f, 0.f, 0.f);
+  const float4 np = inrange ? c.nrm[i] : make_float4(0.f, 0.f, 0.f, 0.f);
   int cnt = 0;
-  if (np.w != 0.f) {
-    const float d_pi = 1.0f / (2.0f * 3.14159265358979323846f);
-    radius_visit(c, p.x, p.y, p.z, r2, [&](int pos, float, const float4& q) {
-      cnt++;
-      if (pos == i) return;
-      const float4 nq = __ldg(&c.nrm[pos]);
-      if (nq.w == 0.f) return;
-      float f1, f2, f3;
-      if (!pair_features(p, np, q, nq, f1, f2, f3)) return;
-      hist[bin11(11.0f * ((f1 + 3.14159265358979323846f) * d_pi))][threadIdx.x]++;
-      hist[11 + bin11(11.0f * ((f2 + 1.0f) * 0.5f))][threadIdx.x]++;
-      hist[22 + bin11(11.0f * ((f3 + 1.0f) * 0.5f))][threadIdx.x]++;
-    });
-  }
+  const float d_pi = 1.0f / (2.0f * 3.14159265358979323846f);
+  radius_visit_batched<RV_BUF>(c, inrange && np.w != 0.f, p.x, p.y, p.z, r2, spos, sd2, [&](int pos, float) {
+    cnt++;
+    if (pos == i) return;
+    const float4 nq = __ldg(&c.nrm[pos]);
+    if (nq.w == 0.f) return;
+    const float4 q = __ldg(&c.pts[pos]);
+    float f1, f2, f3;
+    if (!pair_features(p, np, q, nq, f1, f2, f3)) return;
+    hist[bin11(11.0f * ((f1 + 3.14159265358979323846f) * d_pi))][threadIdx.x]++;
+    hist[11 + bin11(11.0f * ((f2 + 1.0f) * 0.5f))][threadIdx.x]++;
+    hist[22 + bin11(11.0f * ((f3 + 1.0f) * 0.5f))][threadIdx.x]++;
+  });
+  if (!inrange) return;
+  float* out = c.spfh + (size_t)i * FPAD;
   const float incr = cnt >= 2 ? 100.0f / (float)(cnt - 1) : 0.f;
 #pragma unroll
   for (int k = 0; k < FDIM; k++) out[k] = (float)hist[k][threadIdx.x] * incr;
@@ -125,43 +129,44 @@ __global__ void __launch_bounds__(STEP_THREADS) k_spfh(const CloudDev* clouds, f
 __global__ void __launch_bounds__(STEP_THREADS) k_fpfh(const CloudDev* clouds, float r2) {
   const CloudDev& c = clouds[blockIdx.y];
   const int i = blockIdx.x * STEP_THREADS + threadIdx.x;
-  if (i >= c.n) return;
-  const float4 p = c.pts[i];
+  __shared__ int spos[RV_BUF * STEP_THREADS];
+  __shared__ float sd2[RV_BUF * STEP_THREADS];
+  const bool inrange = i < c.n;
+  const float4 p = inrange ? c.pts[i] : make_float4(0.f, 0.f, 0.f, 0.f);
   float h[FDIM];
 #pragma unroll
   for (int k = 0; k < FDIM; k++) h[k] = 0.f;
   float s0 = 0.f, s1 = 0.f, s2 = 0.f;
-  if (c.nrm[i].w != 0.f) {
-    radius_visit(c, p.x, p.y, p.z, r2, [&](int pos, float d2, const float4&) {
-      if (d2 == 0.f) return;
-      const float w = 1.0f / d2;
-      const float4* s4 = reinterpret_cast<const float4*>(c.spfh + (size_t)pos * FPAD);
-      float s[FPAD];
+  radius_visit_batched<RV_BUF>(c, inrange && c.nrm[inrange ? i : 0].w != 0.f, p.x, p.y, p.z, r2, spos, sd2, [&](int pos, float d2) {
+    if (d2 == 0.f) return;
+    const float w = 1.0f / d2;
+    const float4* s4 = reinterpret_cast<const float4*>(c.spfh + (size_t)pos * FPAD);
+    float s[FPAD];
 #pragma unroll
-      for (int k = 0; k < 9; k++) {
-        const float4 v = __ldg(&s4[k]);
-        s[4 * k] = v.x; s[4 * k + 1] = v.y; s[4 * k + 2] = v.z; s[4 * k + 3] = v.w;
-      }
+    for (int k = 0; k < 9; k++) {
+      const float4 v = __ldg(&s4[k]);
+      s[4 * k] = v.x; s[4 * k + 1] = v.y; s[4 * k + 2] = v.z; s[4 * k + 3] = v.w;
+    }
 #pragma unroll
-      for (int k = 0; k < 11; k++) {
-        const float v = s[k] * w;
-        s0 += v;
-        h[k] += v;
-      }
+    for (int k = 0; k < 11; k++) {
+      const float v = s[k] * w;
+      s0 += v;
+      h[k] += v;
+    }
 #pragma unroll
-      for (int k = 11; k < 22; k++) {
-        const float v = s[k] * w;
-        s1 += v;
-        h[k] += v;
-      }
+    for (int k = 11; k < 22; k++) {
+      const float v = s[k] * w;
+      s1 += v;
+      h[k] += v;
+    }
 #pragma unroll
-      for (int k = 22; k < 33; k++) {
-        const float v = s[k] * w;
-        s2 += v;
-        h[k] += v;
-      }
-    });
-  }
+    for (int k = 22; k < 33; k++) {
+      const float v = s[k] * w;
+      s2 += v;
+      h[k] += v;
+    }
+  });
+  if (!inrange) return;
   const float sc0 = s0 != 0.f ? 100.0f / s0 : 0.f, sc1 = s1 != 0.f ? 100.0f / s1 : 0.f, sc2 = s2 != 0.f ? 100.0f / s2 : 0.f;
   float* out = c.fpfh + (size_t)i * FPAD;
   bool any = false;
@@ -212,22 +217,102 @@ __device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned pari
 constexpr int NN_THREADS = 128;  // 4 warps, each owning 32 queries
 constexpr int NN_TILE = 64;      // base descriptors per smem tile: 64 * 144 B = 9216 B per cp.async.bulk
 constexpr int NN_QCAP = 96;      // per-warp survivor queue (drained whenever it holds >= 32 entries)
+constexpr int NN_DENSE = 48;     // survivors of one (query, tile) test from which the tile is refined lane-per-record
 
-// Exact 33-D 1-NN by filter-and-refine.  Measured on voxelised KITTI-shaped scans: only ~4% of (query, base) pairs can
-// beat the query's current best once a decent match is known, but a warp of 32 queries almost never agrees to skip
-// the same base record.  So a warp takes ONE query at a time and lets its 32 lanes test 32 base records against the
-// block-norm lower bound  sum_k (|a_k| - |b_k|)^2 <= |a - b|^2  (k = the three 11-bin sub-histograms, ~12
-// instructions); survivors are queued and refined 32 at a time with the full fp32 distance in the oracle's
-// operation order, so every lane of a refine step does useful work.  Results are exact: the bound is a true lower
-// bound, it is applied with a relative margin of 1e-4 against rounding, and ties go to the lower original index via
-// the packed (d2 bits, index) 64-bit minimum.
-// mode 0: queries = every point of fj (sorted order), base = fi; writes nn/dis by ORIGINAL j
-// mode 1: queries = fi points listed in `need` (original i), base = fj; writes rnn by ORIGINAL i
+// ---- norm-space ordering of the descriptors (the matcher's view) -------------------------------------------------
+__device__ __forceinline__ uint32_t spread10(uint32_t v) {
+  v = (v | (v << 16)) & 0x030000FFu;
+  v = (v | (v << 8)) & 0x0300F00Fu;
+  v = (v | (v << 4)) & 0x030C30C3u;
+  v = (v | (v << 2)) & 0x09249249u;
+  return v;
+}
+// sort key of sorted position p: Morton code of the three block norms (each in [0, 100]) at 10 bits; unusable
+// descriptors go to the end
+__global__ void __launch_bounds__(256) k_fcode(const CloudDev* clouds) {
+  const CloudDev& c = clouds[blockIdx.y];
+  const int p = blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= c.n) return;
+  const float4 nr = c.fnorm[p];
+  const bool ok = c.fpfh[(size_t)p * FPAD + 34] != 0.f;
+  const uint32_t q0 = min(1023u, (uint32_t)(nr.x * 10.23f)), q1 = min(1023u, (uint32_t)(nr.y * 10.23f)), q2 = min(1023u, (uint32_t)(nr.z * 10.23f));
+  c.keys[0][p] = ok ? ((spread10(q2) << 2) | (spread10(q1) << 1) | spread10(q0)) : 0x3FFFFFFFu;
+  c.vals[0][p] = (uint32_t)p;
+}
+// gather the records into code order and box every tile of NN_TILE records in norm space.  One 64-thread block per tile.
+__global__ void __launch_bounds__(NN_TILE) k_fgather(const CloudDev* clouds) {
+  const CloudDev& c = clouds[blockIdx.y];
+  const int t = blockIdx.x;
+  if (t * NN_TILE >= c.n) return;
+  const int r = t * NN_TILE + threadIdx.x;
+  float lo[3] = {INFINITY, INFINITY, INFINITY}, hi[3] = {-INFINITY, -INFINITY, -INFINITY};
+  int usable = 0;
+  if (r < c.n) {
+    const int p = (int)c.vals[0][r];
+    const float4* s4 = reinterpret_cast<const float4*>(c.fpfh + (size_t)p * FPAD);
+    float4* d4 = reinterpret_cast<float4*>(c.fpfh_s + (size_t)r * FPAD);
+    float4 last;
+#pragma unroll
+    for (int k = 0; k < 9; k++) {
+      last = s4[k];
+      d4[k] = last;
+    }
+    const float4 nr = c.fnorm[p];
+    c.fnorm_s[r] = nr;
+    c.fcode_s[r] = c.keys[0][r];
+    if (last.z != 0.f) {  // slot 34
+      usable = 1;
+      lo[0] = hi[0] = nr.x; lo[1] = hi[1] = nr.y; lo[2] = hi[2] = nr.z;
+    }
+  }
+  __shared__ float red[2][7];
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+#pragma unroll
+    for (int d = 0; d < 3; d++) {
+      lo[d] = fminf(lo[d], __shfl_xor_sync(0xffffffffu, lo[d], o));
+      hi[d] = fmaxf(hi[d], __shfl_xor_sync(0xffffffffu, hi[d], o));
+    }
+    usable += __shfl_xor_sync(0xffffffffu, usable, o);
+  }
+  if ((threadIdx.x & 31) == 0) {
+    float* w = red[threadIdx.x >> 5];
+    w[0] = lo[0]; w[1] = lo[1]; w[2] = lo[2]; w[3] = hi[0]; w[4] = hi[1]; w[5] = hi[2]; w[6] = (float)usable;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    c.ftile[2 * t] = make_float4(fminf(red[0][0], red[1][0]), fminf(red[0][1], red[1][1]), fminf(red[0][2], red[1][2]), red[0][6] + red[1][6]);
+    c.ftile[2 * t + 1] = make_float4(fmaxf(red[0][3], red[1][3]), fmaxf(red[0][4], red[1][4]), fmaxf(red[0][5], red[1][5]), 0.f);
+  }
+}
+
+// lower bound of the filter's record test over every record of a tile: distance from the query's norm triple to the
+// tile's box.  Same operation order as the record test and rounding is monotone, so box_lb <= record lower bound.
+__device__ __forceinline__ float tile_lb(const float4& qn, const float4& lo, const float4& hi) {
+  const float e0 = fmaxf(fmaxf(lo.x - qn.x, qn.x - hi.x), 0.f), e1 = fmaxf(fmaxf(lo.y - qn.y, qn.y - hi.y), 0.f),
+              e2 = fmaxf(fmaxf(lo.z - qn.z, qn.z - hi.z), 0.f);
+  return (e0 * e0 + e1 * e1) + e2 * e2;
+}
+
+// Exact 33-D 1-NN by filter-and-refine over norm-ordered tiles.
+//  * Both clouds are held in the order of the Morton code of their three block norms (k_fcode / k_fgather), so the 128
+//    queries of a block are similar and a base tile of 64 records is a small box in norm space.
+//  * A block starts at the base tile nearest to its own queries (binary search of the code) and sweeps up, then down:
+//    good matches are found in the first tiles and the bound is tight from then on.
+//  * Per tile: every lane tests ITS query against the tile box (one test instead of 64); tiles nobody in the block
+//    needs are not even fetched (__syncthreads_or), tiles are fetched by cp.async.bulk (TMA) one ahead.
+//  * Per (needed query, tile): the 32 lanes test 32+32 records against the block-norm lower bound
+//    sum_k (|a_k| - |b_k|)^2 <= |a - b|^2, ballot-compact the survivors into a per-warp queue, and refine 32 queued
+//    pairs at a time with the full fp32 distance in the oracle's operation order.
+// Exact: both bounds are true lower bounds applied with a margin against rounding; ties go to the lower original index
+// through the packed (d2 bits, index) 64-bit minimum, so the visiting order does not matter.
+// mode 0: queries = fj, base = fi; writes nn/dis by ORIGINAL j
+// mode 1: queries = the fi points that were hit (first_j != INT_MAX), base = fj; writes rnn by ORIGINAL i
 __global__ void __launch_bounds__(NN_THREADS) k_feat_nn(const MatchDev* pairs, int mode, float thr2) {
   const MatchDev& P = pairs[blockIdx.y];
   const CloudDev& Q = mode == 0 ? P.fj : P.fi;
   const CloudDev& B = mode == 0 ? P.fi : P.fj;
-  const int nq = mode == 0 ? Q.n : P.counters[0];
+  const int nq = Q.n;
   const int q0 = blockIdx.x * NN_THREADS;
   if (q0 >= nq) return;
   __shared__ __align__(128) float tile[2][NN_TILE * FPAD];
@@ -237,61 +322,91 @@ __global__ void __launch_bounds__(NN_THREADS) k_feat_nn(const MatchDev* pairs, i
   __shared__ unsigned long long sbest[NN_THREADS / 32][32];
   __shared__ unsigned short queue[NN_THREADS / 32][NN_QCAP];
   __shared__ __align__(8) unsigned long long full[2];
+  __shared__ int s_t0;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const float lim = __int_as_float(__float_as_int(thr2) + 1);  // nextafter(thr2, +inf): d2 == thr2 still qualifies
   // stage this thread's query (row `lane` of its warp)
   const int qi = q0 + threadIdx.x;
-  const bool active = qi < nq;
   int qorig = -1;
+  bool qok = false;
+  float4 qn = make_float4(0.f, 0.f, 0.f, 0.f);
   {
-    int qpos = 0;
-    if (active) {
-      if (mode == 0) {
-        qpos = qi;
-      } else {
-        qorig = P.need[qi];
-        qpos = Q.rank[qorig];
-      }
-    }
-    const float4* q4 = reinterpret_cast<const float4*>(Q.fpfh + (size_t)qpos * FPAD);
+    const bool inrange = qi < nq;
+    const float4* q4 = reinterpret_cast<const float4*>(Q.fpfh_s + (size_t)(inrange ? qi : 0) * FPAD);
     float4* d4 = reinterpret_cast<float4*>(&sq[warp][lane * FPAD]);
     float4 last = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
     for (int k = 0; k < 9; k++) {
-      const float4 v = active ? q4[k] : make_float4(0.f, 0.f, 0.f, 0.f);
+      const float4 v = inrange ? q4[k] : make_float4(0.f, 0.f, 0.f, 0.f);
       d4[k] = v;
       if (k == 8) last = v;
     }
-    if (mode == 0) qorig = __float_as_int(last.y);
-    const bool qok = active && last.z != 0.f;
-    float4 qn = active ? Q.fnorm[qpos] : make_float4(0.f, 0.f, 0.f, 0.f);
-    qn.w = qok ? 1.f : 0.f;
-    sqn[warp][lane] = qn;
+    qorig = __float_as_int(last.y);
+    qok = inrange && last.z != 0.f;
+    if (inrange) qn = Q.fnorm_s[qi];
     // reverse search: i was reached from j0 = first_j[i] at distance dis[j0], and the metric is symmetric, so that
     // very pair is a valid starting candidate -- the filter is tight from the first tile on
     unsigned long long init = ((unsigned long long)__float_as_uint(lim) << 32) | 0xFFFFFFFFull;
-    if (mode == 1 && active) {
+    if (mode == 1 && qok) {
       const int j0 = P.first_j[qorig];
-      init = ((unsigned long long)__float_as_uint(P.dis[j0]) << 32) | (unsigned)j0;
+      if (j0 == 0x7FFFFFFF) qok = false;  // nobody asked for this point
+      else init = ((unsigned long long)__float_as_uint(P.dis[j0]) << 32) | (unsigned)j0;
     }
+    qn.w = qok ? 1.f : 0.f;
+    sqn[warp][lane] = qn;
     sbest[warp][lane] = init;
   }
+  if (!__syncthreads_or(qok ? 1 : 0)) {  // nothing to search for in this block
+    if (mode == 0 && qi < nq && qorig >= 0) {
+      P.nn[qorig] = -1;
+      P.dis[qorig] = lim;
+    }
+    return;
+  }
+  const int nb = B.n;
+  const int ntiles = (nb + NN_TILE - 1) / NN_TILE;
   if (threadIdx.x == 0) {
     mbar_init(&full[0], 1);
     mbar_init(&full[1], 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    // first tile: where the code of the block's middle query would sit in the base order
+    const uint32_t code = Q.fcode_s[min(nq - 1, q0 + NN_THREADS / 2)];
+    int lo = 0, hi = nb;
+    while (lo < hi) {
+      const int mid = (lo + hi) >> 1;
+      if (B.fcode_s[mid] < code) lo = mid + 1;
+      else hi = mid;
+    }
+    s_t0 = min(ntiles - 1, lo / NN_TILE);
   }
   __syncthreads();
-  const int nb = B.n;
-  const int ntiles = (nb + NN_TILE - 1) / NN_TILE;
-  auto issue = [&](int t) {
+  const int t0 = s_t0, up = ntiles - t0;
+  auto visit = [&](int k) { return k < up ? t0 + k : t0 - 1 - (k - up); };
+  const float4* boxes = B.ftile;
+  // does this thread's query still need tile t?
+  auto my_need = [&](int t) {
+    if (!qok) return false;
+    const float4 lo4 = __ldg(&boxes[2 * t]), hi4 = __ldg(&boxes[2 * t + 1]);
+    if (lo4.w == 0.f) return false;  // no usable record in the tile
+    const float bound = fminf(lim, __uint_as_float((unsigned)(sbest[warp][lane] >> 32))) * 1.0001f + 1e-3f;
+    return tile_lb(qn, lo4, hi4) <= bound;
+  };
+  // first visit index >= k whose tile somebody in the block needs (ntiles if none).  Always at least one barrier: it
+  // also orders "every warp is done with the buffer about to be refilled" before the refill.
+  auto next_needed = [&](int k) {
+    for (;;) {
+      const int any = __syncthreads_or((k < ntiles && my_need(visit(k))) ? 1 : 0);
+      if (any || k >= ntiles) return k;
+      k++;
+    }
+  };
+  auto issue = [&](int t, int buf) {
     const int cnt = min(NN_TILE, nb - t * NN_TILE);
     const unsigned bytes = (unsigned)cnt * FPAD * 4, nbytes = (unsigned)cnt * 16;
-    mbar_expect_tx(&full[t & 1], bytes + nbytes);
-    bulk_g2s(tile[t & 1], B.fpfh + (size_t)t * NN_TILE * FPAD, bytes, &full[t & 1]);
-    bulk_g2s(tnorm[t & 1], B.fnorm + (size_t)t * NN_TILE, nbytes, &full[t & 1]);
+    mbar_expect_tx(&full[buf], bytes + nbytes);
+    bulk_g2s(tile[buf], B.fpfh_s + (size_t)t * NN_TILE * FPAD, bytes, &full[buf]);
+    bulk_g2s(tnorm[buf], B.fnorm_s + (size_t)t * NN_TILE, nbytes, &full[buf]);
   };
-  if (threadIdx.x == 0) issue(0);
   int qn_count = 0;  // entries in this warp's queue (warp-uniform)
   // refine up to 32 queued (query, record) pairs: one per lane
   auto drain = [&](const float* tb, int take) {
@@ -318,7 +433,9 @@ __global__ void __launch_bounds__(NN_THREADS) k_feat_nn(const MatchDev* pairs, i
         const float e0 = x.x - y.x;
         d += e0 * e0;
       }
-      if (d < lim) atomicMin(&sbest[warp][ql], ((unsigned long long)__float_as_uint(d) << 32) | (unsigned)__float_as_int(y.y));
+      // most refined pairs do not beat the current best (near-duplicate descriptors): look before the atomic
+      const unsigned long long cand = ((unsigned long long)__float_as_uint(d) << 32) | (unsigned)__float_as_int(y.y);
+      if (d < lim && cand < sbest[warp][ql]) atomicMin(&sbest[warp][ql], cand);
     }
     __syncwarp();
     // compact the rest of the queue to the front
@@ -332,49 +449,104 @@ __global__ void __launch_bounds__(NN_THREADS) k_feat_nn(const MatchDev* pairs, i
     __syncwarp();
     qn_count = rest;
   };
-  for (int t = 0; t < ntiles; t++) {
-    if (threadIdx.x == 0 && t + 1 < ntiles) issue(t + 1);
-    mbar_wait(&full[t & 1], (t >> 1) & 1);
-    const float* tb = tile[t & 1];
-    const float4* tn = tnorm[t & 1];
-    const int cnt = min(NN_TILE, nb - t * NN_TILE);
-    // this lane's two base records of the tile: block norms and usability
-    float4 bn0 = make_float4(0.f, 0.f, 0.f, 0.f), bn1 = bn0;
-    bool ok0 = false, ok1 = false;
-    if (lane < cnt) {
-      bn0 = tn[lane];
-      ok0 = tb[lane * FPAD + 34] != 0.f;
+  int cur = next_needed(0);
+  if (cur < ntiles && threadIdx.x == 0) issue(visit(cur), 0);
+  for (int it = 0; cur < ntiles; it++) {
+    const int nxt = next_needed(cur + 1);
+    if (nxt < ntiles && threadIdx.x == 0) issue(visit(nxt), (it + 1) & 1);
+    const int t = visit(cur);
+    mbar_wait(&full[it & 1], (it >> 1) & 1);
+    unsigned mask = __ballot_sync(0xffffffffu, my_need(t));  // the bound may have tightened since the block-level decision
+    if (mask) {
+      const float* tb = tile[it & 1];
+      const float4* tn = tnorm[it & 1];
+      const int cnt = min(NN_TILE, nb - t * NN_TILE);
+      // this lane's two base records of the tile: block norms and usability
+      float4 bn0 = make_float4(0.f, 0.f, 0.f, 0.f), bn1 = bn0;
+      bool ok0 = false, ok1 = false;
+      if (lane < cnt) {
+        bn0 = tn[lane];
+        ok0 = tb[lane * FPAD + 34] != 0.f;
+      }
+      if (lane + 32 < cnt) {
+        bn1 = tn[lane + 32];
+        ok1 = tb[(lane + 32) * FPAD + 34] != 0.f;
+      }
+      while (mask) {
+        const int ql = __ffs(mask) - 1;
+        mask &= mask - 1;
+        const float4 qv = sqn[warp][ql];  // broadcast
+        const float bound = fminf(lim, __uint_as_float((unsigned)(sbest[warp][ql] >> 32))) * 1.0001f + 1e-3f;
+        float e0 = qv.x - bn0.x, e1 = qv.y - bn0.y, e2 = qv.z - bn0.z;
+        const bool p0 = ok0 && ((e0 * e0 + e1 * e1) + e2 * e2 <= bound);
+        e0 = qv.x - bn1.x; e1 = qv.y - bn1.y; e2 = qv.z - bn1.z;
+        const bool p1 = ok1 && ((e0 * e0 + e1 * e1) + e2 * e2 <= bound);
+        const unsigned m0 = __ballot_sync(0xffffffffu, p0), m1 = __ballot_sync(0xffffffffu, p1);
+        if (__popc(m0) + __popc(m1) >= NN_DENSE) {
+          // most of the tile survives (a cluster of near-identical descriptors): skip the queue, every lane refines
+          // its own two records against the broadcast query row -- conflict-free shared-memory reads on both sides
+          const float4* a4 = reinterpret_cast<const float4*>(&sq[warp][ql * FPAD]);
+          const float4* b0 = reinterpret_cast<const float4*>(tb + lane * FPAD);
+          const float4* b1 = reinterpret_cast<const float4*>(tb + (lane + 32) * FPAD);
+          float d0 = 0.f, d1 = 0.f;
+          float4 x, y0 = make_float4(0.f, 0.f, 0.f, 0.f), y1 = y0;
+#pragma unroll
+          for (int k = 0; k < 8; k++) {
+            x = a4[k];
+            float e;
+            if (p0) {
+              y0 = b0[k];
+              e = x.x - y0.x; d0 += e * e;
+              e = x.y - y0.y; d0 += e * e;
+              e = x.z - y0.z; d0 += e * e;
+              e = x.w - y0.w; d0 += e * e;
+            }
+            if (p1) {
+              y1 = b1[k];
+              e = x.x - y1.x; d1 += e * e;
+              e = x.y - y1.y; d1 += e * e;
+              e = x.z - y1.z; d1 += e * e;
+              e = x.w - y1.w; d1 += e * e;
+            }
+          }
+          x = a4[8];
+          unsigned long long cand = 0xFFFFFFFFFFFFFFFFull;
+          if (p0) {
+            y0 = b0[8];
+            const float e = x.x - y0.x;
+            d0 += e * e;
+            if (d0 < lim) cand = ((unsigned long long)__float_as_uint(d0) << 32) | (unsigned)__float_as_int(y0.y);
+          }
+          if (p1) {
+            y1 = b1[8];
+            const float e = x.x - y1.x;
+            d1 += e * e;
+            if (d1 < lim) cand = min(cand, ((unsigned long long)__float_as_uint(d1) << 32) | (unsigned)__float_as_int(y1.y));
+          }
+          if (cand < sbest[warp][ql]) atomicMin(&sbest[warp][ql], cand);
+          __syncwarp();
+          continue;
+        }
+        const unsigned lt = (1u << lane) - 1u;
+        if (p0) queue[warp][qn_count + __popc(m0 & lt)] = (unsigned short)((ql << 8) | lane);
+        const int c0 = __popc(m0);
+        if (p1) queue[warp][qn_count + c0 + __popc(m1 & lt)] = (unsigned short)((ql << 8) | (lane + 32));
+        qn_count += c0 + __popc(m1);
+        __syncwarp();
+        while (qn_count >= 32) drain(tb, 32);
+      }
+      while (qn_count > 0) drain(tb, min(qn_count, 32));  // the queue refers to THIS tile: empty it before the tile is refilled
     }
-    if (lane + 32 < cnt) {
-      bn1 = tn[lane + 32];
-      ok1 = tb[(lane + 32) * FPAD + 34] != 0.f;
-    }
-    for (int ql = 0; ql < 32; ql++) {
-      const float4 qn = sqn[warp][ql];  // broadcast
-      if (qn.w == 0.f) continue;        // inactive / unusable query (warp-uniform)
-      const float bound = fminf(lim, __uint_as_float((unsigned)(sbest[warp][ql] >> 32))) * 1.0001f + 1e-3f;
-      float e0 = qn.x - bn0.x, e1 = qn.y - bn0.y, e2 = qn.z - bn0.z;
-      const bool p0 = ok0 && ((e0 * e0 + e1 * e1) + e2 * e2 <= bound);
-      e0 = qn.x - bn1.x; e1 = qn.y - bn1.y; e2 = qn.z - bn1.z;
-      const bool p1 = ok1 && ((e0 * e0 + e1 * e1) + e2 * e2 <= bound);
-      const unsigned m0 = __ballot_sync(0xffffffffu, p0), m1 = __ballot_sync(0xffffffffu, p1);
-      const unsigned lt = (1u << lane) - 1u;
-      if (p0) queue[warp][qn_count + __popc(m0 & lt)] = (unsigned short)((ql << 8) | lane);
-      const int c0 = __popc(m0);
-      if (p1) queue[warp][qn_count + c0 + __popc(m1 & lt)] = (unsigned short)((ql << 8) | (lane + 32));
-      qn_count += c0 + __popc(m1);
-      __syncwarp();
-      while (qn_count >= 32) drain(tb, 32);
-    }
-    while (qn_count > 0) drain(tb, min(qn_count, 32));  // the queue refers to THIS tile: empty it before the tile is refilled
-    __syncthreads();
+    cur = nxt;
   }
-  if (active) {
+  if (qi < nq && (mode == 0 || qok)) {
     const unsigned long long b = sbest[warp][lane];
     const int bo = (int)(b & 0xFFFFFFFFull);
     if (mode == 0) {
-      P.nn[qorig] = bo;  // 0xFFFFFFFF -> -1: nothing within the gate
-      P.dis[qorig] = __uint_as_float((unsigned)(b >> 32));
+      if (qorig >= 0) {
+        P.nn[qorig] = bo;  // 0xFFFFFFFF -> -1: nothing within the gate
+        P.dis[qorig] = __uint_as_float((unsigned)(b >> 32));
+      }
     } else {
       P.rnn[qorig] = bo;
     }
@@ -1498,12 +1670,18 @@ __global__ void __launch_bounds__(256) k_transform_raw(const CloudDev* clouds, c
 // ------------------------------------------------------------------------------------------------
 // host launchers
 // ------------------------------------------------------------------------------------------------
+int launch_radix_sort(const CloudDev* d_clouds, int count, int max_n, int npass, cudaStream_t s);  // index_build.cu
+
 int launch_fpfh(const CloudDev* d_clouds, int count, int max_n, float normal_r2, float fpfh_r2, cudaStream_t s) {
   dim3 grid((max_n + STEP_THREADS - 1) / STEP_THREADS, count);
   k_normals<<<grid, STEP_THREADS, 0, s>>>(d_clouds, normal_r2);
   k_spfh<<<grid, STEP_THREADS, 0, s>>>(d_clouds, fpfh_r2);
   k_fpfh<<<grid, STEP_THREADS, 0, s>>>(d_clouds, fpfh_r2);
-  return 3;
+  // the matcher's view: records in the order of their block-norm Morton code, boxed per tile
+  k_fcode<<<dim3((max_n + 255) / 256, count), 256, 0, s>>>(d_clouds);
+  const int ls = launch_radix_sort(d_clouds, count, max_n, 4, s);  // 30-bit keys, 4 passes: result back in keys[0] / vals[0]
+  k_fgather<<<dim3((max_n + NN_TILE - 1) / NN_TILE, count), NN_TILE, 0, s>>>(d_clouds);
+  return 5 + ls;
 }
 
 size_t solve_smem_bytes() { return sizeof(SolveSmem); }
@@ -1522,7 +1700,6 @@ int launch_quatro_match_solve(const MatchDev* d_pairs, int count, int max_ni, in
   k_cloud_scale<<<dim3(64, count, 2), 256, 0, s>>>(d_pairs); l++;
   k_feat_nn<<<dim3((max_nj + NN_THREADS - 1) / NN_THREADS, count), NN_THREADS, 0, s>>>(d_pairs, 0, prm.thr2); l++;
   k_first_hit<<<dim3((max_nj + 255) / 256, count), 256, 0, s>>>(d_pairs, prm.thr2); l++;
-  k_need<<<dim3((max_ni + 255) / 256, count), 256, 0, s>>>(d_pairs); l++;
   k_feat_nn<<<dim3((max_ni + NN_THREADS - 1) / NN_THREADS, count), NN_THREADS, 0, s>>>(d_pairs, 1, prm.thr2); l++;
   k_mutual<<<count, 1024, 0, s>>>(d_pairs, prm.thr2, prm.advanced); l++;
   k_tuple_trials<<<dim3(128, count), 256, 0, s>>>(d_pairs, prm); l++;
