@@ -214,10 +214,9 @@ __device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned pari
   }
 }
 
-constexpr int NN_THREADS = 128;  // 4 warps, each owning 32 queries
+constexpr int NN_THREADS = 128;  // 4 warps, each owning 32 queries (measured: 64 and 32 threads per block are slower)
 constexpr int NN_TILE = 64;      // base descriptors per smem tile: 64 * 144 B = 9216 B per cp.async.bulk
 constexpr int NN_QCAP = 96;      // per-warp survivor queue (drained whenever it holds >= 32 entries)
-constexpr int NN_DENSE = 48;     // survivors of one (query, tile) test from which the tile is refined lane-per-record
 
 // ---- norm-space ordering of the descriptors (the matcher's view) -------------------------------------------------
 __device__ __forceinline__ uint32_t spread10(uint32_t v) {
@@ -482,51 +481,6 @@ __global__ void __launch_bounds__(NN_THREADS) k_feat_nn(const MatchDev* pairs, i
         e0 = qv.x - bn1.x; e1 = qv.y - bn1.y; e2 = qv.z - bn1.z;
         const bool p1 = ok1 && ((e0 * e0 + e1 * e1) + e2 * e2 <= bound);
         const unsigned m0 = __ballot_sync(0xffffffffu, p0), m1 = __ballot_sync(0xffffffffu, p1);
-        if (__popc(m0) + __popc(m1) >= NN_DENSE) {
-          // most of the tile survives (a cluster of near-identical descriptors): skip the queue, every lane refines
-          // its own two records against the broadcast query row -- conflict-free shared-memory reads on both sides
-          const float4* a4 = reinterpret_cast<const float4*>(&sq[warp][ql * FPAD]);
-          const float4* b0 = reinterpret_cast<const float4*>(tb + lane * FPAD);
-          const float4* b1 = reinterpret_cast<const float4*>(tb + (lane + 32) * FPAD);
-          float d0 = 0.f, d1 = 0.f;
-          float4 x, y0 = make_float4(0.f, 0.f, 0.f, 0.f), y1 = y0;
-#pragma unroll
-          for (int k = 0; k < 8; k++) {
-            x = a4[k];
-            float e;
-            if (p0) {
-              y0 = b0[k];
-              e = x.x - y0.x; d0 += e * e;
-              e = x.y - y0.y; d0 += e * e;
-              e = x.z - y0.z; d0 += e * e;
-              e = x.w - y0.w; d0 += e * e;
-            }
-            if (p1) {
-              y1 = b1[k];
-              e = x.x - y1.x; d1 += e * e;
-              e = x.y - y1.y; d1 += e * e;
-              e = x.z - y1.z; d1 += e * e;
-              e = x.w - y1.w; d1 += e * e;
-            }
-          }
-          x = a4[8];
-          unsigned long long cand = 0xFFFFFFFFFFFFFFFFull;
-          if (p0) {
-            y0 = b0[8];
-            const float e = x.x - y0.x;
-            d0 += e * e;
-            if (d0 < lim) cand = ((unsigned long long)__float_as_uint(d0) << 32) | (unsigned)__float_as_int(y0.y);
-          }
-          if (p1) {
-            y1 = b1[8];
-            const float e = x.x - y1.x;
-            d1 += e * e;
-            if (d1 < lim) cand = min(cand, ((unsigned long long)__float_as_uint(d1) << 32) | (unsigned)__float_as_int(y1.y));
-          }
-          if (cand < sbest[warp][ql]) atomicMin(&sbest[warp][ql], cand);
-          __syncwarp();
-          continue;
-        }
         const unsigned lt = (1u << lane) - 1u;
         if (p0) queue[warp][qn_count + __popc(m0 & lt)] = (unsigned short)((ql << 8) | lane);
         const int c0 = __popc(m0);
