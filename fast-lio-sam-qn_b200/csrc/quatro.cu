@@ -21,19 +21,27 @@ namespace b200 {
 // ------------------------------------------------------------------------------------------------
 // Q1 normals
 // ------------------------------------------------------------------------------------------------
+constexpr int RV_BUF = 16;     // deferred-neighbour buffer per thread (radius_visit_batched), positions only
+constexpr int RV_BUF_D2 = 16;  // ... when the distance travels with the position (k_fpfh)
+
 __global__ void __launch_bounds__(STEP_THREADS) k_normals(const CloudDev* clouds, float r2) {
   const CloudDev& c = clouds[blockIdx.y];
   const int i = blockIdx.x * STEP_THREADS + threadIdx.x;
-  if (i >= c.n) return;
-  const float4 p = c.pts[i];
+  __shared__ int spos[RV_BUF * STEP_THREADS];
+  __shared__ int wstack[STEP_THREADS / 32][MAX_STACK];
+  const bool inrange = i < c.n;
+  const float4 p = inrange ? c.pts[i] : make_float4(0.f, 0.f, 0.f, 0.f);
   double m0 = 0, m1 = 0, m2 = 0, c0 = 0, c1 = 0, c2 = 0, c3 = 0, c4 = 0, c5 = 0;
   int cnt = 0;
-  radius_visit(c, p.x, p.y, p.z, r2, [&](int, float, const float4& q) {
+  // the fp64 moments are the heavy part: accumulate them warp-convergently (same neighbour order as the traversal)
+  radius_visit_warp<RV_BUF>(c, inrange, p.x, p.y, p.z, r2, spos, nullptr, wstack[threadIdx.x >> 5], [&](int pos, float) {
+    const float4 q = __ldg(&c.pts[pos]);
     const double x = (double)q.x - (double)p.x, y = (double)q.y - (double)p.y, z = (double)q.z - (double)p.z;
     m0 += x; m1 += y; m2 += z;
     c0 += x * x; c1 += x * y; c2 += x * z; c3 += y * y; c4 += y * z; c5 += z * z;
     cnt++;
   });
+  if (!inrange) return;
   if (cnt < 3) {
     c.nrm[i] = make_float4(0.f, 0.f, 0.f, 0.f);
     return;
@@ -88,14 +96,12 @@ __device__ __forceinline__ int bin11(float v) {
 // ------------------------------------------------------------------------------------------------
 // Q2 SPFH: per-thread 33-bin integer histogram in shared memory (bin-major => conflict free)
 // ------------------------------------------------------------------------------------------------
-constexpr int RV_BUF = 16;  // deferred-neighbour buffer per thread (radius_visit_batched)
-
 __global__ void __launch_bounds__(STEP_THREADS) k_spfh(const CloudDev* clouds, float r2) {
   const CloudDev& c = clouds[blockIdx.y];
   const int i = blockIdx.x * STEP_THREADS + threadIdx.x;
   __shared__ unsigned short hist[FDIM][STEP_THREADS];
   __shared__ int spos[RV_BUF * STEP_THREADS];
-  __shared__ float sd2[RV_BUF * STEP_THREADS];
+  __shared__ int wstack[STEP_THREADS / 32][MAX_STACK];
 #pragma unroll
   for (int k = 0; k < FDIM; k++) hist[k][threadIdx.x] = 0;
   const bool inrange = i < c.n;
@@ -103,7 +109,7 @@ __global__ void __launch_bounds__(STEP_THREADS) k_spfh(const CloudDev* clouds, f
   const float4 np = inrange ? c.nrm[i] : make_float4(0.f, 0.f, 0.f, 0.f);
   int cnt = 0;
   const float d_pi = 1.0f / (2.0f * 3.14159265358979323846f);
-  radius_visit_batched<RV_BUF>(c, inrange && np.w != 0.f, p.x, p.y, p.z, r2, spos, sd2, [&](int pos, float) {
+  radius_visit_warp<RV_BUF>(c, inrange && np.w != 0.f, p.x, p.y, p.z, r2, spos, nullptr, wstack[threadIdx.x >> 5], [&](int pos, float) {
     cnt++;
     if (pos == i) return;
     const float4 nq = __ldg(&c.nrm[pos]);
@@ -129,15 +135,16 @@ __global__ void __launch_bounds__(STEP_THREADS) k_spfh(const CloudDev* clouds, f
 __global__ void __launch_bounds__(STEP_THREADS) k_fpfh(const CloudDev* clouds, float r2) {
   const CloudDev& c = clouds[blockIdx.y];
   const int i = blockIdx.x * STEP_THREADS + threadIdx.x;
-  __shared__ int spos[RV_BUF * STEP_THREADS];
-  __shared__ float sd2[RV_BUF * STEP_THREADS];
+  __shared__ int spos[RV_BUF_D2 * STEP_THREADS];
+  __shared__ float sd2[RV_BUF_D2 * STEP_THREADS];
+  __shared__ int wstack[STEP_THREADS / 32][MAX_STACK];
   const bool inrange = i < c.n;
   const float4 p = inrange ? c.pts[i] : make_float4(0.f, 0.f, 0.f, 0.f);
   float h[FDIM];
 #pragma unroll
   for (int k = 0; k < FDIM; k++) h[k] = 0.f;
   float s0 = 0.f, s1 = 0.f, s2 = 0.f;
-  radius_visit_batched<RV_BUF>(c, inrange && c.nrm[inrange ? i : 0].w != 0.f, p.x, p.y, p.z, r2, spos, sd2, [&](int pos, float d2) {
+  radius_visit_warp<RV_BUF_D2>(c, inrange && c.nrm[inrange ? i : 0].w != 0.f, p.x, p.y, p.z, r2, spos, sd2, wstack[threadIdx.x >> 5], [&](int pos, float d2) {
     if (d2 == 0.f) return;
     const float w = 1.0f / d2;
     const float4* s4 = reinterpret_cast<const float4*>(c.spfh + (size_t)pos * FPAD);
