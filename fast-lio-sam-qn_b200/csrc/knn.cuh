@@ -247,76 +247,12 @@ __device__ __forceinline__ void radius_visit(const CloudDev& c, float qx, float 
   }
 }
 
-// Fixed-radius traversal with DEFERRED, warp-convergent processing.  radius_visit runs the callback wherever the
-// traversal of each thread happens to be, so a heavy callback executes with ~5 of 32 lanes active (ncu:
-// thread_inst_executed_per_inst 4.75 for the SPFH kernel).  Here every thread only COLLECTS the neighbours it meets
-// (position, d2) into its column of a small shared-memory buffer; whenever a thread holds more than BUF - LEAF
-// entries (or has finished) it waits, the warp reconverges, and all lanes run the callback over their buffered
-// entries in lockstep.  Neighbours are delivered in exactly the order radius_visit delivers them.
-// With BUF = 16 the SASS profile still shows half of the instructions in the traversal phase at 4-7 active lanes (lanes
-// fill their buffers at different rates and wait), but BUF = 48 / 32 measured SLOWER (fpfh family 2.94 -> 3.20 ms):
-// the shared memory costs more occupancy than the longer rounds win.
-// Must be called by every thread of the warp (pass active = false for padding threads).
-// spos / sd2: [BUF][blockDim.x] shared arrays.
-// sd2 may be nullptr when the callback does not need the distance (it then receives 0).
-template <int BUF, typename F>
-__device__ __forceinline__ void radius_visit_batched(const CloudDev& c, bool active, float qx, float qy, float qz, float r2, int* spos,
-                                                     float* sd2, F&& f) {
-  const float4* __restrict__ pts = c.pts;
-  const float4* __restrict__ tn = c.tnodes;
-  const int tid = threadIdx.x, stride = blockDim.x;
-  int stack_ref[MAX_STACK];
-  int sp = 0;
-  int ref = c.root_ref;
-  bool done = !active;
-  int cnt = 0;
-  for (;;) {
-    while (!done && cnt <= BUF - LEAF) {
-      while (ref >= 0) {
-        const float4 a0 = __ldg(&tn[4 * ref]), a1 = __ldg(&tn[4 * ref + 1]);
-        const float4 b0 = __ldg(&tn[4 * ref + 2]), b1 = __ldg(&tn[4 * ref + 3]);
-        const bool in0 = box_dist2_rn(qx, qy, qz, a0, a1) < r2;
-        const bool in1 = box_dist2_rn(qx, qy, qz, b0, b1) < r2;
-        const int r0 = __float_as_int(a0.w), r1 = __float_as_int(b0.w);
-        if (in0 && in1) {
-          stack_ref[sp++] = r1;
-          ref = r0;
-        } else if (in0) {
-          ref = r0;
-        } else if (in1) {
-          ref = r1;
-        } else {
-          ref = 0x7FFFFFFF;  // dead end
-          break;
-        }
-      }
-      if (ref < 0) {
-        const int code = -1 - ref;
-        const int base = code >> 4, n = code & 15;
-        for (int j = 0; j < n; j++) {
-          const float4 p = __ldg(&pts[base + j]);
-          const float d2 = dist2_rn(qx, qy, qz, p.x, p.y, p.z);
-          if (d2 < r2) {
-            spos[cnt * stride + tid] = base + j;
-            if (sd2) sd2[cnt * stride + tid] = d2;
-            cnt++;
-          }
-        }
-      }
-      if (sp == 0) done = true;
-      else ref = stack_ref[--sp];
-    }
-    const int most = __reduce_max_sync(0xffffffffu, cnt);  // also the reconvergence point of the warp
-    for (int e = 0; e < most; e++)
-      if (e < cnt) f(spos[e * stride + tid], sd2 ? sd2[e * stride + tid] : 0.f);
-    cnt = 0;
-    if (__all_sync(0xffffffffu, done)) break;
-  }
-}
-
-// Fixed-radius search with a WARP-SHARED traversal.  The 32 queries of a warp are Morton-neighbours, so their balls
-// overlap almost completely; instead of 32 private stack traversals (SASS profile of the batched variant above: half
-// of all instructions in the traversal phase at 4-7 active lanes) the warp walks the tree once: a node is entered if
+// Fixed-radius search with a WARP-SHARED traversal and deferred, lockstep processing of the hits.
+// History (profiles/README.md): with the callback inside a per-thread traversal (radius_visit) the SPFH kernel ran with
+// 4.75 of 32 lanes active; collecting hits per thread and processing them warp-convergently brought that to 12.7, but
+// the SASS profile still had half of all instructions in the private traversals at 4-7 active lanes (lanes fill their
+// buffers at different rates and wait; a bigger buffer cost more occupancy than it won).  The 32 queries of a warp
+// are Morton-neighbours, so their balls overlap almost completely; the warp therefore walks the tree once: a node is entered if
 // ANY lane's own exact box test passes (the same per-lane criterion as radius_visit, so nothing is missed), the
 // stack is warp-uniform, every lane tests every point of a visited leaf against its own query and collects its own
 // hits, and whenever some lane's buffer could overflow the whole warp processes what it has collected, in lockstep.
