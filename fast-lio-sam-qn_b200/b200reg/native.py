@@ -72,6 +72,7 @@ EXPORTS = [
     "b200reg_quatro_align", "b200reg_loop_closure", "b200reg_default_loop_config", "b200reg_keyframes_create",
     "b200reg_keyframes_destroy", "b200reg_keyframes_add", "b200reg_keyframes_set_pose", "b200reg_keyframes_size",
     "b200reg_knn_bruteforce", "b200reg_fetch_closest_keyframes", "b200reg_assemble_clouds", "b200reg_cloud_points", "b200reg_perform_loop_closure",
+    "b200reg_loop_factor_from_poses", "b200reg_loop_factors",
 ]
 
 
@@ -87,6 +88,16 @@ def lib():
     return _lib
 
 
+class LoopFactor(C.Structure):
+    """b200reg_loop_factor: the BetweenFactor the reference adds for an accepted loop (fast_lio_sam_qn.cpp:220-237)."""
+    _fields_ = [("from_idx", C.c_int32), ("to_idx", C.c_int32), ("valid", C.c_int32), ("reserved", C.c_int32),
+                ("measurement", C.c_double * 16), ("variances", C.c_double * 6)]
+
+    def as_dict(self):
+        return dict(from_idx=self.from_idx, to_idx=self.to_idx, valid=bool(self.valid),
+                    measurement=np.array(self.measurement).reshape(4, 4), variances=np.array(self.variances))
+
+
 class B200RegError(RuntimeError):
     pass
 
@@ -94,6 +105,16 @@ class B200RegError(RuntimeError):
 def _check(rc):
     if rc != 0:
         raise B200RegError("b200reg error %d: %s" % (rc, lib().b200reg_last_error().decode()))
+
+
+def loop_factor_from_poses(T_between, pose_latest, pose_closest, score, valid=True, from_idx=0, to_idx=0):
+    """Host arithmetic only (no context / GPU needed)."""
+    f = LoopFactor()
+    arr = [np.ascontiguousarray(m, np.float64) for m in (T_between, pose_latest, pose_closest)]
+    _check(lib().b200reg_loop_factor_from_poses(arr[0].ctypes.data_as(C.c_void_p), arr[1].ctypes.data_as(C.c_void_p),
+                                                arr[2].ctypes.data_as(C.c_void_p), C.c_double(score), int(bool(valid)),
+                                                int(from_idx), int(to_idx), C.byref(f)))
+    return f.as_dict()
 
 
 def default_params():
@@ -388,3 +409,12 @@ class Keyframes:
         if raw:
             return res, qi
         return [r.as_dict() for r in res], [x.as_dict() for x in qi]
+
+    def loop_factors(self, query_idx, closest_idx, raw_results):
+        """The BetweenFactor records of a perform_loop_closure(..., raw=True) batch (fast_lio_sam_qn.cpp:220-237)."""
+        q = np.ascontiguousarray(query_idx, np.int32)
+        cidx = np.ascontiguousarray(closest_idx, np.int32)
+        out = (LoopFactor * len(q))()
+        _check(lib().b200reg_loop_factors(self.ctx.h, self.h, len(q), q.ctypes.data_as(C.c_void_p), cidx.ctypes.data_as(C.c_void_p),
+                                          raw_results, out))
+        return [f.as_dict() for f in out]

@@ -1192,6 +1192,86 @@ int b200reg_keyframes_set_pose(b200reg_ctx* c, b200reg_keyframes* kf, int idx, c
   return B200REG_OK;
 }
 
+// ---- result consumption (host arithmetic only) -------------------------------------------------------
+namespace {
+// poseEigToGtsamPose (utilities.hpp:67-75): tf::Matrix3x3::getRPY (getEulerYPR, solution 1), then gtsam::Rot3::RzRyRx
+void pose_rpy_roundtrip(const double* P, double R[9], double t[3]) {
+  const double m00 = P[0], m10 = P[4], m20 = P[8], m21 = P[9], m22 = P[10];
+  double roll, pitch, yaw;
+  if (fabs(m20) >= 1.0) {  // gimbal-lock branch of tf's getEulerYPR (tf is not vendored; restated from
+                           // tf/LinearMath/Matrix3x3.h: yaw = 0, roll = atan2(m21, m22) in both sub-cases)
+    yaw = 0.0;
+    roll = atan2(m21, m22);
+    pitch = m20 < 0 ? M_PI / 2.0 : -M_PI / 2.0;
+  } else {
+    pitch = -asin(m20);
+    const double cp = cos(pitch);
+    roll = atan2(m21 / cp, m22 / cp);
+    yaw = atan2(m10 / cp, m00 / cp);
+  }
+  const double cx = cos(roll), sx = sin(roll), cy = cos(pitch), sy = sin(pitch), cz = cos(yaw), sz = sin(yaw);
+  // Rz(yaw) * Ry(pitch) * Rx(roll)
+  R[0] = cz * cy; R[1] = cz * sy * sx - sz * cx; R[2] = cz * sy * cx + sz * sx;
+  R[3] = sz * cy; R[4] = sz * sy * sx + cz * cx; R[5] = sz * sy * cx - cz * sx;
+  R[6] = -sy;     R[7] = cy * sx;                R[8] = cy * cx;
+  t[0] = P[3]; t[1] = P[7]; t[2] = P[11];
+}
+}  // namespace
+
+int b200reg_loop_factor_from_poses(const double* Tb, const double* Pl, const double* Pc, double score, int valid, int from_idx,
+                                   int to_idx, b200reg_loop_factor* out) {
+  if (!Tb || !Pl || !Pc || !out) return fail(B200REG_EINVAL, "bad argument");
+  double F[16];  // pose_between_eig_ * latest.pose_corrected_eig_ (Matrix4d product)
+  for (int r = 0; r < 4; r++)
+    for (int cidx = 0; cidx < 4; cidx++) {
+      double s = 0;
+      for (int k = 0; k < 4; k++) s += Tb[4 * r + k] * Pl[4 * k + cidx];
+      F[4 * r + cidx] = s;
+    }
+  double R1[9], t1[3], R2[9], t2[3];
+  pose_rpy_roundtrip(F, R1, t1);
+  pose_rpy_roundtrip(Pc, R2, t2);
+  // Pose3::between: inverse(from) * to = (R1^T R2, R1^T (t2 - t1))
+  double* M = out->measurement;
+  for (int r = 0; r < 3; r++) {
+    for (int cidx = 0; cidx < 3; cidx++) {
+      double s = 0;
+      for (int k = 0; k < 3; k++) s += R1[3 * k + r] * R2[3 * k + cidx];
+      M[4 * r + cidx] = s;
+    }
+    double s = 0;
+    for (int k = 0; k < 3; k++) s += R1[3 * k + r] * (t2[k] - t1[k]);
+    M[4 * r + 3] = s;
+  }
+  M[12] = M[13] = M[14] = 0.0;
+  M[15] = 1.0;
+  for (int k = 0; k < 6; k++) out->variances[k] = score;
+  out->from_idx = from_idx;
+  out->to_idx = to_idx;
+  out->valid = valid ? 1 : 0;
+  out->reserved = 0;
+  return B200REG_OK;
+}
+
+int b200reg_loop_factors(b200reg_ctx* c, const b200reg_keyframes* kf, int count, const int32_t* query_idx, const int32_t* closest_idx,
+                         const b200reg_result* results, b200reg_loop_factor* out) {
+  if (!c || !kf || count <= 0 || !query_idx || !closest_idx || !results || !out) return fail(B200REG_EINVAL, "bad argument");
+  const int nk = (int)kf->pts.size();
+  for (int i = 0; i < count; i++) {
+    if (query_idx[i] < 0 || query_idx[i] >= nk || closest_idx[i] >= nk) return fail(B200REG_EINVAL, "keyframe index out of range");
+    if (closest_idx[i] < 0) {  // no candidate: the reference returns before any registration (fast_lio_sam_qn.cpp:213-216)
+      memset(&out[i], 0, sizeof(b200reg_loop_factor));
+      out[i].from_idx = query_idx[i];
+      out[i].to_idx = -1;
+      continue;
+    }
+    const int rc = b200reg_loop_factor_from_poses(results[i].T, &kf->poses[16 * (size_t)query_idx[i]], &kf->poses[16 * (size_t)closest_idx[i]],
+                                                  results[i].fitness, results[i].valid, query_idx[i], closest_idx[i], &out[i]);
+    if (rc) return rc;
+  }
+  return B200REG_OK;
+}
+
 int b200reg_fetch_closest_keyframes(b200reg_ctx* c, b200reg_keyframes* kf, int count, const int32_t* query_idx, double radius,
                                     double tdiff, int32_t* closest_out) {
   if (!c || !kf || count <= 0 || !query_idx || !closest_out) return fail(B200REG_EINVAL, "bad argument");

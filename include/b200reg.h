@@ -220,6 +220,28 @@ int b200reg_perform_loop_closure(b200reg_ctx* ctx, b200reg_keyframes* kf, int co
                                  const int32_t* closest_idx, const b200reg_loop_config* cfg, b200reg_result* out,
                                  b200reg_quatro_info* quatro_out);
 
+/* Result consumption (fast_lio_sam_qn/src/fast_lio_sam_qn.cpp:220-237): the loop constraint the
+ * reference hands to GTSAM for an accepted registration,
+ *   BetweenFactor<Pose3>(latest.idx_, closest_idx, pose_from.between(pose_to), Diagonal::Variances(score x 6)),
+ *   pose_from = poseEigToGtsamPose(pose_between_eig_ * latest.pose_corrected_eig_)   ("take care of the order", :224)
+ *   pose_to   = poseEigToGtsamPose(closest.pose_corrected_eig_)
+ * with poseEigToGtsamPose's roll/pitch/yaw round trip (utilities.hpp:67-75: tf getRPY, then Rot3::RzRyRx).  The pose
+ * graph itself (GTSAM iSAM2) stays with the caller; corrected poses come back through b200reg_keyframes_set_pose.   */
+typedef struct b200reg_loop_factor {
+  int32_t from_idx;        /* key of the latest keyframe                                        */
+  int32_t to_idx;          /* key of the matched keyframe                                       */
+  int32_t valid;           /* RegistrationOutput::is_valid_; 0: the reference adds no factor    */
+  int32_t reserved;
+  double measurement[16];  /* pose_from.between(pose_to), row-major 4x4                         */
+  double variances[6];     /* score in every slot                                               */
+} b200reg_loop_factor;
+/* Pure host arithmetic (no context, no GPU): one factor from explicit poses.                                        */
+int b200reg_loop_factor_from_poses(const double* T_between16, const double* pose_latest16, const double* pose_closest16,
+                                   double score, int valid, int from_idx, int to_idx, b200reg_loop_factor* out);
+/* The factors of a batch of b200reg_perform_loop_closure results, poses taken from the keyframe store.              */
+int b200reg_loop_factors(b200reg_ctx* ctx, const b200reg_keyframes* kf, int count, const int32_t* query_idx,
+                         const int32_t* closest_idx, const b200reg_result* results, b200reg_loop_factor* out);
+
 /* Output cloud of align(): final_transformation_ applied to the source in fp32
  * (lsq_registration_impl.hpp:114).  out_xyz: n x 3 floats (host), original point order.       */
 int b200reg_transform_cloud(b200reg_ctx* ctx, const b200reg_cloud* cloud, const float* Tf16, float* out_xyz);

@@ -335,3 +335,34 @@ def set_src_and_dst_cloud(kf_clouds, kf_poses, src_idx, dst_idx, submap_range=5,
         src = transform_pcd(kf_clouds[src_idx], kf_poses[src_idx])
         dst = transform_pcd(kf_clouds[dst_idx], kf_poses[dst_idx]) if enable_quatro else merged(dst_idx)
     return voxelize(src, voxel_res), voxelize(dst, voxel_res)
+
+
+# ---------------------------------------------------------------------------------------------
+# result consumption
+def _pose_rpy_roundtrip(P):
+    """poseEigToGtsamPose (fast_lio_sam_qn/include/utilities.hpp:67-75): tf getRPY, then gtsam Rot3::RzRyRx."""
+    P = np.asarray(P, np.float64)
+    m20 = P[2, 0]
+    if abs(m20) >= 1.0:  # gimbal lock branch of tf's getEulerYPR
+        yaw, roll = 0.0, np.arctan2(P[2, 1], P[2, 2])
+        pitch = np.pi / 2 if m20 < 0 else -np.pi / 2
+    else:
+        pitch = -np.arcsin(m20)
+        cp = np.cos(pitch)
+        roll = np.arctan2(P[2, 1] / cp, P[2, 2] / cp)
+        yaw = np.arctan2(P[1, 0] / cp, P[0, 0] / cp)
+    cx, sx, cy, sy, cz, sz = np.cos(roll), np.sin(roll), np.cos(pitch), np.sin(pitch), np.cos(yaw), np.sin(yaw)
+    Rz = np.array([[cz, -sz, 0], [sz, cz, 0], [0, 0, 1]])
+    Ry = np.array([[cy, 0, sy], [0, 1, 0], [-sy, 0, cy]])
+    Rx = np.array([[1, 0, 0], [0, cx, -sx], [0, sx, cx]])
+    return Rz @ Ry @ Rx, P[:3, 3].copy()
+
+
+def loop_factor(T_between, pose_latest, pose_closest, score):
+    """BetweenFactor measurement + variances of an accepted loop (fast_lio_sam_qn/src/fast_lio_sam_qn.cpp:220-231)."""
+    R1, t1 = _pose_rpy_roundtrip(np.asarray(T_between, np.float64) @ np.asarray(pose_latest, np.float64))
+    R2, t2 = _pose_rpy_roundtrip(pose_closest)
+    M = np.eye(4)
+    M[:3, :3] = R1.T @ R2
+    M[:3, 3] = R1.T @ (t2 - t1)
+    return M, np.full(6, float(score))

@@ -85,3 +85,24 @@ def test_perform_loop_closure_matches_oracle(ctx, store, oracle, synth, seq):
         o = oracle.gicp_align(src, dst)
         rot, tr = synth.se3_error(res2[k]["T"], o["T"])
         assert rot < 3e-4 and tr < 3e-3, (k, rot, tr)
+
+
+def test_loop_factors_close_the_loop(ctx, store, oracle, synth, seq):
+    """Result consumption (fast_lio_sam_qn.cpp:220-237): the factor records of a batch equal the oracle's, and applying
+    the measurement brings the drifted latest keyframe back onto the truth relative to the matched one."""
+    queries = np.array([137, 20, 118], np.int32)
+    closest = store.fetch_closest(queries)
+    raw, _ = store.perform_loop_closure(queries, closest, raw=True)
+    facs = store.loop_factors(queries, closest, raw)
+    assert facs[1]["to_idx"] == -1 and not facs[1]["valid"]  # no candidate: nothing for the graph
+    for k in (0, 2):
+        q, c = int(queries[k]), int(closest[k])
+        f = facs[k]
+        assert (f["from_idx"], f["to_idx"]) == (q, c) and f["valid"] == bool(raw[k].valid)
+        T = np.array(raw[k].T).reshape(4, 4)
+        M, var = oracle.loop_factor(T, seq["poses"][q], seq["poses"][c], raw[k].fitness)
+        assert np.abs(f["measurement"] - M).max() < 1e-12 and np.array_equal(f["variances"], var)
+        # the measured relative pose is the TRUE relative pose of the two keyframes (drift removed)
+        true_rel = np.linalg.inv(seq["true_poses"][q]) @ seq["true_poses"][c]
+        rot, tr = synth.se3_error(f["measurement"], true_rel)
+        assert rot < 2e-2 and tr < 0.3, (k, rot, tr)
