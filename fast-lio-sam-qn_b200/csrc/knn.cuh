@@ -311,8 +311,9 @@ __device__ __forceinline__ void radius_visit_warp(const CloudDev& c, bool active
       if (__any_sync(FULL, cnt > BUF - LEAF)) flush();
     }
     if (sp == 0) break;
-    __syncwarp();
+    __syncwarp();  // the pushes of this round are visible to every lane ...
     ref = wstack[--sp];
+    __syncwarp();  // ... and every lane has popped before the slot can be pushed again
   }
   flush();
 }
