@@ -917,7 +917,7 @@ int b200reg_quatro_align(b200reg_ctx* c, int count, b200reg_cloud* const* src, b
       o = align_up(o + bytes, 256);
       return r;
     };
-    const size_t o_nn = take(nj * 4), o_dis = take(nj * 4), o_fj = take(ni * 4), o_need = take(ni * 4), o_rnn = take(ni * 4);
+    const size_t o_nn = take(nj * 4), o_dis = take(nj * 4), o_fj = take(ni * 4), o_rnn = take(ni * 4);
     // advancedMatching: the cross-checked set has at most nj members; the solver workspace is sized for the next
     // power of two (>= 1024, <= BIGC)
     int cap = 1024;
@@ -944,7 +944,6 @@ int b200reg_quatro_align(b200reg_ctx* c, int count, b200reg_cloud* const* src, b
     m.nn = (int*)(slab + o_nn);
     m.dis = (float*)(slab + o_dis);
     m.first_j = (int*)(slab + o_fj);
-    m.need = (int*)(slab + o_need);
     m.rnn = (int*)(slab + o_rnn);
     m.corres = (int*)(slab + o_cor);
     m.tkey = (unsigned*)(slab + o_tk);

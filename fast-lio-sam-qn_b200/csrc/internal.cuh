@@ -137,11 +137,10 @@ struct MatchDev {
   int* nn;             // [nj] original fi index of the 1-NN of fj point j (by ORIGINAL j), -1 if none
   float* dis;          // [nj]
   int* first_j;        // [ni] min original j that hit i (INT_MAX if none)
-  int* need;           // [ni] compacted original i's that need the reverse search
   int* rnn;            // [ni] original j returned by the reverse search (by ORIGINAL i)
   int* corres;         // [2 * nj] mutual (i, j) pairs, ascending j
   unsigned* tkey;      // [nj] first (trial*4 + slot) at which correspondence r would be added
-  int* counters;       // [0] n_need, [1] ncorr, [2] n_out, [3] valid, [4] clique size, [5] gnc iterations
+  int* counters;       // [0] unused, [1] ncorr, [2] n_out, [3] valid, [4] clique size, [5] gnc iterations
   double* stats;       // [0..2] sum fi, [3..5] sum fj, then floats: mean fi(3) mean fj(3) scale (as float bits in doubles)
   int* out_corr;       // [2 * corr_cap] final (src, dst) pairs (corr_cap = MAXC, or BigSolveWs::cap for advancedMatching)
   double* T;           // [16] row-major result

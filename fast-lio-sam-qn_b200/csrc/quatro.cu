@@ -6,11 +6,14 @@
 //   Q1 k_normals        pcl::NormalEstimation, radius 0.9, viewpoint (0,0,0)       third_party/Quatro/src/fpfh.cc:27-32
 //   Q2 k_spfh           FPFHEstimationOMP::computePointSPFHSignature                fpfh.cc:35-39
 //   Q3 k_fpfh           FPFHEstimationOMP::weightPointSPFHSignature                 fpfh.cc:35-39
+//      k_fcode / k_fgather               the matcher's view: descriptors in block-norm Morton order, boxed per 64-record tile
 //   Q4 k_feat_nn        FLANN KDTreeSingleIndex exact 1-NN in 33-D (both directions) third_party/Quatro/src/matcher.cc:378-399, 597-636
-//      k_first_hit / k_need / k_mutual   gate + first-hit reverse search + mutual check   matcher.cc:412-455
+//      k_first_hit / k_mutual            gate + first-hit reverse search + mutual check   matcher.cc:412-455
 //      k_cloud_sum / k_cloud_scale       Matcher::normalizePoints                         matcher.cc:58-116
 //      k_tuple_trials / k_tuple_select   tuple test (<= 100 ncorr trials, stop at > max)  matcher.cc:461-538
+//      k_adv_select                      Matcher::advancedMatching tail (sort + unique)   matcher.cc:118-356
 //   Q5 k_teaser_solve   RobustRegistrationSolver::solve, QUATRO + PMC_HEU           call site third_party/Quatro/src/quatro_module.cc:69-76
+//      k_big_*                           the same solve over a global-memory workspace for > 512 correspondences
 // Deliberate definitions where the reference is seed- or race-dependent are listed in oracle/oracle_quatro.cpp.
 #include "internal.cuh"
 #include "knn.cuh"
@@ -534,13 +537,6 @@ __global__ void __launch_bounds__(256) k_first_hit(const MatchDev* pairs, float 
   const int i = P.nn[j];
   if (i < 0 || P.dis[j] > thr2) return;
   atomicMin(&P.first_j[i], j);
-}
-
-__global__ void __launch_bounds__(256) k_need(const MatchDev* pairs) {
-  const MatchDev& P = pairs[blockIdx.y];
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= P.fi.n) return;
-  if (P.first_j[i] != 0x7FFFFFFF) P.need[atomicAdd(&P.counters[0], 1)] = i;  // order irrelevant: results land by index
 }
 
 // ordered compaction over ascending original j: keep (i, j) iff j was the first hit of i AND nn_j(i) == j.
