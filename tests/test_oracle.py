@@ -124,3 +124,30 @@ def test_lm_state_machine_edge_cases(oracle, synth):
     p.max_corr_dist = 1e-4  # nothing matches: H = 0, the step is zero, delta = I => "converged" like the reference
     r = oracle.gicp_align(src, dst, params=p)
     assert np.allclose(r["T"], np.eye(4))
+
+
+def test_quatro_matchers_known_answers(oracle, synth):
+    """Matcher::optimizedMatching / advancedMatching restatements on a small pair: structural properties the reference's
+    code guarantees (matcher.cc:118-356, 358-561), plus the planted motion recovered by the QUATRO solve from either."""
+    src, dst, Texp = synth.make_pair(2000, 8000, 9000, mode="quatro")
+    _, _, fs = oracle.fpfh(src)
+    _, _, fd = oracle.fpfh(dst)
+    adv = oracle.match_advanced(src, dst, fs, fd)
+    cross = oracle.match_advanced(src, dst, fs, fd, tuple_test=False)
+    opt, mutual = oracle.match(src, dst, fs, fd)
+    # sorted + unique (src, dst) pairs (matcher.cc:353-355); the tuple test only removes cross-checked pairs
+    key = lambda c: c[:, 0].astype(np.int64) * (1 << 32) + c[:, 1]
+    assert np.all(np.diff(key(adv)) > 0) and np.all(np.diff(key(cross)) > 0)
+    assert set(map(tuple, adv)) <= set(map(tuple, cross))
+    # the cross check is a bijection between the matched subsets
+    assert len(set(cross[:, 0])) == len(cross) == len(set(cross[:, 1]))
+    # swapping the arguments swaps the columns (fi/fj swap, matcher.cc:125-130): same set of physical pairs
+    adv_sw = oracle.match_advanced(dst, src, fd, fs)
+    assert set(map(tuple, adv_sw[:, ::-1])) == set(map(tuple, adv))
+    # optimizedMatching: gated + capped at max_corres + 3 (break AFTER exceeding, matcher.cc:537)
+    assert 0 < len(opt) <= 203 and len(mutual) >= len(opt)
+    # both correspondence sets put the solver inside the refinement's basin of the planted motion
+    for corr in (adv, opt):
+        r = oracle.quatro_solve(src, dst, corr)
+        rot, tr = synth.se3_error(r["T"], Texp)
+        assert r["valid"] and rot < 0.06 and tr < 3.5, (len(corr), rot, tr)
