@@ -5,4 +5,5 @@ torch.distributed sharding); the product is csrc/*.cu.
 """
 from . import synth  # noqa: F401
 from .native import (B200RegError, Context, GicpParams, QuatroInfo, QuatroParams, Result, default_params,  # noqa: F401
-                     default_quatro_params, Keyframes, LoopConfig, default_loop_config)
+                     default_quatro_params, Keyframes, LoopConfig, LoopFactor, default_loop_config,
+                     loop_factor_from_poses)
