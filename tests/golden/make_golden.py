@@ -7,6 +7,9 @@ oracle/_ref = the reference's own nanoflann kd-tree); the GPU box only reads the
                          nano_gicp/nanoflann.hpp:100-114) on a 3000-point KITTI-shaped cloud
   gicp_oracle_3k.npz     the CPU oracle's Nano-GICP outputs on a 3000 x 3500 pair (covariances, one
                          linearization, the full align) -- pins the oracle against silent drift
+  quatro_oracle_2k.npz   the CPU oracle's Quatro outputs on a 2000 x 2300 pair (normals / FPFH samples, both matchers'
+                         correspondence lists, both solves) -- same purpose (`python make_golden.py quatro` writes
+                         only this one)
 """
 import os
 import sys
@@ -22,7 +25,25 @@ from b200reg import synth  # noqa: E402
 from oracle import oracle  # noqa: E402
 
 
+def quatro_golden():
+    src, dst, Texp = synth.make_pair(4343, 2000, 2300, mode="quatro")
+    src3, dst3 = np.ascontiguousarray(src[:, :3]), np.ascontiguousarray(dst[:, :3])
+    ns, _, fs = oracle.fpfh(src3)
+    nd, _, fd = oracle.fpfh(dst3)
+    opt, mutual = oracle.match(src3, dst3, fs, fd)
+    adv = oracle.match_advanced(src3, dst3, fs, fd)
+    so, sa = oracle.quatro_solve(src3, dst3, opt), oracle.quatro_solve(src3, dst3, adv)
+    np.savez_compressed(os.path.join(HERE, "quatro_oracle_2k.npz"), src=src3, dst=dst3, T_expected=Texp,
+                        normals_src_sample=ns[::25], fpfh_src_sample=fs[::25], fpfh_dst_sample=fd[::25],
+                        corr_opt=opt, n_mutual=len(mutual), corr_adv=adv,
+                        T_opt=so["T"], clique_opt=so["clique"], gnc_opt=so["gnc_iters"],
+                        T_adv=sa["T"], clique_adv=sa["clique"], gnc_adv=sa["gnc_iters"])
+    print("quatro golden:", len(opt), "optimized /", len(adv), "advanced correspondences; cliques", len(so["clique"]), len(sa["clique"]))
+
+
 def main():
+    if len(sys.argv) > 1 and sys.argv[1] == "quatro":
+        return quatro_golden()
     assert os.path.exists(oracle.ref_so_path()), "build oracle/_ref first (make -C oracle ref)"
     src, dst, Texp = synth.make_pair(4242, 3000, 3500)
     src3, dst3 = np.ascontiguousarray(src[:, :3]), np.ascontiguousarray(dst[:, :3])
@@ -47,6 +68,7 @@ def main():
                         corr=lin["corr"], sqd=lin["sqd"], T=res["T"], Tf=res["Tf"], fitness=res["fitness"],
                         converged=res["converged"], iterations=res["iterations"], n_linearize=res["n_linearize"],
                         n_error=res["n_error"], trace=res["trace"])
+    quatro_golden()
     print("wrote", os.listdir(HERE))
 
 

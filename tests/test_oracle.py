@@ -151,3 +151,20 @@ def test_quatro_matchers_known_answers(oracle, synth):
         r = oracle.quatro_solve(src, dst, corr)
         rot, tr = synth.se3_error(r["T"], Texp)
         assert r["valid"] and rot < 0.06 and tr < 3.5, (len(corr), rot, tr)
+
+
+def test_quatro_oracle_matches_committed_golden(oracle):
+    """Guards the (reference-unpinned) Quatro restatement against silent drift: tests/golden/quatro_oracle_2k.npz."""
+    g = np.load(os.path.join(GOLD, "quatro_oracle_2k.npz"))
+    ns, _, fs = oracle.fpfh(g["src"])
+    _, _, fd = oracle.fpfh(g["dst"])
+    assert np.array_equal(np.isnan(ns[::25]), np.isnan(g["normals_src_sample"]))
+    assert np.nanmax(np.abs(ns[::25] - g["normals_src_sample"])) < 1e-6
+    assert np.abs(fs[::25] - g["fpfh_src_sample"]).max() < 1e-4 and np.abs(fd[::25] - g["fpfh_dst_sample"]).max() < 1e-4
+    opt, mutual = oracle.match(g["src"], g["dst"], fs, fd)
+    adv = oracle.match_advanced(g["src"], g["dst"], fs, fd)
+    assert np.array_equal(opt, g["corr_opt"]) and len(mutual) == int(g["n_mutual"]) and np.array_equal(adv, g["corr_adv"])
+    for corr, T, clique, gnc in ((opt, g["T_opt"], g["clique_opt"], g["gnc_opt"]), (adv, g["T_adv"], g["clique_adv"], g["gnc_adv"])):
+        r = oracle.quatro_solve(g["src"], g["dst"], corr)
+        assert np.array_equal(r["clique"], clique) and r["gnc_iters"] == int(gnc)
+        assert np.abs(r["T"] - T).max() < 1e-9
