@@ -8,6 +8,9 @@
 One "step" = LoopClosure::icpAlignment (fast_lio_sam_qn/src/loop_closure.cpp:110-136: two index
 builds, two covariance passes, align, fitness) over one batch of `--pairs` synthetic 100k x 100k
 pairs per rank (BASELINE.json configs[1]).  Prints ONE JSON line (rank 0).
+Other workloads (not the headline): --workload quatro = configs[2], LoopClosure::coarseToFineAlignment on scans
+voxelised at 0.3 m (--matching optimized|advanced selects the Quatro matcher); --workload sequence = configs[4],
+loopTimerFunc over a device-resident KITTI-05-shaped keyframe sequence.
 
   value   : pairs/s with the raw xyz already resident in HBM when the timed region starts
   e2e     : pairs/s through the same C-ABI call from PINNED HOST buffers (H2D of every cloud and
