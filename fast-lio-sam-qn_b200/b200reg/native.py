@@ -20,13 +20,14 @@ class GicpParams(C.Structure):
 
 
 class Result(C.Structure):
-    _fields_ = [("T", C.c_double * 16), ("Tf", C.c_float * 16), ("fitness", C.c_double), ("converged", C.c_int32),
+    _fields_ = [("T", C.c_double * 16), ("Tf", C.c_float * 16), ("pose_between", C.c_double * 16), ("fitness", C.c_double),
+                ("converged", C.c_int32),
                 ("valid", C.c_int32), ("iterations", C.c_int32), ("n_linearize", C.c_int32), ("n_error", C.c_int32),
                 ("lm_failed", C.c_int32), ("status", C.c_int32), ("reserved", C.c_int32)]
 
     def as_dict(self):
         return dict(T=np.array(self.T).reshape(4, 4), Tf=np.array(self.Tf, np.float32).reshape(4, 4),
-                    fitness=self.fitness, converged=bool(self.converged), valid=bool(self.valid),
+                    pose_between=np.array(self.pose_between).reshape(4, 4), fitness=self.fitness, converged=bool(self.converged), valid=bool(self.valid),
                     iterations=self.iterations, n_linearize=self.n_linearize, n_error=self.n_error,
                     lm_failed=bool(self.lm_failed), status=self.status)
 
@@ -72,7 +73,8 @@ EXPORTS = [
     "b200reg_quatro_align", "b200reg_loop_closure", "b200reg_default_loop_config", "b200reg_keyframes_create",
     "b200reg_keyframes_destroy", "b200reg_keyframes_add", "b200reg_keyframes_set_pose", "b200reg_keyframes_size",
     "b200reg_knn_bruteforce", "b200reg_fetch_closest_keyframes", "b200reg_assemble_clouds", "b200reg_cloud_points", "b200reg_perform_loop_closure",
-    "b200reg_loop_factor_from_poses", "b200reg_loop_factors",
+    "b200reg_loop_factor_from_poses", "b200reg_loop_factors", "b200reg_compute_error", "b200reg_assemble_clouds_at",
+    "b200reg_struct_size",
 ]
 
 
@@ -85,6 +87,7 @@ def lib():
         _lib.b200reg_version.restype = C.c_char_p
         _lib.b200reg_ctx_launch_count.restype = C.c_int64
         _lib.b200reg_cloud_size.restype = C.c_size_t
+        _lib.b200reg_struct_size.restype = C.c_size_t
     return _lib
 
 
@@ -348,6 +351,15 @@ class Context:
                                        corr.ctypes.data_as(C.c_void_p), sqd.ctypes.data_as(C.c_void_p)))
         return dict(H=H, b=b, err=err.value, corr=corr, sqd=sqd)
 
+    def compute_error(self, src, tgt, T_lin, T_trial, max_corr_dist=52.5):
+        """NanoGICP::compute_error at T_trial with the stale correspondences / Mahalanobis matrices of a linearize at T_lin."""
+        Tl = np.ascontiguousarray(T_lin, np.float64).reshape(16)
+        Tt = np.ascontiguousarray(T_trial, np.float64).reshape(16)
+        err = C.c_double()
+        _check(lib().b200reg_compute_error(self.h, src.h, tgt.h, Tl.ctypes.data_as(C.c_void_p), Tt.ctypes.data_as(C.c_void_p),
+                                           C.c_double(max_corr_dist), C.byref(err)))
+        return err.value
+
 
 class Keyframes:
     """Device-resident keyframe store (PosePcd records) + batched loopTimerFunc pieces."""
@@ -387,13 +399,20 @@ class Keyframes:
         return out
 
     def assemble(self, src_idx, dst_idx, cfg=None, n_keyframes=0):
+        """n_keyframes: keyframes.size() the sub-map bounds see -- one int for the batch (0 = the store's size) or one per pair."""
         cfg = cfg or default_loop_config()
         s = np.ascontiguousarray(src_idx, np.int32)
         d = np.ascontiguousarray(dst_idx, np.int32)
         cnt = len(s)
         so, do = (C.c_void_p * cnt)(), (C.c_void_p * cnt)()
-        _check(lib().b200reg_assemble_clouds(self.ctx.h, self.h, cnt, s.ctypes.data_as(C.c_void_p), d.ctypes.data_as(C.c_void_p),
-                                             C.byref(cfg), int(n_keyframes), so, do))
+        if np.ndim(n_keyframes) > 0:
+            nk = np.ascontiguousarray(n_keyframes, np.int32)
+            assert len(nk) == cnt
+            _check(lib().b200reg_assemble_clouds_at(self.ctx.h, self.h, cnt, s.ctypes.data_as(C.c_void_p), d.ctypes.data_as(C.c_void_p),
+                                                    C.byref(cfg), nk.ctypes.data_as(C.c_void_p), so, do))
+        else:
+            _check(lib().b200reg_assemble_clouds(self.ctx.h, self.h, cnt, s.ctypes.data_as(C.c_void_p), d.ctypes.data_as(C.c_void_p),
+                                                 C.byref(cfg), int(n_keyframes), so, do))
         mk = lambda h: Cloud(self.ctx, C.c_void_p(h), int(lib().b200reg_cloud_size(C.c_void_p(h))))
         return [mk(so[i]) for i in range(cnt)], [mk(do[i]) for i in range(cnt)]
 

@@ -4,6 +4,7 @@
 #include <cuda_runtime.h>
 
 #include <algorithm>
+#include <cstddef>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -26,6 +27,7 @@ int launch_quatro_match_solve(const MatchDev* d_pairs, int count, int max_ni, in
 void launch_transform_raw(const CloudDev* d_clouds, const double* d_T16s, int count, int max_n, float4* const* d_outs, cudaStream_t s);
 int launch_fetch_closest(const double* d_pos, const double* d_stamp, const int* d_queries, int count, double radius, double tdiff,
                          int* d_out, cudaStream_t s);
+cudaError_t quatro_init_device();
 int launch_assemble_voxelize(const AssembleJob* d_jobs, const CloudDev* d_sort, int count, int max_total, const KeyframeDev* d_kfs,
                              const double* d_poses, float inv_leaf, cudaStream_t s);
 }  // namespace b200
@@ -159,7 +161,18 @@ void b200reg_default_gicp_params(b200reg_gicp_params* p) {
 }
 
 const char* b200reg_last_error(void) { return g_err.c_str(); }
-const char* b200reg_version(void) { return "b200reg 0.1 (sm_100a)"; }
+const char* b200reg_version(void) { return "b200reg 0.2 (sm_100a)"; }
+size_t b200reg_struct_size(int which) {
+  switch (which) {
+    case 0: return sizeof(b200reg_gicp_params);
+    case 1: return sizeof(b200reg_result);
+    case 2: return sizeof(b200reg_quatro_params);
+    case 3: return sizeof(b200reg_quatro_info);
+    case 4: return sizeof(b200reg_loop_config);
+    case 5: return sizeof(b200reg_loop_factor);
+    default: return 0;
+  }
+}
 
 int b200reg_ctx_create(int device, b200reg_ctx** out) {
   if (!out) return fail(B200REG_EINVAL, "out is NULL");
@@ -167,8 +180,16 @@ int b200reg_ctx_create(int device, b200reg_ctx** out) {
   if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0 || device < 0 || device >= ndev)
     return fail(B200REG_ENODEV, "no usable CUDA device (this library has no CPU fallback)");
   CU(cudaSetDevice(device));
+  CU(quatro_init_device());
   b200reg_ctx* c = new b200reg_ctx;
   c->device = device;
+  struct Undo {  // a failure half way must not leak the context
+    b200reg_ctx* c;
+    bool ok = false;
+    ~Undo() {
+      if (!ok) b200reg_ctx_destroy(c);
+    }
+  } undo{c};
   CU(cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking));
   CU(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
   c->stream = c->own_stream;
@@ -182,6 +203,7 @@ int b200reg_ctx_create(int device, b200reg_ctx** out) {
   CU(cudaMemPoolSetAttribute(c->pool, cudaMemPoolAttrReleaseThreshold, &thr));
   CU(cudaMalloc(&c->d_done, sizeof(int)));
   CU(cudaMallocHost(&c->h_done, sizeof(int)));
+  undo.ok = true;
   *out = c;
   return B200REG_OK;
 }
@@ -189,11 +211,11 @@ int b200reg_ctx_create(int device, b200reg_ctx** out) {
 int b200reg_ctx_destroy(b200reg_ctx* c) {
   if (!c) return B200REG_OK;
   cudaSetDevice(c->device);
-  cudaStreamSynchronize(c->stream);
-  cudaFree(c->d_done);
-  cudaFreeHost(c->h_done);
-  cudaStreamDestroy(c->own_stream);
-  cudaStreamDestroy(c->copy_stream);
+  if (c->stream) cudaStreamSynchronize(c->stream);
+  if (c->d_done) cudaFree(c->d_done);
+  if (c->h_done) cudaFreeHost(c->h_done);
+  if (c->own_stream) cudaStreamDestroy(c->own_stream);
+  if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
   if (c->pool) cudaMemPoolDestroy(c->pool);
   delete c;
   return B200REG_OK;
@@ -530,6 +552,9 @@ int b200reg_gicp_align(b200reg_ctx* c, int count, b200reg_cloud* const* src, b20
     r.fitness = st.fitness;
     r.converged = st.converged;
     r.valid = (st.converged && st.fitness < params->icp_score_thr) ? 1 : 0;
+    for (int a = 0; a < 16; a++) r.pose_between[a] = (a % 5 == 0) ? 1.0 : 0.0;  // RegistrationOutput default (loop_closure.h:64-70)
+    if (r.valid)  // getFinalTransformation().cast<double>() (loop_closure.cpp:133)
+      for (int a = 0; a < 12; a++) r.pose_between[a] = (double)st.Tf[a];
     r.iterations = st.nr_iterations;
     r.n_linearize = st.n_lin;
     r.n_error = st.n_err;
@@ -763,6 +788,45 @@ int b200reg_linearize(b200reg_ctx* c, const b200reg_cloud* src, const b200reg_cl
     if (corr_out) corr_out[o] = to;
     if (sqd_out) sqd_out[o] = sqd[p_];
   }
+  return B200REG_OK;
+}
+
+int b200reg_compute_error(b200reg_ctx* c, const b200reg_cloud* src, const b200reg_cloud* tgt, const double* T_lin16,
+                          const double* T_trial16, double max_corr_dist, double* err) {
+  if (!c || !src || !tgt || !T_lin16 || !T_trial16 || !err) return fail(B200REG_EINVAL, "bad argument");
+  if (!src->has_cov || !tgt->has_cov) return fail(B200REG_ESTATE, "covariances not computed");
+  CU(cudaSetDevice(c->device));
+  cudaStream_t s = c->stream;
+  Scratch scratch(c);
+  PairWork w;
+  b200reg_cloud* sp = const_cast<b200reg_cloud*>(src);
+  b200reg_cloud* tp = const_cast<b200reg_cloud*>(tgt);
+  int rc;
+  if ((rc = make_pair_work(c, 1, &sp, &tp, w, scratch))) return rc;
+  b200reg_gicp_params p;
+  b200reg_default_gicp_params(&p);
+  p.max_corr_dist = max_corr_dist;
+  const GicpParamsDev prm = to_dev(p);
+  double* d_guess = nullptr;
+  CU(scratch.alloc((void**)&d_guess, sizeof(double) * 16));
+  CU(cudaMemcpyAsync(d_guess, T_lin16, sizeof(double) * 16, cudaMemcpyHostToDevice, s));
+  CU(cudaMemsetAsync(c->d_done, 0, sizeof(int), s));
+  launch_gicp_init(w.d_states, d_guess, 1, prm, s);
+  launch_gicp_step(w.d_pairs, w.d_states, 1, w.max_n, prm, c->d_done, s);  // linearize: correspondences + Mahalanobis, phase -> TRIAL
+  // overwrite the trial pose the LM controller prepared with the caller's
+  double Rt[9], tt[3];
+  for (int a = 0; a < 3; a++) {
+    for (int b = 0; b < 3; b++) Rt[3 * a + b] = T_trial16[4 * a + b];
+    tt[a] = T_trial16[4 * a + 3];
+  }
+  CU(cudaMemcpyAsync((char*)w.d_states + offsetof(PairState, Rt), Rt, sizeof(Rt), cudaMemcpyHostToDevice, s));
+  CU(cudaMemcpyAsync((char*)w.d_states + offsetof(PairState, tt), tt, sizeof(tt), cudaMemcpyHostToDevice, s));
+  launch_gicp_step(w.d_pairs, w.d_states, 1, w.max_n, prm, c->d_done, s);  // compute_error at the trial pose
+  c->launches += 3;
+  PairState st;
+  CU(cudaMemcpyAsync(&st, w.d_states, sizeof(PairState), cudaMemcpyDeviceToHost, s));
+  CU(cudaStreamSynchronize(s));
+  *err = st.y_trial;
   return B200REG_OK;
 }
 
@@ -1046,6 +1110,7 @@ static int coarse_to_fine_on_clouds(b200reg_ctx* c, int count, b200reg_cloud* co
     for (int k = 0; k < 16; k++) {
       out[i].T[k] = qi[i].T[k];
       out[i].Tf[k] = (float)qi[i].T[k];
+      out[i].pose_between[k] = qi[i].T[k];  // an invalid coarse stage returns what quatro::align returned (loop_closure.cpp:144-148)
     }
     out[i].fitness = 1.7976931348623157e308;  // RegistrationOutput::score_ default (loop_closure.h:68)
     if (qi[i].valid) vidx.push_back(i);
@@ -1101,10 +1166,14 @@ static int coarse_to_fine_on_clouds(b200reg_ctx* c, int count, b200reg_cloud* co
       }
       for (int a = 0; a < 4; a++)
         for (int b = 0; b < 4; b++) {
-          double v = 0;
-          for (int m = 0; m < 4; m++) v += F[4 * a + m] * Q[4 * m + b];
-          r.T[4 * a + b] = v;
+          double v = 0, pb = 0;
+          for (int m = 0; m < 4; m++) {
+            v += F[4 * a + m] * Q[4 * m + b];
+            pb += gres[k].pose_between[4 * a + m] * Q[4 * m + b];  // fine_output.pose_between_eig_ is Identity when the fine
+          }                                                        // stage is not valid: the reference then keeps I * Q
+          r.T[4 * a + b] = v;           // telemetry: the solver's own final transform composed with the coarse stage
           r.Tf[4 * a + b] = (float)v;
+          r.pose_between[4 * a + b] = pb;
         }
       out[i] = r;
     }
@@ -1264,7 +1333,7 @@ int b200reg_loop_factors(b200reg_ctx* c, const b200reg_keyframes* kf, int count,
       out[i].to_idx = -1;
       continue;
     }
-    const int rc = b200reg_loop_factor_from_poses(results[i].T, &kf->poses[16 * (size_t)query_idx[i]], &kf->poses[16 * (size_t)closest_idx[i]],
+    const int rc = b200reg_loop_factor_from_poses(results[i].pose_between, &kf->poses[16 * (size_t)query_idx[i]], &kf->poses[16 * (size_t)closest_idx[i]],
                                                   results[i].fitness, results[i].valid, query_idx[i], closest_idx[i], &out[i]);
     if (rc) return rc;
   }
@@ -1300,9 +1369,18 @@ int b200reg_fetch_closest_keyframes(b200reg_ctx* c, b200reg_keyframes* kf, int c
 
 int b200reg_assemble_clouds(b200reg_ctx* c, b200reg_keyframes* kf, int count, const int32_t* src_idx, const int32_t* dst_idx,
                             const b200reg_loop_config* cfg, int n_keyframes, b200reg_cloud** src_out, b200reg_cloud** dst_out) {
-  if (!c || !kf || count <= 0 || !src_idx || !dst_idx || !cfg || !src_out || !dst_out) return fail(B200REG_EINVAL, "bad argument");
-  const int nk = n_keyframes > 0 ? n_keyframes : (int)kf->pts.size();
-  if (nk > (int)kf->pts.size()) return fail(B200REG_EINVAL, "n_keyframes exceeds the store");
+  if (!kf || count <= 0) return fail(B200REG_EINVAL, "bad argument");
+  std::vector<int32_t> nks(count, n_keyframes > 0 ? n_keyframes : (int)kf->pts.size());
+  return b200reg_assemble_clouds_at(c, kf, count, src_idx, dst_idx, cfg, nks.data(), src_out, dst_out);
+}
+
+int b200reg_assemble_clouds_at(b200reg_ctx* c, b200reg_keyframes* kf, int count, const int32_t* src_idx, const int32_t* dst_idx,
+                               const b200reg_loop_config* cfg, const int32_t* n_keyframes, b200reg_cloud** src_out,
+                               b200reg_cloud** dst_out) {
+  if (!c || !kf || count <= 0 || !src_idx || !dst_idx || !cfg || !n_keyframes || !src_out || !dst_out)
+    return fail(B200REG_EINVAL, "bad argument");
+  for (int i = 0; i < count; i++)
+    if (n_keyframes[i] <= 0 || n_keyframes[i] > (int)kf->pts.size()) return fail(B200REG_EINVAL, "n_keyframes out of range");
   const int range = cfg->num_submap_keyframes;
   if (2 * range + 1 > MAXSEG) return fail(B200REG_EINVAL, "num_submap_keyframes too large");
   if (!(cfg->voxel_res > 0)) return fail(B200REG_EINVAL, "voxel_res must be positive");
@@ -1316,6 +1394,7 @@ int b200reg_assemble_clouds(b200reg_ctx* c, b200reg_keyframes* kf, int count, co
   for (int j = 0; j < njobs; j++) {
     const bool is_src = j < count;
     const int centre = is_src ? src_idx[j] : dst_idx[j - count];
+    const int nk = n_keyframes[is_src ? j : j - count];  // keyframes.size() at this pair's tick
     if (centre < 0 || centre >= nk) return fail(B200REG_EINVAL, "keyframe index out of range");
     AssembleJob& J = jobs[j];
     memset(&J, 0, sizeof(J));
@@ -1437,6 +1516,7 @@ int b200reg_perform_loop_closure(b200reg_ctx* c, b200reg_keyframes* kf, int coun
     memset(&out[i], 0, sizeof(b200reg_result));  // dummy output whose is_valid is false (loop_closure.cpp:201-204)
     out[i].T[0] = out[i].T[5] = out[i].T[10] = out[i].T[15] = 1.0;
     out[i].Tf[0] = out[i].Tf[5] = out[i].Tf[10] = out[i].Tf[15] = 1.f;
+    out[i].pose_between[0] = out[i].pose_between[5] = out[i].pose_between[10] = out[i].pose_between[15] = 1.0;
     out[i].fitness = 1.7976931348623157e308;
     if (quatro_out) memset(&quatro_out[i], 0, sizeof(b200reg_quatro_info));
     if (closest_idx[i] >= 0) {
@@ -1448,11 +1528,11 @@ int b200reg_perform_loop_closure(b200reg_ctx* c, b200reg_keyframes* kf, int coun
   if (qs.empty()) return B200REG_OK;
   const int m = (int)qs.size();
   // at the time query q was the latest keyframe the vector held q + 1 keyframes (fast_lio_sam_qn.cpp:205-219); a batch
-  // replays several ticks, so the "size" the submap bounds see is taken per batch from the largest query
-  int nk = 0;
-  for (int q : qs) nk = std::max(nk, q + 1);
+  // replays several ticks, so every pair carries the size its own tick saw (the sub-map bounds of loop_closure.cpp:72,79,100)
+  std::vector<int32_t> nks(m);
+  for (int k = 0; k < m; k++) nks[k] = qs[k] + 1;
   std::vector<b200reg_cloud*> sc(m, nullptr), dc(m, nullptr);
-  int rc = b200reg_assemble_clouds(c, kf, m, qs.data(), cs.data(), cfg, nk, sc.data(), dc.data());
+  int rc = b200reg_assemble_clouds_at(c, kf, m, qs.data(), cs.data(), cfg, nks.data(), sc.data(), dc.data());
   std::vector<b200reg_result> res(m);
   std::vector<b200reg_quatro_info> qi(m);
   if (!rc) {

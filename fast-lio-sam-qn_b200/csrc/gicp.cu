@@ -155,6 +155,7 @@ __device__ void lm_update(PairState* st, const double* sums, const GicpParamsDev
     lm_prepare_trial(st);
   } else if (phase == PH_TRIAL) {
     const double yi = sums[0];
+    st->y_trial = yi;
     st->n_err++;
     double denom = 0;
     for (int i = 0; i < 6; i++) denom += st->d[i] * (st->lambda * st->d[i] - st->b[i]);
@@ -207,6 +208,7 @@ __global__ void k_gicp_init(PairState* states, const double* guess16, int count,
   st->lambda = -1.0;
   st->nu = 2.0;
   st->y0 = 0.0;
+  st->y_trial = 0.0;
   st->fitness = 0.0;
   st->phase = PH_LINEARIZE;
   st->outer_it = 0;

@@ -83,6 +83,7 @@ struct PairState {
   double d[6];
   double H[36], b[6];
   double y0;
+  double y_trial;       // sum of errors of the last compute_error pass
   double lambda, nu;
   double fitness;
   float Tf[12];  // x0.cast<float>() rows (r0 r1 r2 t)

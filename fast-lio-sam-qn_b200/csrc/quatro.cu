@@ -102,7 +102,7 @@ __device__ __forceinline__ int bin11(float v) {
 __global__ void __launch_bounds__(STEP_THREADS) k_spfh(const CloudDev* clouds, float r2) {
   const CloudDev& c = clouds[blockIdx.y];
   const int i = blockIdx.x * STEP_THREADS + threadIdx.x;
-  __shared__ unsigned short hist[FDIM][STEP_THREADS];
+  __shared__ unsigned int hist[FDIM][STEP_THREADS];  // 32-bit: an un-voxelised cloud can hold > 65535 neighbours in the radius
   __shared__ int spos[RV_BUF * STEP_THREADS];
   __shared__ int wstack[STEP_THREADS / 32][MAX_STACK];
 #pragma unroll
@@ -1644,13 +1644,15 @@ int launch_fpfh(const CloudDev* d_clouds, int count, int max_n, float normal_r2,
 size_t solve_smem_bytes() { return sizeof(SolveSmem); }
 int launch_big_solve(const MatchDev* d_pairs, int count, const QuatroParamsDev& prm, cudaStream_t s);
 
+// Opt-in shared-memory sizes are a PER-DEVICE function attribute: b200reg_ctx_create calls this after cudaSetDevice, so
+// every context (one per GPU in a multi-GPU process) gets them on its own device.
+cudaError_t quatro_init_device() {
+  cudaError_t e = cudaFuncSetAttribute(k_teaser_solve, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SolveSmem));
+  if (e != cudaSuccess) return e;
+  return cudaFuncSetAttribute(k_adv_select, cudaFuncAttributeMaxDynamicSharedMemorySize, BIGC * 8);
+}
+
 int launch_quatro_match_solve(const MatchDev* d_pairs, int count, int max_ni, int max_nj, const QuatroParamsDev& prm, cudaStream_t s) {
-  static bool attr_set = false;
-  if (!attr_set) {
-    cudaFuncSetAttribute(k_teaser_solve, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SolveSmem));
-    cudaFuncSetAttribute(k_adv_select, cudaFuncAttributeMaxDynamicSharedMemorySize, BIGC * 8);
-    attr_set = true;
-  }
   int l = 0;
   k_match_init<<<dim3((max_ni + 255) / 256, count), 256, 0, s>>>(d_pairs); l++;
   k_cloud_sum<<<dim3(1, count, 2), 1024, 0, s>>>(d_pairs); l++;

@@ -62,6 +62,10 @@ typedef struct b200reg_gicp_params {
 typedef struct b200reg_result {
   double T[16];        /* final SE(3), fp64, row-major: maps src onto dst                      */
   float Tf[16];        /* x0.cast<float>() -- what getFinalTransformation() returns            */
+  double pose_between[16]; /* RegistrationOutput::pose_between_eig_ exactly as the reference leaves it
+                          (loop_closure.cpp:129-134, 156): icpAlignment: Tf.cast<double>() when valid, Identity otherwise;
+                          coarseToFineAlignment: (valid fine stage ? Tf_fine : Identity) * T_quatro, or the coarse
+                          stage's own output when Quatro itself is invalid; Identity for the dummy output        */
   double fitness;      /* getFitnessScore(): mean 1-NN d^2 over ALL source points              */
   int32_t converged;   /* hasConverged()                                                       */
   int32_t valid;       /* converged && fitness < icp_score_thr (loop_closure.cpp:129)          */
@@ -106,6 +110,9 @@ void b200reg_default_gicp_params(b200reg_gicp_params* p);
 void b200reg_default_quatro_params(b200reg_quatro_params* p);
 const char* b200reg_last_error(void);
 const char* b200reg_version(void);
+/* sizeof() of the ABI structs as compiled into the library, so that a binding (ctypes, cgo, JNI ...) can check its own
+ * layout at load time: 0 gicp_params, 1 result, 2 quatro_params, 3 quatro_info, 4 loop_config, 5 loop_factor.  0 = unknown. */
+size_t b200reg_struct_size(int which);
 
 /* ---- context ---------------------------------------------------------------------- */
 int b200reg_ctx_create(int device, b200reg_ctx** out);
@@ -213,6 +220,12 @@ int b200reg_assemble_clouds(b200reg_ctx* ctx, b200reg_keyframes* kf, int count, 
                             const int32_t* dst_idx, const b200reg_loop_config* cfg, int n_keyframes,
                             b200reg_cloud** src_out, b200reg_cloud** dst_out);
 /* Points of a cloud in their ORIGINAL order as (x, y, z) (debug tap for the assembled / voxelised clouds).    */
+/* Same with the size of the keyframe vector given PER PAIR (n_keyframes[i] = latest keyframe index + 1 at the tick the
+ * pair was formed): a batch that replays several loopTimerFunc ticks sees, for each query, exactly the sub-map bounds
+ * `i < keyframes.size() - 1` the reference evaluated at that tick (loop_closure.cpp:72,79,100).                      */
+int b200reg_assemble_clouds_at(b200reg_ctx* ctx, b200reg_keyframes* kf, int count, const int32_t* src_idx,
+                               const int32_t* dst_idx, const b200reg_loop_config* cfg, const int32_t* n_keyframes,
+                               b200reg_cloud** src_out, b200reg_cloud** dst_out);
 int b200reg_cloud_points(b200reg_ctx* ctx, const b200reg_cloud* cloud, float* xyz_out);
 /* LoopClosure::performLoopClosure (loop_closure.cpp:168-205) for `count` query keyframes with given closest
  * indices (-1 = no candidate -> invalid dummy output): assemble, then coarse-to-fine (enable_quatro) or GICP only. */
@@ -264,6 +277,10 @@ int b200reg_get_covariances(b200reg_ctx* ctx, const b200reg_cloud* cloud, double
 int b200reg_linearize(b200reg_ctx* ctx, const b200reg_cloud* src, const b200reg_cloud* tgt, const double* T16,
                       double max_corr_dist, double* H36, double* b6, double* err, int32_t* corr_out,
                       float* sqd_out);
+/* NanoGICP::compute_error (nano_gicp_impl.hpp:272-296) in isolation: correspondences and Mahalanobis matrices are
+ * taken from ONE linearize at T_lin16 (they stay stale, as in step_lm), then sum e^T M e is evaluated at T_trial16.  */
+int b200reg_compute_error(b200reg_ctx* ctx, const b200reg_cloud* src, const b200reg_cloud* tgt, const double* T_lin16,
+                          const double* T_trial16, double max_corr_dist, double* err);
 
 #ifdef __cplusplus
 }

@@ -52,6 +52,7 @@ def lib():
     if _LIB is None:
         _LIB = C.CDLL(build())
         _LIB.orc_linearize.restype = C.c_double
+        _LIB.orc_compute_error.restype = C.c_double
         _LIB.orc_num_threads.restype = C.c_int
     return _LIB
 
@@ -160,6 +161,17 @@ def linearize(src, tgt, cov_src, cov_tgt, T, max_corr_dist=52.5):
                             C.c_double(max_corr_dist), _p(H, C.c_double), _p(b, C.c_double), _p(corr, C.c_int),
                             _p(sqd, C.c_float), _p(mah, C.c_double))
     return dict(H=H, b=b, err=y, corr=corr, sqd=sqd, mahal=mah)
+
+
+def compute_error(src, tgt, cov_src, cov_tgt, T_lin, T_trial, max_corr_dist=52.5):
+    """NanoGICP::compute_error at T_trial with the correspondences / Mahalanobis matrices of a linearize at T_lin."""
+    src, tgt = _f32(src), _f32(tgt)
+    cov_src = np.ascontiguousarray(cov_src, np.float64)
+    cov_tgt = np.ascontiguousarray(cov_tgt, np.float64)
+    Tl, Tt = np.ascontiguousarray(T_lin, np.float64), np.ascontiguousarray(T_trial, np.float64)
+    return lib().orc_compute_error(_p(src, C.c_float), len(src), src.shape[1], _p(tgt, C.c_float), len(tgt), tgt.shape[1],
+                                   _p(cov_src, C.c_double), _p(cov_tgt, C.c_double), _p(Tl, C.c_double), _p(Tt, C.c_double),
+                                   C.c_double(max_corr_dist))
 
 
 def gicp_align(src, tgt, params=None, guess=None, want_aligned=False, want_trace=False):

@@ -508,6 +508,17 @@ double orc_linearize(const float* src, int N, int sstride, const float* tgt, int
   return y;
 }
 
+// NanoGICP::compute_error in isolation (nano_gicp_impl.hpp:272-296): correspondences and Mahalanobis matrices from one
+// update_correspondences at T_lin (stale, as inside step_lm), sum of e^T M e at T_trial.
+double orc_compute_error(const float* src, int N, int sstride, const float* tgt, int M, int tstride, const double* cov_src,
+                         const double* cov_tgt, const double* T_lin16, const double* T_trial16, double max_corr_dist) {
+  Index index;
+  index.build(tgt, M, tstride);
+  GicpProblem P{src, N, sstride, tgt, M, tstride, &index, cov_src, cov_tgt, max_corr_dist, {}, {}, {}};
+  update_correspondences(P, iso_from_rowmajor16(T_lin16));
+  return compute_error(P, iso_from_rowmajor16(T_trial16));
+}
+
 // LoopClosure::icpAlignment (QN/src/loop_closure.cpp:110-136) = setInputSource +
 // calculateSourceCovariances + setInputTarget + calculateTargetCovariances +
 // align (pcl::Registration::align -> LsqRegistration::computeTransformation,

@@ -40,7 +40,14 @@ def test_struct_layouts_match_header():
     from b200reg import native
     assert ctypes.sizeof(native.GicpParams) == 56
     assert native.default_params().regularization == 3  # PLANE
-    assert ctypes.sizeof(native.Result) == 16 * 8 + 16 * 4 + 8 + 8 * 4
+    assert ctypes.sizeof(native.Result) == 16 * 8 + 16 * 4 + 16 * 8 + 8 + 8 * 4
+    # the binding's layouts against what the compiler laid out (b200reg_struct_size)
+    lib = native.lib()
+    lib.b200reg_struct_size.restype = ctypes.c_size_t
+    for which, st in enumerate((native.GicpParams, native.Result, native.QuatroParams, native.QuatroInfo, native.LoopConfig,
+                                native.LoopFactor)):
+        assert lib.b200reg_struct_size(which) == ctypes.sizeof(st), st.__name__
+    assert native.Result.pose_between.offset == 192
     p = native.default_params()
     assert (p.k_correspondences, p.max_iterations, p.lm_max_iterations) == (15, 32, 10)
     assert (p.max_corr_dist, p.transformation_eps, p.rotation_eps, p.icp_score_thr) == (52.5, 0.01, 2e-3, 1.5)

@@ -81,7 +81,7 @@ def test_perform_loop_closure_matches_oracle(ctx, store, oracle, synth, seq):
     res2, _ = store.perform_loop_closure(queries[:2], closest[:2], cfg)
     for k in range(2):
         q, c = int(queries[k]), int(closest[k])
-        src, dst = oracle.set_src_and_dst_cloud(seq["clouds"], seq["poses"], q, c, enable_quatro=False, n_keyframes=int(queries[:2].max()) + 1)
+        src, dst = oracle.set_src_and_dst_cloud(seq["clouds"], seq["poses"], q, c, enable_quatro=False, n_keyframes=q + 1)
         o = oracle.gicp_align(src, dst)
         rot, tr = synth.se3_error(res2[k]["T"], o["T"])
         assert rot < 3e-4 and tr < 3e-3, (k, rot, tr)
@@ -99,10 +99,41 @@ def test_loop_factors_close_the_loop(ctx, store, oracle, synth, seq):
         q, c = int(queries[k]), int(closest[k])
         f = facs[k]
         assert (f["from_idx"], f["to_idx"]) == (q, c) and f["valid"] == bool(raw[k].valid)
-        T = np.array(raw[k].T).reshape(4, 4)
+        T = np.array(raw[k].pose_between).reshape(4, 4)  # RegistrationOutput::pose_between_eig_ is what the factor is built from
         M, var = oracle.loop_factor(T, seq["poses"][q], seq["poses"][c], raw[k].fitness)
         assert np.abs(f["measurement"] - M).max() < 1e-12 and np.array_equal(f["variances"], var)
         # the measured relative pose is the TRUE relative pose of the two keyframes (drift removed)
         true_rel = np.linalg.inv(seq["true_poses"][q]) @ seq["true_poses"][c]
         rot, tr = synth.se3_error(f["measurement"], true_rel)
         assert rot < 2e-2 and tr < 0.3, (k, rot, tr)
+
+
+def test_batched_queries_see_their_own_keyframe_count(ctx, store, oracle, seq):
+    """A batch replays several loopTimerFunc ticks: the sub-map bound `i < keyframes.size() - 1` (loop_closure.cpp:72,79,100)
+    is evaluated with size = query + 1 PER QUERY, so a batch equals the one-by-one replay -- also for the non-maximal
+    queries, whose merged clouds must not reach past (or onto) their own query keyframe."""
+    import b200reg
+    cfg = b200reg.default_loop_config()
+    cfg.enable_submap_matching = 1
+    # closest keyframes chosen within the sub-map range of their query so that the bound actually bites
+    queries = np.array([60, 100, 139], np.int32)
+    closest = np.array([57, 97, 136], np.int32)
+    sc, dc = store.assemble(queries, closest, cfg, n_keyframes=queries + 1)
+    for k in range(3):
+        q, c = int(queries[k]), int(closest[k])
+        os_, od_ = oracle.set_src_and_dst_cloud(seq["clouds"], seq["poses"], q, c, submap_range=5, voxel_res=0.3,
+                                                enable_quatro=True, enable_submap_matching=True, n_keyframes=q + 1)
+        for cloud, want in ((sc[k], os_), (dc[k], od_)):
+            got = ctx.cloud_points(cloud)
+            assert got.shape[0] == want.shape[0], (k, got.shape, want.shape)
+            assert np.abs(got - want[:, :3]).max() < 2e-4
+    # the batch-wide bound (the old behaviour: size = max(query) + 1) gives DIFFERENT clouds for the non-maximal queries
+    sc2, dc2 = store.assemble(queries, closest, cfg, n_keyframes=int(queries.max()) + 1)
+    assert sc2[0].n != sc[0].n and sc2[2].n == sc[2].n
+    # and the batched driver equals the one-by-one replay bit for bit
+    res, _ = store.perform_loop_closure(queries, closest, cfg)
+    for k in range(3):
+        single, _ = store.perform_loop_closure(queries[k:k + 1], closest[k:k + 1], cfg)
+        assert np.array_equal(res[k]["T"], single[0]["T"]) and res[k]["fitness"] == single[0]["fitness"]
+    for c in sc + dc + sc2 + dc2:
+        c.destroy()
