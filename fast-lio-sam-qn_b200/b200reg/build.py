@@ -6,7 +6,7 @@ from concurrent.futures import ThreadPoolExecutor
 PKG = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 CSRC = os.path.join(PKG, "csrc")
 REPO = os.path.dirname(PKG)
-SOURCES = ["api.cu", "index_build.cu", "gicp.cu", "quatro.cu", "assemble.cu"]
+SOURCES = ["api.cu", "index_build.cu", "gicp.cu", "quatro.cu", "assemble.cu", "batch.cu"]
 EXTRA = {"quatro.cu": ["-fmad=false"],    # fixed fp32 operation order for the FPFH / matcher arithmetic
          "assemble.cu": ["-fmad=false"]}  # transformPcd / VoxelGrid / candidate distances as the (FMA-free) reference computes them
 HEADERS = ["internal.cuh", "knn.cuh", "smallmath.cuh", os.path.join(REPO, "include", "b200reg.h")]
@@ -40,7 +40,8 @@ def build_native(force=False, verbose=False):
 
     with ThreadPoolExecutor(len(SOURCES)) as ex:
         objs = list(ex.map(cc, SOURCES))
-    r = subprocess.run([NVCC, "-shared", "-o", LIB, "-ccbin", "/usr/bin/g++"] + objs, capture_output=True, text=True)
+    # libdl for the run-time NCCL binding (b200reg_comm_*), pthread for the batch driver's worker threads
+    r = subprocess.run([NVCC, "-shared", "-o", LIB, "-ccbin", "/usr/bin/g++"] + objs + ["-ldl", "-lpthread"], capture_output=True, text=True)
     if r.returncode != 0:
         raise RuntimeError("link failed:\n" + r.stderr)
     return LIB

@@ -23,7 +23,7 @@ class Result(C.Structure):
     _fields_ = [("T", C.c_double * 16), ("Tf", C.c_float * 16), ("pose_between", C.c_double * 16), ("fitness", C.c_double),
                 ("converged", C.c_int32),
                 ("valid", C.c_int32), ("iterations", C.c_int32), ("n_linearize", C.c_int32), ("n_error", C.c_int32),
-                ("lm_failed", C.c_int32), ("status", C.c_int32), ("reserved", C.c_int32)]
+                ("lm_failed", C.c_int32), ("status", C.c_int32), ("tag", C.c_int32)]
 
     def as_dict(self):
         return dict(T=np.array(self.T).reshape(4, 4), Tf=np.array(self.Tf, np.float32).reshape(4, 4),
@@ -74,7 +74,11 @@ EXPORTS = [
     "b200reg_keyframes_destroy", "b200reg_keyframes_add", "b200reg_keyframes_set_pose", "b200reg_keyframes_size",
     "b200reg_knn_bruteforce", "b200reg_fetch_closest_keyframes", "b200reg_assemble_clouds", "b200reg_cloud_points", "b200reg_perform_loop_closure",
     "b200reg_loop_factor_from_poses", "b200reg_loop_factors", "b200reg_compute_error", "b200reg_assemble_clouds_at",
-    "b200reg_struct_size",
+    "b200reg_struct_size", "b200reg_set_last_error",
+    "b200reg_batch_create", "b200reg_batch_destroy", "b200reg_batch_submit_icp", "b200reg_batch_submit_loop_closure",
+    "b200reg_batch_wait", "b200reg_batch_wait_all", "b200reg_batch_launch_count", "b200reg_batch_depth",
+    "b200reg_comm_unique_id", "b200reg_comm_init", "b200reg_comm_destroy", "b200reg_comm_rank", "b200reg_comm_world",
+    "b200reg_allgather_results",
 ]
 
 
@@ -88,6 +92,9 @@ def lib():
         _lib.b200reg_ctx_launch_count.restype = C.c_int64
         _lib.b200reg_cloud_size.restype = C.c_size_t
         _lib.b200reg_struct_size.restype = C.c_size_t
+        _lib.b200reg_batch_submit_icp.restype = C.c_int64
+        _lib.b200reg_batch_submit_loop_closure.restype = C.c_int64
+        _lib.b200reg_batch_launch_count.restype = C.c_int64
     return _lib
 
 
@@ -189,6 +196,26 @@ class Context:
             name, ms, by, ln = C.c_char_p(), C.c_double(), C.c_double(), C.c_int64()
             _check(lib().b200reg_ctx_get_profile(self.h, f, C.byref(name), C.byref(ms), C.byref(by), C.byref(ln)))
             out[name.value.decode()] = dict(ms=ms.value, algo_bytes=by.value, launches=ln.value)
+        return out
+
+    # -- the path's one collective: all-gather of the result records over NCCL --------
+    def comm_init(self, unique_id, rank, world):
+        """unique_id: the 128 bytes rank 0 got from comm_unique_id(), shipped to every rank by the caller."""
+        buf = (C.c_ubyte * 128).from_buffer_copy(bytes(unique_id))
+        _check(lib().b200reg_comm_init(self.h, buf, int(rank), int(world)))
+
+    def comm_destroy(self):
+        _check(lib().b200reg_comm_destroy(self.h))
+
+    @property
+    def comm_world(self):
+        return int(lib().b200reg_comm_world(self.h))
+
+    def allgather_results(self, local):
+        """local: (Result * n) ctypes array of this rank -> (Result * (world * n)) with every rank's records, rank order."""
+        n = len(local)
+        out = (Result * (self.comm_world * n))()
+        _check(lib().b200reg_allgather_results(self.h, local, n, out))
         return out
 
     # -- clouds ------------------------------------------------------------------------
@@ -359,6 +386,79 @@ class Context:
         _check(lib().b200reg_compute_error(self.h, src.h, tgt.h, Tl.ctypes.data_as(C.c_void_p), Tt.ctypes.data_as(C.c_void_p),
                                            C.c_double(max_corr_dist), C.byref(err)))
         return err.value
+
+
+def comm_unique_id():
+    """ncclGetUniqueId through the C ABI (rank 0 calls it; the 128 bytes go to the other ranks by any side channel)."""
+    buf = (C.c_ubyte * 128)()
+    _check(lib().b200reg_comm_unique_id(buf))
+    return bytes(buf)
+
+
+class Batch:
+    """b200reg_batch: `depth` engine contexts on their own host threads (C++), jobs round-robin (include/b200reg.h)."""
+
+    def __init__(self, device=0, depth=3):
+        self.h = C.c_void_p()
+        _check(lib().b200reg_batch_create(int(device), int(depth), C.byref(self.h)))
+        self._keep = {}
+
+    def close(self):
+        if self.h:
+            lib().b200reg_batch_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    @property
+    def depth(self):
+        return int(lib().b200reg_batch_depth(self.h))
+
+    @property
+    def launch_count(self):
+        return int(lib().b200reg_batch_launch_count(self.h))
+
+    @staticmethod
+    def _arrays(src_ptrs, src_ns, tgt_ptrs, tgt_ns):
+        cnt = len(src_ptrs)
+        return (cnt, (C.c_void_p * cnt)(*src_ptrs), (C.c_size_t * cnt)(*src_ns), (C.c_void_p * cnt)(*tgt_ptrs),
+                (C.c_size_t * cnt)(*tgt_ns))
+
+    def submit_icp(self, src_ptrs, src_ns, tgt_ptrs, tgt_ns, stride_bytes, on_device, params=None):
+        """LoopClosure::icpAlignment for a batch of raw addresses; returns a ticket (wait() gives the Result array)."""
+        cnt, sp, sn, tp, tn = self._arrays(src_ptrs, src_ns, tgt_ptrs, tgt_ns)
+        prm = params or default_params()
+        res = (Result * cnt)()
+        t = lib().b200reg_batch_submit_icp(self.h, cnt, sp, sn, tp, tn, C.c_size_t(stride_bytes), int(bool(on_device)), C.byref(prm), res)
+        if t < 0:
+            _check(int(t))
+        self._keep[t] = (res, None)
+        return t
+
+    def submit_loop_closure(self, src_ptrs, src_ns, tgt_ptrs, tgt_ns, stride_bytes, on_device, qparams=None, gparams=None):
+        cnt, sp, sn, tp, tn = self._arrays(src_ptrs, src_ns, tgt_ptrs, tgt_ns)
+        qp = qparams or default_quatro_params()
+        gp = gparams or default_params()
+        res = (Result * cnt)()
+        qi = (QuatroInfo * cnt)()
+        t = lib().b200reg_batch_submit_loop_closure(self.h, cnt, sp, sn, tp, tn, C.c_size_t(stride_bytes), int(bool(on_device)),
+                                                    C.byref(qp), C.byref(gp), res, qi)
+        if t < 0:
+            _check(int(t))
+        self._keep[t] = (res, qi)
+        return t
+
+    def wait(self, ticket, want_latency=False, want_quatro=False):
+        lat = C.c_double()
+        rc = lib().b200reg_batch_wait(self.h, C.c_int64(ticket), C.byref(lat))
+        res, qi = self._keep.pop(ticket)
+        _check(rc)
+        out = (res, qi) if want_quatro else res
+        return (out, lat.value) if want_latency else out
 
 
 class Keyframes:

@@ -81,3 +81,33 @@ def register_sharded(register_fn, srcs, dsts, dist=None, device="cpu", costs=Non
     allrec = torch.empty((world * slots, RECORD_DOUBLES), dtype=torch.float64, device=device)
     dist.all_gather_into_tensor(allrec, rec)
     return unpack_records(allrec.cpu().numpy(), n)
+
+
+def register_sharded_native(ctx, register_raw_fn, srcs, dsts, costs=None):
+    """The same sharded batch with the collective behind the C ABI: every rank registers its shard, tags each
+    b200reg_result with its global pair index, and ONE b200reg_allgather_results (ncclAllGather of the full records on
+    the context's communicator, or a copy when the context has none) leaves all results on every rank.
+
+    register_raw_fn(list_of_src, list_of_dst) -> ctypes (Result * n) array.  Returns native.Result records in pair order.
+    """
+    from .native import Result, lib
+    n = len(srcs)
+    world = ctx.comm_world
+    rank = max(0, int(lib().b200reg_comm_rank(ctx.h)))
+    mine = shard_pairs(n, world, rank, costs)
+    slots = (n + world - 1) // world
+    local = (Result * slots)()
+    for s in range(slots):
+        local[s].status = -100  # empty slot of a ragged last shard
+        local[s].tag = -1
+    if mine:
+        res = register_raw_fn([srcs[i] for i in mine], [dsts[i] for i in mine])
+        for s, (i, r) in enumerate(zip(mine, res)):
+            local[s] = r
+            local[s].tag = i
+    allr = ctx.allgather_results(local)
+    out = [None] * n
+    for r in allr:
+        if r.tag >= 0 and r.status != -100:
+            out[r.tag] = r
+    return out

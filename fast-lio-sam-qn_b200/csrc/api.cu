@@ -2,12 +2,15 @@
 // Host orchestration only; every arithmetic step of the path runs in the kernels of
 // index_build.cu / gicp.cu.  There is no CPU fallback anywhere in this library.
 #include <cuda_runtime.h>
+#include <dlfcn.h>
+#include <nccl.h>  // types only: the library is dlopen()ed in b200reg_comm_*
 
 #include <algorithm>
 #include <cstddef>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <mutex>
 #include <string>
 #include <vector>
 
@@ -17,9 +20,9 @@
 namespace b200 {
 int launch_index_build(const CloudDev* d_clouds, int count, int max_n, cudaStream_t s);
 int launch_covariances(const CloudDev* d_clouds, int count, int max_n, int k, int method, cudaStream_t s);
-void launch_gicp_init(PairState* states, const double* d_guess, int count, const GicpParamsDev& prm, cudaStream_t s);
-void launch_gicp_step(const PairDev* pairs, PairState* states, int count, int max_n, const GicpParamsDev& prm,
-                      int* done_counter, cudaStream_t s);
+void launch_gicp_init(const PairDev* pairs, PairState* states, const double* d_guess, int count, const GicpParamsDev& prm,
+                      LmSched* sched, cudaStream_t s);
+void launch_gicp_step(const PairDev* pairs, PairState* states, int blocks, const GicpParamsDev& prm, LmSched* sched, cudaStream_t s);
 int launch_knn_queries(const CloudDev& c, const float* d_q, int nq, int qstride, int k, int* idx, float* d2, cudaStream_t s, int brute);
 void launch_transform_out(const CloudDev& c, const float* d_Tf, float* d_out3, cudaStream_t s);
 int launch_fpfh(const CloudDev* d_clouds, int count, int max_n, float normal_r2, float fpfh_r2, cudaStream_t s);
@@ -56,8 +59,11 @@ struct b200reg_ctx {
   cudaStream_t copy_stream = nullptr;  // H2D uploads of later chunks overlap the compute of earlier ones
   cudaMemPool_t pool = nullptr;        // per-context pool: reuse never adds dependencies on another context's streams
   int pipeline_chunks = 4;
-  int* d_done = nullptr;   // device counter of finished pairs
-  int* h_done = nullptr;   // pinned mirror
+  int sm_count = 148;
+  LmSched* h_sched = nullptr;  // pinned mirror of the schedule header the LM loop polls
+  // the path's one collective (b200reg_comm_*): NCCL communicator of this rank
+  ncclComm_t comm = nullptr;
+  int rank = -1, world = 1;
   int64_t launches = 0;
   int step_chunk = 8;      // step kernels issued between two host polls
   // optional per-kernel-family timing with CUDA events on the launching stream
@@ -161,6 +167,7 @@ void b200reg_default_gicp_params(b200reg_gicp_params* p) {
 }
 
 const char* b200reg_last_error(void) { return g_err.c_str(); }
+void b200reg_set_last_error(const char* message) { g_err = message ? message : ""; }
 const char* b200reg_version(void) { return "b200reg 0.2 (sm_100a)"; }
 size_t b200reg_struct_size(int which) {
   switch (which) {
@@ -201,8 +208,8 @@ int b200reg_ctx_create(int device, b200reg_ctx** out) {
   CU(cudaMemPoolCreate(&c->pool, &props));
   uint64_t thr = UINT64_MAX;
   CU(cudaMemPoolSetAttribute(c->pool, cudaMemPoolAttrReleaseThreshold, &thr));
-  CU(cudaMalloc(&c->d_done, sizeof(int)));
-  CU(cudaMallocHost(&c->h_done, sizeof(int)));
+  CU(cudaDeviceGetAttribute(&c->sm_count, cudaDevAttrMultiProcessorCount, device));
+  CU(cudaMallocHost(&c->h_sched, sizeof(LmSched)));
   undo.ok = true;
   *out = c;
   return B200REG_OK;
@@ -212,8 +219,8 @@ int b200reg_ctx_destroy(b200reg_ctx* c) {
   if (!c) return B200REG_OK;
   cudaSetDevice(c->device);
   if (c->stream) cudaStreamSynchronize(c->stream);
-  if (c->d_done) cudaFree(c->d_done);
-  if (c->h_done) cudaFreeHost(c->h_done);
+  if (c->comm) b200reg_comm_destroy(c);
+  if (c->h_sched) cudaFreeHost(c->h_sched);
   if (c->own_stream) cudaStreamDestroy(c->own_stream);
   if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
   if (c->pool) cudaMemPoolDestroy(c->pool);
@@ -456,7 +463,10 @@ struct PairWork {  // device memory comes from the caller's Scratch and goes bac
   std::vector<PairDev> pairs;
   PairDev* d_pairs = nullptr;
   PairState* d_states = nullptr;
+  LmSched* d_sched = nullptr;
+  LmSched sched_host;  // staging for the header upload (lives as long as the PairWork)
   int max_n = 0;
+  long total_blocks = 0;  // work items of one step with every pair active
 };
 
 static int make_pair_work(b200reg_ctx* c, int count, b200reg_cloud* const* src, b200reg_cloud* const* tgt, PairWork& w, Scratch& scratch) {
@@ -480,9 +490,22 @@ static int make_pair_work(b200reg_ctx* c, int count, b200reg_cloud* const* src, 
     p.mahal = (double*)(slab + o_mah);
     p.partial = (double*)(slab + o_par);
     w.max_n = std::max(w.max_n, N);
+    w.total_blocks += nblk;
   }
   CU(scratch.alloc((void**)&w.d_pairs, sizeof(PairDev) * count));
   CU(scratch.alloc((void**)&w.d_states, sizeof(PairState) * count));
+  {  // schedule header + active[count] + prefix[count + 1]
+    char* sm = nullptr;
+    CU(scratch.alloc((void**)&sm, 64 + sizeof(int) * (2 * (size_t)count + 1)));
+    LmSched hs;
+    memset(&hs, 0, sizeof(hs));
+    hs.active = (int*)(sm + 64);
+    hs.prefix = hs.active + count;
+    w.d_sched = (LmSched*)sm;
+    static_assert(sizeof(LmSched) <= 64, "LmSched header");
+    w.sched_host = hs;
+    CU(cudaMemcpyAsync(w.d_sched, &w.sched_host, sizeof(LmSched), cudaMemcpyHostToDevice, s));
+  }
   CU(cudaMemcpyAsync(w.d_pairs, w.pairs.data(), sizeof(PairDev) * count, cudaMemcpyHostToDevice, s));
   return B200REG_OK;
 }
@@ -515,24 +538,29 @@ int b200reg_gicp_align(b200reg_ctx* c, int count, b200reg_cloud* const* src, b20
     CU(scratch.alloc((void**)&d_guess, sizeof(double) * 16 * count));
     CU(cudaMemcpyAsync(d_guess, guess16, sizeof(double) * 16 * count, cudaMemcpyHostToDevice, s));
   }
-  CU(cudaMemsetAsync(c->d_done, 0, sizeof(int), s));
-  launch_gicp_init(w.d_states, d_guess, count, prm, s);
+  launch_gicp_init(w.d_pairs, w.d_states, d_guess, count, prm, w.d_sched, s);
   c->launches++;
   // worst case: every outer iteration burns lm_max_iterations trials, plus the fitness pass
   const long max_steps = (long)std::max(params->max_iterations, 0) * (1 + std::max(params->lm_max_iterations, 1)) + 2;
   long steps = 0;
+  // The step kernel walks a device-side list of (active pair, block) work items and its last block rebuilds that list,
+  // so a finished pair costs nothing from the next step on; the host only sizes the persistent grid and polls `done`.
+  const long cap = (long)c->sm_count * 8;  // resident blocks of k_gicp_step (128 threads, <= 64 registers)
+  long items = w.total_blocks;
   for (;;) {
     {
       ProfScope ps(c, CLS_STEP);
+      const int blocks = (int)std::max(1L, std::min(items, cap));
       for (int j = 0; j < c->step_chunk; j++) {
-        launch_gicp_step(w.d_pairs, w.d_states, count, w.max_n, prm, c->d_done, s);
+        launch_gicp_step(w.d_pairs, w.d_states, blocks, prm, w.d_sched, s);
         c->launches++;
         steps++;
       }
     }
-    CU(cudaMemcpyAsync(c->h_done, c->d_done, sizeof(int), cudaMemcpyDeviceToHost, s));
+    CU(cudaMemcpyAsync(c->h_sched, w.d_sched, sizeof(LmSched), cudaMemcpyDeviceToHost, s));
     CU(cudaStreamSynchronize(s));
-    if (*c->h_done >= count) break;
+    if (c->h_sched->done >= count) break;
+    items = c->h_sched->total_items;
     if (steps > max_steps) return fail(B200REG_ESTATE, "LM state machine did not terminate");
   }
   std::vector<PairState> states(count);
@@ -763,9 +791,8 @@ int b200reg_linearize(b200reg_ctx* c, const b200reg_cloud* src, const b200reg_cl
   double* d_guess = nullptr;
   CU(scratch.alloc((void**)&d_guess, sizeof(double) * 16));
   CU(cudaMemcpyAsync(d_guess, T16, sizeof(double) * 16, cudaMemcpyHostToDevice, s));
-  CU(cudaMemsetAsync(c->d_done, 0, sizeof(int), s));
-  launch_gicp_init(w.d_states, d_guess, 1, prm, s);
-  launch_gicp_step(w.d_pairs, w.d_states, 1, w.max_n, prm, c->d_done, s);  // exactly one linearize pass
+  launch_gicp_init(w.d_pairs, w.d_states, d_guess, 1, prm, w.d_sched, s);
+  launch_gicp_step(w.d_pairs, w.d_states, (int)std::min(w.total_blocks, (long)c->sm_count * 8), prm, w.d_sched, s);  // exactly one linearize pass
   c->launches += 2;
   PairState st;
   const int N = src->dev.n, M = tgt->dev.n;
@@ -810,9 +837,9 @@ int b200reg_compute_error(b200reg_ctx* c, const b200reg_cloud* src, const b200re
   double* d_guess = nullptr;
   CU(scratch.alloc((void**)&d_guess, sizeof(double) * 16));
   CU(cudaMemcpyAsync(d_guess, T_lin16, sizeof(double) * 16, cudaMemcpyHostToDevice, s));
-  CU(cudaMemsetAsync(c->d_done, 0, sizeof(int), s));
-  launch_gicp_init(w.d_states, d_guess, 1, prm, s);
-  launch_gicp_step(w.d_pairs, w.d_states, 1, w.max_n, prm, c->d_done, s);  // linearize: correspondences + Mahalanobis, phase -> TRIAL
+  const int blocks = (int)std::min(w.total_blocks, (long)c->sm_count * 8);
+  launch_gicp_init(w.d_pairs, w.d_states, d_guess, 1, prm, w.d_sched, s);
+  launch_gicp_step(w.d_pairs, w.d_states, blocks, prm, w.d_sched, s);  // linearize: correspondences + Mahalanobis, phase -> TRIAL
   // overwrite the trial pose the LM controller prepared with the caller's
   double Rt[9], tt[3];
   for (int a = 0; a < 3; a++) {
@@ -821,7 +848,7 @@ int b200reg_compute_error(b200reg_ctx* c, const b200reg_cloud* src, const b200re
   }
   CU(cudaMemcpyAsync((char*)w.d_states + offsetof(PairState, Rt), Rt, sizeof(Rt), cudaMemcpyHostToDevice, s));
   CU(cudaMemcpyAsync((char*)w.d_states + offsetof(PairState, tt), tt, sizeof(tt), cudaMemcpyHostToDevice, s));
-  launch_gicp_step(w.d_pairs, w.d_states, 1, w.max_n, prm, c->d_done, s);  // compute_error at the trial pose
+  launch_gicp_step(w.d_pairs, w.d_states, blocks, prm, w.d_sched, s);  // compute_error at the trial pose
   c->launches += 3;
   PairState st;
   CU(cudaMemcpyAsync(&st, w.d_states, sizeof(PairState), cudaMemcpyDeviceToHost, s));
@@ -1200,6 +1227,117 @@ int b200reg_loop_closure(b200reg_ctx* c, int count, const float* const* src_xyz,
   if (!rc) rc = coarse_to_fine_on_clouds(c, count, clouds.data(), clouds.data() + count, qp, gp, out, quatro_out);
   for (b200reg_cloud* cl : clouds) b200reg_cloud_destroy(c, cl);
   return rc;
+}
+
+// ---- the one collective: all-gather of the result records over NCCL ------------------------
+namespace {
+struct NcclApi {
+  void* h = nullptr;
+  decltype(&ncclGetUniqueId) GetUniqueId = nullptr;
+  decltype(&ncclCommInitRank) CommInitRank = nullptr;
+  decltype(&ncclCommDestroy) CommDestroy = nullptr;
+  decltype(&ncclAllGather) AllGather = nullptr;
+  decltype(&ncclGetErrorString) GetErrorString = nullptr;
+  std::string err;
+};
+NcclApi* nccl_api() {  // loaded once per process; a process that already holds libnccl.so.2 (torch) shares that copy
+  static NcclApi api;
+  static bool tried = false;
+  static std::mutex mu;
+  std::lock_guard<std::mutex> lk(mu);
+  if (tried) return &api;
+  tried = true;
+  const char* names[] = {getenv("B200REG_NCCL_LIB"), "libnccl.so.2", "libnccl.so"};
+  for (const char* n : names) {
+    if (!n) continue;
+    api.h = dlopen(n, RTLD_NOW | RTLD_LOCAL);
+    if (api.h) break;
+  }
+  if (!api.h) {
+    api.err = std::string("cannot load libnccl.so.2: ") + dlerror();
+    return &api;
+  }
+  api.GetUniqueId = (decltype(api.GetUniqueId))dlsym(api.h, "ncclGetUniqueId");
+  api.CommInitRank = (decltype(api.CommInitRank))dlsym(api.h, "ncclCommInitRank");
+  api.CommDestroy = (decltype(api.CommDestroy))dlsym(api.h, "ncclCommDestroy");
+  api.AllGather = (decltype(api.AllGather))dlsym(api.h, "ncclAllGather");
+  api.GetErrorString = (decltype(api.GetErrorString))dlsym(api.h, "ncclGetErrorString");
+  if (!api.GetUniqueId || !api.CommInitRank || !api.CommDestroy || !api.AllGather || !api.GetErrorString) {
+    api.err = "libnccl.so.2 lacks a required symbol";
+    dlclose(api.h);
+    api.h = nullptr;
+  }
+  return &api;
+}
+}  // namespace
+#define NC(call)                                                                                               \
+  do {                                                                                                         \
+    ncclResult_t _r = (call);                                                                                  \
+    if (_r != ncclSuccess) return fail(B200REG_ENCCL, std::string(#call) + ": " + api->GetErrorString(_r)); \
+  } while (0)
+
+static_assert(sizeof(ncclUniqueId) == B200REG_UNIQUE_ID_BYTES, "ncclUniqueId is 128 bytes");
+
+int b200reg_comm_unique_id(void* id_out) {
+  if (!id_out) return fail(B200REG_EINVAL, "id_out is NULL");
+  NcclApi* api = nccl_api();
+  if (!api->h) return fail(B200REG_ENCCL, api->err);
+  ncclUniqueId id;
+  NC(api->GetUniqueId(&id));
+  memcpy(id_out, &id, sizeof(id));
+  return B200REG_OK;
+}
+
+int b200reg_comm_init(b200reg_ctx* c, const void* id128, int rank, int world) {
+  if (!c || !id128 || world < 1 || rank < 0 || rank >= world) return fail(B200REG_EINVAL, "bad argument");
+  if (c->comm) return fail(B200REG_ESTATE, "the context already has a communicator");
+  NcclApi* api = nccl_api();
+  if (!api->h) return fail(B200REG_ENCCL, api->err);
+  CU(cudaSetDevice(c->device));
+  ncclUniqueId id;
+  memcpy(&id, id128, sizeof(id));
+  NC(api->CommInitRank(&c->comm, world, id, rank));
+  c->rank = rank;
+  c->world = world;
+  return B200REG_OK;
+}
+
+int b200reg_comm_destroy(b200reg_ctx* c) {
+  if (!c) return fail(B200REG_EINVAL, "ctx is NULL");
+  if (!c->comm) return B200REG_OK;
+  NcclApi* api = nccl_api();
+  cudaSetDevice(c->device);
+  cudaStreamSynchronize(c->stream);
+  ncclComm_t comm = c->comm;
+  c->comm = nullptr;
+  c->rank = -1;
+  c->world = 1;
+  NC(api->CommDestroy(comm));
+  return B200REG_OK;
+}
+
+int b200reg_comm_rank(const b200reg_ctx* c) { return c ? c->rank : -1; }
+int b200reg_comm_world(const b200reg_ctx* c) { return c ? c->world : 1; }
+
+int b200reg_allgather_results(b200reg_ctx* c, const b200reg_result* local, int n_local, b200reg_result* all_out) {
+  if (!c || !local || n_local <= 0 || !all_out) return fail(B200REG_EINVAL, "bad argument");
+  const size_t bytes = sizeof(b200reg_result) * (size_t)n_local;
+  if (!c->comm || c->world == 1) {
+    if (all_out != local) memcpy(all_out, local, bytes);
+    return B200REG_OK;
+  }
+  NcclApi* api = nccl_api();
+  CU(cudaSetDevice(c->device));
+  cudaStream_t s = c->stream;
+  Scratch scratch(c);
+  char *d_local = nullptr, *d_all = nullptr;
+  CU(scratch.alloc((void**)&d_local, bytes));
+  CU(scratch.alloc((void**)&d_all, bytes * c->world));
+  CU(cudaMemcpyAsync(d_local, local, bytes, cudaMemcpyHostToDevice, s));
+  NC(api->AllGather(d_local, d_all, bytes, ncclChar, c->comm, s));
+  CU(cudaMemcpyAsync(all_out, d_all, bytes * c->world, cudaMemcpyDeviceToHost, s));
+  CU(cudaStreamSynchronize(s));
+  return B200REG_OK;
 }
 
 // ---- "next" rows: keyframe store, candidate search, cloud assembly ----------------------------

@@ -132,7 +132,7 @@ __device__ void lm_finish(PairState* st, int converged) {
 }
 
 __device__ void lm_update(PairState* st, const double* sums, const GicpParamsDev& prm, int phase, int n_src,
-                          int* done_counter) {
+                          int* done_counter) {  // done_counter = &LmSched::done
   if (phase == PH_LINEARIZE) {
     int k = 0;
     for (int i = 0; i < 6; i++)
@@ -197,29 +197,96 @@ __device__ void lm_update(PairState* st, const double* sums, const GicpParamsDev
   }
 }
 
-__global__ void k_gicp_init(PairState* states, const double* guess16, int count, GicpParamsDev prm) {
-  int p = blockIdx.x * blockDim.x + threadIdx.x;
-  if (p >= count) return;
-  PairState* st = &states[p];
-  for (int i = 0; i < 3; i++) {
-    for (int j = 0; j < 3; j++) st->R[3 * i + j] = guess16 ? guess16[16 * p + 4 * i + j] : (i == j ? 1.0 : 0.0);
-    st->t[i] = guess16 ? guess16[16 * p + 4 * i + 3] : 0.0;
+// Rebuild the work-item schedule from the pairs' phases (one block, any size that is a multiple of 32).
+__device__ void sched_rebuild(const PairDev* pairs, const PairState* states, LmSched* sched) {
+  __shared__ int s_wsum[32];
+  __shared__ int s_wcnt[32];
+  __shared__ int s_carry_items, s_carry_cnt;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  if (threadIdx.x == 0) {
+    s_carry_items = 0;
+    s_carry_cnt = 0;
   }
-  st->lambda = -1.0;
-  st->nu = 2.0;
-  st->y0 = 0.0;
-  st->y_trial = 0.0;
-  st->fitness = 0.0;
-  st->phase = PH_LINEARIZE;
-  st->outer_it = 0;
-  st->inner_it = 0;
-  st->converged = 0;
-  st->lm_failed = 0;
-  st->n_lin = 0;
-  st->n_err = 0;
-  st->nr_iterations = 0;
-  st->arrive = 0;
-  if (prm.max_iterations <= 0) lm_finish(st, 0);
+  __syncthreads();
+  const int n = sched->n_pairs;
+  for (int base = 0; base < n; base += blockDim.x) {
+    const int p = base + threadIdx.x;
+    int nblk = 0;
+    if (p < n && __ldcg(&states[p].phase) != PH_DONE) nblk = (pairs[p].src.n + STEP_THREADS - 1) / STEP_THREADS;
+    const int act = nblk > 0 ? 1 : 0;
+    int isum = nblk, csum = act;  // inclusive warp scans
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int a = __shfl_up_sync(0xffffffffu, isum, o), b = __shfl_up_sync(0xffffffffu, csum, o);
+      if (lane >= o) {
+        isum += a;
+        csum += b;
+      }
+    }
+    if (lane == 31) {
+      s_wsum[warp] = isum;
+      s_wcnt[warp] = csum;
+    }
+    __syncthreads();
+    int woff_i = s_carry_items, woff_c = s_carry_cnt;
+    for (int w = 0; w < warp; w++) {
+      woff_i += s_wsum[w];
+      woff_c += s_wcnt[w];
+    }
+    if (act) {
+      sched->active[woff_c + csum - 1] = p;
+      sched->prefix[woff_c + csum - 1] = woff_i + isum - nblk;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      for (int w = 0; w < nw; w++) {
+        s_carry_items += s_wsum[w];
+        s_carry_cnt += s_wcnt[w];
+      }
+    }
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) {
+    sched->prefix[s_carry_cnt] = s_carry_items;
+    sched->n_active = s_carry_cnt;
+    sched->total_items = s_carry_items;
+    sched->arrive = 0;
+    __threadfence();
+  }
+}
+
+__global__ void __launch_bounds__(256) k_gicp_init(const PairDev* pairs, PairState* states, const double* guess16, int count,
+                                                    GicpParamsDev prm, LmSched* sched) {
+  for (int p = threadIdx.x; p < count; p += blockDim.x) {
+    PairState* st = &states[p];
+    for (int i = 0; i < 3; i++) {
+      for (int j = 0; j < 3; j++) st->R[3 * i + j] = guess16 ? guess16[16 * p + 4 * i + j] : (i == j ? 1.0 : 0.0);
+      st->t[i] = guess16 ? guess16[16 * p + 4 * i + 3] : 0.0;
+    }
+    st->lambda = -1.0;
+    st->nu = 2.0;
+    st->y0 = 0.0;
+    st->y_trial = 0.0;
+    st->fitness = 0.0;
+    st->phase = PH_LINEARIZE;
+    st->outer_it = 0;
+    st->inner_it = 0;
+    st->converged = 0;
+    st->lm_failed = 0;
+    st->n_lin = 0;
+    st->n_err = 0;
+    st->nr_iterations = 0;
+    st->arrive = 0;
+    if (prm.max_iterations <= 0) lm_finish(st, 0);
+  }
+  if (threadIdx.x == 0) {
+    sched->n_pairs = count;
+    sched->done = 0;
+    sched->steps = 0;
+  }
+  __threadfence();
+  __syncthreads();
+  sched_rebuild(pairs, states, sched);
 }
 
 // ---------------------------------------------------------------------------------------
@@ -321,20 +388,31 @@ __global__ void __launch_bounds__(STEP_THREADS, (K <= 16 ? 8 : 4)) k_covariance(
 // SURVEY App. A.6) and runs the LM controller, so no host round trip is needed per iteration.
 // ---------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(STEP_THREADS, 8) k_gicp_step(const PairDev* pairs, PairState* states, GicpParamsDev prm,
-                                                             int* done_counter) {
-  const PairDev& P = pairs[blockIdx.y];
-  PairState* st = &states[blockIdx.y];
-  const int N = P.src.n;
-  const int nblk = (N + STEP_THREADS - 1) / STEP_THREADS;
-  if ((int)blockIdx.x >= nblk) return;
-  const int phase = st->phase;
-  if (phase == PH_DONE) return;
-  const bool seeded = st->n_lin > 0;  // P.corr holds the previous linearization's correspondences
-
+                                                             LmSched* sched) {
   __shared__ double s_T[12];
   __shared__ float s_Tf[12];
   __shared__ double s_red[STEP_THREADS / 32][NRED];
   __shared__ bool s_last;
+  // the schedule is stable for the whole step: only the LAST block to finish rewrites it (see the end of the kernel)
+  const int total_items = sched->total_items;
+  const int n_active = sched->n_active;
+  for (int item = blockIdx.x; item < total_items; item += gridDim.x) {
+  // work item -> (active pair, block of that pair): binary search of the exclusive prefix (block-uniform)
+  int lo = 0, hi = n_active - 1;
+  while (lo < hi) {
+    const int mid = (lo + hi + 1) >> 1;
+    if (__ldg(&sched->prefix[mid]) <= item) lo = mid; else hi = mid - 1;
+  }
+  const int pair_id = __ldg(&sched->active[lo]);
+  const int blk = item - __ldg(&sched->prefix[lo]);
+  const PairDev& P = pairs[pair_id];
+  PairState* st = &states[pair_id];
+  const int N = P.src.n;
+  const int nblk = (N + STEP_THREADS - 1) / STEP_THREADS;
+  const int phase = st->phase;  // written by the previous step's controller; PH_DONE pairs are not in the list
+  const bool seeded = st->n_lin > 0;  // P.corr holds the previous linearization's correspondences
+
+  __syncthreads();  // the previous item's shared state is no longer needed
   if (threadIdx.x < 12) {
     const int r = threadIdx.x / 4, cc = threadIdx.x % 4;
     double v;
@@ -345,7 +423,7 @@ __global__ void __launch_bounds__(STEP_THREADS, 8) k_gicp_step(const PairDev* pa
   }
   __syncthreads();
 
-  const int i = blockIdx.x * STEP_THREADS + threadIdx.x;
+  const int i = blk * STEP_THREADS + threadIdx.x;
   const int nred = phase == PH_LINEARIZE ? NRED : 1;
   double v[NRED];
 #pragma unroll
@@ -484,7 +562,7 @@ __global__ void __launch_bounds__(STEP_THREADS, 8) k_gicp_step(const PairDev* pa
     double x = 0;
 #pragma unroll
     for (int w = 0; w < STEP_THREADS / 32; w++) x += s_red[w][threadIdx.x];
-    P.partial[(size_t)blockIdx.x * NRED + threadIdx.x] = x;
+    P.partial[(size_t)blk * NRED + threadIdx.x] = x;
     __threadfence();
   }
   __syncthreads();
@@ -493,10 +571,8 @@ __global__ void __launch_bounds__(STEP_THREADS, 8) k_gicp_step(const PairDev* pa
     s_last = (prev == (unsigned)(nblk - 1));
   }
   __syncthreads();
-  if (!s_last) return;
-  __threadfence();
-  // last block: deterministic sum over blocks (4 interleaved chains, then a fixed 4-way add)
-  {
+  if (s_last) {  // last block of this pair: deterministic sum over blocks (4 interleaved chains, then a fixed 4-way add)
+    __threadfence();
     const int j = threadIdx.x & 31, g = threadIdx.x >> 5;
     double x = 0;
     if (j < nred)
@@ -512,9 +588,23 @@ __global__ void __launch_bounds__(STEP_THREADS, 8) k_gicp_step(const PairDev* pa
         sums[k] = s;
       }
       st->arrive = 0;
-      lm_update(st, sums, prm, phase, N, done_counter);
+      lm_update(st, sums, prm, phase, N, &sched->done);
+      __threadfence();
     }
   }
+  }  // work items
+  // ---- end of the step: the last block to get here rebuilds the schedule from the pairs' new phases
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence();
+    const unsigned prev = atomicAdd(&sched->arrive, 1u);
+    s_last = (prev == gridDim.x - 1);
+  }
+  __syncthreads();
+  if (!s_last) return;
+  __threadfence();
+  if (threadIdx.x == 0) sched->steps++;
+  sched_rebuild(pairs, states, sched);
 }
 
 // ---------------------------------------------------------------------------------------
@@ -626,14 +716,15 @@ int launch_covariances(const CloudDev* d_clouds, int count, int max_n, int k, in
   return 1;
 }
 
-void launch_gicp_init(PairState* states, const double* d_guess, int count, const GicpParamsDev& prm, cudaStream_t s) {
-  k_gicp_init<<<(count + 63) / 64, 64, 0, s>>>(states, d_guess, count, prm);
+void launch_gicp_init(const PairDev* pairs, PairState* states, const double* d_guess, int count, const GicpParamsDev& prm,
+                      LmSched* sched, cudaStream_t s) {
+  k_gicp_init<<<1, 256, 0, s>>>(pairs, states, d_guess, count, prm, sched);
 }
 
-void launch_gicp_step(const PairDev* pairs, PairState* states, int count, int max_n, const GicpParamsDev& prm,
-                      int* done_counter, cudaStream_t s) {
-  dim3 grid((max_n + STEP_THREADS - 1) / STEP_THREADS, count);
-  k_gicp_step<<<grid, STEP_THREADS, 0, s>>>(pairs, states, prm, done_counter);
+// One LM step over every still-active pair.  `blocks`: persistent grid size (work items are strided over it); the
+// kernel is correct for any value >= 1.
+void launch_gicp_step(const PairDev* pairs, PairState* states, int blocks, const GicpParamsDev& prm, LmSched* sched, cudaStream_t s) {
+  k_gicp_step<<<blocks, STEP_THREADS, 0, s>>>(pairs, states, prm, sched);
 }
 
 int launch_knn_queries(const CloudDev& c, const float* d_q, int nq, int qstride, int k, int* idx, float* d2, cudaStream_t s, int brute) {

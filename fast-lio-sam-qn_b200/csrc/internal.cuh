@@ -98,6 +98,20 @@ struct PairState {
   int pad;
 };
 
+// Device-side schedule of one batched LM solve: the step kernel runs over WORK ITEMS (one 128-point block of one
+// still-active pair); the last block of every step rebuilds the list from the pairs' phases, so finished pairs cost
+// nothing from the next step on and the host (or a CUDA-graph while node) only ever looks at `done`.
+struct LmSched {
+  int n_pairs;
+  int n_active;           // pairs whose phase != PH_DONE
+  int total_items;        // sum over active pairs of ceil(src.n / STEP_THREADS)
+  int done;               // pairs that reached PH_DONE (host polls this)
+  unsigned int arrive;    // blocks that finished the current step
+  int steps;              // step kernels executed
+  int* active;            // [n_pairs] ids of the active pairs, ascending
+  int* prefix;            // [n_pairs + 1] exclusive prefix of their block counts
+};
+
 struct PairDev {
   CloudDev src, tgt;
   int* corr;       // [src.n] sorted target position or -1 (per sorted source position)

@@ -74,7 +74,8 @@ typedef struct b200reg_result {
   int32_t n_error;     /* number of compute_error() passes                                     */
   int32_t lm_failed;   /* "lm not converged!!" (lsq_registration_impl.hpp:105-108)             */
   int32_t status;      /* 0 ok; <0 error for this pair                                         */
-  int32_t reserved;
+  int32_t tag;         /* caller-defined, set to 0 by the engine and carried through b200reg_allgather_results
+                          (e.g. the global pair index of a sharded batch)                                      */
 } b200reg_result;
 
 /* Mirrors QuatroConfig (fast_lio_sam_qn/include/loop_closure.h:38-50) and the quatro<T> constructor arguments
@@ -108,7 +109,8 @@ typedef struct b200reg_quatro_info {
 
 void b200reg_default_gicp_params(b200reg_gicp_params* p);
 void b200reg_default_quatro_params(b200reg_quatro_params* p);
-const char* b200reg_last_error(void);
+const char* b200reg_last_error(void);                /* message of the calling thread's last failure               */
+void b200reg_set_last_error(const char* message);  /* used by the batch driver to hand a worker's message over     */
 const char* b200reg_version(void);
 /* sizeof() of the ABI structs as compiled into the library, so that a binding (ctypes, cgo, JNI ...) can check its own
  * layout at load time: 0 gicp_params, 1 result, 2 quatro_params, 3 quatro_info, 4 loop_config, 5 loop_factor.  0 = unknown. */
@@ -254,6 +256,46 @@ int b200reg_loop_factor_from_poses(const double* T_between16, const double* pose
 /* The factors of a batch of b200reg_perform_loop_closure results, poses taken from the keyframe store.              */
 int b200reg_loop_factors(b200reg_ctx* ctx, const b200reg_keyframes* kf, int count, const int32_t* query_idx,
                          const int32_t* closest_idx, const b200reg_result* results, b200reg_loop_factor* out);
+
+/* ---- batch driver (SURVEY.md §8(b)(2) "b200reg_batch"): `depth` engine contexts, each on its own host thread with its own
+ *      streams and memory pool, take alternate jobs, so the PCIe upload and the host-side polling of one job hide behind
+ *      the kernels of the others.  The reference registers ONE pair per timer tick (fast_lio_sam_qn.cpp:203-219); a
+ *      batch of independent candidate pairs is this engine's unit of work.
+ *      Jobs are submitted from ONE host thread; the pointer arrays are copied at submit time, the point buffers and the
+ *      output arrays must stay valid until the job has been waited for. ------------------------------------------------ */
+typedef struct b200reg_batch b200reg_batch;
+int b200reg_batch_create(int device, int depth, b200reg_batch** out);
+int b200reg_batch_destroy(b200reg_batch* b);
+/* LoopClosure::icpAlignment (loop_closure.cpp:110-136) for `count` pairs; returns a ticket >= 0 or a B200REG_E* code. */
+int64_t b200reg_batch_submit_icp(b200reg_batch* b, int count, const float* const* src_xyz, const size_t* src_n,
+                                 const float* const* tgt_xyz, const size_t* tgt_n, size_t stride_bytes, int on_device,
+                                 const b200reg_gicp_params* params, b200reg_result* out);
+/* LoopClosure::coarseToFineAlignment (loop_closure.cpp:138-159) for `count` pairs. */
+int64_t b200reg_batch_submit_loop_closure(b200reg_batch* b, int count, const float* const* src_xyz, const size_t* src_n,
+                                          const float* const* tgt_xyz, const size_t* tgt_n, size_t stride_bytes,
+                                          int on_device, const b200reg_quatro_params* qparams,
+                                          const b200reg_gicp_params* gparams, b200reg_result* out,
+                                          b200reg_quatro_info* quatro_out);
+/* Blocks until the job is done; returns ITS status (the message is then in b200reg_last_error of the calling thread).
+ * latency_ms (optional): submit -> completion on the host clock.  A ticket can be waited for once.               */
+int b200reg_batch_wait(b200reg_batch* b, int64_t ticket, double* latency_ms);
+int b200reg_batch_wait_all(b200reg_batch* b);
+int64_t b200reg_batch_launch_count(const b200reg_batch* b);
+int b200reg_batch_depth(const b200reg_batch* b);
+
+/* ---- the ONE collective of the path: all-gather of the fixed-size result records over NCCL.
+ *      Rank 0 makes the id, the caller ships its 128 bytes to the other ranks by any means (MPI, a file, torch.distributed),
+ *      every rank calls b200reg_comm_init on its own context.  NCCL is loaded at run time (libnccl.so.2). -------------- */
+#define B200REG_UNIQUE_ID_BYTES 128
+int b200reg_comm_unique_id(void* id_out128);
+int b200reg_comm_init(b200reg_ctx* ctx, const void* id128, int rank, int world);
+int b200reg_comm_destroy(b200reg_ctx* ctx);
+int b200reg_comm_rank(const b200reg_ctx* ctx);   /* -1 without a communicator */
+int b200reg_comm_world(const b200reg_ctx* ctx);  /* 1 without a communicator  */
+/* ncclAllGather of n_local records per rank on the context's stream: all_out holds world * n_local records in rank
+ * order on EVERY rank (bytes identical for any world size given the same shards).  Without a communicator (world 1)
+ * it is a copy.                                                                                                   */
+int b200reg_allgather_results(b200reg_ctx* ctx, const b200reg_result* local, int n_local, b200reg_result* all_out);
 
 /* Output cloud of align(): final_transformation_ applied to the source in fp32
  * (lsq_registration_impl.hpp:114).  out_xyz: n x 3 floats (host), original point order.       */

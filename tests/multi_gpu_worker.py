@@ -38,6 +38,17 @@ def main():
     for p, r in zip(pairs, single):
         rot, tr = synth.se3_error(r["T"], p[2])
         assert r["converged"] and rot < 2e-2 and tr < 0.5
+    # the same batch with the collective BEHIND the C ABI (b200reg_comm_init + b200reg_allgather_results = ncclAllGather of
+    # the full result records); the 128-byte unique id travels over the process group that is already up
+    from b200reg.sharding import register_sharded_native
+    box = [b200reg.comm_unique_id() if rank == 0 else None]
+    dist.broadcast_object_list(box, src=0)
+    ctx.comm_init(box[0], rank, int(os.environ["WORLD_SIZE"]))
+    native = register_sharded_native(ctx, lambda s, d: ctx.icp_alignment(s, d, raw=True), srcs, dsts, costs=costs)
+    for a, c in zip(native, single):
+        assert np.array(a.T).tobytes() == c["T"].tobytes() and a.fitness == c["fitness"] and a.n_linearize == c["n_linearize"]
+        assert bool(a.valid) == c["valid"]
+    ctx.comm_destroy()
     ctx.close()
     dist.barrier()
     dist.destroy_process_group()
