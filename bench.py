@@ -2,23 +2,28 @@
 """bench.py -- loop-closure registrations/sec on 100k-point KITTI-shaped pairs (BASELINE.json metric).
 
     python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path
-    python bench.py --impl reference --steps K --warmup W    # the reference's CPU path (oracle port)
+    python bench.py --impl reference --steps K --warmup W    # the reference's CPU path (oracle port + reference nanoflann)
     torchrun ... bench.py --gpus N ...                       # one rank per GPU, weak scaling
 
-One "step" = LoopClosure::icpAlignment (fast_lio_sam_qn/src/loop_closure.cpp:110-136: two index
-builds, two covariance passes, align, fitness) over one batch of `--pairs` synthetic 100k x 100k
-pairs per rank (BASELINE.json configs[1]).  Prints ONE JSON line (rank 0).
-Other workloads (not the headline): --workload quatro = configs[2], LoopClosure::coarseToFineAlignment on scans
-voxelised at 0.3 m (--matching optimized|advanced selects the Quatro matcher); --workload sequence = configs[4],
-loopTimerFunc over a device-resident KITTI-05-shaped keyframe sequence.
+Headline (configs[1]): one "step" = LoopClosure::icpAlignment (fast_lio_sam_qn/src/loop_closure.cpp:110-136: two index
+builds, two covariance passes, align, fitness) over 256 synthetic 100k x 100k pairs per rank, issued as 16 jobs of 16 pairs
+to the C ABI's batch driver (b200reg_batch_*, three engine contexts on C++ host threads).  The jobs rotate over 4 DISTINCT
+sub-batches (64 distinct pairs, 205 MB of raw points per rank -- more than the 126 MB L2), nothing is replaced or skipped.
+Prints ONE JSON line (rank 0):
 
-  value   : pairs/s with the raw xyz already resident in HBM when the timed region starts
-  e2e     : pairs/s through the same C-ABI call from PINNED HOST buffers (H2D of every cloud and
-            D2H of the results inside the timed region)
-  roofline: dominant kernel family, algorithmic bytes / CUDA-event time on the
-            launching stream, against MEASURED_PEAKS.json hbm_gbs
-  cpu_baseline: the CPU oracle (restated Nano-GICP + the reference's own nanoflann from oracle/_ref)
-            on the host cores, bounded sample
+  value    : pairs/s with the raw xyz already resident in HBM when the timed region starts
+  e2e      : pairs/s through the same C-ABI calls from PINNED HOST buffers (H2D of every cloud of every job and D2H of
+             the result records inside the timed region)
+  roofline : dominant kernel family, algorithmic bytes / CUDA-event time on the launching stream,
+             against MEASURED_PEAKS.json hbm_gbs
+  cpu_baseline: the CPU oracle (restated Nano-GICP + the reference's own nanoflann from oracle/_ref), bounded sample
+  parity   : the GPU transforms of the sampled pairs against the CPU oracle's (1e-4 rad / 1e-3 m, counters equal,
+             first-linearize correspondences bit-exact); a miss aborts the run
+  latency  : ms per single pair through one C-ABI call on an idle GPU (the reference's published "ms per ICP" view)
+  secondary: the other BASELINE configs measured in the same run: configs[2] full loop closure (Quatro + Nano-GICP) on
+             0.3 m-voxelised and on RAW 100k scans, configs[4] the 2761-keyframe KITTI-05-shaped sequence through
+             loopTimerFunc's steps, and for N > 1 configs[3] the 512-pair batch sharded over the ranks with one
+             NCCL all-gather of the result records per batch (b200reg_allgather_results)
 """
 import argparse
 import ctypes
@@ -28,6 +33,7 @@ import subprocess
 import sys
 import tempfile
 import time
+from concurrent.futures import ThreadPoolExecutor
 
 REPO = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, REPO)
@@ -35,41 +41,87 @@ sys.path.insert(0, os.path.join(REPO, "fast-lio-sam-qn_b200"))
 
 import numpy as np  # noqa: E402
 
-METRIC = "loop_closure_registrations_per_sec_100k_pt_pairs"  # --workload quatro reports the same unit on configs[2]
+METRIC = "loop_closure_registrations_per_sec_100k_pt_pairs"
 UNIT = "pairs/s"
 N_POINTS = 100000
+JOB_PAIRS = 16        # pairs per b200reg_batch job
+DISTINCT_JOBS = 4     # distinct sub-batches the jobs rotate over (4 x 16 pairs x 3.2 MB = 205 MB > L2)
+JOBS_PER_STEP = 16    # 256 pairs per step per rank
+ROT_TOL, TRANS_TOL = 1e-4, 1e-3
 
 
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--pairs", type=int, default=16, help="pairs per step per rank")
-    ap.add_argument("--points", type=int, default=None)
-    ap.add_argument("--workload", default="gicp", choices=["gicp", "quatro", "sequence"],
-                    help="gicp = configs[1] (the headline); quatro = configs[2] Quatro+Nano-GICP full loop closure; "
-                         "sequence = configs[4] loopTimerFunc over a KITTI-05-shaped keyframe sequence held on the device")
-    ap.add_argument("--matching", default="optimized", choices=["optimized", "advanced"],
-                    help="quatro workload: Matcher::optimizedMatching (config.yaml:32) or advancedMatching (matcher.cc:118)")
-    ap.add_argument("--keyframes", type=int, default=600, help="sequence workload: keyframes generated (KITTI 05: 2761)")
+    ap.add_argument("--points", type=int, default=N_POINTS)
+    ap.add_argument("--depth", type=int, default=int(os.environ.get("B200REG_PIPE_DEPTH", "3")), help="engine contexts of the batch driver")
+    ap.add_argument("--secondary", default="all", help="comma list of secondary workloads: voxel,raw,sequence,batch512 | all | none")
+    ap.add_argument("--keyframes", type=int, default=2761, help="sequence workload: keyframes generated (KITTI 05: 2761)")
+    ap.add_argument("--matching", default="optimized", choices=["optimized", "advanced"])
     ap.add_argument("--cpu-sample-pairs", type=int, default=6)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     return ap.parse_args()
 
 
-def make_pairs(rank, n_pairs, n_points, mode="gicp"):
+# ---------------------------------------------------------------------------------------------------------------------
+# inputs
+# ---------------------------------------------------------------------------------------------------------------------
+def gen_pairs(seeds, n_points, mode="gicp", voxel=None, threads=None):
+    """synth.make_pair for every seed (the generator runs OpenMP inside; a few Python threads keep the cores busy)."""
     from b200reg import synth
-    pairs = []
-    for i in range(n_pairs):
-        seed = (1000 if mode == "gicp" else 2000) + rank * n_pairs + i  # config 2 seeds 1000.., config 3 2000..
-        # config 3 inputs are voxelised at 0.3 m like setSrcAndDstCloud does (loop_closure.cpp:107): --points raw returns -> ~1/4
-        src, dst, Texp = synth.make_pair(seed, n_points, n_points, mode=mode, voxel=0.3 if mode == "quatro" else None)
-        pairs.append((src, dst, Texp))
-    return pairs
+    threads = threads or max(1, min(16, (os.cpu_count() or 8) // 8))
+    with ThreadPoolExecutor(threads) as ex:
+        return list(ex.map(lambda s: synth.make_pair(s, n_points, n_points, mode=mode, voxel=voxel), seeds))
 
 
+def primary_seeds(rank):
+    """config 2 uses seeds 1000...; every rank owns 64 consecutive seeds."""
+    n = JOB_PAIRS * DISTINCT_JOBS
+    return [1000 + rank * n + i for i in range(n)]
+
+
+def primary_config(args):
+    """The workload description -- identical in the b200 and the reference arm."""
+    return {"workload": "configs[1]: Nano-GICP %dk-pt KITTI-shaped scan pairs (LoopClosure::icpAlignment: 2 index builds + 2 kNN-15 "
+                        "covariance passes + LM align + fitness)" % (args.points // 1000),
+            "points_per_cloud": args.points, "pairs_per_step_per_gpu": JOB_PAIRS * JOBS_PER_STEP,
+            "distinct_pairs_per_gpu": JOB_PAIRS * DISTINCT_JOBS,
+            "seeds": "1000 + 64*rank + i, i < 64 (no pair replaced or skipped)",
+            "l2": "the jobs of a step rotate over 4 distinct 16-pair sub-batches: %.0f MB of raw points per rank (> 126 MB L2); "
+                  "every job rebuilds all derived data from the raw xyz" % (2 * JOB_PAIRS * DISTINCT_JOBS * args.points * 16 / 1e6)}
+
+
+class Arena:
+    """Pinned-host and device copies of a list of pairs, grouped into jobs of `per_job` pairs."""
+
+    def __init__(self, pairs, per_job):
+        import torch
+        self.pairs = pairs
+        self.hs = [torch.from_numpy(np.ascontiguousarray(p[0])).pin_memory() for p in pairs]
+        self.hd = [torch.from_numpy(np.ascontiguousarray(p[1])).pin_memory() for p in pairs]
+        self.ds = [t.cuda(non_blocking=True) for t in self.hs]
+        self.dd = [t.cuda(non_blocking=True) for t in self.hd]
+        torch.cuda.synchronize()
+        self.stride = self.hs[0].shape[1] * 4
+        self.jobs = [list(range(i, min(i + per_job, len(pairs)))) for i in range(0, len(pairs), per_job)]
+
+    def job(self, j, on_device):
+        idx = self.jobs[j % len(self.jobs)]
+        s = self.ds if on_device else self.hs
+        d = self.dd if on_device else self.hd
+        return ([s[i].data_ptr() for i in idx], [s[i].shape[0] for i in idx], [d[i].data_ptr() for i in idx],
+                [d[i].shape[0] for i in idx], self.stride, int(on_device))
+
+    def h2d_bytes(self, j):
+        return sum(self.hs[i].numel() * 4 + self.hd[i].numel() * 4 for i in self.jobs[j % len(self.jobs)])
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# host / clocks
+# ---------------------------------------------------------------------------------------------------------------------
 def cpu_info():
     model = "unknown"
     try:
@@ -84,59 +136,24 @@ def cpu_info():
 
 
 def calibrate_threads(orc, fn, pair):
-    """Pick the OpenMP thread count that makes the CPU path FASTEST on this host (all logical CPUs is not always it:
-    on the 128-thread GPU-box Xeon the guided-schedule loops run 8x slower at 128 threads than at 32)."""
+    """Pick the OpenMP thread count that makes the CPU path FASTEST on this host, best of 3 runs per candidate (all
+    logical CPUs is not always it: on the 128-thread GPU-box Xeon the guided-schedule loops are slowest at 128)."""
     ncpu = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
     cands = sorted({max(1, ncpu >> k) for k in range(0, 4)}, reverse=True)
     best, best_t = cands[0], float("inf")
-    src, dst = pair[0], pair[1]  # the full-size pair: the best thread count depends on the problem size
+    src, dst = pair[0], pair[1]
     for n in cands:
         orc.lib().orc_set_num_threads(n)
         fn(src[:20000], dst[:20000])  # spin the pool up at this width
-        t0 = time.perf_counter()
-        fn(src, dst)
-        dt = time.perf_counter() - t0
+        dt = float("inf")
+        for _ in range(3):
+            t0 = time.perf_counter()
+            fn(src, dst)
+            dt = min(dt, time.perf_counter() - t0)
         if dt < best_t:
             best, best_t = n, dt
     orc.lib().orc_set_num_threads(best)
     return best, ncpu
-
-
-def oracle_fn(orc, workload, matching="optimized"):
-    if workload == "gicp":
-        return orc.gicp_align
-    if matching == "optimized":
-        return orc.coarse_to_fine
-    qp = orc.QuatroParams.default()
-    qp.use_optimized_matching = 0
-    return lambda s, d: orc.coarse_to_fine(s, d, qparams=qp)
-
-
-def run_cpu(pairs, budget_s=20.0, max_pairs=6, workload="gicp", matching="optimized"):
-    """Time the CPU oracle (kNN through the reference's nanoflann when oracle/_ref exists)."""
-    from oracle import oracle as orc
-    orc.lib()
-    used_ref = orc.use_ref_nanoflann(True) == 0
-    fn = oracle_fn(orc, workload, matching)
-    threads, ncpu = calibrate_threads(orc, fn, pairs[0])
-    times = []
-    t_start = time.perf_counter()
-    for i in range(max_pairs):
-        src, dst, _ = pairs[i % len(pairs)]
-        t0 = time.perf_counter()
-        fn(src, dst)
-        times.append(time.perf_counter() - t0)
-        if time.perf_counter() - t_start > budget_s:
-            break
-    per_pair = float(np.mean(times))
-    return dict(value=1.0 / per_pair, unit=UNIT, cores=threads, logical_cpus=ncpu, kind="port",
-                ms_per_pair=1e3 * per_pair, best_ms_per_pair=1e3 * float(np.min(times)),
-                sample="%d pairs of %dk x %dk points, serial over pairs, OpenMP over points; restated %s "
-                       "(oracle/) with kNN = %s" %
-                       (len(times), len(pairs[0][0]) // 1000, len(pairs[0][1]) // 1000,
-                        "Nano-GICP" if workload == "gicp" else "Quatro (FPFH + brute-force 33-D matching + QUATRO solve) + Nano-GICP",
-                        "reference nanoflann (oracle/_ref)" if used_ref else "oracle kd-tree (oracle/_ref missing)"),
-                cpu_model=cpu_info()[0])
 
 
 class ClockSampler:
@@ -186,14 +203,13 @@ class ClockSampler:
 
 def ncu_traffic(kernel_family, workload):
     """dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel, from the committed
-    `ncu --set full` capture of this round (profiles/traffic.json, written by profiles/extract_traffic.py)."""
+    `ncu --set full` capture (profiles/traffic.json, written by profiles/extract_traffic.py)."""
     p = os.path.join(REPO, "profiles", "traffic.json")
     if not os.path.exists(p):
         return None
     with open(p) as f:
         t = json.load(f)
-    e = t.get(workload, {}).get(kernel_family)
-    return e
+    return t.get(workload, {}).get(kernel_family)
 
 
 def peaks():
@@ -204,172 +220,195 @@ def peaks():
     return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
 
 
-def main_reference(args):
-    rank = int(os.environ.get("RANK", "0"))
-    if rank != 0:
-        return
-    n_pairs = 2
-    pairs = make_pairs(0, n_pairs, args.points, args.workload)
+# ---------------------------------------------------------------------------------------------------------------------
+# the CPU arm (oracle port; kNN through the reference's own nanoflann when oracle/_ref is built)
+# ---------------------------------------------------------------------------------------------------------------------
+def oracle_setup():
     from oracle import oracle as orc
     orc.lib()
     used_ref = orc.use_ref_nanoflann(True) == 0
-    fn = oracle_fn(orc, args.workload, args.matching)
+    return orc, used_ref
+
+
+def run_cpu(fn, pairs, max_pairs, budget_s, what, orc, used_ref):
+    """Time fn(src, dst) on a bounded sample; returns (cpu_baseline dict, list of results)."""
     threads, ncpu = calibrate_threads(orc, fn, pairs[0])
-    for _ in range(max(args.warmup, 1)):
-        fn(pairs[0][0], pairs[0][1])
+    times, outs = [], []
+    t_start = time.perf_counter()
+    for i in range(min(max_pairs, len(pairs))):
+        t0 = time.perf_counter()
+        outs.append(fn(pairs[i][0], pairs[i][1]))
+        times.append(time.perf_counter() - t0)
+        if time.perf_counter() - t_start > budget_s:
+            break
+    per_pair = float(np.mean(times))
+    return dict(value=1.0 / per_pair, unit=UNIT, cores=threads, logical_cpus=ncpu, kind="port",
+                ms_per_pair=1e3 * per_pair, best_ms_per_pair=1e3 * float(np.min(times)),
+                sample="%d pairs of %d x %d points, serial over pairs, OpenMP over points; restated %s (oracle/) with kNN = %s"
+                       % (len(times), len(pairs[0][0]), len(pairs[0][1]), what,
+                          "reference nanoflann (oracle/_ref)" if used_ref else "oracle kd-tree (oracle/_ref missing)"),
+                cpu_model=cpu_info()[0]), outs
+
+
+def main_reference(args):
+    """The reference's CPU path on the SAME workload (config identical to the b200 arm, same seeds): every step is a
+    bounded sample of the step's 256 pairs -- its first REF_PAIRS pairs, rotating through the rank-0 seeds."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    REF_PAIRS = 2
+    n_distinct = min(JOB_PAIRS * DISTINCT_JOBS, REF_PAIRS * max(1, min(args.steps, 8)))
+    pairs = gen_pairs(primary_seeds(0)[:n_distinct], args.points)
+    orc, used_ref = oracle_setup()
+    threads, ncpu = calibrate_threads(orc, orc.gicp_align, pairs[0])
+    for w in range(max(args.warmup, 1)):
+        orc.gicp_align(pairs[w % len(pairs)][0], pairs[w % len(pairs)][1])
     t0 = time.perf_counter()
-    for s in range(args.steps):
-        for src, dst, _ in pairs:
-            fn(src, dst)
+    k = 0
+    for _ in range(args.steps):
+        for _ in range(REF_PAIRS):
+            src, dst, _t = pairs[k % len(pairs)]
+            orc.gicp_align(src, dst)
+            k += 1
     dt = time.perf_counter() - t0
-    val = n_pairs * args.steps / dt
-    sample = ("each step = %d pairs of %dk x %dk points run serially, all host threads per pair; CPU port of "
-              "LoopClosure::icpAlignment with kNN = %s" % (n_pairs, args.points // 1000, args.points // 1000,
-                                                            "reference nanoflann (oracle/_ref)" if used_ref else "oracle kd-tree"))
+    val = REF_PAIRS * args.steps / dt
+    sample = ("each step = the first %d pairs of the step's %d (seeds 1000..%d in rotation), run serially with all host threads "
+              "per pair; CPU port of LoopClosure::icpAlignment with kNN = %s"
+              % (REF_PAIRS, JOB_PAIRS * JOBS_PER_STEP, 1000 + len(pairs) - 1, "reference nanoflann (oracle/_ref)" if used_ref else "oracle kd-tree"))
     print(json.dumps({
         "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak",
-        "vs_baseline": None, "dtype": "f32 points / f64 solver", "data": "synthetic",
-        "config": {"workload": workload_name(args), "pairs_per_step": n_pairs, "points_per_cloud": args.points},
+        "vs_baseline": None, "dtype": "f32 points+kNN / f64 covariance+solver", "data": "synthetic",
+        "config": primary_config(args),
         "cpu_baseline": {"value": val, "unit": UNIT, "cores": threads, "logical_cpus": ncpu, "kind": "port", "sample": sample,
                          "cpu_model": cpu_info()[0]},
         "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }))
 
 
-def workload_name(args):
-    if args.workload == "gicp":
-        return ("configs[1]: Nano-GICP %dk-pt KITTI-shaped scan pair (LoopClosure::icpAlignment: 2 index builds + "
-                "2 kNN-15 covariance passes + LM align + fitness)" % (args.points // 1000))
-    return ("configs[2]: Quatro+Nano-GICP full loop closure on %dk-pt scans voxelised at 0.3 m (LoopClosure::"
-            "coarseToFineAlignment: FPFH -> %sMatching -> QUATRO solve -> transform -> GICP refine)" % (args.points // 1000, args.matching))
+# ---------------------------------------------------------------------------------------------------------------------
+# the b200 arm
+# ---------------------------------------------------------------------------------------------------------------------
+class Runner:
+    """Timed regions over the C ABI's batch driver: CUDA events around, barrier + synchronize on both sides, max over ranks."""
 
+    def __init__(self, batch, ctx, dist, stream, depth):
+        self.batch, self.ctx, self.dist, self.stream, self.depth = batch, ctx, dist, stream, depth
 
-def main_sequence(args):
-    """configs[4]: every keyframe with a loop candidate goes through fetchClosestKeyframeIdx + setSrcAndDstCloud +
-    coarse-to-fine registration, all from device-resident keyframes (fast_lio_sam_qn.cpp:203-252)."""
-    import torch
-    import b200reg
-    from b200reg import synth
-    if not torch.cuda.is_available():
-        raise SystemExit("bench.py: no CUDA device -- the b200 arm has no CPU fallback")
-    torch.cuda.set_device(0)
-    B = args.pairs
-    pts = 30000 if args.points is None else args.points  # ~120k returns / 4 (kitti.launch:7)
-    seq = synth.make_sequence(5, args.keyframes, pts_per_keyframe=pts)
-    ctx = b200reg.Context(0)
-    stream = torch.cuda.Stream()
-    ctx.set_stream(stream.cuda_stream)
-    kf = ctx.keyframes()
-    for c, T, t in zip(seq["clouds"], seq["poses"], seq["stamps"]):
-        kf.add(c, T, t)
-    ctx.synchronize()
-    cfg = b200reg.default_loop_config()
-    allq = np.arange(args.keyframes, dtype=np.int32)
-    closest_all = kf.fetch_closest(allq, cfg.loop_detection_radius, cfg.loop_detection_timediff_threshold)
-    cand = allq[closest_all >= 0]
-    if len(cand) < B:
-        raise SystemExit("bench.py: sequence too short for loop candidates (%d)" % len(cand))
-    batches = [cand[i:i + B] for i in range(0, len(cand) - B + 1, B)]
-    pinned = [torch.from_numpy(seq["clouds"][q]).pin_memory() for q in cand[:B]]
-
-    def step(i, ingest):
-        q = batches[i % len(batches)]
-        if ingest:  # e2e: the step's query keyframes arrive from the host first (odomPcdCallback -> keyframe store)
-            for j, qq in enumerate(q):
-                kf.add(pinned[j % len(pinned)].numpy(), seq["poses"][qq], seq["stamps"][qq])
-        cl = kf.fetch_closest(q, cfg.loop_detection_radius, cfg.loop_detection_timediff_threshold)
-        return kf.perform_loop_closure(q, cl, cfg, raw=True)
-
-    def timed(ingest, steps):
+    def run(self, n_jobs, submit, jobs_per_step=None, gather=False):
+        """Submit n_jobs (at most 2*depth in flight), wait in order; after every jobs_per_step jobs all-gather that
+        step's result records over the context's communicator.  Returns (ms, launches, results per job, job latencies)."""
+        import torch
+        from b200reg import native
+        dist = self.dist
+        if dist is not None:
+            dist.barrier()
         torch.cuda.synchronize()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        l0 = ctx.launch_count
-        with torch.cuda.stream(stream):
-            e0.record(stream)
-            for i in range(steps):
-                out = step(i, ingest)
-            e1.record(stream)
+        l0 = self.batch.launch_count + self.ctx.launch_count
+        e0.record(self.stream)
+        self.stream.synchronize()
+        window = 2 * self.depth
+        inflight, results, lats, step_buf, gathered = [], [], [], [], None
+        nxt = 0
+        while nxt < n_jobs or inflight:
+            while nxt < n_jobs and len(inflight) < window:
+                inflight.append(submit(nxt))
+                nxt += 1
+            res, lat = self.batch.wait(inflight.pop(0), want_latency=True)
+            results.append(res)
+            lats.append(lat)
+            if gather and jobs_per_step:
+                step_buf.append(res)
+                if len(step_buf) == jobs_per_step:  # the ONE collective of the path: this step's result records
+                    n = sum(len(r) for r in step_buf)
+                    local = (native.Result * n)()
+                    k = 0
+                    for r in step_buf:
+                        ctypes.memmove(ctypes.byref(local, k * ctypes.sizeof(native.Result)), r, ctypes.sizeof(r))
+                        k += len(r)
+                    gathered = self.ctx.allgather_results(local)
+                    step_buf = []
         torch.cuda.synchronize()
-        return e0.elapsed_time(e1), ctx.launch_count - l0, out
+        e1.record(self.stream)
+        self.stream.synchronize()
+        if dist is not None:
+            dist.barrier()
+        ms = e0.elapsed_time(e1)
+        if dist is not None:
+            t = torch.tensor([ms], dtype=torch.float64, device="cuda")
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        return ms, self.batch.launch_count + self.ctx.launch_count - l0, results, lats, gathered
 
-    sampler = ClockSampler(0)
-    for i in range(args.warmup):
-        step(i, False)
-    steps = min(args.steps, 4 * len(batches))
-    ms_dev, launches, out = timed(False, steps)
-    ms_e2e, _, _ = timed(True, steps)
-    clocks = sampler.stop()
+
+def check_accuracy(results, pairs, what):
+    """The batch must land on its ground truth.  Individual synthetic pairs may legitimately defeat GICP itself (the CPU
+    oracle diverges identically on them): they are counted and reported, never replaced; a batch that mostly fails
+    means broken kernels and aborts the run."""
+    from b200reg import synth
+    worst = [0.0, 0.0]
+    off = []
+    for i, (r, p) in enumerate(zip(results, pairs)):
+        rot, tr = synth.se3_error(np.array(r.T).reshape(4, 4), p[2])
+        if not r.converged or rot > 1e-2 or tr > 0.1:
+            off.append(i)
+        else:
+            worst = [max(worst[0], rot), max(worst[1], tr)]
+    if len(off) > max(1, len(pairs) // 4):
+        raise SystemExit("bench.py: %d of %d %s registrations missed the ground truth -- refusing to report a number" % (len(off), len(pairs), what))
+    return dict(worst_rot_rad_vs_gt=worst[0], worst_trans_m_vs_gt=worst[1], pairs_off_ground_truth=off,
+                mean_linearize_passes=float(np.mean([r.n_linearize for r in results])),
+                max_linearize_passes=int(max(r.n_linearize for r in results)))
+
+
+def parity_vs_oracle(gpu_results, cpu_results, what, gpu_T=lambda r: np.array(r.T).reshape(4, 4)):
+    """GPU transforms against the CPU oracle's on the same pairs; aborts on a miss (the bar of BASELINE.json)."""
+    from b200reg import synth
+    worst = [0.0, 0.0]
+    for i, (g, o) in enumerate(zip(gpu_results, cpu_results)):
+        rot, tr = synth.se3_error(gpu_T(g), o["T"])
+        worst = [max(worst[0], rot), max(worst[1], tr)]
+        og = o.get("gicp", o)
+        if rot > ROT_TOL or tr > TRANS_TOL or bool(g.converged) != bool(o["converged"]) or g.n_linearize != og["n_linearize"]:
+            raise SystemExit("bench.py: %s parity miss on sampled pair %d: rot %.3e rad, trans %.3e m, converged %s/%s, linearize %d/%d"
+                             % (what, i, rot, tr, bool(g.converged), o["converged"], g.n_linearize, og["n_linearize"]))
+    return dict(pairs=len(cpu_results), worst_rot=worst[0], worst_trans=worst[1], counters_equal=True,
+                tolerance="%g rad / %g m" % (ROT_TOL, TRANS_TOL))
+
+
+def percentiles(x):
+    x = np.asarray(x, np.float64)
+    return dict(p50=float(np.percentile(x, 50)), p99=float(np.percentile(x, 99)), max=float(x.max()), n=int(len(x)))
+
+
+def family_table(prof, prof_steps):
+    tot_ms = sum(v["ms"] for v in prof.values())
+    return {k: dict(ms_per_step=v["ms"] / prof_steps, launches_per_step=v["launches"] / prof_steps,
+                    algo_gb_per_step=v["algo_bytes"] / prof_steps / 1e9,
+                    achieved_gbs=(v["algo_bytes"] / (v["ms"] * 1e-3) / 1e9) if v["ms"] > 0 else 0.0,
+                    share=v["ms"] / tot_ms if tot_ms > 0 else 0.0) for k, v in prof.items() if v["ms"] > 0}
+
+
+def profile_families(ctx, fn, reps):
+    """Per-kernel-family CUDA-event timing on the launching stream (one context, so the families do not overlap)."""
     ctx.set_profiling(True)
     ctx.reset_profile()
-    prof_steps = min(3, steps)
-    for i in range(prof_steps):
-        step(i, False)
+    for i in range(reps):
+        fn(i)
     prof = ctx.get_profile()
     ctx.set_profiling(False)
-    n_valid = sum(1 for r in out[0] if r.valid)
-    peak, peak_src = peaks()
-    fam = max((k for k in prof), key=lambda k: prof[k]["ms"])
-    tot_ms = sum(v["ms"] for v in prof.values())
-    f = prof[fam]
-    achieved = f["algo_bytes"] / (f["ms"] * 1e-3) / 1e9 if f["ms"] > 0 else 0.0
-    res = {
-        "metric": "loop_closure_attempts_per_sec_kitti05_shaped_sequence", "value": B * steps / (ms_dev * 1e-3), "unit": UNIT,
-        "n_gpus": 1, "steps": steps, "warmup": args.warmup, "ms_per_step": ms_dev / steps, "higher_is_better": True,
-        "scaling": "weak", "vs_baseline": None, "dtype": "f32 points+kNN+features / f64 covariance+solver", "data": "synthetic",
-        "config": {"workload": "configs[4]: loopTimerFunc over a synthetic KITTI-05-shaped sequence of %d keyframes x %dk points kept "
-                               "on the device: fetchClosestKeyframeIdx + setSrcAndDstCloud (transform, voxel 0.3 m) + Quatro + Nano-GICP"
-                               % (args.keyframes, pts // 1000), "attempts_per_step": B, "candidates": int(len(cand)),
-                   "l2": "each step touches %d distinct keyframe pairs (%.0f MB of points) and rebuilds all derived data"
-                         % (B, 2 * B * pts * 16 / 1e6)},
-        "e2e": {"value": B * steps / (ms_e2e * 1e-3), "unit": UNIT, "ms_per_step": ms_e2e / steps,
-                "h2d_bytes_per_step": B * pts * 16, "d2h_bytes_per_step": B * ctypes.sizeof(b200reg.Result)},
-        "gpu_launches": launches,
-        "roofline": {"bound": "hbm", "kernel": fam, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                     "traffic": None, "peak_source": peak_src},
-        "kernels": {k: dict(ms_per_step=v["ms"] / prof_steps, share=v["ms"] / tot_ms if tot_ms else 0.0) for k, v in prof.items()},
-        "clocks": clocks, "accuracy": {"valid_in_last_batch": n_valid, "batch": B},
-    }
-    if not args.no_cpu_baseline:
-        from oracle import oracle as orc
-        orc.lib()
-        orc.use_ref_nanoflann(True)
-        q0 = batches[0]
-        c0 = kf.fetch_closest(q0)
-
-        def cpu_one(src_dst):
-            return orc.coarse_to_fine(src_dst[0], src_dst[1])
-        pair0 = orc.set_src_and_dst_cloud(seq["clouds"], seq["poses"], int(q0[0]), int(c0[0]), n_keyframes=int(q0[0]) + 1)
-        threads, ncpu = calibrate_threads(orc, lambda a, b: orc.coarse_to_fine(a, b), pair0)
-        t0 = time.perf_counter()
-        nrun = 0
-        for qq, cc in zip(q0[:6], c0[:6]):
-            pos = seq["poses"][:int(qq) + 1, :3, 3]
-            orc.fetch_closest(pos, seq["stamps"], int(qq))
-            s_, d_ = orc.set_src_and_dst_cloud(seq["clouds"], seq["poses"], int(qq), int(cc), n_keyframes=int(qq) + 1)
-            orc.coarse_to_fine(s_, d_)
-            nrun += 1
-        dt = time.perf_counter() - t0
-        res["cpu_baseline"] = {"value": nrun / dt, "unit": UNIT, "cores": threads, "logical_cpus": ncpu, "kind": "port",
-                               "sample": "%d loop attempts (candidate search + assembly + Quatro + GICP), CPU oracle" % nrun,
-                               "cpu_model": cpu_info()[0]}
-    print(json.dumps(res))
-    kf.destroy()
-    ctx.close()
+    return prof
 
 
 def main():
     args = parse()
-    if args.workload == "sequence" and args.impl == "b200":
-        return main_sequence(args)
-    if args.points is None:
-        args.points = N_POINTS
     if args.impl == "reference":
         return main_reference(args)
 
     import torch
     import b200reg
-    from b200reg import native
+    from b200reg import native, synth
 
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -393,217 +432,306 @@ def main():
             sys.stdout.flush()
             os.dup2(saved, 1)
             os.close(saved)
+    sec = set() if args.secondary == "none" else set(("voxel,raw,sequence,batch512" if args.secondary == "all" else args.secondary).split(","))
 
-    B = args.pairs
-    pairs = make_pairs(rank, B, args.points, args.workload)
     ctx = b200reg.Context(local_rank)
-    # A synthetic pair on which GICP itself diverges (about 1 seed in 128; the CPU oracle diverges identically) runs all 32
-    # outer iterations and would alone set the max-over-ranks time of its rank: such pairs are replaced by the next seed.
-    replaced = []
-    if args.workload == "gicp":
-        from b200reg import synth as _synth
-        for attempt in range(3):
-            chk = ctx.icp_alignment([p[0] for p in pairs], [p[1] for p in pairs])
-            badi = [i for i, r in enumerate(chk) if not r["converged"]]
-            if not badi:
-                break
-            for i in badi:
-                seed = 1000 + rank * B + i + 10000 * (attempt + 1)
-                replaced.append(seed)
-                pairs[i] = _synth.make_pair(seed, args.points, args.points, mode="gicp")
     stream = torch.cuda.Stream()
     ctx.set_stream(stream.cuda_stream)
+    if world > 1:  # the data-path collective lives behind the C ABI; the 128-byte id rides on the process group that is up
+        box = [b200reg.comm_unique_id() if rank == 0 else None]
+        dist.broadcast_object_list(box, src=0)
+        ctx.comm_init(box[0], rank, world)
+    batch = b200reg.Batch(local_rank, depth=args.depth)
+    runner = Runner(batch, ctx, dist, stream, args.depth)
     prm = b200reg.default_params()
     qprm = native.default_quatro_params()
     qprm.use_optimized_matching = 1 if args.matching == "optimized" else 0
     res_bytes = ctypes.sizeof(native.Result)
 
-    # host (pinned) and device copies of the raw x,y,z,intensity records (16 B stride)
-    host_src = [torch.from_numpy(p[0]).pin_memory() for p in pairs]
-    host_dst = [torch.from_numpy(p[1]).pin_memory() for p in pairs]
-    dev_src = [t.cuda(non_blocking=True) for t in host_src]
-    dev_dst = [t.cuda(non_blocking=True) for t in host_dst]
-    torch.cuda.synchronize()
-    ns_s = [t.shape[0] for t in host_src]
-    ns_d = [t.shape[0] for t in host_dst]
-    stride = host_src[0].shape[1] * 4
-    h2d_bytes = sum(t.numel() * 4 for t in host_src + host_dst)
-    gather_buf = torch.zeros(world * B, 16, dtype=torch.float64, device="cuda") if world > 1 else None
-    stage_h = torch.zeros(B, 16, dtype=torch.float64).pin_memory() if world > 1 else None
-    stage_d = torch.zeros(B, 16, dtype=torch.float64, device="cuda") if world > 1 else None
+    # ---- headline: configs[1] -----------------------------------------------------------------------------------------
+    pairs = gen_pairs(primary_seeds(rank), args.points)
+    arena = Arena(pairs, JOB_PAIRS)
 
-    def step(on_device):
-        srcs = dev_src if on_device else host_src
-        dsts = dev_dst if on_device else host_dst
-        if args.workload == "gicp":
-            res = ctx.icp_alignment_ptrs([t.data_ptr() for t in srcs], ns_s, [t.data_ptr() for t in dsts], ns_d, stride,
-                                         on_device, prm)
-        else:
-            res, _ = ctx.loop_closure_ptrs([t.data_ptr() for t in srcs], ns_s, [t.data_ptr() for t in dsts], ns_d, stride,
-                                           on_device, qprm, prm)
-        if world > 1:  # the ONE collective of the path: all-gather of the 4x4 transforms
-            rec = np.frombuffer(res, dtype=np.uint8).reshape(B, res_bytes)[:, :128]  # Result.T = first 16 doubles
-            stage_h.numpy()[:] = np.ascontiguousarray(rec).view(np.float64)
-            with torch.cuda.stream(stream):
-                stage_d.copy_(stage_h, non_blocking=True)
-                dist.all_gather_into_tensor(gather_buf, stage_d)
-        return res
+    def submit_icp(on_device):
+        return lambda j: batch.submit_icp(*arena.job(j, on_device), prm)
 
-    def timed(on_device, steps):
-        if dist is not None:
-            dist.barrier()
+    sampler = ClockSampler(local_rank) if rank == 0 else None  # samples from the warm-up on: same load as the timed region
+    warm_jobs = max(args.warmup, 3) * max(DISTINCT_JOBS, 2 * args.depth)  # every context sees every sub-batch, both arms
+    runner.run(warm_jobs, submit_icp(True))
+    runner.run(warm_jobs, submit_icp(False))
+    n_jobs = args.steps * JOBS_PER_STEP
+    ms_dev, launches, res_dev, lat_dev, _ = runner.run(n_jobs, submit_icp(True), JOBS_PER_STEP, gather=world > 1)
+    ms_e2e, _, res_e2e, lat_e2e, _ = runner.run(n_jobs, submit_icp(False), JOBS_PER_STEP, gather=world > 1)
+    clocks = sampler.stop() if sampler else None
+
+    # one result per distinct pair (jobs 0..3 of the device arm), bit-identical across repeats and arms
+    flat = [r for j in range(DISTINCT_JOBS) for r in res_dev[j]]
+    for j in range(DISTINCT_JOBS, len(res_dev)):
+        if bytes(res_dev[j]) != bytes(res_dev[j % DISTINCT_JOBS]) or bytes(res_e2e[j]) != bytes(res_dev[j % DISTINCT_JOBS]):
+            raise SystemExit("bench.py: repeated jobs over the same pairs returned different bytes (job %d)" % j)
+    accuracy = check_accuracy(flat, pairs, "icpAlignment")
+    accuracy["not_converged_seeds"] = [primary_seeds(rank)[i] for i in accuracy.pop("pairs_off_ground_truth")]
+
+    # per-kernel-family timing (one context, one 16-pair job at a time, rotating over the distinct sub-batches)
+    prof_steps = 8
+    prof = profile_families(ctx, lambda i: ctx.icp_alignment_ptrs(*arena.job(i, True), prm), prof_steps)
+
+    out = None
+    if rank == 0:
+        total_pairs = world * JOB_PAIRS * n_jobs
+        peak, peak_src = peaks()
+        fam = max((k for k in prof if k != "misc"), key=lambda k: prof[k]["ms"])
+        f = prof[fam]
+        achieved = f["algo_bytes"] / (f["ms"] * 1e-3) / 1e9 if f["ms"] > 0 else 0.0
+        cfg = primary_config(args)  # identical to the reference arm's
+        parallelism = ("pairs sharded over %d ranks (64 distinct pairs each), no data-path collective but ONE ncclAllGather of the "
+                       "step's result records per step through b200reg_allgather_results" % world) if world > 1 else "single GPU"
+        out = {
+            "metric": METRIC, "value": total_pairs / (ms_dev * 1e-3), "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms_dev / args.steps, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32 points+kNN / f64 covariance+solver", "data": "synthetic",
+            "config": cfg, "parallelism": parallelism,
+            "driver": "b200reg_batch (C ABI, csrc/batch.cu): %d engine contexts on C++ host threads, %d-pair jobs, at most %d jobs in flight"
+                      % (args.depth, JOB_PAIRS, 2 * args.depth),
+            "timed_region_s": ms_dev * 1e-3,
+            "e2e": {"value": total_pairs / (ms_e2e * 1e-3), "unit": UNIT, "ms_per_step": ms_e2e / args.steps,
+                    "h2d_bytes_per_step": sum(arena.h2d_bytes(j) for j in range(JOBS_PER_STEP)),
+                    "d2h_bytes_per_step": JOB_PAIRS * JOBS_PER_STEP * res_bytes, "timed_region_s": ms_e2e * 1e-3},
+            "gpu_launches": launches,
+            "roofline": {"bound": "hbm", "kernel": fam, "achieved": achieved, "peak": peak, "unit": "GB/s",
+                         "frac": achieved / peak, "traffic": ncu_traffic(fam, "gicp"), "peak_source": peak_src,
+                         "note": "algorithmic bytes per SURVEY.md §8(d) / CUDA-event time of that kernel family on the launching "
+                                 "stream, %d profiled 16-pair jobs on one context after the timed region" % prof_steps},
+            "kernels": family_table(prof, prof_steps),
+            "clocks": clocks,
+            "accuracy": accuracy,
+            "job_latency_ms_under_load": {"device_resident": percentiles(lat_dev), "from_host": percentiles(lat_e2e),
+                                          "note": "submit -> completion of one 16-pair job with up to %d jobs in flight" % (2 * args.depth)},
+        }
+
+    # ---- single-pair latency through ONE C-ABI call on an idle GPU (the reference's "ms per ICP" view) ---------------------
+    if rank == 0:
+        lat1 = []
+        for i in range(32):
+            k = (2 * i) % len(arena.hs)
+            hs, hd = arena.hs[k], arena.hd[k]
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            ctx.icp_alignment_ptrs([hs.data_ptr()], [hs.shape[0]], [hd.data_ptr()], [hd.shape[0]], arena.stride, 0, prm)
+            lat1.append(1e3 * (time.perf_counter() - t0))
+        out["latency"] = {"single_pair_icp_alignment_ms": percentiles(lat1[2:]),
+                          "note": "one 100k x 100k pair per b200reg_icp_alignment call from pinned host buffers, idle GPU, wall clock around the "
+                                  "call (upload, 2 index builds, 2 covariance passes, LM, fitness, result read-back): what NanoGICP::align's "
+                                  "caller times in fast_lio_sam_qn.cpp:212-243"}
+
+    # ---- CPU oracle on a bounded sample of the same pairs + parity of the GPU transforms against it ------------------------
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        orc, used_ref = oracle_setup()
+        out["cpu_baseline"], cpu_res = run_cpu(orc.gicp_align, pairs, args.cpu_sample_pairs, 20.0, "Nano-GICP", orc, used_ref)
+        par = parity_vs_oracle(flat[:len(cpu_res)], cpu_res, "icpAlignment")
+        # correspondences of the first linearize of pair 0: bit-exact indices and fp32 distances at 100k x 100k
+        cs, ct = ctx.create_clouds([pairs[0][0], pairs[0][1]])
+        ctx.covariances([cs, ct], 15)
+        lin = ctx.linearize(cs, ct, np.eye(4))
+        ol = orc.linearize(pairs[0][0], pairs[0][1], ctx.get_covariances(cs), ctx.get_covariances(ct), np.eye(4))
+        par["corr_exact"] = bool(np.array_equal(lin["corr"], ol["corr"]) and np.array_equal(lin["sqd"], ol["sqd"]))
+        cs.destroy(); ct.destroy()
+        if not par["corr_exact"]:
+            raise SystemExit("bench.py: first-linearize correspondences differ from the oracle's")
+        out["parity"] = par
+
+    # ---- secondary workloads -------------------------------------------------------------------------------------------
+    secondary = {}
+    if world == 1:
+        if "voxel" in sec:
+            secondary["loop_closure_voxelised"] = bench_loop_closure(args, runner, batch, ctx, qprm, prm, voxel=0.3, n_pairs=64, per_job=16,
+                                                                     jobs=24, cpu_pairs=3)
+        if "raw" in sec:
+            secondary["loop_closure_raw_100k"] = bench_loop_closure(args, runner, batch, ctx, qprm, prm, voxel=None, n_pairs=8, per_job=4,
+                                                                    jobs=6, cpu_pairs=1)
+        if "sequence" in sec:
+            secondary["sequence_kitti05_shaped"] = bench_sequence(args, ctx, stream)
+    elif "batch512" in sec:
+        secondary["batch_512_pairs_sharded"] = bench_batch512(args, runner, batch, ctx, dist, prm, rank, world)
+    if rank == 0:
+        if secondary:
+            out["secondary"] = secondary
+        print(json.dumps(out))
+    batch.close()
+    if dist is not None:
+        dist.barrier()
+    if world > 1:
+        ctx.comm_destroy()
+    ctx.close()
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+def bench_loop_closure(args, runner, batch, ctx, qprm, prm, voxel, n_pairs, per_job, jobs, cpu_pairs):
+    """configs[2]: LoopClosure::coarseToFineAlignment (FPFH -> matching -> QUATRO solve -> transform -> GICP refine),
+    SURVEY §8(d) seeds 2000..., on scans voxelised at 0.3 m like setSrcAndDstCloud (loop_closure.cpp:107) or RAW."""
+    from b200reg import native
+    pairs = gen_pairs([2000 + i for i in range(n_pairs)], args.points, mode="quatro", voxel=voxel)
+    arena = Arena(pairs, per_job)
+
+    def submit(on_device):
+        return lambda j: batch.submit_loop_closure(*arena.job(j, on_device), qprm, prm)
+    njobs_distinct = len(arena.jobs)
+    runner.run(max(njobs_distinct, 2 * runner.depth), submit(True))
+    runner.run(max(njobs_distinct, 2 * runner.depth), submit(False))
+    ms_dev, launches, res, lat, _ = runner.run(jobs, submit(True))
+    ms_e2e, _, _, lat_h, _ = runner.run(jobs, submit(False))
+    flat = [r for j in range(njobs_distinct) for r in res[j]]
+    acc = check_accuracy(flat, pairs, "coarse-to-fine")
+    acc["not_converged_seeds"] = [2000 + i for i in acc.pop("pairs_off_ground_truth")]
+    prof = profile_families(ctx, lambda i: ctx.loop_closure_ptrs(*arena.job(i, True), qprm, prm), njobs_distinct)
+    sizes = [len(p[0]) for p in pairs] + [len(p[1]) for p in pairs]
+    out = {"metric": "full_loop_closure_registrations_per_sec", "unit": UNIT,
+           "workload": "configs[2]: Quatro+Nano-GICP full loop closure (LoopClosure::coarseToFineAlignment, %sMatching) on %s"
+                       % (args.matching, ("%dk-pt scans voxelised at %.1f m" % (args.points // 1000, voxel)) if voxel else
+                          ("RAW %dk x %dk-pt scans (no voxel grid)" % (args.points // 1000, args.points // 1000))),
+           "points_per_cloud": {"min": int(min(sizes)), "median": int(np.median(sizes)), "max": int(max(sizes))},
+           "distinct_pairs": n_pairs, "pairs_per_job": per_job, "jobs_timed": jobs, "seeds": "2000 + i",
+           "value": per_job * jobs / (ms_dev * 1e-3), "timed_region_s": ms_dev * 1e-3,
+           "e2e": {"value": per_job * jobs / (ms_e2e * 1e-3), "unit": UNIT,
+                   "h2d_bytes_per_job": arena.h2d_bytes(0), "d2h_bytes_per_job": per_job * (ctypes.sizeof(native.Result) + ctypes.sizeof(native.QuatroInfo))},
+           "gpu_launches": launches, "kernels": family_table(prof, njobs_distinct), "accuracy": acc,
+           "job_latency_ms_under_load": percentiles(lat)}
+    if not args.no_cpu_baseline:
+        orc, used_ref = oracle_setup()
+        qp = orc.QuatroParams.default()
+        qp.use_optimized_matching = 1 if args.matching == "optimized" else 0
+        out["cpu_baseline"], cpu_res = run_cpu(lambda s, d: orc.coarse_to_fine(s, d, qparams=qp), pairs, cpu_pairs, 40.0,
+                                               "Quatro (FPFH + brute-force 33-D matching + QUATRO solve) + Nano-GICP", orc, used_ref)
+        # parity at the bar: the fine stage on the SAME coarse transform (the two coarse stages differ by fp32 summation order
+        # of the descriptors and are only required to agree to the refinement's basin, tests/test_gpu_quatro.py)
+        single, qi = ctx.loop_closure([p[0] for p in pairs[:len(cpu_res)]], [p[1] for p in pairs[:len(cpu_res)]], qparams=qprm, gparams=prm)
+        same = [orc.coarse_to_fine(p[0], p[1], qparams=qp, quatro_T=q["T"]) for p, q in zip(pairs, qi)]
+
+        class _R:  # adapter: dict -> attribute access
+            def __init__(self, d):
+                self.T, self.converged, self.n_linearize = d["T"].reshape(-1), d["converged"], d["n_linearize"]
+        out["parity"] = parity_vs_oracle([_R(r) for r in single], same, "coarse-to-fine (fine stage on the same coarse transform)")
+        from b200reg import synth
+        pipe = [synth.se3_error(r["T"], o["T"]) for r, o in zip(single, cpu_res)]
+        out["parity"]["complete_pipelines_worst_rot"] = float(max(p[0] for p in pipe))
+        out["parity"]["complete_pipelines_worst_trans"] = float(max(p[1] for p in pipe))
+    return out
+
+
+def bench_sequence(args, ctx, stream):
+    """configs[4]: every keyframe of a synthetic KITTI-05-shaped sequence that has a loop candidate goes through
+    fetchClosestKeyframeIdx + setSrcAndDstCloud + coarse-to-fine registration, all from device-resident keyframes
+    (loopTimerFunc, fast_lio_sam_qn.cpp:203-252)."""
+    import torch
+    import b200reg
+    from b200reg import synth
+    B = 16
+    pts = 30000  # ~120k returns / 4 (kitti.launch:7)
+    seq = synth.make_sequence(5, args.keyframes, pts_per_keyframe=pts, threads=max(1, (os.cpu_count() or 8) // 8))
+    kf = ctx.keyframes()
+    for c, T, t in zip(seq["clouds"], seq["poses"], seq["stamps"]):
+        kf.add(c, T, t)
+    ctx.synchronize()
+    cfg = b200reg.default_loop_config()
+    allq = np.arange(args.keyframes, dtype=np.int32)
+    closest_all = kf.fetch_closest(allq, cfg.loop_detection_radius, cfg.loop_detection_timediff_threshold)
+    cand = allq[closest_all >= 0]
+    if len(cand) < B:
+        kf.destroy()
+        return {"unavailable": "sequence too short for loop candidates (%d)" % len(cand)}
+    batches = [cand[i:i + B] for i in range(0, len(cand) - B + 1, B)]
+    pinned = [torch.from_numpy(seq["clouds"][q]).pin_memory() for q in cand[:B]]
+
+    def step(i, ingest):
+        q = batches[i % len(batches)]
+        if ingest:  # e2e: the step's query keyframes arrive from the host first (odomPcdCallback -> keyframe store)
+            for j, qq in enumerate(q):
+                kf.add(pinned[j % len(pinned)].numpy(), seq["poses"][qq], seq["stamps"][qq])
+        cl = kf.fetch_closest(q, cfg.loop_detection_radius, cfg.loop_detection_timediff_threshold)
+        return kf.perform_loop_closure(q, cl, cfg, raw=True)
+
+    def timed(ingest, steps):
         torch.cuda.synchronize()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         l0 = ctx.launch_count
+        nvalid = 0
         with torch.cuda.stream(stream):
             e0.record(stream)
-            for _ in range(steps):
-                res = step(on_device)
+            for i in range(steps):
+                out = step(i, ingest)
+                nvalid += sum(1 for r in out[0] if r.valid)
             e1.record(stream)
         torch.cuda.synchronize()
-        if dist is not None:
-            dist.barrier()
-        ms = e0.elapsed_time(e1)
-        if dist is not None:
-            t = torch.tensor([ms], dtype=torch.float64, device="cuda")
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            ms = float(t.item())
-        return ms, ctx.launch_count - l0, res
+        return e0.elapsed_time(e1), ctx.launch_count - l0, nvalid
 
-    # Both timed arms go through the package's double-buffered driver -- two contexts on two host threads take alternate
-    # steps, so one step's H2D + polling hide behind the other's kernels (b200reg/pipeline.py).  In the e2e arm every
-    # step still uploads all of its inputs from pinned host memory and reads its results back.
-    from b200reg.pipeline import PipelinedRegistrar
-    depth = int(os.environ.get("B200REG_PIPE_DEPTH", "3"))
-    pipe = PipelinedRegistrar(local_rank, depth=depth)
+    for i in range(3):
+        step(i, False)
+    steps = len(batches)  # every candidate of the sequence exactly once
+    ms_dev, launches, nvalid = timed(False, steps)
+    ms_e2e, _, _ = timed(True, min(steps, 16))
+    prof = profile_families(ctx, lambda i: step(i, False), min(4, steps))
+    res = {"metric": "loop_closure_attempts_per_sec_kitti05_shaped_sequence", "unit": UNIT,
+           "workload": "configs[4]: loopTimerFunc over a synthetic KITTI-05-shaped sequence of %d keyframes x %dk points kept on the device: "
+                       "fetchClosestKeyframeIdx + setSrcAndDstCloud (transform, voxel 0.3 m) + Quatro + Nano-GICP for EVERY keyframe that has a "
+                       "loop candidate, %d per call" % (args.keyframes, pts // 1000, B),
+           "keyframes": args.keyframes, "candidates": int(len(cand)), "attempts_timed": B * steps, "valid_loops": int(nvalid),
+           "value": B * steps / (ms_dev * 1e-3), "timed_region_s": ms_dev * 1e-3, "ms_per_attempt": ms_dev / (B * steps),
+           "e2e": {"value": B * min(steps, 16) / (ms_e2e * 1e-3), "unit": UNIT, "h2d_bytes_per_call": B * pts * 16,
+                   "d2h_bytes_per_call": B * ctypes.sizeof(b200reg.Result),
+                   "note": "the 16 query keyframes of every call are ingested from pinned host memory first"},
+           "gpu_launches": launches, "kernels": family_table(prof, min(4, steps))}
+    if not args.no_cpu_baseline:
+        orc, used_ref = oracle_setup()
+        q0 = batches[0]
+        c0 = kf.fetch_closest(q0)
+        pair0 = orc.set_src_and_dst_cloud(seq["clouds"], seq["poses"], int(q0[0]), int(c0[0]), n_keyframes=int(q0[0]) + 1)
+        threads, ncpu = calibrate_threads(orc, lambda a, b: orc.coarse_to_fine(a, b), pair0)
+        t0 = time.perf_counter()
+        nrun = 0
+        for qq, cc in zip(q0[:6], c0[:6]):
+            pos = seq["poses"][:int(qq) + 1, :3, 3]
+            orc.fetch_closest(pos, seq["stamps"], int(qq))
+            s_, d_ = orc.set_src_and_dst_cloud(seq["clouds"], seq["poses"], int(qq), int(cc), n_keyframes=int(qq) + 1)
+            orc.coarse_to_fine(s_, d_)
+            nrun += 1
+        dt = time.perf_counter() - t0
+        res["cpu_baseline"] = {"value": nrun / dt, "unit": UNIT, "cores": threads, "logical_cpus": ncpu, "kind": "port",
+                               "sample": "%d loop attempts (candidate search + assembly + Quatro + GICP), CPU oracle" % nrun,
+                               "cpu_model": cpu_info()[0]}
+    kf.destroy()
+    return res
 
-    def run_pipelined(steps, on_device):
-        if dist is not None:
-            dist.barrier()
-        torch.cuda.synchronize()
-        e0 = torch.cuda.Event(enable_timing=True)
-        ends = [torch.cuda.Event(enable_timing=True) for _ in pipe.ctxs]
-        e0.record(stream)
-        stream.synchronize()
-        srcs = dev_src if on_device else host_src
-        dsts = dev_dst if on_device else host_dst
-        l0 = pipe.launch_count
-        sp, tp = [t.data_ptr() for t in srcs], [t.data_ptr() for t in dsts]
-        if args.workload == "gicp":
-            futs = [pipe.icp_alignment_ptrs(sp, ns_s, tp, ns_d, stride, int(on_device), prm) for _ in range(steps)]
-        else:
-            futs = [pipe.loop_closure_ptrs(sp, ns_s, tp, ns_d, stride, int(on_device), qprm, prm) for _ in range(steps)]
-        outs = [pipe.wait(f) for f in futs]
-        if world > 1:  # the step results of this rank, gathered once per step like the device arm
-            for r_ in outs:
-                rec = np.frombuffer(r_, dtype=np.uint8).reshape(B, res_bytes)[:, :128]
-                stage_h.numpy()[:] = np.ascontiguousarray(rec).view(np.float64)
-                with torch.cuda.stream(stream):
-                    stage_d.copy_(stage_h, non_blocking=True)
-                    dist.all_gather_into_tensor(gather_buf, stage_d)
-        pipe.synchronize()
-        torch.cuda.synchronize()
-        e1 = torch.cuda.Event(enable_timing=True)
-        e1.record(stream)
-        stream.synchronize()
-        if dist is not None:
-            dist.barrier()
-        ms = e0.elapsed_time(e1)
-        if dist is not None:
-            t = torch.tensor([ms], dtype=torch.float64, device="cuda")
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            ms = float(t.item())
-        return ms, pipe.launch_count - l0, outs[-1]
 
-    sampler = ClockSampler(local_rank) if rank == 0 else None  # samples from the warm-up on: same load as the timed region
-    for _ in range(args.warmup):
-        step(True)
-        step(False)
-    if pipe is not None:  # every context of the pipeline must see both arms at least twice before anything is timed
-        run_pipelined(max(2 * depth, args.warmup), True)
-        run_pipelined(max(2 * depth, args.warmup), False)
-        run_pipelined(depth, True)
+def bench_batch512(args, runner, batch, ctx, dist, prm, rank, world):
+    """configs[3]: ONE batch of 512 keyframe-pair candidates (SURVEY §8(d) seeds 3000...3511) sharded over the ranks in
+    contiguous blocks (b200reg/sharding.py), registered in 16-pair jobs, then ONE ncclAllGather of the 512 result
+    records (b200reg_allgather_results).  Strong scaling: the batch is fixed, the shard shrinks with N."""
+    from b200reg import native
+    from b200reg.sharding import shard_pairs
+    mine = shard_pairs(512, world, rank)
+    pairs = gen_pairs([3000 + i for i in mine], args.points)
+    arena = Arena(pairs, JOB_PAIRS)
+    njobs = len(arena.jobs)
+    reps = 3
 
-    if pipe is not None:  # both arms through the same double-buffered driver
-        ms_dev, launches, res = run_pipelined(args.steps, True)
-        ms_e2e, _, res_h = run_pipelined(args.steps, False)
-    else:
-        ms_dev, launches, res = timed(True, args.steps)
-        ms_e2e, _, res_h = timed(False, args.steps)
-    clocks = sampler.stop() if sampler else None
-
-    # per-kernel-family CUDA-event timing on the launching stream (same workload, same stream)
-    ctx.set_profiling(True)
-    ctx.reset_profile()
-    prof_steps = max(2, min(args.steps, 5))
-    for _ in range(prof_steps):
-        step(True)
-    prof = ctx.get_profile()
-    ctx.set_profiling(False)
-
-    # correctness guard: the batch must land on its ground truth.  Individual synthetic pairs may legitimately defeat
-    # GICP itself (seed 1104 ends 1.6 rad off on the CPU oracle too, with identical numbers), so single failures are
-    # counted and reported; a batch that mostly fails means broken kernels and aborts the run.
-    from b200reg import synth
-    worst = (0.0, 0.0)
-    n_off = 0
-    for r, p in zip(res, pairs):
-        T = np.array(r.T).reshape(4, 4)
-        rot, tr = synth.se3_error(T, p[2])
-        if not r.converged or rot > 1e-2 or tr > 0.1:
-            n_off += 1
-        else:
-            worst = (max(worst[0], rot), max(worst[1], tr))
-    if n_off > max(1, len(pairs) // 4):
-        raise SystemExit("bench.py: %d of %d registrations missed the ground truth -- refusing to report a number" % (n_off, len(pairs)))
-
-    if rank == 0:
-        total_pairs = world * B * args.steps
-        value = total_pairs / (ms_dev * 1e-3)
-        e2e = total_pairs / (ms_e2e * 1e-3)
-        peak, peak_src = peaks()
-        fam = max((k for k in prof if k != "misc"), key=lambda k: prof[k]["ms"])
-        tot_ms = sum(v["ms"] for v in prof.values())
-        f = prof[fam]
-        achieved = f["algo_bytes"] / (f["ms"] * 1e-3) / 1e9 if f["ms"] > 0 else 0.0
-        kernels = {k: dict(ms_per_step=v["ms"] / prof_steps, launches_per_step=v["launches"] / prof_steps,
-                           algo_gb_per_step=v["algo_bytes"] / prof_steps / 1e9,
-                           achieved_gbs=(v["algo_bytes"] / (v["ms"] * 1e-3) / 1e9) if v["ms"] > 0 else 0.0,
-                           share=v["ms"] / tot_ms if tot_ms > 0 else 0.0) for k, v in prof.items()}
-        out = {
-            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": ms_dev / args.steps, "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": "f32 points+kNN / f64 covariance+solver",
-            "data": "synthetic",
-            "config": {"workload": workload_name(args), "pairs_per_step_per_gpu": B, "points_per_cloud": args.points,
-                       "seeds": "1000+rank*B+i" + ("; replaced on rank 0 (GICP diverges on the CPU oracle too): %s" % replaced if replaced else ""),
-                       "l2": "working set per step (%.0f MB raw + ~%.0f MB derived) exceeds the 126 MB L2; clouds are "
-                             "rebuilt from raw xyz every step" % (h2d_bytes / 1e6, B * 2 * args.points * 100 / 1e6),
-                       "parallelism": "pairs sharded over ranks, one NCCL all-gather of 4x4 transforms per step" if world > 1 else "single GPU",
-                       "driver": ("b200reg.pipeline.PipelinedRegistrar(depth=%d): contexts on separate host threads take alternate steps" % depth)
-                                 if pipe is not None else "single context"},
-            "e2e": {"value": e2e, "unit": UNIT, "ms_per_step": ms_e2e / args.steps, "h2d_bytes_per_step": h2d_bytes,
-                    "d2h_bytes_per_step": B * res_bytes,
-                    "driver": ("b200reg.pipeline.PipelinedRegistrar(depth=%d)" % depth) if pipe is not None else "single context"},
-            "gpu_launches": launches,
-            "roofline": {"bound": "hbm", "kernel": fam, "achieved": achieved, "peak": peak, "unit": "GB/s",
-                         "frac": achieved / peak, "traffic": ncu_traffic(fam, args.workload), "peak_source": peak_src,
-                         "note": "algorithmic bytes per SURVEY.md §8(d) / CUDA-event time of that kernel family on the "
-                                 "launching stream, %d profiled steps after the timed region" % prof_steps},
-            "kernels": kernels,
-            "clocks": clocks,
-            "accuracy": {"worst_rot_rad_vs_gt": worst[0], "worst_trans_m_vs_gt": worst[1], "pairs_off_ground_truth_rank0": n_off,
-                         "mean_linearize_passes": float(np.mean([r.n_linearize for r in res]))},
-        }
-        if world == 1 and not args.no_cpu_baseline:
-            out["cpu_baseline"] = run_cpu(pairs, max_pairs=args.cpu_sample_pairs, workload=args.workload, matching=args.matching)
-        print(json.dumps(out))
-    if pipe is not None:
-        pipe.close()
-    if dist is not None:
-        dist.barrier()
-        dist.destroy_process_group()
-    ctx.close()
+    def submit(j):
+        return batch.submit_icp(*arena.job(j, True), prm)
+    runner.run(njobs, submit, njobs, gather=True)  # warm-up
+    ms = []
+    for _ in range(reps):
+        m, launches, res, _, gathered = runner.run(njobs, submit, njobs, gather=True)
+        ms.append(m)
+    if rank != 0:
+        return None
+    recs = list(gathered)
+    T_ok = sum(1 for r in recs if r.converged)
+    return {"metric": "batch_512_registrations_per_sec", "unit": UNIT,
+            "workload": "configs[3]: batch of 512 keyframe-pair loop candidates (%dk x %dk points, seeds 3000..3511) sharded over %d GPUs, "
+                        "%d pairs per rank, one ncclAllGather of the 512 result records (%d bytes each) per batch"
+                        % (args.points // 1000, args.points // 1000, world, len(mine), ctypes.sizeof(native.Result)),
+            "scaling": "strong", "value": 512.0 / (min(ms) * 1e-3), "ms_per_batch": {"best": min(ms), "all": ms},
+            "gathered_records": len(recs), "converged": T_ok, "inputs": "resident in HBM", "gpu_launches_rank0": launches}
 
 
 if __name__ == "__main__":

@@ -20,14 +20,16 @@ class GicpParams(C.Structure):
 
 
 class Result(C.Structure):
-    _fields_ = [("T", C.c_double * 16), ("Tf", C.c_float * 16), ("pose_between", C.c_double * 16), ("fitness", C.c_double),
+    _fields_ = [("T", C.c_double * 16), ("Tf", C.c_float * 16), ("pose_between", C.c_double * 16), ("final_hessian", C.c_double * 36),
+                ("fitness", C.c_double),
                 ("converged", C.c_int32),
                 ("valid", C.c_int32), ("iterations", C.c_int32), ("n_linearize", C.c_int32), ("n_error", C.c_int32),
                 ("lm_failed", C.c_int32), ("status", C.c_int32), ("tag", C.c_int32)]
 
     def as_dict(self):
         return dict(T=np.array(self.T).reshape(4, 4), Tf=np.array(self.Tf, np.float32).reshape(4, 4),
-                    pose_between=np.array(self.pose_between).reshape(4, 4), fitness=self.fitness, converged=bool(self.converged), valid=bool(self.valid),
+                    pose_between=np.array(self.pose_between).reshape(4, 4),
+                    final_hessian=np.array(self.final_hessian).reshape(6, 6), fitness=self.fitness, converged=bool(self.converged), valid=bool(self.valid),
                     iterations=self.iterations, n_linearize=self.n_linearize, n_error=self.n_error,
                     lm_failed=bool(self.lm_failed), status=self.status)
 
@@ -74,7 +76,7 @@ EXPORTS = [
     "b200reg_keyframes_destroy", "b200reg_keyframes_add", "b200reg_keyframes_set_pose", "b200reg_keyframes_size",
     "b200reg_knn_bruteforce", "b200reg_fetch_closest_keyframes", "b200reg_assemble_clouds", "b200reg_cloud_points", "b200reg_perform_loop_closure",
     "b200reg_loop_factor_from_poses", "b200reg_loop_factors", "b200reg_compute_error", "b200reg_assemble_clouds_at",
-    "b200reg_struct_size", "b200reg_set_last_error",
+    "b200reg_struct_size", "b200reg_set_last_error", "b200reg_set_covariances",
     "b200reg_batch_create", "b200reg_batch_destroy", "b200reg_batch_submit_icp", "b200reg_batch_submit_loop_closure",
     "b200reg_batch_wait", "b200reg_batch_wait_all", "b200reg_batch_launch_count", "b200reg_batch_depth",
     "b200reg_comm_unique_id", "b200reg_comm_init", "b200reg_comm_destroy", "b200reg_comm_rank", "b200reg_comm_world",
@@ -242,6 +244,11 @@ class Context:
     def covariances(self, clouds, k=15, method=3):
         arr = (C.c_void_p * len(clouds))(*[c.h for c in clouds])
         _check(lib().b200reg_clouds_covariances_ex(self.h, len(clouds), arr, int(k), int(method)))
+
+    def set_covariances(self, cloud, cov):
+        """NanoGICP::setSource/TargetCovariances: (n, 3, 3) float64 in the ORIGINAL point order."""
+        cov = np.ascontiguousarray(cov, np.float64).reshape(cloud.n, 9)
+        _check(lib().b200reg_set_covariances(self.h, cloud.h, cov.ctypes.data_as(C.c_void_p), C.c_size_t(cloud.n)))
 
     # -- registration ------------------------------------------------------------------
     def gicp_align(self, srcs, tgts, params=None, guesses=None):

@@ -104,7 +104,7 @@ def se3_error(T_est, T_ref):
     return float(np.arccos(c)), float(np.linalg.norm(E[:3, 3]))
 
 
-def make_sequence(seed, n_keyframes, pts_per_keyframe=30000, spacing=0.8, speed=8.0, drift_xy=0.01, drift_yaw_deg=0.01):
+def make_sequence(seed, n_keyframes, pts_per_keyframe=30000, spacing=0.8, speed=8.0, drift_xy=0.01, drift_yaw_deg=0.01, threads=1):
     """KITTI-05-shaped keyframe sequence: laps of a two-lane street (U-turns at both ends,
     411 m per lap) so that every place is revisited after > 30 s; one scan per keyframe in the LiDAR frame; odometry
     poses = true poses with a slow random-walk drift.  Returns dict(clouds, poses (n,4,4), true_poses, stamps)."""
@@ -126,13 +126,19 @@ def make_sequence(seed, n_keyframes, pts_per_keyframe=30000, spacing=0.8, speed=
             x, y, yaw = -half - r * np.sin(a), r * np.cos(a), np.pi + a
         return se3(yaw=yaw, t=(x, y, 1.73))
 
-    clouds, poses, true_poses, stamps = [], [], [], []
+    poses, true_poses, stamps = [], [], []
     D = np.eye(4)
     for k in range(n_keyframes):
         Tt = pose_at(k * spacing)
         D = D @ se3(yaw=np.deg2rad(rng.normal(0, drift_yaw_deg)), t=(rng.normal(0, drift_xy), rng.normal(0, drift_xy), rng.normal(0, drift_xy * 0.1)))
-        clouds.append(scan(seed, 7919 * seed + k, Tt, pts_per_keyframe))
         true_poses.append(Tt)
         poses.append(D @ Tt)
         stamps.append(k * spacing / speed)
+    # the scans depend only on (seed, k, true pose): generating them on several threads gives the same clouds
+    if threads > 1:
+        from concurrent.futures import ThreadPoolExecutor
+        with ThreadPoolExecutor(threads) as ex:
+            clouds = list(ex.map(lambda k: scan(seed, 7919 * seed + k, true_poses[k], pts_per_keyframe), range(n_keyframes)))
+    else:
+        clouds = [scan(seed, 7919 * seed + k, true_poses[k], pts_per_keyframe) for k in range(n_keyframes)]
     return dict(clouds=clouds, poses=np.array(poses), true_poses=np.array(true_poses), stamps=np.array(stamps))

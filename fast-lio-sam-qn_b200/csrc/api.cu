@@ -25,6 +25,7 @@ void launch_gicp_init(const PairDev* pairs, PairState* states, const double* d_g
 void launch_gicp_step(const PairDev* pairs, PairState* states, int blocks, const GicpParamsDev& prm, LmSched* sched, cudaStream_t s);
 int launch_knn_queries(const CloudDev& c, const float* d_q, int nq, int qstride, int k, int* idx, float* d2, cudaStream_t s, int brute);
 void launch_transform_out(const CloudDev& c, const float* d_Tf, float* d_out3, cudaStream_t s);
+void launch_set_covariances(const CloudDev& c, const double* d_cov9, cudaStream_t s);
 int launch_fpfh(const CloudDev* d_clouds, int count, int max_n, float normal_r2, float fpfh_r2, cudaStream_t s);
 int launch_quatro_match_solve(const MatchDev* d_pairs, int count, int max_ni, int max_nj, const QuatroParamsDev& prm, cudaStream_t s);
 void launch_transform_raw(const CloudDev* d_clouds, const double* d_T16s, int count, int max_n, float4* const* d_outs, cudaStream_t s);
@@ -143,6 +144,7 @@ struct b200reg_cloud {
   void* slab = nullptr;    // persistent allocation (pts, tnodes, cov, rank)
   void* fslab = nullptr;   // Quatro features (nrm, spfh, fpfh), allocated on demand
   bool has_cov = false;
+  bool cov_user = false;   // set by b200reg_set_covariances: never recomputed on demand (nano_gicp_impl.hpp:162-167)
   int cov_k = 0;
   int cov_method = 3;
   bool has_fpfh = false;
@@ -419,7 +421,7 @@ int b200reg_clouds_covariances_ex(b200reg_ctx* c, int count, b200reg_cloud* cons
   int max_n = 0;
   for (int i = 0; i < count; i++) {
     if (!clouds[i]) return fail(B200REG_EINVAL, "NULL cloud");
-    if (clouds[i]->has_cov && clouds[i]->cov_k == k && clouds[i]->cov_method == method) continue;
+    if (clouds[i]->has_cov && !clouds[i]->cov_user && clouds[i]->cov_k == k && clouds[i]->cov_method == method) continue;
     bool dup = false;
     for (int j = 0; j < i; j++) dup |= clouds[j] == clouds[i];
     if (dup) continue;
@@ -440,9 +442,28 @@ int b200reg_clouds_covariances_ex(b200reg_ctx* c, int count, b200reg_cloud* cons
   CU(cudaGetLastError());
   for (int i = 0; i < count; i++) {
     clouds[i]->has_cov = true;
+    clouds[i]->cov_user = false;
     clouds[i]->cov_k = k;
     clouds[i]->cov_method = method;
   }
+  return B200REG_OK;
+}
+
+int b200reg_set_covariances(b200reg_ctx* c, b200reg_cloud* cl, const double* cov9, size_t n) {
+  if (!c || !cl || !cov9) return fail(B200REG_EINVAL, "bad argument");
+  if (n != (size_t)cl->dev.n) return fail(B200REG_EINVAL, "covariance count differs from the cloud size");
+  CU(cudaSetDevice(c->device));
+  cudaStream_t s = c->stream;
+  Scratch scratch(c);
+  double* d_cov9 = nullptr;
+  CU(scratch.alloc((void**)&d_cov9, n * 72));
+  CU(cudaMemcpyAsync(d_cov9, cov9, n * 72, cudaMemcpyHostToDevice, s));
+  launch_set_covariances(cl->dev, d_cov9, s);
+  c->launches++;
+  CU(cudaGetLastError());
+  CU(cudaStreamSynchronize(s));  // the caller's buffer may go away
+  cl->has_cov = true;
+  cl->cov_user = true;
   return B200REG_OK;
 }
 
@@ -523,8 +544,11 @@ int b200reg_gicp_align(b200reg_ctx* c, int count, b200reg_cloud* const* src, b20
     for (int i = 0; i < count; i++) {
       if (!src[i] || !tgt[i]) return fail(B200REG_EINVAL, "NULL cloud");
       const int m = params->regularization;
-      if (!src[i]->has_cov || src[i]->cov_k != params->k_correspondences || src[i]->cov_method != m) need.push_back(src[i]);
-      if (!tgt[i]->has_cov || tgt[i]->cov_k != params->k_correspondences || tgt[i]->cov_method != m) need.push_back(tgt[i]);
+      auto stale = [&](const b200reg_cloud* cl) {
+        return !cl->has_cov || (!cl->cov_user && (cl->cov_k != params->k_correspondences || cl->cov_method != m));
+      };
+      if (stale(src[i])) need.push_back(src[i]);
+      if (stale(tgt[i])) need.push_back(tgt[i]);
     }
     if (!need.empty() &&
         (rc = b200reg_clouds_covariances_ex(c, (int)need.size(), need.data(), params->k_correspondences, params->regularization)))
@@ -577,6 +601,8 @@ int b200reg_gicp_align(b200reg_ctx* c, int count, b200reg_cloud* const* src, b20
     r.T[15] = 1.0;
     for (int a = 0; a < 12; a++) r.Tf[a] = st.Tf[a];
     r.Tf[15] = 1.0f;
+    if (st.n_lin > 0) memcpy(r.final_hessian, st.H, sizeof(r.final_hessian));
+    else for (int a = 0; a < 6; a++) r.final_hessian[7 * a] = 1.0;  // final_hessian_.setIdentity() (lsq_registration_impl.hpp:62)
     r.fitness = st.fitness;
     r.converged = st.converged;
     r.valid = (st.converged && st.fitness < params->icp_score_thr) ? 1 : 0;

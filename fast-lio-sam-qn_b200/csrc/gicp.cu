@@ -692,6 +692,15 @@ __global__ void __launch_bounds__(STEP_THREADS) k_knn_brute(CloudDev c, const fl
   }
 }
 
+// setSourceCovariances / setTargetCovariances: caller's 3x3 blocks (original order) -> packed symmetric, sorted order
+__global__ void __launch_bounds__(256) k_set_covariances(CloudDev c, const double* cov9) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= c.n) return;
+  const double* m = cov9 + (size_t)__float_as_int(c.pts[i].w) * 9;
+  double* o = c.cov + (size_t)i * 6;
+  o[0] = m[0]; o[1] = m[1]; o[2] = m[2]; o[3] = m[4]; o[4] = m[5]; o[5] = m[8];  // upper triangle of the row-major block
+}
+
 // output cloud: final fp32 transform in the pcl::transformPointCloud order, ORIGINAL point order
 __global__ void __launch_bounds__(256) k_transform_out(CloudDev c, const float* Tf, float* out3) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -743,6 +752,10 @@ int launch_knn_queries(const CloudDev& c, const float* d_q, int nq, int qstride,
   else if (k <= 32) k_knn_queries<32><<<grid, STEP_THREADS, 0, s>>>(c, d_q, nq, qstride, k, idx, d2);
   else return -1;
   return 1;
+}
+
+void launch_set_covariances(const CloudDev& c, const double* d_cov9, cudaStream_t s) {
+  k_set_covariances<<<(c.n + 255) / 256, 256, 0, s>>>(c, d_cov9);
 }
 
 void launch_transform_out(const CloudDev& c, const float* d_Tf, float* d_out3, cudaStream_t s) {

@@ -60,6 +60,25 @@ struct Mat4 {
 };
 using Matrix4f = Mat4<float>;
 using Matrix4d = Mat4<double>;
+// column-major R x C, the subset of Eigen::Matrix<S,R,C> getFinalHessian()'s callers use
+template <typename S, int R, int C>
+struct Matrix {
+  S m[R * C];
+  Matrix() {
+    for (int i = 0; i < R * C; i++) m[i] = S(0);
+  }
+  static Matrix Identity() {
+    Matrix r;
+    for (int i = 0; i < (R < C ? R : C); i++) r.m[i * R + i] = S(1);
+    return r;
+  }
+  S& operator()(int r, int c) { return m[R * c + r]; }
+  S operator()(int r, int c) const { return m[R * c + r]; }
+  S* data() { return m; }
+  const S* data() const { return m; }
+  static constexpr int rows() { return R; }
+  static constexpr int cols() { return C; }
+};
 template <typename T>
 using aligned_allocator = std::allocator<T>;
 }  // namespace Eigen

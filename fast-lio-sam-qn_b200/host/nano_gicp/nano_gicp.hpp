@@ -10,9 +10,10 @@
 //   * the class does not derive from pcl::Registration (nothing in fast_lio_sam_qn/src uses it polymorphically);
 //   * setNumThreads is accepted and ignored; RANSAC* / EuclideanFitnessEpsilon setters are stored and never read,
 //     exactly like the reference's LSQ path;
-//   * only RegularizationMethod::PLANE (the default, nano_gicp_impl.hpp:61) is built; k may be 1..32;
-//   * source_kdtree_/target_kdtree_ do not exist (the index is a device-side LBVH); covariances are materialised on
-//     the host lazily by getSource/TargetCovariances().
+//   * all five RegularizationMethods are built (PLANE is the default, nano_gicp_impl.hpp:61); k may be 1..32;
+//   * source_kdtree_/target_kdtree_ do not exist (the index is a device-side LBVH); covariances live on the device and are
+//     materialised on the host lazily by getSource/TargetCovariances() as Eigen::Matrix4d (4th row/column zero, like the
+//     reference's, nano_gicp_impl.hpp:354); setSource/TargetCovariances upload the caller's.
 #pragma once
 #include <array>
 #include <cmath>
@@ -39,8 +40,9 @@ class NanoGICP {
   using PointCloudTarget = pcl::PointCloud<PointTarget>;
   using PointCloudTargetPtr = typename PointCloudTarget::Ptr;
   using PointCloudTargetConstPtr = typename PointCloudTarget::ConstPtr;
-  using Cov = std::array<double, 16>;  // column-major 4x4 like Eigen::Matrix4d (4th row/col zero)
-  using CovVector = std::vector<Cov>;
+  using Cov = Eigen::Matrix4d;  // 4th row/col zero (nano_gicp_impl.hpp:354)
+  using CovVector = std::vector<Eigen::Matrix4d, Eigen::aligned_allocator<Eigen::Matrix4d>>;  // nano_gicp.hpp:91-106
+  using Matrix6d = Eigen::Matrix<double, 6, 6>;
 
   NanoGICP() {
     b200reg_default_gicp_params(&prm_);
@@ -50,6 +52,7 @@ class NanoGICP {
     prm_.max_corr_dist = std::sqrt(std::numeric_limits<double>::max());  // corr_dist_threshold_ = FLT_MAX-ish (:59)
     final_.fill(0.f);
     final_[0] = final_[5] = final_[10] = final_[15] = 1.f;
+    final_hessian_ = Matrix6d::Identity();  // lsq_registration_impl.hpp:62
   }
   ~NanoGICP() { release(); }
   NanoGICP(const NanoGICP&) = delete;
@@ -117,6 +120,11 @@ class NanoGICP {
   bool calculateTargetCovariances() { return covariances(tgt_, &tgt_cov_ok_); }
   CovVector getSourceCovariances() { return fetch_covs(src_, &src_cov_ok_); }
   CovVector getTargetCovariances() { return fetch_covs(tgt_, &tgt_cov_ok_); }
+  // nano_gicp.hpp:91-93, nano_gicp_impl.hpp:142-150: the caller's covariances replace the computed ones
+  void setSourceCovariances(const CovVector& covs) { push_covs(src_, covs, &src_cov_ok_); }
+  void setTargetCovariances(const CovVector& covs) { push_covs(tgt_, covs, &tgt_cov_ok_); }
+  // lsq_registration.hpp:88: H of the last linearize (Identity before the first align)
+  const Matrix6d& getFinalHessian() const { return final_hessian_; }
 
   // ---- pcl::Registration::align: identity guess unless given
   void align(PointCloudSource& output) { align(output, Matrix4::Identity()); }
@@ -139,6 +147,8 @@ class NanoGICP {
     src_cov_ok_ = tgt_cov_ok_ = true;
     converged_ = res_.converged != 0;
     for (int i = 0; i < 16; i++) final_[i] = res_.Tf[i];
+    for (int r = 0; r < 6; r++)
+      for (int c = 0; c < 6; c++) final_hessian_(r, c) = res_.final_hessian[6 * r + c];
     // output = transformPointCloud(*input_, final_transformation_) (lsq_registration_impl.hpp:114): all fields kept
     std::vector<float> xyz(3 * input_->size());
     b200reg_transform_cloud(b200reg_host::context(), src_, res_.Tf, xyz.data());
@@ -214,11 +224,26 @@ class NanoGICP {
     b200reg_get_covariances(b200reg_host::context(), cl, c9.data());
     out.resize(n);
     for (size_t i = 0; i < n; i++) {
-      out[i].fill(0.0);
-      for (int r = 0; r < 3; r++)
-        for (int c = 0; c < 3; c++) out[i][4 * c + r] = c9[9 * i + 3 * r + c];
+      Cov m;
+      for (int r = 0; r < 4; r++)
+        for (int c = 0; c < 4; c++) m(r, c) = (r < 3 && c < 3) ? c9[9 * i + 3 * r + c] : 0.0;
+      out[i] = m;
     }
     return out;
+  }
+  void push_covs(b200reg_cloud* cl, const CovVector& covs, bool* ok) {
+    if (!cl) return;
+    if (covs.size() != b200reg_cloud_size(cl)) {
+      std::fprintf(stderr, "b200reg: %zu covariances for a cloud of %zu points\n", covs.size(), b200reg_cloud_size(cl));
+      return;
+    }
+    std::vector<double> c9(9 * covs.size());
+    for (size_t i = 0; i < covs.size(); i++)
+      for (int r = 0; r < 3; r++)
+        for (int c = 0; c < 3; c++) c9[9 * i + 3 * r + c] = covs[i](r, c);
+    const int rc = b200reg_set_covariances(b200reg_host::context(), cl, c9.data(), covs.size());
+    if (rc != 0) std::fprintf(stderr, "b200reg: set_covariances failed (%d): %s\n", rc, b200reg_last_error());
+    *ok = rc == 0;
   }
 
   b200reg_gicp_params prm_;
@@ -229,6 +254,7 @@ class NanoGICP {
   b200reg_cloud* tgt_ = nullptr;
   bool src_cov_ok_ = false, tgt_cov_ok_ = false, converged_ = false;
   std::array<float, 16> final_;
+  Matrix6d final_hessian_;
   int ransac_iterations_ = 0;
   double euclidean_fitness_epsilon_ = 0, ransac_threshold_ = 0;
 };

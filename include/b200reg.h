@@ -66,6 +66,8 @@ typedef struct b200reg_result {
                           (loop_closure.cpp:129-134, 156): icpAlignment: Tf.cast<double>() when valid, Identity otherwise;
                           coarseToFineAlignment: (valid fine stage ? Tf_fine : Identity) * T_quatro, or the coarse
                           stage's own output when Quatro itself is invalid; Identity for the dummy output        */
+  double final_hessian[36]; /* LsqRegistration::getFinalHessian() (lsq_registration.hpp:88): H of the last linearize,
+                          6x6 row-major (symmetric); Identity before any (lsq_registration_impl.hpp:62)            */
   double fitness;      /* getFitnessScore(): mean 1-NN d^2 over ALL source points              */
   int32_t converged;   /* hasConverged()                                                       */
   int32_t valid;       /* converged && fitness < icp_score_thr (loop_closure.cpp:129)          */
@@ -144,6 +146,10 @@ size_t b200reg_cloud_size(const b200reg_cloud* cloud);
 /* NanoGICP::calculateSourceCovariances / calculateTargetCovariances
  * (third_party/nano_gicp/include/nano_gicp/impl/nano_gicp_impl.hpp:151-159, 298-357), batched. */
 int b200reg_clouds_covariances(b200reg_ctx* ctx, int count, b200reg_cloud* const* clouds, int k);
+/* NanoGICP::setSourceCovariances / setTargetCovariances (nano_gicp.hpp:91-93, nano_gicp_impl.hpp:142-150): the caller's
+ * per-point covariances (n x 9 doubles: the row-major 3x3 block of each Matrix4d, ORIGINAL point order) replace the
+ * computed ones; align() then does not recompute them (nano_gicp_impl.hpp:162-167) until the input cloud changes.   */
+int b200reg_set_covariances(b200reg_ctx* ctx, b200reg_cloud* cloud, const double* cov9, size_t n);
 /* Same with an explicit RegularizationMethod (setRegularizationMethod, nano_gicp.hpp:84); the plain call uses PLANE. */
 int b200reg_clouds_covariances_ex(b200reg_ctx* ctx, int count, b200reg_cloud* const* clouds, int k, int method);
 

@@ -7,6 +7,10 @@
 #include <nano_gicp/point_type_nano_gicp.hpp>
 #include <quatro/quatro_module.h>
 
+#if defined(B200REG_EXPECT_PCL) && !defined(B200REG_HAVE_PCL)
+#error "the PCL/Eigen configuration of the facade was requested but b200reg_compat.hpp did not select it"
+#endif
+
 #include <cstdio>
 #include <cstring>
 #include <fstream>
@@ -98,9 +102,57 @@ struct Client {
   }
 };
 
+// The rest of the class surface (nano_gicp.hpp:84-106, lsq_registration.hpp:84-92) that fast_lio_sam_qn/src does not call:
+// covariance getters / setters with the reference's container type, getFinalHessian, swapSourceAndTarget, timing of a
+// second align() on unchanged inputs (the single-pair latency a caller of NanoGICP::align sees).
+static int surface(const pcl::PointCloud<PointType>& src, const pcl::PointCloud<PointType>& dst) {
+  using Gicp = nano_gicp::NanoGICP<PointType, PointType>;
+  Client c;
+  const RegistrationOutput r1 = c.icpAlignment(src, dst);
+  const Eigen::Matrix<double, 6, 6> H1 = c.nano_gicp_.getFinalHessian();
+  // round trip: the computed covariances handed back through the setters must reproduce the registration bit for bit
+  std::vector<Eigen::Matrix4d, Eigen::aligned_allocator<Eigen::Matrix4d>> cs = c.nano_gicp_.getSourceCovariances();
+  std::vector<Eigen::Matrix4d, Eigen::aligned_allocator<Eigen::Matrix4d>> ct = c.nano_gicp_.getTargetCovariances();
+  Gicp g2;
+  g2.setCorrespondenceRandomness(15);
+  g2.setMaximumIterations(32);
+  g2.setMaxCorrespondenceDistance(52.5);
+  g2.setTransformationEpsilon(0.01);
+  pcl::PointCloud<PointType>::Ptr sp(new pcl::PointCloud<PointType>(src)), dp(new pcl::PointCloud<PointType>(dst));
+  g2.setInputSource(sp);
+  g2.setInputTarget(dp);
+  g2.setSourceCovariances(cs);
+  g2.setTargetCovariances(ct);
+  pcl::PointCloud<PointType> out;
+  g2.align(out);
+  const Eigen::Matrix4f T1 = c.nano_gicp_.getFinalTransformation(), T2 = g2.getFinalTransformation();
+  int same = 1;
+  for (int i = 0; i < 4; i++)
+    for (int j = 0; j < 4; j++) same &= T1(i, j) == T2(i, j);
+  // scaled covariances change the weighting, hence (slightly) the optimum: the setters are really used
+  for (auto& m : cs)
+    for (int i = 0; i < 3; i++)
+      for (int j = 0; j < 3; j++) m(i, j) *= (i == 2 || j == 2) ? 4.0 : 1.0;
+  g2.setSourceCovariances(cs);
+  g2.align(out);
+  const Eigen::Matrix4f T3 = g2.getFinalTransformation();
+  int differs = 0;
+  for (int i = 0; i < 4; i++)
+    for (int j = 0; j < 4; j++) differs |= T1(i, j) != T3(i, j);
+  int cov_struct = cs.size() == src.size();
+  for (size_t i = 0; i < ct.size(); i += 97) cov_struct &= ct[i](3, 3) == 0.0 && ct[i](0, 3) == 0.0 && ct[i](0, 1) == ct[i](1, 0);
+  std::printf("{\"valid\": %d, \"setters_roundtrip_same\": %d, \"scaled_covs_differ\": %d, \"cov_struct\": %d, \"score\": %.17g, \"H\": [",
+              r1.is_valid_ ? 1 : 0, same, differs, cov_struct, r1.score_);
+  for (int i = 0; i < 6; i++)
+    for (int j = 0; j < 6; j++) std::printf("%.17g%s", H1(i, j), (i == 5 && j == 5) ? "" : ", ");
+  std::printf("]}\n");
+  return 0;
+}
+
 int main(int argc, char** argv) {
   if (argc < 4) return 2;
   const auto src = load(argv[1]), dst = load(argv[2]);
+  if (std::string(argv[3]) == "surface") return surface(src, dst);
   Client c;
   const RegistrationOutput r = std::string(argv[3]) == "quatro" ? c.coarseToFineAlignment(src, dst) : c.icpAlignment(src, dst);
   std::printf("{\"valid\": %d, \"converged\": %d, \"score\": %.17g, \"aligned\": %zu, \"T\": [", r.is_valid_ ? 1 : 0, r.is_converged_ ? 1 : 0,

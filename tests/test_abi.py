@@ -40,7 +40,7 @@ def test_struct_layouts_match_header():
     from b200reg import native
     assert ctypes.sizeof(native.GicpParams) == 56
     assert native.default_params().regularization == 3  # PLANE
-    assert ctypes.sizeof(native.Result) == 16 * 8 + 16 * 4 + 16 * 8 + 8 + 8 * 4
+    assert ctypes.sizeof(native.Result) == 16 * 8 + 16 * 4 + 16 * 8 + 36 * 8 + 8 + 8 * 4
     # the binding's layouts against what the compiler laid out (b200reg_struct_size)
     lib = native.lib()
     lib.b200reg_struct_size.restype = ctypes.c_size_t

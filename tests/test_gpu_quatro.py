@@ -29,18 +29,27 @@ def test_normals_and_fpfh_match_oracle(ctx, oracle, qpair):
     dots = np.einsum("ij,ij->i", gn[ok], on[ok])
     assert np.quantile(dots, 0.01) > 1 - 1e-6
     assert (dots > 0.999).mean() > 0.995
-    # FPFH: fp32 accumulation order differs (tree order vs sorted order); PCL's own float accumulation noise is ~1e-3
+    # FPFH, stage-isolated (<= 1e-3 abs per bin): the GPU's OWN normals through the oracle's SPFH/FPFH.
+    # What is left is the fp32 summation order (tree-walk order vs the oracle's sorted order): EVERY bin of EVERY point
+    # within 1e-3 (measured max 1.8e-4, profiles/r02/diag_fpfh.txt).
+    _, of2 = oracle.fpfh_from_normals(dst, np.where(np.isnan(gn), np.nan, gn), 1.5)
+    err2 = np.abs(gf - of2).max(1)
+    assert err2.max() < 1e-3, np.quantile(err2, [0.5, 0.9, 0.99, 1.0])
+    # complete pipelines (each side with its own normals): identical to 1e-3 per bin except where a fp64 eigen-solver
+    # round-off flips a float normal in an ill-conditioned (near-isotropic / collinear) neighbourhood; such a point changes
+    # the SPFH of everything within the FPFH radius and through it the FPFH within twice the radius -- nowhere else.
     err = np.abs(gf - of).max(1)
-    assert np.median(err) < 1e-3
-    assert np.quantile(err, 0.98) < 5e-2
+    assert np.quantile(err, 0.98) < 1e-3, np.quantile(err, [0.5, 0.98, 0.999, 1.0])
+    bad_n = np.flatnonzero(~ok | (gn != on).any(1))  # any float difference of a normal can move a pair feature across a bin edge
+    off = np.flatnonzero(err > 1e-3)
+    if len(off):
+        assert len(bad_n) > 0
+        d = np.linalg.norm(dst[off, None, :3] - dst[None, bad_n, :3], axis=2).min(1)
+        assert d.max() <= 2 * 1.5 + 1e-3, "an FPFH deviation away from any differing normal"
     # structure: each 11-bin block sums to 100 (or the descriptor is all zero)
     sums = gf.reshape(-1, 3, 11).sum(2)
     nz = np.abs(gf).sum(1) > 0
     assert np.allclose(sums[nz], 100.0, atol=2e-2)
-    # stage isolation: FPFH from the GPU's OWN normals through the oracle agrees tightly
-    _, of2 = oracle.fpfh_from_normals(dst, np.where(np.isnan(gn), np.nan, gn), 1.5)
-    err2 = np.abs(gf - of2).max(1)
-    assert np.quantile(err2, 0.99) < 5e-3, np.quantile(err2, [0.5, 0.9, 0.99, 1.0])
     cl.destroy()
 
 
