@@ -77,6 +77,7 @@ EXPORTS = [
     "b200reg_knn_bruteforce", "b200reg_fetch_closest_keyframes", "b200reg_assemble_clouds", "b200reg_cloud_points", "b200reg_perform_loop_closure",
     "b200reg_loop_factor_from_poses", "b200reg_loop_factors", "b200reg_compute_error", "b200reg_assemble_clouds_at",
     "b200reg_struct_size", "b200reg_set_last_error", "b200reg_set_covariances",
+    "b200reg_keyframes_add_world", "b200reg_keyframes_get", "b200reg_keyframes_cloud_size",
     "b200reg_batch_create", "b200reg_batch_destroy", "b200reg_batch_submit_icp", "b200reg_batch_submit_loop_closure",
     "b200reg_batch_wait", "b200reg_batch_wait_all", "b200reg_batch_launch_count", "b200reg_batch_depth",
     "b200reg_comm_unique_id", "b200reg_comm_init", "b200reg_comm_destroy", "b200reg_comm_rank", "b200reg_comm_world",
@@ -94,6 +95,7 @@ def lib():
         _lib.b200reg_ctx_launch_count.restype = C.c_int64
         _lib.b200reg_cloud_size.restype = C.c_size_t
         _lib.b200reg_struct_size.restype = C.c_size_t
+        _lib.b200reg_keyframes_cloud_size.restype = C.c_size_t
         _lib.b200reg_batch_submit_icp.restype = C.c_int64
         _lib.b200reg_batch_submit_loop_closure.restype = C.c_int64
         _lib.b200reg_batch_launch_count.restype = C.c_int64
@@ -493,6 +495,27 @@ class Keyframes:
         if rc < 0:
             _check(rc)
         return rc
+
+    def add_world(self, cloud_xyzi_world, position, quat_xyzw, stamp):
+        """PosePcd::PosePcd (pose_pcd.hpp:21-43): world-frame scan + odometry (position, quaternion x y z w) -> keyframe."""
+        a = np.ascontiguousarray(cloud_xyzi_world, np.float32)
+        assert a.ndim == 2 and a.shape[1] >= 4
+        p = np.ascontiguousarray(position, np.float64).reshape(3)
+        q = np.ascontiguousarray(quat_xyzw, np.float64).reshape(4)
+        rc = lib().b200reg_keyframes_add_world(self.ctx.h, self.h, a.ctypes.data_as(C.c_void_p), C.c_size_t(len(a)), C.c_size_t(a.shape[1] * 4),
+                                               p.ctypes.data_as(C.c_void_p), q.ctypes.data_as(C.c_void_p), C.c_double(stamp))
+        if rc < 0:
+            _check(rc)
+        return rc
+
+    def get(self, idx):
+        """-> (cloud (n,4) float32 in the LiDAR frame, corrected pose (4,4), timestamp)."""
+        n = int(lib().b200reg_keyframes_cloud_size(self.h, int(idx)))
+        pts = np.empty((n, 4), np.float32)
+        pose = np.empty(16, np.float64)
+        ts = C.c_double()
+        _check(lib().b200reg_keyframes_get(self.ctx.h, self.h, int(idx), pts.ctypes.data_as(C.c_void_p), pose.ctypes.data_as(C.c_void_p), C.byref(ts)))
+        return pts, pose.reshape(4, 4), ts.value
 
     def set_pose(self, idx, pose):
         T = np.ascontiguousarray(pose, np.float64).reshape(16)

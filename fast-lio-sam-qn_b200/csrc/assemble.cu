@@ -168,6 +168,26 @@ __global__ void __launch_bounds__(256) k_voxel_centroid(const AssembleJob* jobs,
   J.out[v] = make_float4(s0 / c, s1 / c, s2 / c, s3 / c);
 }
 
+// PosePcd ingest (fast_lio_sam_qn/include/pose_pcd.hpp:37-39): FAST-LIO publishes the scan in the WORLD frame; the keyframe keeps
+// it in the LiDAR frame: pcd_ = transformPcd(tmp_pcd, pose_eig_.inverse()) -- double math, float result, intensity carried.
+// raw: (x, y, z, intensity) records `stride` floats apart (device copy of the message payload).
+__global__ void __launch_bounds__(256) k_ingest_world(const float* raw, int stride, int n, const double* Tinv, float4* out) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const float* p = raw + (size_t)i * stride;
+  const double x = p[0], y = p[1], z = p[2];
+  float4 o;
+  o.x = (float)(Tinv[0] * x + Tinv[1] * y + Tinv[2] * z + Tinv[3]);
+  o.y = (float)(Tinv[4] * x + Tinv[5] * y + Tinv[6] * z + Tinv[7]);
+  o.z = (float)(Tinv[8] * x + Tinv[9] * y + Tinv[10] * z + Tinv[11]);
+  o.w = p[3];
+  out[i] = o;
+}
+
+void launch_ingest_world(const float* d_raw, int stride, int n, const double* d_Tinv, float4* d_out, cudaStream_t s) {
+  k_ingest_world<<<(n + 255) / 256, 256, 0, s>>>(d_raw, stride, n, d_Tinv, d_out);
+}
+
 int launch_fetch_closest(const double* d_pos, const double* d_stamp, const int* d_queries, int count, double radius, double tdiff,
                          int* d_out, cudaStream_t s) {
   k_fetch_closest<<<(count * 32 + 255) / 256, 256, 0, s>>>(d_pos, d_stamp, d_queries, count, radius, tdiff, d_out);

@@ -214,6 +214,16 @@ int b200reg_keyframes_destroy(b200reg_ctx* ctx, b200reg_keyframes* kf);
  * `stride_bytes` apart (host memory), its corrected pose (row-major 4x4) and timestamp.  Returns the index.   */
 int b200reg_keyframes_add(b200reg_ctx* ctx, b200reg_keyframes* kf, const float* xyzi, size_t n, size_t stride_bytes,
                           const double* pose16, double timestamp);
+/* The PosePcd constructor itself (pose_pcd.hpp:21-43) as a device step: the scan arrives in the WORLD frame with the odometry
+ * pose as position + quaternion (x, y, z, w; nav_msgs::Odometry); pose_eig_ = [tf::Matrix3x3(q) | p], pose_corrected_eig_ =
+ * pose_eig_, and the stored cloud is transformPcd(scan, pose_eig_.inverse()) (LiDAR frame).  Returns the index.        */
+int b200reg_keyframes_add_world(b200reg_ctx* ctx, b200reg_keyframes* kf, const float* xyzi_world, size_t n, size_t stride_bytes,
+                                const double* position3, const double* quat_xyzw, double timestamp);
+/* Read a keyframe back: its LiDAR-frame cloud (n x 4 floats: x, y, z, intensity; NULL to skip), corrected pose (16 doubles,
+ * row-major; NULL to skip) and timestamp (NULL to skip) -- what the reference saves per keyframe (fast_lio_sam_qn.cpp:344-376). */
+int b200reg_keyframes_get(b200reg_ctx* ctx, const b200reg_keyframes* kf, int idx, float* xyzi_out, double* pose16_out,
+                          double* timestamp_out);
+size_t b200reg_keyframes_cloud_size(const b200reg_keyframes* kf, int idx);
 /* pose_corrected_eig_ rewrite after an accepted loop (fast_lio_sam_qn/src/fast_lio_sam_qn.cpp:180-188).     */
 int b200reg_keyframes_set_pose(b200reg_ctx* ctx, b200reg_keyframes* kf, int idx, const double* pose16);
 int b200reg_keyframes_size(const b200reg_keyframes* kf);

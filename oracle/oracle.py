@@ -317,6 +317,18 @@ def transform_pcd(pts, T):
     return out
 
 
+def pose_pcd_ingest(world_pts, position, quat_xyzw):
+    """PosePcd::PosePcd (pose_pcd.hpp:21-43): -> (cloud in the LiDAR frame (n,4) float32, pose_eig_ (4,4))."""
+    pts = np.ascontiguousarray(world_pts, np.float32)
+    pos = np.ascontiguousarray(position, np.float64)
+    q = np.ascontiguousarray(quat_xyzw, np.float64)
+    out = np.empty_like(pts)
+    pose = np.empty(16, np.float64)
+    lib().orc_pose_pcd_ingest(_p(pts, C.c_float), len(pts), pts.shape[1], _p(pos, C.c_double), _p(q, C.c_double), _p(out, C.c_float),
+                              _p(pose, C.c_double))
+    return out, pose.reshape(4, 4)
+
+
 def voxelize(pts, leaf):
     """pcl::VoxelGrid restated; pts (n,4) x,y,z,intensity -> (m,4) centroids in voxel-index order."""
     pts = np.ascontiguousarray(pts, np.float32)

@@ -662,6 +662,41 @@ int orc_gicp_align(const float* src, int N, int sstride, const float* tgt, int M
 // ===========================================================================================
 extern "C" {
 
+// PosePcd::PosePcd (fast_lio_sam_qn/include/pose_pcd.hpp:21-43): pose_eig_ from the odometry quaternion (tf::Matrix3x3(q),
+// restated from tf/LinearMath/Matrix3x3.h setRotation) and position; the world-frame scan goes into the LiDAR frame with
+// pose_eig_.inverse() -- here by Gauss-Jordan elimination with partial pivoting (deliberately NOT the product's cofactor
+// formula).  pose16_out: row-major pose_eig_ (= pose_corrected_eig_).
+void orc_transform_pcd(const float* in, int n, int stride, const double* T16, float* out);
+void orc_pose_pcd_ingest(const float* world, int n, int stride, const double* pos3, const double* quat_xyzw, float* out, double* pose16_out) {
+  const double x = quat_xyzw[0], y = quat_xyzw[1], z = quat_xyzw[2], w = quat_xyzw[3];
+  const double d = x * x + y * y + z * z + w * w, s = 2.0 / d;
+  const double xs = x * s, ys = y * s, zs = z * s, wx = w * xs, wy = w * ys, wz = w * zs;
+  const double xx = x * xs, xy = x * ys, xz = x * zs, yy = y * ys, yz = y * zs, zz = z * zs;
+  double P[16] = {1.0 - (yy + zz), xy - wz, xz + wy, pos3[0], xy + wz, 1.0 - (xx + zz), yz - wx, pos3[1],
+                  xz - wy, yz + wx, 1.0 - (xx + yy), pos3[2], 0, 0, 0, 1};
+  if (pose16_out) std::memcpy(pose16_out, P, sizeof(P));
+  double A[4][8];
+  for (int r = 0; r < 4; r++)
+    for (int c = 0; c < 8; c++) A[r][c] = c < 4 ? P[4 * r + c] : (c - 4 == r ? 1.0 : 0.0);
+  for (int col = 0; col < 4; col++) {
+    int piv = col;
+    for (int r = col + 1; r < 4; r++)
+      if (std::fabs(A[r][col]) > std::fabs(A[piv][col])) piv = r;
+    for (int c = 0; c < 8; c++) std::swap(A[col][c], A[piv][c]);
+    const double pv = A[col][col];
+    for (int c = 0; c < 8; c++) A[col][c] /= pv;
+    for (int r = 0; r < 4; r++)
+      if (r != col) {
+        const double f = A[r][col];
+        for (int c = 0; c < 8; c++) A[r][c] -= f * A[col][c];
+      }
+  }
+  double Tinv[16];
+  for (int r = 0; r < 4; r++)
+    for (int c = 0; c < 4; c++) Tinv[4 * r + c] = A[r][4 + c];
+  orc_transform_pcd(world, n, stride, Tinv, out);
+}
+
 // transformPcd (fast_lio_sam_qn/include/utilities.hpp:164-175): pcl::transformPointCloud with a Matrix4d --
 // per point double math, result cast to float; other fields (intensity) copied.
 void orc_transform_pcd(const float* in, int n, int stride, const double* T16, float* out /* n x stride */) {

@@ -137,3 +137,29 @@ def test_batched_queries_see_their_own_keyframe_count(ctx, store, oracle, seq):
         assert np.array_equal(res[k]["T"], single[0]["T"]) and res[k]["fitness"] == single[0]["fitness"]
     for c in sc + dc + sc2 + dc2:
         c.destroy()
+
+
+def test_pose_pcd_ingest_matches_oracle(ctx, oracle, synth, seq):
+    """Row f4: the PosePcd constructor (pose_pcd.hpp:21-43) as a device step -- the world-frame scan FAST-LIO publishes goes into
+    the LiDAR frame with pose_eig_.inverse(), the pose comes from the odometry quaternion -- against the oracle, and a keyframe
+    ingested that way registers exactly like one added in the LiDAR frame."""
+    from b200reg import io as bio
+    kf = ctx.keyframes()
+    worst = 0.0
+    for k in (3, 70, 137):
+        T = seq["poses"][k]
+        lidar = seq["clouds"][k]
+        world = synth.to_map_frame(lidar, T)  # what FAST-LIO publishes (world frame)
+        q = bio._rot_to_quat(T[:3, :3])
+        q = q * 1.0000001  # odometry quaternions are never exactly unit: tf's setRotation divides by |q|^2
+        idx = kf.add_world(world, T[:3, 3], q, seq["stamps"][k])
+        got, pose, ts = kf.get(idx)
+        want, opose = oracle.pose_pcd_ingest(world, T[:3, 3], q)
+        assert np.abs(pose - opose).max() < 1e-15 and ts == seq["stamps"][k]
+        assert np.array_equal(got[:, 3], want[:, 3])                       # intensity carried
+        ulp = np.spacing(np.abs(want[:, :3]).astype(np.float32))
+        assert (np.abs(got[:, :3] - want[:, :3]) <= ulp).all()            # two different 4x4 inverses: at most one float ulp apart
+        assert (got[:, :3] == want[:, :3]).mean() > 0.9999
+        worst = max(worst, np.abs(got[:, :3] - lidar[:, :3]).max())
+    assert worst < 2e-5  # back in the LiDAR frame: the original scan up to the float round trip through the world frame
+    kf.destroy()
