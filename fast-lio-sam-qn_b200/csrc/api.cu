@@ -19,6 +19,7 @@
 
 namespace b200 {
 int launch_index_build(const CloudDev* d_clouds, int count, int max_n, cudaStream_t s);
+size_t radix_sort_ws_bytes(int n, int key_bits);
 int launch_covariances(const CloudDev* d_clouds, int count, int max_n, int k, int method, cudaStream_t s);
 void launch_gicp_init(const PairDev* pairs, PairState* states, const double* d_guess, int count, const GicpParamsDev& prm,
                       LmSched* sched, cudaStream_t s);
@@ -307,6 +308,18 @@ int b200reg_clouds_create(b200reg_ctx* c, int count, const float* const* xyz, co
       }
     }
   } guard{c, out, count};
+  // sort work memory and AABB arrival flags of the whole batch: ONE allocation, ONE memset
+  std::vector<size_t> z_ws(count), z_fl(count);
+  size_t z_total = 0;
+  for (int i = 0; i < count; i++) {
+    z_ws[i] = z_total;
+    z_total = align_up(z_total + radix_sort_ws_bytes((int)n[i], 30), 256);
+    z_fl[i] = z_total;
+    z_total = align_up(z_total + (size_t)std::max((int)n[i] - 1, 1) * 4, 256);
+  }
+  char* zeroed = nullptr;
+  CU(scratch.alloc((void**)&zeroed, z_total));
+  CU(cudaMemsetAsync(zeroed, 0, z_total, s));
   for (int i = 0; i < count; i++) {
     b200reg_cloud* cl = new b200reg_cloud;
     out[i] = cl;
@@ -314,7 +327,6 @@ int b200reg_clouds_create(b200reg_ctx* c, int count, const float* const* xyz, co
     d.n = (int)n[i];
     d.root_ref = d.n <= LEAF ? leaf_ref(0, d.n) : 0;
     d.raw_stride = (int)(stride_bytes / 4);
-    const int ntiles = (d.n + SORT_TILE - 1) / SORT_TILE;
     const size_t nn = (size_t)std::max(d.n - 1, 1);
     // persistent slab
     size_t o_pts = 0;
@@ -337,19 +349,16 @@ int b200reg_clouds_create(b200reg_ctx* c, int count, const float* const* xyz, co
     d.fnorm_s = nullptr;
     d.ftile = nullptr;
     d.fcode_s = nullptr;
-    // temporary slab (sort buffers, histogram, tree scratch, bbox, and the raw records when uploading)
+    // temporary slab (sort buffers, tree scratch, bbox partials, and the raw records when uploading)
     size_t t_k0 = 0;
     size_t t_k1 = align_up(t_k0 + (size_t)d.n * 4, 256);
     size_t t_v0 = align_up(t_k1 + (size_t)d.n * 4, 256);
     size_t t_v1 = align_up(t_v0 + (size_t)d.n * 4, 256);
-    size_t t_h = align_up(t_v1 + (size_t)d.n * 4, 256);
-    size_t t_f = align_up(t_h + (size_t)RADIX * ntiles * 4, 256);
-    size_t t_i = align_up(t_f + nn * 4, 256);
+    size_t t_i = align_up(t_v1 + (size_t)d.n * 4, 256);
     size_t t_pn = align_up(t_i + nn * sizeof(int4), 256);
     size_t t_pl = align_up(t_pn + nn * 4, 256);
-    size_t t_nb = align_up(t_pl + (size_t)d.n * 4, 256);
-    size_t t_b = align_up(t_nb + 2 * nn * sizeof(float4), 256);
-    size_t t_raw = align_up(t_b + 32, 256);
+    size_t t_b = align_up(t_pl + (size_t)d.n * 4, 256);
+    size_t t_raw = align_up(t_b + 6 * BBOX_BLOCKS * sizeof(float), 256);
     size_t t_total = t_raw + (on_device ? 0 : align_up((size_t)d.n * stride_bytes, 256));
     char* tmp = nullptr;
     CU(scratch.alloc((void**)&tmp, t_total));
@@ -357,14 +366,12 @@ int b200reg_clouds_create(b200reg_ctx* c, int count, const float* const* xyz, co
     d.keys[1] = (uint32_t*)(tmp + t_k1);
     d.vals[0] = (uint32_t*)(tmp + t_v0);
     d.vals[1] = (uint32_t*)(tmp + t_v1);
-    d.hist = (uint32_t*)(tmp + t_h);
-    d.flags = (uint32_t*)(tmp + t_f);
+    d.hist = (uint32_t*)(zeroed + z_ws[i]);
+    d.flags = (uint32_t*)(zeroed + z_fl[i]);
     d.info = (int4*)(tmp + t_i);
     d.parent_node = (int*)(tmp + t_pn);
     d.parent_leaf = (int*)(tmp + t_pl);
-    d.nbox = (float4*)(tmp + t_nb);
     d.bbox = (float*)(tmp + t_b);
-    CU(cudaMemsetAsync(d.flags, 0, nn * 4, s));
     if (on_device) {
       d.raw = xyz[i];
     } else {
@@ -390,7 +397,6 @@ int b200reg_clouds_create(b200reg_ctx* c, int count, const float* const* xyz, co
     d.keys[0] = d.keys[1] = d.vals[0] = d.vals[1] = d.hist = d.flags = nullptr;
     d.info = nullptr;
     d.parent_node = d.parent_leaf = nullptr;
-    d.nbox = nullptr;
     d.bbox = nullptr;
   }
   guard.ok = true;
@@ -941,15 +947,16 @@ int b200reg_clouds_fpfh(b200reg_ctx* c, int count, b200reg_cloud* const* clouds,
     descs.push_back(cl->dev);
     {  // sort buffers of the norm-code ordering (scratch: only this call uses them)
       CloudDev& d = descs.back();
-      const size_t n = d.n, nt = (n + SORT_TILE - 1) / SORT_TILE;
-      const size_t s_k = align_up(n * 4, 256);
+      const size_t n = d.n;
+      const size_t s_k = align_up(n * 4, 256), s_ws = align_up(radix_sort_ws_bytes((int)n, 30), 256);
       char* sb = nullptr;
-      CU(scratch.alloc((void**)&sb, 4 * s_k + align_up((size_t)RADIX * nt * 4, 256)));
+      CU(scratch.alloc((void**)&sb, 4 * s_k + s_ws));
       d.keys[0] = (uint32_t*)sb;
       d.keys[1] = (uint32_t*)(sb + s_k);
       d.vals[0] = (uint32_t*)(sb + 2 * s_k);
       d.vals[1] = (uint32_t*)(sb + 3 * s_k);
       d.hist = (uint32_t*)(sb + 4 * s_k);
+      CU(cudaMemsetAsync(d.hist, 0, s_ws, s));
     }
     max_n = std::max(max_n, cl->dev.n);
   }
@@ -1661,7 +1668,6 @@ int b200reg_assemble_clouds_at(b200reg_ctx* c, b200reg_keyframes* kf, int count,
     J.total = J.seg_off[J.nseg];
     if (J.total <= 0) return fail(B200REG_EINVAL, "empty merged cloud");
     const size_t n = J.total;
-    const int ntiles = (J.total + SORT_TILE - 1) / SORT_TILE;
     size_t o = 0;
     auto take = [&](size_t bytes) {
       size_t r = o;
@@ -1669,7 +1675,7 @@ int b200reg_assemble_clouds_at(b200reg_ctx* c, b200reg_keyframes* kf, int count,
       return r;
     };
     const size_t o_m = take(n * 16), o_o = take(n * 16), o_h = take(n * 4), o_b = take(32), o_c = take(16);
-    const size_t o_k0 = take(n * 4), o_k1 = take(n * 4), o_v0 = take(n * 4), o_v1 = take(n * 4), o_hist = take((size_t)RADIX * ntiles * 4);
+    const size_t o_k0 = take(n * 4), o_k1 = take(n * 4), o_v0 = take(n * 4), o_v1 = take(n * 4), o_hist = take(radix_sort_ws_bytes(J.total, 32));
     char* slab = nullptr;
     CU(scratch.alloc((void**)&slab, o));
     J.merged = (float4*)(slab + o_m);
@@ -1682,6 +1688,7 @@ int b200reg_assemble_clouds_at(b200reg_ctx* c, b200reg_keyframes* kf, int count,
     J.sort.vals[0] = (uint32_t*)(slab + o_v0);
     J.sort.vals[1] = (uint32_t*)(slab + o_v1);
     J.sort.hist = (uint32_t*)(slab + o_hist);
+    CU(cudaMemsetAsync(J.sort.hist, 0, radix_sort_ws_bytes(J.total, 32), s));
     CloudDev& sd = sorts[j];
     memset(&sd, 0, sizeof(sd));
     sd.n = J.total;

@@ -8,7 +8,8 @@
 
 namespace b200 {
 
-int launch_radix_sort(const CloudDev* d_clouds, int count, int max_n, int npass, cudaStream_t s);
+int launch_radix_sort(const CloudDev* d_clouds, int count, int max_n, int key_bits, cudaStream_t s);
+int radix_sort_result_buf(int key_bits);
 
 // one warp per query keyframe q (treated as the LATEST keyframe: candidates are idx < q)
 __global__ void __launch_bounds__(256) k_fetch_closest(const double* pos, const double* stamp, const int* queries, int count, double radius,
@@ -201,10 +202,10 @@ int launch_assemble_voxelize(const AssembleJob* d_jobs, const CloudDev* d_sort, 
   k_assemble_init<<<count, 32, 0, s>>>(d_jobs); l++;
   k_assemble<<<dim3(min((max_total + 255) / 256, 1184), count), 256, 0, s>>>(d_jobs, d_kfs, d_poses); l++;
   k_voxel_keys<<<dim3((max_total + 255) / 256, count), 256, 0, s>>>(d_jobs, inv_leaf); l++;
-  const int npass = 4;
-  l += launch_radix_sort(d_sort, count, max_total, npass, s);
-  k_voxel_heads<<<count, 1024, 0, s>>>(d_jobs, npass & 1); l++;
-  k_voxel_centroid<<<dim3((max_total + 255) / 256, count), 256, 0, s>>>(d_jobs, npass & 1); l++;
+  l += launch_radix_sort(d_sort, count, max_total, 32, s);  // voxel indices use up to 31 bits: 3 passes of 11 bits
+  const int kbuf = radix_sort_result_buf(32);
+  k_voxel_heads<<<count, 1024, 0, s>>>(d_jobs, kbuf); l++;
+  k_voxel_centroid<<<dim3((max_total + 255) / 256, count), 256, 0, s>>>(d_jobs, kbuf); l++;
   return l;
 }
 

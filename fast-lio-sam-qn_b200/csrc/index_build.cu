@@ -5,10 +5,17 @@
 // B200-first design: instead of a serial top-down pointer tree, every cloud becomes a
 // Morton-sorted point array with a linear BVH on top (Karras 2012 radix tree, built with one
 // thread per node, no recursion).  All clouds of a batch are built together: blockIdx.y is the
-// cloud.  Steps: bbox (atomic min/max) -> 30-bit Morton keys -> stable LSD radix sort (4 x 8 bit;
-// stable => the layout, and with it every later reduction order, is deterministic) -> gather into
-// float4 (w carries the original index) -> radix-tree topology -> bottom-up AABBs with arrival
-// flags, writing the two-children-per-node records the traversal reads (internal.cuh).
+// cloud.  Seven launches per batch (round 1 needed eighteen):
+//   k_bbox            per-block min/max partials (no atomics, no init kernel)
+//   k_morton_ghist    partials -> bbox -> 30-bit Morton keys + the digit histograms of ALL sort passes
+//   k_sort_pass x3    stable LSD radix sort, 10 bits per pass, ONE kernel per pass: tile-local ranks, decoupled
+//                     look-back across the tiles of a cloud for the global offsets (no separate histogram / scan
+//                     kernels), scatter; the last pass writes the sorted float4 points and the rank array directly
+//   k_lbvh_topology   Karras radix tree, one thread per node
+//   k_lbvh_aabb       bottom-up boxes: the work items (collapsed-leaf roots and lone points, ~1 in 6 candidates) are
+//                     compacted inside each block so that climbing warps are fully populated; a child writes its box
+//                     and its reference straight into its half of the parent's traversal record
+// The sort is stable, so the layout -- and with it every later reduction order -- is deterministic.
 // A mid-count split over the same Morton order was measured first and discarded: ranges that
 // straddle octant boundaries give huge overlapping boxes (195 node + 71 leaf visits per 15-NN
 // query vs 29 + 7 with prefix splits on the 100k KITTI-shaped scan).
@@ -17,12 +24,8 @@
 namespace b200 {
 
 // ------------------------------------------------------------------------------------
-__global__ void k_bbox_init(const CloudDev* clouds) {
-  const CloudDev& c = clouds[blockIdx.x];
-  if (threadIdx.x < 3) ((int*)c.bbox)[threadIdx.x] = f2ord(INFINITY);
-  else if (threadIdx.x < 6) ((int*)c.bbox)[threadIdx.x] = f2ord(-INFINITY);
-}
-
+// bounding box: per-block partials, reduced again by every block of the next kernel
+// ------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) k_bbox(const CloudDev* clouds) {
   const CloudDev& c = clouds[blockIdx.y];
   float mn[3] = {INFINITY, INFINITY, INFINITY}, mx[3] = {-INFINITY, -INFINITY, -INFINITY};
@@ -41,12 +44,20 @@ __global__ void __launch_bounds__(256) k_bbox(const CloudDev* clouds) {
       mn[d] = fminf(mn[d], __shfl_xor_sync(0xffffffffu, mn[d], o));
       mx[d] = fmaxf(mx[d], __shfl_xor_sync(0xffffffffu, mx[d], o));
     }
-  if ((threadIdx.x & 31) == 0 && blockIdx.x * blockDim.x < c.n) {
+  __shared__ float red[8][6];
+  const int w = threadIdx.x >> 5;
+  if ((threadIdx.x & 31) == 0) {
 #pragma unroll
     for (int d = 0; d < 3; d++) {
-      atomicMin(&((int*)c.bbox)[d], f2ord(mn[d]));
-      atomicMax(&((int*)c.bbox)[3 + d], f2ord(mx[d]));
+      red[w][d] = mn[d];
+      red[w][3 + d] = mx[d];
     }
+  }
+  __syncthreads();
+  if (threadIdx.x < 6) {
+    float v = red[0][threadIdx.x];
+    for (int k = 1; k < 8; k++) v = threadIdx.x < 3 ? fminf(v, red[k][threadIdx.x]) : fmaxf(v, red[k][threadIdx.x]);
+    c.bbox[6 * blockIdx.x + threadIdx.x] = v;  // partial of block blockIdx.x (empty blocks write +-inf)
   }
 }
 
@@ -59,99 +70,135 @@ __device__ __forceinline__ uint32_t expand10(uint32_t v) {
   return v;
 }
 
-__global__ void __launch_bounds__(256) k_morton(const CloudDev* clouds) {
-  const CloudDev& c = clouds[blockIdx.y];
-  int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= c.n) return;
-  const int* bb = (const int*)c.bbox;
-  float lo[3] = {ord2f(bb[0]), ord2f(bb[1]), ord2f(bb[2])};
-  float ext = fmaxf(fmaxf(ord2f(bb[3]) - lo[0], ord2f(bb[4]) - lo[1]), ord2f(bb[5]) - lo[2]);
-  float scale = ext > 0.f ? 1023.0f / ext : 0.f;  // cubic cells: one scale for all axes
-  const float* p = c.raw + (size_t)i * c.raw_stride;
-  uint32_t q[3];
-#pragma unroll
-  for (int d = 0; d < 3; d++) {
-    float f = (p[d] - lo[d]) * scale;
-    int v = (int)f;
-    q[d] = (uint32_t)min(max(v, 0), 1023);
-  }
-  c.keys[0][i] = (expand10(q[2]) << 2) | (expand10(q[1]) << 1) | expand10(q[0]);
-  c.vals[0][i] = (uint32_t)i;
-}
+// ------------------------------------------------------------------------------------
+// stable LSD radix sort with one kernel per pass
+// ------------------------------------------------------------------------------------
+// Work memory of one sort (CloudDev::hist, ZERO-INITIALISED by the caller), in 32-bit words:
+//   [0, P*R)                  global digit histograms of the P passes (R = 2^BITS bins)
+//   [P*R, P*R + 32)           tile tickets, one per pass
+//   [P*R + 32 + p*T*R ...)    look-back words of pass p: T tiles x R digits, (flag << 30) | count
+constexpr int SORT_PASSES = 3;
+constexpr uint32_t LB_AGG = 1u << 30, LB_INC = 2u << 30, LB_MASK = (1u << 30) - 1u;
 
-// ---- stable LSD radix sort, one 8-bit digit per pass --------------------------------
-// pass p reads keys[p&1], writes keys[(p+1)&1].
-__global__ void __launch_bounds__(SORT_THREADS) k_sort_hist(const CloudDev* clouds, int pass) {
+__host__ __device__ inline int sort_tiles(int n) { return (n + SORT_TILE - 1) / SORT_TILE; }
+template <int BITS>
+__host__ __device__ inline size_t sort_ws_words(int n) {
+  return (size_t)SORT_PASSES * (1 << BITS) + 32 + (size_t)SORT_PASSES * sort_tiles(n) * (1 << BITS);
+}
+size_t radix_sort_ws_bytes(int n, int key_bits) { return 4 * (key_bits <= 30 ? sort_ws_words<10>(n) : sort_ws_words<11>(n)); }
+int radix_sort_result_buf(int) { return SORT_PASSES & 1; }
+
+// block-wide accumulation of the digit histograms of all passes (shared by the fused Morton kernel and k_sort_ghist)
+template <int BITS>
+struct GHist {
+  static constexpr int R = 1 << BITS;
+  uint32_t* h;  // [SORT_PASSES * R] shared memory
+  __device__ void clear() {
+    for (int j = threadIdx.x; j < SORT_PASSES * R; j += blockDim.x) h[j] = 0;
+  }
+  __device__ void add(uint32_t key) {
+#pragma unroll
+    for (int p = 0; p < SORT_PASSES; p++) atomicAdd(&h[p * R + ((key >> (p * BITS)) & (R - 1))], 1u);
+  }
+  __device__ void flush(uint32_t* ws) {
+    for (int j = threadIdx.x; j < SORT_PASSES * R; j += blockDim.x) {
+      const uint32_t v = h[j];
+      if (v) atomicAdd(&ws[j], v);
+    }
+  }
+};
+
+// bbox partials -> Morton keys (cubic cells) + sort histograms.  Grid: (tiles of SORT_TILE points, cloud).
+__global__ void __launch_bounds__(SORT_THREADS) k_morton_ghist(const CloudDev* clouds, int bbox_blocks) {
   const CloudDev& c = clouds[blockIdx.y];
   const int base = blockIdx.x * SORT_TILE;
   if (base >= c.n) return;
-  __shared__ uint32_t h[RADIX];
-  h[threadIdx.x] = 0;
-  __syncthreads();
-  const uint32_t* keys = c.keys[pass & 1];
-  const int shift = pass * RADIX_BITS;
+  __shared__ uint32_t sh[SORT_PASSES * 1024];
+  __shared__ float s_box[6];
+  GHist<10> gh{sh};
+  gh.clear();
+  {  // every block reduces the (few hundred) partials of its cloud again: cheaper than an atomic or a third kernel
+    float v = threadIdx.x % 6 < 3 ? INFINITY : -INFINITY;
+    const int comp = threadIdx.x % 6, lane6 = threadIdx.x / 6;  // 42 groups of 6 threads
+    if (threadIdx.x < 252)
+      for (int b = lane6; b < bbox_blocks; b += 42) {
+        const float x = c.bbox[6 * b + comp];
+        v = comp < 3 ? fminf(v, x) : fmaxf(v, x);
+      }
+    __shared__ float part[252];
+    if (threadIdx.x < 252) part[threadIdx.x] = v;
+    __syncthreads();
+    if (threadIdx.x < 6) {
+      float r = part[threadIdx.x];
+      for (int k = 1; k < 42; k++) r = threadIdx.x < 3 ? fminf(r, part[6 * k + threadIdx.x]) : fmaxf(r, part[6 * k + threadIdx.x]);
+      s_box[threadIdx.x] = r;
+    }
+    __syncthreads();
+  }
+  const float lo0 = s_box[0], lo1 = s_box[1], lo2 = s_box[2];
+  const float ext = fmaxf(fmaxf(s_box[3] - lo0, s_box[4] - lo1), s_box[5] - lo2);
+  const float scale = ext > 0.f ? 1023.0f / ext : 0.f;  // cubic cells: one scale for all axes
 #pragma unroll
   for (int j = 0; j < SORT_ITEMS; j++) {
-    int i = base + j * SORT_THREADS + threadIdx.x;
-    if (i < c.n) atomicAdd(&h[(keys[i] >> shift) & (RADIX - 1)], 1u);
+    const int i = base + j * SORT_THREADS + threadIdx.x;
+    if (i < c.n) {
+      const float* p = c.raw + (size_t)i * c.raw_stride;
+      const uint32_t q0 = (uint32_t)min(max((int)((p[0] - lo0) * scale), 0), 1023);
+      const uint32_t q1 = (uint32_t)min(max((int)((p[1] - lo1) * scale), 0), 1023);
+      const uint32_t q2 = (uint32_t)min(max((int)((p[2] - lo2) * scale), 0), 1023);
+      const uint32_t key = (expand10(q2) << 2) | (expand10(q1) << 1) | expand10(q0);
+      c.keys[0][i] = key;
+      c.vals[0][i] = (uint32_t)i;
+      gh.add(key);
+    }
   }
   __syncthreads();
-  const int ntiles = (c.n + SORT_TILE - 1) / SORT_TILE;
-  c.hist[threadIdx.x * ntiles + blockIdx.x] = h[threadIdx.x];  // digit-major
+  gh.flush(c.hist);
 }
 
-// exclusive scan of the digit-major (digit, tile) table: one block per cloud
-__global__ void __launch_bounds__(1024) k_sort_scan(const CloudDev* clouds) {
-  const CloudDev& c = clouds[blockIdx.x];
-  const int ntiles = (c.n + SORT_TILE - 1) / SORT_TILE;
-  const int total = RADIX * ntiles;
-  __shared__ uint32_t warp_sums[32];
-  __shared__ uint32_t carry;
-  if (threadIdx.x == 0) carry = 0;
-  __syncthreads();
-  for (int base = 0; base < total; base += 1024) {
-    int i = base + threadIdx.x;
-    uint32_t v = i < total ? c.hist[i] : 0u;
-    uint32_t incl = v;
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-      uint32_t t = __shfl_up_sync(0xffffffffu, incl, o);
-      if ((threadIdx.x & 31) >= o) incl += t;
-    }
-    if ((threadIdx.x & 31) == 31) warp_sums[threadIdx.x >> 5] = incl;
-    __syncthreads();
-    if (threadIdx.x < 32) {
-      uint32_t w = warp_sums[threadIdx.x];
-      uint32_t wi = w;
-#pragma unroll
-      for (int o = 1; o < 32; o <<= 1) {
-        uint32_t t = __shfl_up_sync(0xffffffffu, wi, o);
-        if (threadIdx.x >= o) wi += t;
-      }
-      warp_sums[threadIdx.x] = wi - w;  // exclusive
-    }
-    __syncthreads();
-    uint32_t excl = carry + warp_sums[threadIdx.x >> 5] + incl - v;
-    if (i < total) c.hist[i] = excl;
-    __syncthreads();
-    if (threadIdx.x == 1023) carry = excl + v;
-    __syncthreads();
-  }
-}
-
-__global__ void __launch_bounds__(SORT_THREADS) k_sort_scatter(const CloudDev* clouds, int pass) {
+// digit histograms of keys that some other kernel produced (voxel grid, descriptor norm codes)
+template <int BITS>
+__global__ void __launch_bounds__(SORT_THREADS) k_sort_ghist(const CloudDev* clouds) {
   const CloudDev& c = clouds[blockIdx.y];
   const int base = blockIdx.x * SORT_TILE;
   if (base >= c.n) return;
-  constexpr int NW = SORT_THREADS / 32;
-  __shared__ uint32_t cnt[NW][RADIX];
-  for (int j = threadIdx.x; j < NW * RADIX; j += SORT_THREADS) (&cnt[0][0])[j] = 0;
+  extern __shared__ uint32_t sh_dyn[];
+  GHist<BITS> gh{sh_dyn};
+  gh.clear();
   __syncthreads();
+#pragma unroll
+  for (int j = 0; j < SORT_ITEMS; j++) {
+    const int i = base + j * SORT_THREADS + threadIdx.x;
+    if (i < c.n) gh.add(c.keys[0][i]);
+  }
+  __syncthreads();
+  gh.flush(c.hist);
+}
+
+// One pass: reads keys/vals[pass & 1], writes [(pass + 1) & 1].  GATHER (last pass of the index build): instead of the
+// value array the kernel writes the sorted points (w = original index) and the inverse permutation.
+template <int BITS, bool GATHER>
+__global__ void __launch_bounds__(SORT_THREADS) k_sort_pass(const CloudDev* clouds, int pass) {
+  constexpr int R = 1 << BITS, NW = SORT_THREADS / 32, DPT = R / SORT_THREADS;  // digits per thread
+  const CloudDev& c = clouds[blockIdx.y];
+  const int ntiles = sort_tiles(c.n);
+  if ((int)blockIdx.x >= ntiles) return;
+  __shared__ unsigned short cnt[NW][R];  // per-warp digit counts, then exclusive offsets inside the tile (<= SORT_TILE)
+  __shared__ uint32_t gbase[R];          // first output slot of (digit, this tile)
+  __shared__ uint32_t wtot[NW];
+  __shared__ int s_tile;
+  uint32_t* ws = c.hist;
+  uint32_t* look = ws + SORT_PASSES * R + 32 + (size_t)pass * ntiles * R;
+  if (threadIdx.x == 0) s_tile = (int)atomicAdd(&ws[SORT_PASSES * R + pass], 1u);  // tiles start in ticket order: look-back cannot deadlock
+  for (int j = threadIdx.x; j < NW * R; j += SORT_THREADS) (&cnt[0][0])[j] = 0;
+  __syncthreads();
+  const int tile = s_tile;
+  const int base = tile * SORT_TILE;
   const uint32_t* keys = c.keys[pass & 1];
   const uint32_t* vals = c.vals[pass & 1];
   uint32_t* okeys = c.keys[(pass + 1) & 1];
   uint32_t* ovals = c.vals[(pass + 1) & 1];
-  const int shift = pass * RADIX_BITS;
+  const int shift = pass * BITS;
   const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t lt = (1u << lane) - 1u;
   // warp w owns the contiguous run [base + w*32*ITEMS, +32*ITEMS): round r, lane l -> key r*32+l,
@@ -159,51 +206,103 @@ __global__ void __launch_bounds__(SORT_THREADS) k_sort_scatter(const CloudDev* c
   uint32_t key[SORT_ITEMS], val[SORT_ITEMS], rk[SORT_ITEMS];
 #pragma unroll
   for (int r = 0; r < SORT_ITEMS; r++) {
-    int i = base + (w * SORT_ITEMS + r) * 32 + lane;
-    bool ok = i < c.n;
+    const int i = base + (w * SORT_ITEMS + r) * 32 + lane;
+    const bool ok = i < c.n;
     key[r] = ok ? keys[i] : 0xFFFFFFFFu;
     val[r] = ok ? vals[i] : 0u;
-    uint32_t dig = ok ? ((key[r] >> shift) & (RADIX - 1)) : RADIX;  // RADIX = "invalid"
-    uint32_t m = __match_any_sync(0xffffffffu, dig);
-    uint32_t old = ok ? cnt[w][dig] : 0u;
+    const uint32_t dig = ok ? ((key[r] >> shift) & (R - 1)) : (uint32_t)R;  // R = "invalid"
+    const uint32_t m = __match_any_sync(0xffffffffu, dig);
+    const uint32_t old = ok ? cnt[w][dig] : 0u;
     __syncwarp();
-    if (ok && (m & lt) == 0) cnt[w][dig] = old + __popc(m);
+    if (ok && (m & lt) == 0) cnt[w][dig] = (unsigned short)(old + __popc(m));
     __syncwarp();
     rk[r] = old + __popc(m & lt);
   }
   __syncthreads();
-  {  // per digit: exclusive prefix over warps + the global (digit, tile) offset
-    const int ntiles = (c.n + SORT_TILE - 1) / SORT_TILE;
-    uint32_t run = c.hist[threadIdx.x * ntiles + blockIdx.x];
+  // exclusive scan of the global histogram of this pass (every block redoes it: R values, a few dozen instructions)
+  {
+    uint32_t hv[DPT], run = 0;
+#pragma unroll
+    for (int k = 0; k < DPT; k++) {
+      hv[k] = run;
+      run += ws[pass * R + threadIdx.x * DPT + k];
+    }
+    uint32_t incl = run;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const uint32_t t = __shfl_up_sync(0xffffffffu, incl, o);
+      if (lane >= o) incl += t;
+    }
+    if (lane == 31) wtot[w] = incl;
+    __syncthreads();
+    uint32_t woff = 0;
+    for (int ww = 0; ww < w; ww++) woff += wtot[ww];
+    const uint32_t excl = woff + incl - run;
+#pragma unroll
+    for (int k = 0; k < DPT; k++) gbase[threadIdx.x * DPT + k] = excl + hv[k];
+  }
+  __syncthreads();
+  // per digit: exclusive prefix over the warps of this tile, publish the tile's count, look back over earlier tiles
+#pragma unroll
+  for (int k = 0; k < DPT; k++) {
+    const int d = k * SORT_THREADS + threadIdx.x;  // strided: consecutive threads publish consecutive words
+    uint32_t run = 0;
 #pragma unroll
     for (int ww = 0; ww < NW; ww++) {
-      uint32_t t = cnt[ww][threadIdx.x];
-      cnt[ww][threadIdx.x] = run;
+      const uint32_t t = cnt[ww][d];
+      cnt[ww][d] = (unsigned short)run;
       run += t;
     }
+    volatile uint32_t* mine = look + (size_t)tile * R + d;
+    uint32_t excl = 0;
+    if (tile == 0) {
+      *mine = LB_INC | run;
+    } else {
+      *mine = LB_AGG | run;
+      for (int t2 = tile - 1;; t2--) {
+        volatile uint32_t* p = look + (size_t)t2 * R + d;
+        uint32_t v = *p;
+        while ((v >> 30) == 0u) v = *p;
+        excl += v & LB_MASK;
+        if ((v >> 30) == 2u) break;
+      }
+      *mine = LB_INC | (excl + run);
+    }
+    gbase[d] += excl;
   }
   __syncthreads();
 #pragma unroll
   for (int r = 0; r < SORT_ITEMS; r++) {
-    int i = base + (w * SORT_ITEMS + r) * 32 + lane;
+    const int i = base + (w * SORT_ITEMS + r) * 32 + lane;
     if (i < c.n) {
-      uint32_t dig = (key[r] >> shift) & (RADIX - 1);
-      uint32_t dst = cnt[w][dig] + rk[r];
+      const uint32_t dig = (key[r] >> shift) & (R - 1);
+      const uint32_t dst = gbase[dig] + cnt[w][dig] + rk[r];
       okeys[dst] = key[r];
-      ovals[dst] = val[r];
+      if (GATHER) {
+        const float* p = c.raw + (size_t)val[r] * c.raw_stride;
+        c.pts[dst] = make_float4(p[0], p[1], p[2], __int_as_float((int)val[r]));
+        c.rank[val[r]] = (int)dst;
+      } else {
+        ovals[dst] = val[r];
+      }
     }
   }
 }
 
-// sorted float4 array (w = original index) and the inverse permutation
-__global__ void __launch_bounds__(256) k_gather(const CloudDev* clouds, int final_buf) {
-  const CloudDev& c = clouds[blockIdx.y];
-  int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= c.n) return;
-  uint32_t o = c.vals[final_buf][i];
-  const float* p = c.raw + (size_t)o * c.raw_stride;
-  c.pts[i] = make_float4(p[0], p[1], p[2], __int_as_float((int)o));
-  c.rank[o] = i;
+// Stable LSD radix sort of (keys[0], vals[0]) of every descriptor; result in keys/vals[radix_sort_result_buf()].
+// Only the n / keys / vals / hist fields of the descriptors are used (also by the voxel grid, assemble.cu, and the
+// descriptor ordering, quatro.cu); hist must point to radix_sort_ws_bytes() ZEROED bytes.  key_bits <= 30: 3 x 10 bits,
+// otherwise 3 x 11 bits.
+int launch_radix_sort(const CloudDev* d_clouds, int count, int max_n, int key_bits, cudaStream_t s) {
+  const dim3 grid(sort_tiles(max_n), count);
+  if (key_bits <= 30) {
+    k_sort_ghist<10><<<grid, SORT_THREADS, SORT_PASSES * 1024 * 4, s>>>(d_clouds);
+    for (int p = 0; p < SORT_PASSES; p++) k_sort_pass<10, false><<<grid, SORT_THREADS, 0, s>>>(d_clouds, p);
+  } else {
+    k_sort_ghist<11><<<grid, SORT_THREADS, SORT_PASSES * 2048 * 4, s>>>(d_clouds);
+    for (int p = 0; p < SORT_PASSES; p++) k_sort_pass<11, false><<<grid, SORT_THREADS, 0, s>>>(d_clouds, p);
+  }
+  return 1 + SORT_PASSES;
 }
 
 // ---- Karras radix tree over the sorted keys -----------------------------------------
@@ -244,26 +343,56 @@ __global__ void __launch_bounds__(256) k_lbvh_topology(const CloudDev* clouds, i
 
 // Bottom-up AABBs.  Work items: every point whose parent spans > LEAF points (a 1-point leaf) and every internal
 // node that is the root of a collapsed leaf (<= LEAF points, parent > LEAF): it reduces its <= 8 points directly.
-// Each item then climbs; the second arrival at a node owns it, merges the children's boxes and writes the
-// two-children traversal record.  (Starting a climb from every single point, through the tiny sub-trees, cost 2 atomics
-// per node of the full radix tree and made this the slowest build kernel.)
+// Only about one candidate in six is a work item, and a climb is a chain of dependent atomics: the items of a block are
+// therefore compacted first (ballot + prefix), so the warps that stay resident for the climb are fully populated.
+// An item writes its box and its own reference into ITS half of the parent's traversal record and arrives at the
+// parent's flag; the second arrival owns the parent, reads the finished 64-byte record back, merges the two boxes and
+// carries on upwards.  (nbox, the separate per-node box array of round 1, is gone.)
 __global__ void __launch_bounds__(256) k_lbvh_aabb(const CloudDev* clouds) {
   const CloudDev& c = clouds[blockIdx.y];
   const int t = blockIdx.x * blockDim.x + threadIdx.x;
   const int n = c.n;
-  if (n <= LEAF || t >= 2 * n - 1) return;
-  int node;
+  if (n <= LEAF || (int)(blockIdx.x * blockDim.x) >= 2 * n - 1) return;
+  __shared__ int s_items[256];
+  __shared__ int s_wcnt[8];
+  bool is_item = false;
   if (t < n) {  // point t
-    node = c.parent_leaf[t];
-    const int4 pi = c.info[node];
-    if (pi.y - pi.x + 1 <= LEAF) return;  // lives inside a collapsed leaf
-  } else {      // internal node t - n
+    const int4 pi = c.info[c.parent_leaf[t]];
+    is_item = pi.y - pi.x + 1 > LEAF;  // otherwise it lives inside a collapsed leaf
+  } else if (t < 2 * n - 1) {  // internal node t - n
     const int i = t - n;
     const int4 inf = c.info[i];
-    if (i == 0 || inf.y - inf.x + 1 > LEAF) return;
-    const int par = c.parent_node[i];
-    const int4 pi = c.info[par];
-    if (pi.y - pi.x + 1 <= LEAF) return;  // an ancestor is the collapsed-leaf root
+    if (i != 0 && inf.y - inf.x + 1 <= LEAF) {
+      const int4 pi = c.info[c.parent_node[i]];
+      is_item = pi.y - pi.x + 1 > LEAF;  // otherwise an ancestor is the collapsed-leaf root
+    }
+  }
+  const unsigned bal = __ballot_sync(0xffffffffu, is_item);
+  const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (lane == 0) s_wcnt[w] = __popc(bal);
+  __syncthreads();
+  int off = 0, total = 0;
+  for (int k = 0; k < 8; k++) {
+    if (k < w) off += s_wcnt[k];
+    total += s_wcnt[k];
+  }
+  if (is_item) s_items[off + __popc(bal & ((1u << lane) - 1u))] = t;
+  __syncthreads();
+  if ((int)threadIdx.x >= total) return;
+  const int item = s_items[threadIdx.x];
+  // the item's own box, reference and parent
+  float4 lo, hi;
+  int ref, node, first;
+  if (item < n) {
+    const float4 q = c.pts[item];
+    lo = q;
+    hi = q;
+    ref = leaf_ref(item, 1);
+    node = c.parent_leaf[item];
+    first = item;
+  } else {
+    const int i = item - n;
+    const int4 inf = c.info[i];
     float lo0 = INFINITY, lo1 = INFINITY, lo2 = INFINITY, hi0 = -INFINITY, hi1 = -INFINITY, hi2 = -INFINITY;
     for (int p = inf.x; p <= inf.y; p++) {
       const float4 q = c.pts[p];
@@ -271,74 +400,48 @@ __global__ void __launch_bounds__(256) k_lbvh_aabb(const CloudDev* clouds) {
       lo1 = fminf(lo1, q.y); hi1 = fmaxf(hi1, q.y);
       lo2 = fminf(lo2, q.z); hi2 = fmaxf(hi2, q.z);
     }
-    c.nbox[2 * i] = make_float4(lo0, lo1, lo2, 0.f);
-    c.nbox[2 * i + 1] = make_float4(hi0, hi1, hi2, 0.f);
-    __threadfence();
-    node = par;
+    lo = make_float4(lo0, lo1, lo2, 0.f);
+    hi = make_float4(hi0, hi1, hi2, 0.f);
+    ref = leaf_ref(inf.x, inf.y - inf.x + 1);
+    node = c.parent_node[i];
+    first = inf.x;
   }
   for (;;) {
-    if (atomicAdd(&c.flags[node], 1u) == 0u) return;
+    // which child of `node` am I?  child 0 covers [info.x, split], child 1 (split, info.y]: compare first points
+    const int4 pinf = c.info[node];
+    const int k = first > pinf.w ? 1 : 0;
+    float4* rec = c.tnodes + 4 * (size_t)node + 2 * k;
+    __stcg(&rec[0], make_float4(lo.x, lo.y, lo.z, __int_as_float(ref)));
+    __stcg(&rec[1], make_float4(hi.x, hi.y, hi.z, 0.f));
     __threadfence();
-    const int4 inf = c.info[node];
-    const int g = inf.w;
-    float4 lo[2], hi[2];
-    int ref[2];
-#pragma unroll
-    for (int k = 0; k < 2; k++) {
-      const int ch = g + k;
-      if ((inf.z >> k) & 1) {
-        float4 q = c.pts[ch];
-        lo[k] = q;
-        hi[k] = q;
-        ref[k] = leaf_ref(ch, 1);
-      } else {
-        lo[k] = __ldcg(&c.nbox[2 * ch]);
-        hi[k] = __ldcg(&c.nbox[2 * ch + 1]);
-        const int4 ci = c.info[ch];
-        const int cnt = ci.y - ci.x + 1;
-        ref[k] = cnt <= LEAF ? leaf_ref(ci.x, cnt) : ch;
-      }
-    }
-    c.nbox[2 * node] = make_float4(fminf(lo[0].x, lo[1].x), fminf(lo[0].y, lo[1].y), fminf(lo[0].z, lo[1].z), 0.f);
-    c.nbox[2 * node + 1] = make_float4(fmaxf(hi[0].x, hi[1].x), fmaxf(hi[0].y, hi[1].y), fmaxf(hi[0].z, hi[1].z), 0.f);
-    c.tnodes[4 * node + 0] = make_float4(lo[0].x, lo[0].y, lo[0].z, __int_as_float(ref[0]));
-    c.tnodes[4 * node + 1] = make_float4(hi[0].x, hi[0].y, hi[0].z, 0.f);
-    c.tnodes[4 * node + 2] = make_float4(lo[1].x, lo[1].y, lo[1].z, __int_as_float(ref[1]));
-    c.tnodes[4 * node + 3] = make_float4(hi[1].x, hi[1].y, hi[1].z, 0.f);
+    if (atomicAdd(&c.flags[node], 1u) == 0u) return;  // the sibling is still on its way: it will take the parent
+    __threadfence();
+    const float4 olo = __ldcg(&c.tnodes[4 * (size_t)node + 2 * (1 - k)]);
+    const float4 ohi = __ldcg(&c.tnodes[4 * (size_t)node + 2 * (1 - k) + 1]);
     if (node == 0) return;
-    __threadfence();
+    lo = make_float4(fminf(lo.x, olo.x), fminf(lo.y, olo.y), fminf(lo.z, olo.z), 0.f);
+    hi = make_float4(fmaxf(hi.x, ohi.x), fmaxf(hi.y, ohi.y), fmaxf(hi.z, ohi.z), 0.f);
+    ref = node;
+    first = pinf.x;
     node = c.parent_node[node];
   }
 }
 
-// stable LSD radix sort of (keys[0], vals[0]) of every descriptor; result in keys[npass & 1] / vals[npass & 1].
-// Only the n / keys / vals / hist fields of the descriptors are used (also by the voxel grid, assemble.cu).
-int launch_radix_sort(const CloudDev* d_clouds, int count, int max_n, int npass, cudaStream_t s) {
-  const int ntiles = (max_n + SORT_TILE - 1) / SORT_TILE;
-  for (int p = 0; p < npass; p++) {
-    k_sort_hist<<<dim3(ntiles, count), SORT_THREADS, 0, s>>>(d_clouds, p);
-    k_sort_scan<<<count, 1024, 0, s>>>(d_clouds);
-    k_sort_scatter<<<dim3(ntiles, count), SORT_THREADS, 0, s>>>(d_clouds, p);
-  }
-  return 3 * npass;
-}
-
 // ------------------------------------------------------------------------------------
 // host launcher: builds `count` clouds whose descriptors are already in device memory.
+// c.hist = zeroed sort work memory (radix_sort_ws_bytes(n, 30)), c.flags zeroed, c.bbox = 6 * BBOX_BLOCKS floats.
 // Returns the number of kernel launches issued.
 int launch_index_build(const CloudDev* d_clouds, int count, int max_n, cudaStream_t s) {
   int launches = 0;
-  k_bbox_init<<<count, 32, 0, s>>>(d_clouds); launches++;
-  {
-    int gx = min((max_n + 255) / 256, 296);
-    k_bbox<<<dim3(gx, count), 256, 0, s>>>(d_clouds); launches++;
-  }
-  k_morton<<<dim3((max_n + 255) / 256, count), 256, 0, s>>>(d_clouds); launches++;
-  const int npass = 4;  // 30-bit keys
-  launches += launch_radix_sort(d_clouds, count, max_n, npass, s);
-  k_gather<<<dim3((max_n + 255) / 256, count), 256, 0, s>>>(d_clouds, npass & 1); launches++;
+  const int gx = max(1, min((max_n + 255) / 256, BBOX_BLOCKS));
+  k_bbox<<<dim3(gx, count), 256, 0, s>>>(d_clouds); launches++;
+  const dim3 tiles(sort_tiles(max_n), count);
+  k_morton_ghist<<<tiles, SORT_THREADS, 0, s>>>(d_clouds, gx); launches++;
+  k_sort_pass<10, false><<<tiles, SORT_THREADS, 0, s>>>(d_clouds, 0); launches++;
+  k_sort_pass<10, false><<<tiles, SORT_THREADS, 0, s>>>(d_clouds, 1); launches++;
+  k_sort_pass<10, true><<<tiles, SORT_THREADS, 0, s>>>(d_clouds, 2); launches++;
   if (max_n > 1) {
-    k_lbvh_topology<<<dim3((max_n + 254) / 256, count), 256, 0, s>>>(d_clouds, npass & 1); launches++;
+    k_lbvh_topology<<<dim3((max_n + 254) / 256, count), 256, 0, s>>>(d_clouds, SORT_PASSES & 1); launches++;
     k_lbvh_aabb<<<dim3((2 * max_n + 254) / 256, count), 256, 0, s>>>(d_clouds); launches++;
   }
   return launches;

@@ -22,8 +22,7 @@ constexpr int LEAF = 8;            // max points per leaf (8 x 16 B = one 128-B 
 constexpr int SORT_THREADS = 256;  // radix sort tile = SORT_THREADS * SORT_ITEMS keys
 constexpr int SORT_ITEMS = 8;
 constexpr int SORT_TILE = SORT_THREADS * SORT_ITEMS;
-constexpr int RADIX_BITS = 8;
-constexpr int RADIX = 1 << RADIX_BITS;
+constexpr int BBOX_BLOCKS = 296;   // per-block bounding-box partials of one cloud (k_bbox grid.x <= this)
 constexpr int STEP_THREADS = 128;  // threads per block of the per-point kernels
 constexpr int NRED = 28;           // 21 (H upper) + 6 (b) + 1 (err)
 constexpr int FDIM = 33;           // FPFHSignature33
@@ -53,13 +52,12 @@ struct CloudDev {
   // build-time temporaries (freed after the build)
   uint32_t* keys[2];   // sort ping-pong
   uint32_t* vals[2];
-  uint32_t* hist;      // [RADIX * ntiles]
-  uint32_t* flags;     // [n - 1] arrival flags of the bottom-up AABB pass
+  uint32_t* hist;      // radix-sort work memory, ZEROED by the caller: radix_sort_ws_bytes(n, key_bits) (index_build.cu)
+  uint32_t* flags;     // [n - 1] arrival flags of the bottom-up AABB pass, ZEROED by the caller
   int4* info;          // [n - 1] (first, last, leaf-child bits, split)
   int* parent_node;    // [n - 1]
   int* parent_leaf;    // [n]
-  float4* nbox;        // [2 * (n - 1)] node AABBs
-  float* bbox;         // [6] ordered-int encoded min/max
+  float* bbox;         // [6 * BBOX_BLOCKS] per-block min/max partials
 };
 
 // phase of the per-pair LM state machine
@@ -130,7 +128,7 @@ struct KeyframeDev {
 struct SortBufs {  // what the radix sort needs (mirrors the CloudDev fields it reads)
   uint32_t* keys[2];
   uint32_t* vals[2];
-  uint32_t* hist;
+  uint32_t* hist;   // zeroed work memory, radix_sort_ws_bytes(total, 32)
 };
 struct AssembleJob {  // one output cloud of setSrcAndDstCloud
   int nseg, total;

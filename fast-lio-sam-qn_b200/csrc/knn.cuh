@@ -43,6 +43,7 @@ struct KnnSet {
     }
   }
   __device__ __forceinline__ float worst() const { return d[K - 1]; }
+  __device__ __forceinline__ void offer(float cd, int cp, const float4* __restrict__ pts);  // candidate with cd <= worst()
 };
 
 __device__ __forceinline__ int orig_index(const float4* __restrict__ pts, int pos) {
@@ -91,6 +92,95 @@ __device__ __forceinline__ void knn_insert(KnnSet<K>& s, float cd, int cp, const
   }
 }
 
+template <int K>
+__device__ __forceinline__ void KnnSet<K>::offer(float cd, int cp, const float4* __restrict__ pts) {
+  knn_insert<K>(*this, cd, cp, pts);
+}
+
+// The K best candidates as a binary MAX-heap in shared memory, one column per thread ([slot][thread]: the bank is the
+// thread, so the divergent, dynamically indexed accesses of a sift-down are conflict free).  For consumers that need the
+// SET of neighbours and the current worst distance, not their order (the covariance pass): replacing the root costs
+// ~45 instructions against ~120 for the K-long register insertion chain, and the result set no longer occupies 2K
+// registers.  Order between equal distances follows the same rule as everywhere: (d2, ORIGINAL index), ties looked up cold.
+template <int K>
+struct KnnHeap {
+  float* hd;   // column base: slot j at hd[j * stride]
+  int* hp;
+  int stride;
+  float wd;    // cached root distance
+  __device__ __forceinline__ float worst() const { return wd; }
+  __device__ __forceinline__ float d(int j) const { return hd[j * stride]; }
+  __device__ __forceinline__ int p(int j) const { return hp[j * stride]; }
+  __device__ __forceinline__ void set(int j, float dd, int pp) {
+    hd[j * stride] = dd;
+    hp[j * stride] = pp;
+  }
+  // (da, pa) ordered after (db, pb)?
+  static __device__ __forceinline__ bool after(float da, int pa, float db, int pb, const float4* __restrict__ pts) {
+    return da > db || (da == db && orig_index(pts, pa) > orig_index(pts, pb));
+  }
+  // sink (cd, cp) from slot i to its place
+  __device__ __forceinline__ void sift(int i, float cd, int cp, const float4* __restrict__ pts) {
+#pragma unroll 1
+    for (;;) {
+      const int l = 2 * i + 1;
+      if (l >= K) break;
+      int ch = l;
+      float dc = d(l);
+      if (l + 1 < K) {
+        const float dr = d(l + 1);
+        if (dr > dc || (dr == dc && after(dr, p(l + 1), dc, p(l), pts))) {
+          ch = l + 1;
+          dc = dr;
+        }
+      }
+      if (!(dc > cd || (dc == cd && after(dc, p(ch), cd, cp, pts)))) break;
+      set(i, dc, p(ch));
+      i = ch;
+    }
+    set(i, cd, cp);
+  }
+  // slots 0..K-1 hold arbitrary entries: make them a heap (Floyd)
+  __device__ __forceinline__ void heapify(const float4* __restrict__ pts) {
+#pragma unroll 1
+    for (int i = K / 2 - 1; i >= 0; i--) sift(i, d(i), p(i), pts);
+    wd = d(0);
+  }
+  // candidate with cd <= worst(): replaces the root unless it ties with it on a higher original index
+  __device__ __forceinline__ void offer(float cd, int cp, const float4* __restrict__ pts) {
+    if (cd == wd && !(orig_index(pts, cp) < orig_index(pts, p(0)))) return;
+    sift(0, cd, cp, pts);
+    wd = d(0);
+  }
+  // remove the current worst entry of a heap that holds `m` entries (slots 0..m-1); returns m - 1
+  __device__ __forceinline__ int pop(int m, const float4* __restrict__ pts) {
+    const float ld = d(m - 1);
+    const int lp = p(m - 1);
+    set(m - 1, d(0), p(0));  // parked behind the live part, never read again
+    // sift with the live size m - 1
+    int i = 0;
+#pragma unroll 1
+    for (;;) {
+      const int l = 2 * i + 1;
+      if (l >= m - 1) break;
+      int ch = l;
+      float dc = d(l);
+      if (l + 1 < m - 1) {
+        const float dr = d(l + 1);
+        if (dr > dc || (dr == dc && after(dr, p(l + 1), dc, p(l), pts))) {
+          ch = l + 1;
+          dc = dr;
+        }
+      }
+      if (!(dc > ld || (dc == ld && after(dc, p(ch), ld, lp, pts)))) break;
+      set(i, dc, p(ch));
+      i = ch;
+    }
+    if (m - 1 > 0) set(i, ld, lp);
+    return m - 1;
+  }
+};
+
 // Seeding: insert into a set whose first S slots are occupied (slot S is still empty): the chain only has to
 // look at slots 0..S, so filling K seeds costs K^2/2 compare-selects instead of K^2.
 template <int K, int S>
@@ -137,9 +227,8 @@ struct SeedLoop<K, K> {
 
 // Exact K-NN of (qx,qy,qz) in cloud c.  One thread per query; Morton-sorted queries keep
 // neighbouring lanes on neighbouring paths (coherent loads, low divergence).
-template <int K>
-__device__ __forceinline__ void knn_search(const CloudDev& c, float qx, float qy, float qz, KnnSet<K>& res, int skip_lo = 1,
-                                           int skip_hi = 0) {
+template <typename Res>
+__device__ __forceinline__ void knn_walk(const CloudDev& c, float qx, float qy, float qz, Res& res, int skip_lo = 1, int skip_hi = 0) {
   const float4* __restrict__ pts = c.pts;
   const float4* __restrict__ tn = c.tnodes;
   int stack_ref[MAX_STACK];
@@ -188,7 +277,7 @@ __device__ __forceinline__ void knn_search(const CloudDev& c, float qx, float qy
         float dj = dl[0];
 #pragma unroll
         for (int t = 1; t < LEAF; t++) dj = (j == t) ? dl[t] : dj;
-        if (!(dj > res.worst())) knn_insert<K>(res, dj, base + j, pts);
+        if (!(dj > res.worst())) res.offer(dj, base + j, pts);
       }
     }
     bool found = false;
@@ -203,6 +292,12 @@ __device__ __forceinline__ void knn_search(const CloudDev& c, float qx, float qy
     }
     if (!found) break;
   }
+}
+
+template <int K>
+__device__ __forceinline__ void knn_search(const CloudDev& c, float qx, float qy, float qz, KnnSet<K>& res, int skip_lo = 1,
+                                           int skip_hi = 0) {
+  knn_walk<KnnSet<K>>(c, qx, qy, qz, res, skip_lo, skip_hi);
 }
 
 // Fixed-radius traversal: calls f(position, d2) for every point with fp32 d2 < r2 (strict, like FLANN's

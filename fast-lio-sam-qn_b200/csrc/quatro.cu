@@ -257,7 +257,7 @@ __global__ void __launch_bounds__(NN_TILE) k_fgather(const CloudDev* clouds) {
   float lo[3] = {INFINITY, INFINITY, INFINITY}, hi[3] = {-INFINITY, -INFINITY, -INFINITY};
   int usable = 0;
   if (r < c.n) {
-    const int p = (int)c.vals[0][r];
+    const int p = (int)c.vals[1][r];  // radix_sort_result_buf()
     const float4* s4 = reinterpret_cast<const float4*>(c.fpfh + (size_t)p * FPAD);
     float4* d4 = reinterpret_cast<float4*>(c.fpfh_s + (size_t)r * FPAD);
     float4 last;
@@ -268,7 +268,7 @@ __global__ void __launch_bounds__(NN_TILE) k_fgather(const CloudDev* clouds) {
     }
     const float4 nr = c.fnorm[p];
     c.fnorm_s[r] = nr;
-    c.fcode_s[r] = c.keys[0][r];
+    c.fcode_s[r] = c.keys[1][r];
     if (last.z != 0.f) {  // slot 34
       usable = 1;
       lo[0] = hi[0] = nr.x; lo[1] = hi[1] = nr.y; lo[2] = hi[2] = nr.z;
@@ -1627,7 +1627,7 @@ __global__ void __launch_bounds__(256) k_transform_raw(const CloudDev* clouds, c
 // ------------------------------------------------------------------------------------------------
 // host launchers
 // ------------------------------------------------------------------------------------------------
-int launch_radix_sort(const CloudDev* d_clouds, int count, int max_n, int npass, cudaStream_t s);  // index_build.cu
+int launch_radix_sort(const CloudDev* d_clouds, int count, int max_n, int key_bits, cudaStream_t s);  // index_build.cu
 
 int launch_fpfh(const CloudDev* d_clouds, int count, int max_n, float normal_r2, float fpfh_r2, cudaStream_t s) {
   dim3 grid((max_n + STEP_THREADS - 1) / STEP_THREADS, count);
@@ -1636,7 +1636,7 @@ int launch_fpfh(const CloudDev* d_clouds, int count, int max_n, float normal_r2,
   k_fpfh<<<grid, STEP_THREADS, 0, s>>>(d_clouds, fpfh_r2);
   // the matcher's view: records in the order of their block-norm Morton code, boxed per tile
   k_fcode<<<dim3((max_n + 255) / 256, count), 256, 0, s>>>(d_clouds);
-  const int ls = launch_radix_sort(d_clouds, count, max_n, 4, s);  // 30-bit keys, 4 passes: result back in keys[0] / vals[0]
+  const int ls = launch_radix_sort(d_clouds, count, max_n, 30, s);  // 30-bit keys, 3 passes of 10 bits: result in keys[1] / vals[1]
   k_fgather<<<dim3((max_n + NN_TILE - 1) / NN_TILE, count), NN_TILE, 0, s>>>(d_clouds);
   return 5 + ls;
 }
