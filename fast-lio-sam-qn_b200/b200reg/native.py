@@ -85,9 +85,24 @@ EXPORTS = [
 ]
 
 
+def _point_at_bundled_nccl():
+    """b200reg_comm_* load NCCL at run time.  In a Python process the pip-bundled libnccl (site-packages/nvidia/nccl/lib) is
+    the one torch was built against; if the system's older libnccl.so.2 got loaded first under the same soname, a later
+    `import torch` would fail on missing symbols.  So unless the caller chose a library, point the C side at the bundled one."""
+    if os.environ.get("B200REG_NCCL_LIB"):
+        return
+    import sys
+    for base in sys.path:
+        cand = os.path.join(base, "nvidia", "nccl", "lib", "libnccl.so.2")
+        if os.path.exists(cand):
+            os.environ["B200REG_NCCL_LIB"] = cand
+            return
+
+
 def lib():
     global _lib
     if _lib is None:
+        _point_at_bundled_nccl()
         path = LIB if os.path.exists(LIB) and not os.path.exists("/usr/local/cuda/bin/nvcc") else build_native()
         _lib = C.CDLL(path)
         _lib.b200reg_last_error.restype = C.c_char_p

@@ -23,7 +23,8 @@ size_t radix_sort_ws_bytes(int n, int key_bits);
 int launch_covariances(const CloudDev* d_clouds, int count, int max_n, int k, int method, cudaStream_t s);
 void launch_gicp_init(const PairDev* pairs, PairState* states, const double* d_guess, int count, const GicpParamsDev& prm,
                       LmSched* sched, cudaStream_t s);
-void launch_gicp_step(const PairDev* pairs, PairState* states, int blocks, const GicpParamsDev& prm, LmSched* sched, cudaStream_t s);
+int launch_gicp_step(const PairDev* pairs, PairState* states, int blocks_search, int blocks_accum, const GicpParamsDev& prm, LmSched* sched,
+                     cudaStream_t s);
 int launch_knn_queries(const CloudDev& c, const float* d_q, int nq, int qstride, int k, int* idx, float* d2, cudaStream_t s, int brute);
 void launch_transform_out(const CloudDev& c, const float* d_Tf, float* d_out3, cudaStream_t s);
 void launch_set_covariances(const CloudDev& c, const double* d_cov9, cudaStream_t s);
@@ -576,15 +577,14 @@ int b200reg_gicp_align(b200reg_ctx* c, int count, b200reg_cloud* const* src, b20
   long steps = 0;
   // The step kernel walks a device-side list of (active pair, block) work items and its last block rebuilds that list,
   // so a finished pair costs nothing from the next step on; the host only sizes the persistent grid and polls `done`.
-  const long cap = (long)c->sm_count * 8;  // resident blocks of k_gicp_step (128 threads, <= 64 registers)
+  const long cap_s = (long)c->sm_count * 16, cap_a = (long)c->sm_count * 8;  // resident blocks of the search / accumulate kernels
   long items = w.total_blocks;
   for (;;) {
     {
       ProfScope ps(c, CLS_STEP);
-      const int blocks = (int)std::max(1L, std::min(items, cap));
+      const int bs = (int)std::max(1L, std::min(items, cap_s)), ba = (int)std::max(1L, std::min(items, cap_a));
       for (int j = 0; j < c->step_chunk; j++) {
-        launch_gicp_step(w.d_pairs, w.d_states, blocks, prm, w.d_sched, s);
-        c->launches++;
+        c->launches += launch_gicp_step(w.d_pairs, w.d_states, bs, ba, prm, w.d_sched, s);
         steps++;
       }
     }
@@ -825,8 +825,8 @@ int b200reg_linearize(b200reg_ctx* c, const b200reg_cloud* src, const b200reg_cl
   CU(scratch.alloc((void**)&d_guess, sizeof(double) * 16));
   CU(cudaMemcpyAsync(d_guess, T16, sizeof(double) * 16, cudaMemcpyHostToDevice, s));
   launch_gicp_init(w.d_pairs, w.d_states, d_guess, 1, prm, w.d_sched, s);
-  launch_gicp_step(w.d_pairs, w.d_states, (int)std::min(w.total_blocks, (long)c->sm_count * 8), prm, w.d_sched, s);  // exactly one linearize pass
-  c->launches += 2;
+  const int tap_blocks = (int)std::min(w.total_blocks, (long)c->sm_count * 8);
+  c->launches += 1 + launch_gicp_step(w.d_pairs, w.d_states, tap_blocks, tap_blocks, prm, w.d_sched, s);  // exactly one linearize pass
   PairState st;
   const int N = src->dev.n, M = tgt->dev.n;
   std::vector<int> corr(N);
@@ -872,7 +872,7 @@ int b200reg_compute_error(b200reg_ctx* c, const b200reg_cloud* src, const b200re
   CU(cudaMemcpyAsync(d_guess, T_lin16, sizeof(double) * 16, cudaMemcpyHostToDevice, s));
   const int blocks = (int)std::min(w.total_blocks, (long)c->sm_count * 8);
   launch_gicp_init(w.d_pairs, w.d_states, d_guess, 1, prm, w.d_sched, s);
-  launch_gicp_step(w.d_pairs, w.d_states, blocks, prm, w.d_sched, s);  // linearize: correspondences + Mahalanobis, phase -> TRIAL
+  launch_gicp_step(w.d_pairs, w.d_states, blocks, blocks, prm, w.d_sched, s);  // linearize: correspondences + Mahalanobis, phase -> TRIAL
   // overwrite the trial pose the LM controller prepared with the caller's
   double Rt[9], tt[3];
   for (int a = 0; a < 3; a++) {
@@ -881,8 +881,8 @@ int b200reg_compute_error(b200reg_ctx* c, const b200reg_cloud* src, const b200re
   }
   CU(cudaMemcpyAsync((char*)w.d_states + offsetof(PairState, Rt), Rt, sizeof(Rt), cudaMemcpyHostToDevice, s));
   CU(cudaMemcpyAsync((char*)w.d_states + offsetof(PairState, tt), tt, sizeof(tt), cudaMemcpyHostToDevice, s));
-  launch_gicp_step(w.d_pairs, w.d_states, blocks, prm, w.d_sched, s);  // compute_error at the trial pose
-  c->launches += 3;
+  launch_gicp_step(w.d_pairs, w.d_states, blocks, blocks, prm, w.d_sched, s);  // compute_error at the trial pose
+  c->launches += 5;
   PairState st;
   CU(cudaMemcpyAsync(&st, w.d_states, sizeof(PairState), cudaMemcpyDeviceToHost, s));
   CU(cudaStreamSynchronize(s));
@@ -1281,11 +1281,15 @@ NcclApi* nccl_api() {  // loaded once per process; a process that already holds 
   std::lock_guard<std::mutex> lk(mu);
   if (tried) return &api;
   tried = true;
+  // 1. a copy this process already holds (e.g. the one a framework bundles and linked first): two NCCL builds under one
+  //    soname would starve whichever library loads second of its symbols;  2. $B200REG_NCCL_LIB (the Python binding points
+  //    it at the pip-bundled libnccl so that a LATER `import torch` finds the version it was built against);  3. the system's.
+  api.h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_NOLOAD);
   const char* names[] = {getenv("B200REG_NCCL_LIB"), "libnccl.so.2", "libnccl.so"};
   for (const char* n : names) {
-    if (!n) continue;
-    api.h = dlopen(n, RTLD_NOW | RTLD_LOCAL);
     if (api.h) break;
+    if (!n || !*n) continue;
+    api.h = dlopen(n, RTLD_NOW | RTLD_GLOBAL);
   }
   if (!api.h) {
     api.err = std::string("cannot load libnccl.so.2: ") + dlerror();

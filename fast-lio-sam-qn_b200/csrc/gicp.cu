@@ -418,38 +418,95 @@ __global__ void __launch_bounds__(STEP_THREADS, (K <= 16 ? (HEAP ? 10 : 8) : 4))
 }
 
 // ---------------------------------------------------------------------------------------
-// K3/K4/K5 in one kernel, selected by the pair's phase (uniform per block):
-//   PH_LINEARIZE: q = T_f p (fp32), exact 1-NN, gate, M = (C_B + R C_A R^T)^-1, e, J,
-//                 accumulate H (21), b (6), e^T M e                      [update_correspondences + linearize]
-//   PH_TRIAL:     e^T M e at the trial pose with the stale correspondences / M      [compute_error]
-//   PH_FITNESS:   1-NN d^2 of the fp32-transformed source                           [getFitnessScore]
-// Block partials go to HBM; the last block to arrive sums them in a fixed order (deterministic,
-// SURVEY App. A.6) and runs the LM controller, so no host round trip is needed per iteration.
+// K3/K4/K5: one LM step = two kernels over the device-side schedule of (active pair, 128-point block) work items
+// (LmSched, internal.cuh), both persistent (work items are strided over the grid):
+//   k_gicp_search  pairs in PH_LINEARIZE / PH_FITNESS: q = T_f p in fp32, exact 1-NN in the target tree (seeded with the
+//                  previous correspondence), correspondence gate; writes corr / sqd.            [update_correspondences,
+//                  32 registers, 16 blocks per SM: the walk is a chain of dependent L1/L2 loads,   getFitnessScore's search]
+//                  so it runs at full occupancy instead of sharing the fp64 kernel's 64-register budget
+//   k_gicp_accum   PH_LINEARIZE: M = (C_B + R C_A R^T)^-1, e, J, accumulate H (21), b (6), e^T M e        [linearize]
+//                  PH_TRIAL:     e^T M e at the trial pose with the stale correspondences / M         [compute_error]
+//                  PH_FITNESS:   sum of the 1-NN d^2                                               [getFitnessScore]
+//                  Block partials go to HBM; the last block of a pair sums them in a fixed order (deterministic, SURVEY
+//                  App. A.6) and runs the LM controller; the last block of the STEP rebuilds the schedule from the pairs'
+//                  new phases -- no host round trip per iteration, finished pairs cost nothing from the next step on.
 // ---------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(STEP_THREADS, 8) k_gicp_step(const PairDev* pairs, PairState* states, GicpParamsDev prm,
-                                                             LmSched* sched) {
-  __shared__ double s_T[12];
+// work item -> (active pair, block of that pair): binary search of the exclusive prefix (block-uniform)
+__device__ __forceinline__ void locate_item(const LmSched* sched, int n_active, int item, int& pair_id, int& blk) {
+  int lo = 0, hi = n_active - 1;
+  while (lo < hi) {
+    const int mid = (lo + hi + 1) >> 1;
+    if (__ldg(&sched->prefix[mid]) <= item) lo = mid; else hi = mid - 1;
+  }
+  pair_id = __ldg(&sched->active[lo]);
+  blk = item - __ldg(&sched->prefix[lo]);
+}
+
+__global__ void __launch_bounds__(STEP_THREADS, 16) k_gicp_search(const PairDev* pairs, const PairState* states, GicpParamsDev prm,
+                                                                const LmSched* sched) {
   __shared__ float s_Tf[12];
+  const int total_items = sched->total_items;
+  const int n_active = sched->n_active;
+  for (int item = blockIdx.x; item < total_items; item += gridDim.x) {
+    int pair_id, blk;
+    locate_item(sched, n_active, item, pair_id, blk);
+    const PairState* st = &states[pair_id];
+    const int phase = st->phase;
+    if (phase != PH_LINEARIZE && phase != PH_FITNESS) continue;  // block-uniform
+    const PairDev& P = pairs[pair_id];
+    const bool seeded = st->n_lin > 0;  // P.corr holds the previous linearization's correspondences
+    __syncthreads();
+    if (threadIdx.x < 12) {
+      const int r = threadIdx.x / 4, cc = threadIdx.x % 4;
+      s_Tf[threadIdx.x] = phase == PH_FITNESS ? st->Tf[threadIdx.x] : (float)(cc < 3 ? st->R[3 * r + cc] : st->t[r]);
+    }
+    __syncthreads();
+    const int i = blk * STEP_THREADS + threadIdx.x;
+    if (i >= P.src.n) continue;
+    const float4 p = P.src.pts[i];
+    float qx, qy, qz;
+    if (phase == PH_LINEARIZE) {
+      // trans_f * p, summation order ((r0 x + r1 y) + r2 z) + t, no fma (SURVEY App. A.4)
+      qx = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(s_Tf[0], p.x), __fmul_rn(s_Tf[1], p.y)), __fmul_rn(s_Tf[2], p.z)), s_Tf[3]);
+      qy = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(s_Tf[4], p.x), __fmul_rn(s_Tf[5], p.y)), __fmul_rn(s_Tf[6], p.z)), s_Tf[7]);
+      qz = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(s_Tf[8], p.x), __fmul_rn(s_Tf[9], p.y)), __fmul_rn(s_Tf[10], p.z)), s_Tf[11]);
+    } else {  // pcl::transformPointCloud fp32 order x*c0 + (y*c1 + (z*c2 + c3))
+      qx = __fadd_rn(__fmul_rn(s_Tf[0], p.x), __fadd_rn(__fmul_rn(s_Tf[1], p.y), __fadd_rn(__fmul_rn(s_Tf[2], p.z), s_Tf[3])));
+      qy = __fadd_rn(__fmul_rn(s_Tf[4], p.x), __fadd_rn(__fmul_rn(s_Tf[5], p.y), __fadd_rn(__fmul_rn(s_Tf[6], p.z), s_Tf[7])));
+      qz = __fadd_rn(__fmul_rn(s_Tf[8], p.x), __fadd_rn(__fmul_rn(s_Tf[9], p.y), __fadd_rn(__fmul_rn(s_Tf[10], p.z), s_Tf[11])));
+    }
+    KnnSet<1> res;
+    res.init();
+    if (seeded) {  // last iteration's correspondence is almost always still the nearest point: start with its bound
+      const int pp = P.corr[i];
+      if (pp >= 0) {
+        const float4 t = __ldg(&P.tgt.pts[pp]);
+        res.d[0] = dist2_rn(qx, qy, qz, t.x, t.y, t.z);
+        res.p[0] = pp;
+      }
+    }
+    knn_search<1>(P.tgt, qx, qy, qz, res);
+    P.sqd[i] = res.d[0];
+    if (phase == PH_LINEARIZE) P.corr[i] = ((double)res.d[0] < prm.max_corr_dist2) ? res.p[0] : -1;
+  }
+}
+
+__global__ void __launch_bounds__(STEP_THREADS, 8) k_gicp_accum(const PairDev* pairs, PairState* states, GicpParamsDev prm,
+                                                              LmSched* sched) {
+  __shared__ double s_T[12];
   __shared__ double s_red[STEP_THREADS / 32][NRED];
   __shared__ bool s_last;
   // the schedule is stable for the whole step: only the LAST block to finish rewrites it (see the end of the kernel)
   const int total_items = sched->total_items;
   const int n_active = sched->n_active;
   for (int item = blockIdx.x; item < total_items; item += gridDim.x) {
-  // work item -> (active pair, block of that pair): binary search of the exclusive prefix (block-uniform)
-  int lo = 0, hi = n_active - 1;
-  while (lo < hi) {
-    const int mid = (lo + hi + 1) >> 1;
-    if (__ldg(&sched->prefix[mid]) <= item) lo = mid; else hi = mid - 1;
-  }
-  const int pair_id = __ldg(&sched->active[lo]);
-  const int blk = item - __ldg(&sched->prefix[lo]);
+  int pair_id, blk;
+  locate_item(sched, n_active, item, pair_id, blk);
   const PairDev& P = pairs[pair_id];
   PairState* st = &states[pair_id];
   const int N = P.src.n;
   const int nblk = (N + STEP_THREADS - 1) / STEP_THREADS;
   const int phase = st->phase;  // written by the previous step's controller; PH_DONE pairs are not in the list
-  const bool seeded = st->n_lin > 0;  // P.corr holds the previous linearization's correspondences
 
   __syncthreads();  // the previous item's shared state is no longer needed
   if (threadIdx.x < 12) {
@@ -458,7 +515,6 @@ __global__ void __launch_bounds__(STEP_THREADS, 8) k_gicp_step(const PairDev* pa
     if (phase == PH_TRIAL) v = cc < 3 ? st->Rt[3 * r + cc] : st->tt[r];
     else v = cc < 3 ? st->R[3 * r + cc] : st->t[r];
     s_T[threadIdx.x] = v;
-    s_Tf[threadIdx.x] = phase == PH_FITNESS ? st->Tf[threadIdx.x] : (float)v;
   }
   __syncthreads();
 
@@ -469,27 +525,10 @@ __global__ void __launch_bounds__(STEP_THREADS, 8) k_gicp_step(const PairDev* pa
   for (int k = 0; k < NRED; k++) v[k] = 0.0;
 
   if (i < N) {
-    const float4 p = P.src.pts[i];
     if (phase == PH_LINEARIZE) {
-      // trans_f * p, summation order ((r0 x + r1 y) + r2 z) + t, no fma (SURVEY App. A.4)
-      const float qx = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(s_Tf[0], p.x), __fmul_rn(s_Tf[1], p.y)), __fmul_rn(s_Tf[2], p.z)), s_Tf[3]);
-      const float qy = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(s_Tf[4], p.x), __fmul_rn(s_Tf[5], p.y)), __fmul_rn(s_Tf[6], p.z)), s_Tf[7]);
-      const float qz = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(s_Tf[8], p.x), __fmul_rn(s_Tf[9], p.y)), __fmul_rn(s_Tf[10], p.z)), s_Tf[11]);
-      KnnSet<1> res;
-      res.init();
-      if (seeded) {  // last iteration's correspondence is almost always still the nearest point: start with its bound
-        const int pp = P.corr[i];
-        if (pp >= 0) {
-          const float4 t = __ldg(&P.tgt.pts[pp]);
-          res.d[0] = dist2_rn(qx, qy, qz, t.x, t.y, t.z);
-          res.p[0] = pp;
-        }
-      }
-      knn_search<1>(P.tgt, qx, qy, qz, res);
-      const int pos = ((double)res.d[0] < prm.max_corr_dist2) ? res.p[0] : -1;
-      P.corr[i] = pos;
-      P.sqd[i] = res.d[0];
+      const int pos = P.corr[i];  // this step's k_gicp_search
       if (pos >= 0) {
+        const float4 p = P.src.pts[i];
         double R[9];
 #pragma unroll
         for (int r = 0; r < 3; r++)
@@ -540,6 +579,7 @@ __global__ void __launch_bounds__(STEP_THREADS, 8) k_gicp_step(const PairDev* pa
     } else if (phase == PH_TRIAL) {
       const int pos = P.corr[i];
       if (pos >= 0) {
+        const float4 p = P.src.pts[i];
         const float4 pbt = __ldg(&P.tgt.pts[pos]);
         const double ax = p.x, ay = p.y, az = p.z;
         const double e0 = (double)pbt.x - (s_T[0] * ax + s_T[1] * ay + s_T[2] * az + s_T[3]);
@@ -552,22 +592,8 @@ __global__ void __launch_bounds__(STEP_THREADS, 8) k_gicp_step(const PairDev* pa
         const double Me2 = m23.x * e0 + m45.x * e1 + m45.y * e2;
         v[0] = e0 * Me0 + e1 * Me1 + e2 * Me2;
       }
-    } else {  // PH_FITNESS: pcl::transformPointCloud fp32 order x*c0 + (y*c1 + (z*c2 + c3)), then 1-NN
-      const float qx = __fadd_rn(__fmul_rn(s_Tf[0], p.x), __fadd_rn(__fmul_rn(s_Tf[1], p.y), __fadd_rn(__fmul_rn(s_Tf[2], p.z), s_Tf[3])));
-      const float qy = __fadd_rn(__fmul_rn(s_Tf[4], p.x), __fadd_rn(__fmul_rn(s_Tf[5], p.y), __fadd_rn(__fmul_rn(s_Tf[6], p.z), s_Tf[7])));
-      const float qz = __fadd_rn(__fmul_rn(s_Tf[8], p.x), __fadd_rn(__fmul_rn(s_Tf[9], p.y), __fadd_rn(__fmul_rn(s_Tf[10], p.z), s_Tf[11])));
-      KnnSet<1> res;
-      res.init();
-      if (seeded) {
-        const int pp = P.corr[i];
-        if (pp >= 0) {
-          const float4 t = __ldg(&P.tgt.pts[pp]);
-          res.d[0] = dist2_rn(qx, qy, qz, t.x, t.y, t.z);
-          res.p[0] = pp;
-        }
-      }
-      knn_search<1>(P.tgt, qx, qy, qz, res);
-      v[0] = (double)res.d[0];
+    } else {  // PH_FITNESS: mean of the 1-NN d^2 this step's k_gicp_search found
+      v[0] = (double)P.sqd[i];
     }
   }
 
@@ -777,10 +803,13 @@ void launch_gicp_init(const PairDev* pairs, PairState* states, const double* d_g
   k_gicp_init<<<1, 256, 0, s>>>(pairs, states, d_guess, count, prm, sched);
 }
 
-// One LM step over every still-active pair.  `blocks`: persistent grid size (work items are strided over it); the
-// kernel is correct for any value >= 1.
-void launch_gicp_step(const PairDev* pairs, PairState* states, int blocks, const GicpParamsDev& prm, LmSched* sched, cudaStream_t s) {
-  k_gicp_step<<<blocks, STEP_THREADS, 0, s>>>(pairs, states, prm, sched);
+// One LM step over every still-active pair = the search kernel + the accumulate kernel.  blocks_*: persistent grid sizes
+// (work items are strided over them); both kernels are correct for any value >= 1.  Returns the launches issued.
+int launch_gicp_step(const PairDev* pairs, PairState* states, int blocks_search, int blocks_accum, const GicpParamsDev& prm,
+                     LmSched* sched, cudaStream_t s) {
+  k_gicp_search<<<blocks_search, STEP_THREADS, 0, s>>>(pairs, states, prm, sched);
+  k_gicp_accum<<<blocks_accum, STEP_THREADS, 0, s>>>(pairs, states, prm, sched);
+  return 2;
 }
 
 int launch_knn_queries(const CloudDev& c, const float* d_q, int nq, int qstride, int k, int* idx, float* d2, cudaStream_t s, int brute) {
