@@ -21,10 +21,11 @@ namespace b200 {
 int launch_index_build(const CloudDev* d_clouds, int count, int max_n, cudaStream_t s);
 size_t radix_sort_ws_bytes(int n, int key_bits);
 int launch_covariances(const CloudDev* d_clouds, int count, int max_n, int k, int method, cudaStream_t s);
-void launch_gicp_init(const PairDev* pairs, PairState* states, const double* d_guess, int count, const GicpParamsDev& prm,
-                      LmSched* sched, cudaStream_t s);
-int launch_gicp_step(const PairDev* pairs, PairState* states, int blocks_search, int blocks_accum, const GicpParamsDev& prm, LmSched* sched,
-                     cudaStream_t s);
+void launch_gicp_init(const PairDev* pairs, PairState* states, const double* d_guess, LmCall* call, LmSched* sched, cudaStream_t s);
+int launch_gicp_step(const PairDev* pairs, PairState* states, int blocks_search, int blocks_accum, LmCall* call, LmSched* sched, cudaStream_t s);
+cudaError_t lm_graph_build(LmGraph* g, const PairDev* pairs, PairState* states, const double* guess, LmCall* call, LmSched* sched,
+                           int blocks_search, int blocks_accum);
+void lm_graph_destroy(LmGraph* g);
 int launch_knn_queries(const CloudDev& c, const float* d_q, int nq, int qstride, int k, int* idx, float* d2, cudaStream_t s, int brute);
 void launch_transform_out(const CloudDev& c, const float* d_Tf, float* d_out3, cudaStream_t s);
 void launch_set_covariances(const CloudDev& c, const double* d_cov9, cudaStream_t s);
@@ -64,12 +65,23 @@ struct b200reg_ctx {
   cudaMemPool_t pool = nullptr;        // per-context pool: reuse never adds dependencies on another context's streams
   int pipeline_chunks = 4;
   int sm_count = 148;
-  LmSched* h_sched = nullptr;  // pinned mirror of the schedule header the LM loop polls
+  // persistent arena of the batched LM solve: every kernel argument of the solve's CUDA graph points in here, so the graph is
+  // instantiated once and re-launched by every b200reg_gicp_align call until a larger batch makes the arena grow
+  struct LmArena {
+    int cap = 0;
+    PairDev* d_pairs = nullptr;
+    PairState* d_states = nullptr;
+    LmSched* d_sched = nullptr;  // header + active[cap] + prefix[cap + 1]
+    double* d_guess = nullptr;   // [16 * cap]
+    LmCall* d_call = nullptr;
+    LmCall* h_call = nullptr;    // pinned staging
+    PairState* h_states = nullptr;  // pinned read-back
+    LmGraph graph;
+  } lm;
   // the path's one collective (b200reg_comm_*): NCCL communicator of this rank
   ncclComm_t comm = nullptr;
   int rank = -1, world = 1;
   int64_t launches = 0;
-  int step_chunk = 8;      // step kernels issued between two host polls
   // optional per-kernel-family timing with CUDA events on the launching stream
   bool profiling = false;
   struct Span { int cls; cudaEvent_t a, b; };
@@ -156,6 +168,50 @@ struct b200reg_cloud {
 
 static size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
+static void lm_arena_free(b200reg_ctx* c) {
+  auto& a = c->lm;
+  lm_graph_destroy(&a.graph);
+  if (a.d_pairs) cudaFree(a.d_pairs);
+  if (a.d_states) cudaFree(a.d_states);
+  if (a.d_sched) cudaFree(a.d_sched);
+  if (a.d_guess) cudaFree(a.d_guess);
+  if (a.d_call) cudaFree(a.d_call);
+  if (a.h_call) cudaFreeHost(a.h_call);
+  if (a.h_states) cudaFreeHost(a.h_states);
+  a = b200reg_ctx::LmArena();
+}
+
+// make the arena hold `count` pairs and make sure its graph exists
+static int lm_arena_ensure(b200reg_ctx* c, int count) {
+  auto& a = c->lm;
+  if (count > a.cap) {
+    CU(cudaStreamSynchronize(c->stream));  // nothing of an earlier solve may still read the old buffers
+    lm_arena_free(c);
+    const int cap = std::max(16, count + count / 2);
+    CU(cudaMalloc(&a.d_pairs, sizeof(PairDev) * cap));
+    CU(cudaMalloc(&a.d_states, sizeof(PairState) * cap));
+    CU(cudaMalloc((void**)&a.d_sched, 64 + sizeof(int) * (2 * (size_t)cap + 1)));
+    CU(cudaMalloc(&a.d_guess, sizeof(double) * 16 * cap));
+    CU(cudaMalloc(&a.d_call, sizeof(LmCall)));
+    CU(cudaMallocHost(&a.h_call, sizeof(LmCall)));
+    CU(cudaMallocHost(&a.h_states, sizeof(PairState) * cap));
+    LmSched hs;
+    memset(&hs, 0, sizeof(hs));
+    static_assert(sizeof(LmSched) <= 64, "LmSched header");
+    hs.active = (int*)((char*)a.d_sched + 64);
+    hs.prefix = hs.active + cap;
+    CU(cudaMemcpy(a.d_sched, &hs, sizeof(hs), cudaMemcpyHostToDevice));
+    a.cap = cap;
+  }
+  if (!a.graph.exec) {
+    // persistent grids: as many blocks as can be resident (search: 16 per SM at 32 registers, accumulate: 8 per SM);
+    // blocks beyond the current number of work items exit at once
+    const cudaError_t e = lm_graph_build(&a.graph, a.d_pairs, a.d_states, a.d_guess, a.d_call, a.d_sched, c->sm_count * 16, c->sm_count * 8);
+    if (e != cudaSuccess) return fail(B200REG_ECUDA, std::string("building the LM graph: ") + cudaGetErrorString(e));
+  }
+  return B200REG_OK;
+}
+
 extern "C" {
 
 void b200reg_default_gicp_params(b200reg_gicp_params* p) {
@@ -214,7 +270,6 @@ int b200reg_ctx_create(int device, b200reg_ctx** out) {
   uint64_t thr = UINT64_MAX;
   CU(cudaMemPoolSetAttribute(c->pool, cudaMemPoolAttrReleaseThreshold, &thr));
   CU(cudaDeviceGetAttribute(&c->sm_count, cudaDevAttrMultiProcessorCount, device));
-  CU(cudaMallocHost(&c->h_sched, sizeof(LmSched)));
   undo.ok = true;
   *out = c;
   return B200REG_OK;
@@ -225,7 +280,7 @@ int b200reg_ctx_destroy(b200reg_ctx* c) {
   cudaSetDevice(c->device);
   if (c->stream) cudaStreamSynchronize(c->stream);
   if (c->comm) b200reg_comm_destroy(c);
-  if (c->h_sched) cudaFreeHost(c->h_sched);
+  lm_arena_free(c);
   if (c->own_stream) cudaStreamDestroy(c->own_stream);
   if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
   if (c->pool) cudaMemPoolDestroy(c->pool);
@@ -490,15 +545,18 @@ static GicpParamsDev to_dev(const b200reg_gicp_params& p) {
 
 struct PairWork {  // device memory comes from the caller's Scratch and goes back with it
   std::vector<PairDev> pairs;
-  PairDev* d_pairs = nullptr;
+  PairDev* d_pairs = nullptr;     // only with own_arrays (the debug taps): scratch copies of the solve's argument arrays
   PairState* d_states = nullptr;
   LmSched* d_sched = nullptr;
+  LmCall* d_call = nullptr;
   LmSched sched_host;  // staging for the header upload (lives as long as the PairWork)
+  LmCall call_host;
   int max_n = 0;
   long total_blocks = 0;  // work items of one step with every pair active
 };
 
-static int make_pair_work(b200reg_ctx* c, int count, b200reg_cloud* const* src, b200reg_cloud* const* tgt, PairWork& w, Scratch& scratch) {
+static int make_pair_work(b200reg_ctx* c, int count, b200reg_cloud* const* src, b200reg_cloud* const* tgt, PairWork& w, Scratch& scratch,
+                          bool own_arrays, const GicpParamsDev* prm) {
   cudaStream_t s = c->stream;
   w.pairs.resize(count);
   for (int i = 0; i < count; i++) {
@@ -521,8 +579,16 @@ static int make_pair_work(b200reg_ctx* c, int count, b200reg_cloud* const* src, 
     w.max_n = std::max(w.max_n, N);
     w.total_blocks += nblk;
   }
+  if (!own_arrays) return B200REG_OK;  // b200reg_gicp_align: the argument arrays live in the context's LM arena
   CU(scratch.alloc((void**)&w.d_pairs, sizeof(PairDev) * count));
   CU(scratch.alloc((void**)&w.d_states, sizeof(PairState) * count));
+  CU(scratch.alloc((void**)&w.d_call, sizeof(LmCall)));
+  memset(&w.call_host, 0, sizeof(LmCall));
+  w.call_host.count = count;
+  w.call_host.has_guess = 1;
+  w.call_host.max_steps = 1 << 30;
+  w.call_host.prm = *prm;
+  CU(cudaMemcpyAsync(w.d_call, &w.call_host, sizeof(LmCall), cudaMemcpyHostToDevice, s));
   {  // schedule header + active[count] + prefix[count + 1]
     char* sm = nullptr;
     CU(scratch.alloc((void**)&sm, 64 + sizeof(int) * (2 * (size_t)count + 1)));
@@ -562,41 +628,37 @@ int b200reg_gicp_align(b200reg_ctx* c, int count, b200reg_cloud* const* src, b20
         (rc = b200reg_clouds_covariances_ex(c, (int)need.size(), need.data(), params->k_correspondences, params->regularization)))
       return rc;
   }
-  PairWork w;
-  if ((rc = make_pair_work(c, count, src, tgt, w, scratch))) return rc;
   const GicpParamsDev prm = to_dev(*params);
-  double* d_guess = nullptr;
-  if (guess16) {
-    CU(scratch.alloc((void**)&d_guess, sizeof(double) * 16 * count));
-    CU(cudaMemcpyAsync(d_guess, guess16, sizeof(double) * 16 * count, cudaMemcpyHostToDevice, s));
-  }
-  launch_gicp_init(w.d_pairs, w.d_states, d_guess, count, prm, w.d_sched, s);
-  c->launches++;
+  PairWork w;
+  if ((rc = make_pair_work(c, count, src, tgt, w, scratch, false, nullptr))) return rc;
+  if ((rc = lm_arena_ensure(c, count))) return rc;
+  auto& A = c->lm;
+  // per-call inputs of the graph: pair descriptors, guesses, the call record
+  CU(cudaMemcpyAsync(A.d_pairs, w.pairs.data(), sizeof(PairDev) * count, cudaMemcpyHostToDevice, s));
+  if (guess16) CU(cudaMemcpyAsync(A.d_guess, guess16, sizeof(double) * 16 * count, cudaMemcpyHostToDevice, s));
+  LmCall& hc = *A.h_call;
+  memset(&hc, 0, sizeof(hc));
+  hc.count = count;
+  hc.has_guess = guess16 ? 1 : 0;
   // worst case: every outer iteration burns lm_max_iterations trials, plus the fitness pass
-  const long max_steps = (long)std::max(params->max_iterations, 0) * (1 + std::max(params->lm_max_iterations, 1)) + 2;
-  long steps = 0;
-  // The step kernel walks a device-side list of (active pair, block) work items and its last block rebuilds that list,
-  // so a finished pair costs nothing from the next step on; the host only sizes the persistent grid and polls `done`.
-  const long cap_s = (long)c->sm_count * 16, cap_a = (long)c->sm_count * 8;  // resident blocks of the search / accumulate kernels
-  long items = w.total_blocks;
-  for (;;) {
-    {
-      ProfScope ps(c, CLS_STEP);
-      const int bs = (int)std::max(1L, std::min(items, cap_s)), ba = (int)std::max(1L, std::min(items, cap_a));
-      for (int j = 0; j < c->step_chunk; j++) {
-        c->launches += launch_gicp_step(w.d_pairs, w.d_states, bs, ba, prm, w.d_sched, s);
-        steps++;
-      }
-    }
-    CU(cudaMemcpyAsync(c->h_sched, w.d_sched, sizeof(LmSched), cudaMemcpyDeviceToHost, s));
-    CU(cudaStreamSynchronize(s));
-    if (c->h_sched->done >= count) break;
-    items = c->h_sched->total_items;
-    if (steps > max_steps) return fail(B200REG_ESTATE, "LM state machine did not terminate");
+  hc.max_steps = std::max(params->max_iterations, 0) * (1 + std::max(params->lm_max_iterations, 1)) + 2;
+  hc.cond_handle = A.graph.cond_handle;
+  hc.prm = prm;
+  CU(cudaMemcpyAsync(A.d_call, A.h_call, sizeof(LmCall), cudaMemcpyHostToDevice, s));
+  {
+    // init kernel + device-side while loop over {search, accumulate}: ONE launch, ONE synchronisation per solve
+    ProfScope ps(c, CLS_STEP);
+    CU(cudaGraphLaunch(A.graph.exec, s));
   }
-  std::vector<PairState> states(count);
-  CU(cudaMemcpyAsync(states.data(), w.d_states, sizeof(PairState) * count, cudaMemcpyDeviceToHost, s));
+  PairState* states = A.h_states;
+  CU(cudaMemcpyAsync(states, A.d_states, sizeof(PairState) * count, cudaMemcpyDeviceToHost, s));
+  CU(cudaMemcpyAsync(A.h_call, A.d_call, sizeof(LmCall), cudaMemcpyDeviceToHost, s));
+  LmSched hsched;
+  CU(cudaMemcpyAsync(&hsched, A.d_sched, sizeof(LmSched), cudaMemcpyDeviceToHost, s));
   CU(cudaStreamSynchronize(s));
+  c->launches += 1 + 2 * (int64_t)hsched.steps;  // init + (search, accumulate) per executed step, counted by the device
+  if (c->profiling) c->prof_launches[CLS_STEP] += 1 + 2 * (int64_t)hsched.steps;
+  if (A.h_call->overrun) return fail(B200REG_ESTATE, "LM state machine did not terminate");
   for (int i = 0; i < count; i++) {
     const PairState& st = states[i];
     b200reg_result& r = out[i];
@@ -816,17 +878,17 @@ int b200reg_linearize(b200reg_ctx* c, const b200reg_cloud* src, const b200reg_cl
   b200reg_cloud* sp = const_cast<b200reg_cloud*>(src);
   b200reg_cloud* tp = const_cast<b200reg_cloud*>(tgt);
   int rc;
-  if ((rc = make_pair_work(c, 1, &sp, &tp, w, scratch))) return rc;
   b200reg_gicp_params p;
   b200reg_default_gicp_params(&p);
   p.max_corr_dist = max_corr_dist;
   const GicpParamsDev prm = to_dev(p);
+  if ((rc = make_pair_work(c, 1, &sp, &tp, w, scratch, true, &prm))) return rc;
   double* d_guess = nullptr;
   CU(scratch.alloc((void**)&d_guess, sizeof(double) * 16));
   CU(cudaMemcpyAsync(d_guess, T16, sizeof(double) * 16, cudaMemcpyHostToDevice, s));
-  launch_gicp_init(w.d_pairs, w.d_states, d_guess, 1, prm, w.d_sched, s);
+  launch_gicp_init(w.d_pairs, w.d_states, d_guess, w.d_call, w.d_sched, s);
   const int tap_blocks = (int)std::min(w.total_blocks, (long)c->sm_count * 8);
-  c->launches += 1 + launch_gicp_step(w.d_pairs, w.d_states, tap_blocks, tap_blocks, prm, w.d_sched, s);  // exactly one linearize pass
+  c->launches += 1 + launch_gicp_step(w.d_pairs, w.d_states, tap_blocks, tap_blocks, w.d_call, w.d_sched, s);  // exactly one linearize pass
   PairState st;
   const int N = src->dev.n, M = tgt->dev.n;
   std::vector<int> corr(N);
@@ -862,17 +924,17 @@ int b200reg_compute_error(b200reg_ctx* c, const b200reg_cloud* src, const b200re
   b200reg_cloud* sp = const_cast<b200reg_cloud*>(src);
   b200reg_cloud* tp = const_cast<b200reg_cloud*>(tgt);
   int rc;
-  if ((rc = make_pair_work(c, 1, &sp, &tp, w, scratch))) return rc;
   b200reg_gicp_params p;
   b200reg_default_gicp_params(&p);
   p.max_corr_dist = max_corr_dist;
   const GicpParamsDev prm = to_dev(p);
+  if ((rc = make_pair_work(c, 1, &sp, &tp, w, scratch, true, &prm))) return rc;
   double* d_guess = nullptr;
   CU(scratch.alloc((void**)&d_guess, sizeof(double) * 16));
   CU(cudaMemcpyAsync(d_guess, T_lin16, sizeof(double) * 16, cudaMemcpyHostToDevice, s));
   const int blocks = (int)std::min(w.total_blocks, (long)c->sm_count * 8);
-  launch_gicp_init(w.d_pairs, w.d_states, d_guess, 1, prm, w.d_sched, s);
-  launch_gicp_step(w.d_pairs, w.d_states, blocks, blocks, prm, w.d_sched, s);  // linearize: correspondences + Mahalanobis, phase -> TRIAL
+  launch_gicp_init(w.d_pairs, w.d_states, d_guess, w.d_call, w.d_sched, s);
+  launch_gicp_step(w.d_pairs, w.d_states, blocks, blocks, w.d_call, w.d_sched, s);  // linearize: correspondences + Mahalanobis, phase -> TRIAL
   // overwrite the trial pose the LM controller prepared with the caller's
   double Rt[9], tt[3];
   for (int a = 0; a < 3; a++) {
@@ -881,7 +943,7 @@ int b200reg_compute_error(b200reg_ctx* c, const b200reg_cloud* src, const b200re
   }
   CU(cudaMemcpyAsync((char*)w.d_states + offsetof(PairState, Rt), Rt, sizeof(Rt), cudaMemcpyHostToDevice, s));
   CU(cudaMemcpyAsync((char*)w.d_states + offsetof(PairState, tt), tt, sizeof(tt), cudaMemcpyHostToDevice, s));
-  launch_gicp_step(w.d_pairs, w.d_states, blocks, blocks, prm, w.d_sched, s);  // compute_error at the trial pose
+  launch_gicp_step(w.d_pairs, w.d_states, blocks, blocks, w.d_call, w.d_sched, s);  // compute_error at the trial pose
   c->launches += 5;
   PairState st;
   CU(cudaMemcpyAsync(&st, w.d_states, sizeof(PairState), cudaMemcpyDeviceToHost, s));

@@ -200,7 +200,7 @@ __device__ void lm_update(PairState* st, const double* sums, const GicpParamsDev
 }
 
 // Rebuild the work-item schedule from the pairs' phases (one block, any size that is a multiple of 32).
-__device__ void sched_rebuild(const PairDev* pairs, const PairState* states, LmSched* sched) {
+__device__ void sched_rebuild(const PairDev* pairs, const PairState* states, LmSched* sched, LmCall* call) {
   __shared__ int s_wsum[32];
   __shared__ int s_wcnt[32];
   __shared__ int s_carry_items, s_carry_cnt;
@@ -253,12 +253,23 @@ __device__ void sched_rebuild(const PairDev* pairs, const PairState* states, LmS
     sched->n_active = s_carry_cnt;
     sched->total_items = s_carry_items;
     sched->arrive = 0;
+    int again = s_carry_cnt > 0 ? 1 : 0;
+    if (again && sched->steps > call->max_steps) {  // the state machine always terminates; this only guards the device loop
+      call->overrun = 1;
+      again = 0;
+    }
     __threadfence();
+    // the while node of the solve's CUDA graph runs the two step kernels again as long as a pair is active
+    if (call->cond_handle) cudaGraphSetConditional((cudaGraphConditionalHandle)call->cond_handle, again);
   }
 }
 
-__global__ void __launch_bounds__(256) k_gicp_init(const PairDev* pairs, PairState* states, const double* guess16, int count,
-                                                    GicpParamsDev prm, LmSched* sched) {
+__global__ void __launch_bounds__(256) k_gicp_init(const PairDev* pairs, PairState* states, const double* guess_buf, LmCall* call,
+                                                    LmSched* sched) {
+  const int count = call->count;
+  const double* guess16 = call->has_guess ? guess_buf : nullptr;
+  const GicpParamsDev prm = call->prm;
+  if (threadIdx.x == 0) call->overrun = 0;
   for (int p = threadIdx.x; p < count; p += blockDim.x) {
     PairState* st = &states[p];
     for (int i = 0; i < 3; i++) {
@@ -288,7 +299,7 @@ __global__ void __launch_bounds__(256) k_gicp_init(const PairDev* pairs, PairSta
   }
   __threadfence();
   __syncthreads();
-  sched_rebuild(pairs, states, sched);
+  sched_rebuild(pairs, states, sched, call);
 }
 
 // ---------------------------------------------------------------------------------------
@@ -442,9 +453,10 @@ __device__ __forceinline__ void locate_item(const LmSched* sched, int n_active, 
   blk = item - __ldg(&sched->prefix[lo]);
 }
 
-__global__ void __launch_bounds__(STEP_THREADS, 16) k_gicp_search(const PairDev* pairs, const PairState* states, GicpParamsDev prm,
+__global__ void __launch_bounds__(STEP_THREADS, 16) k_gicp_search(const PairDev* pairs, const PairState* states, const LmCall* call,
                                                                 const LmSched* sched) {
   __shared__ float s_Tf[12];
+  const double max_corr_dist2 = call->prm.max_corr_dist2;
   const int total_items = sched->total_items;
   const int n_active = sched->n_active;
   for (int item = blockIdx.x; item < total_items; item += gridDim.x) {
@@ -487,12 +499,11 @@ __global__ void __launch_bounds__(STEP_THREADS, 16) k_gicp_search(const PairDev*
     }
     knn_search<1>(P.tgt, qx, qy, qz, res);
     P.sqd[i] = res.d[0];
-    if (phase == PH_LINEARIZE) P.corr[i] = ((double)res.d[0] < prm.max_corr_dist2) ? res.p[0] : -1;
+    if (phase == PH_LINEARIZE) P.corr[i] = ((double)res.d[0] < max_corr_dist2) ? res.p[0] : -1;
   }
 }
 
-__global__ void __launch_bounds__(STEP_THREADS, 8) k_gicp_accum(const PairDev* pairs, PairState* states, GicpParamsDev prm,
-                                                              LmSched* sched) {
+__global__ void __launch_bounds__(STEP_THREADS, 8) k_gicp_accum(const PairDev* pairs, PairState* states, LmCall* call, LmSched* sched) {
   __shared__ double s_T[12];
   __shared__ double s_red[STEP_THREADS / 32][NRED];
   __shared__ bool s_last;
@@ -653,7 +664,7 @@ __global__ void __launch_bounds__(STEP_THREADS, 8) k_gicp_accum(const PairDev* p
         sums[k] = s;
       }
       st->arrive = 0;
-      lm_update(st, sums, prm, phase, N, &sched->done);
+      lm_update(st, sums, call->prm, phase, N, &sched->done);
       __threadfence();
     }
   }
@@ -669,7 +680,8 @@ __global__ void __launch_bounds__(STEP_THREADS, 8) k_gicp_accum(const PairDev* p
   if (!s_last) return;
   __threadfence();
   if (threadIdx.x == 0) sched->steps++;
-  sched_rebuild(pairs, states, sched);
+  __syncthreads();
+  sched_rebuild(pairs, states, sched, call);
 }
 
 // ---------------------------------------------------------------------------------------
@@ -798,18 +810,78 @@ int launch_covariances(const CloudDev* d_clouds, int count, int max_n, int k, in
   return 1;
 }
 
-void launch_gicp_init(const PairDev* pairs, PairState* states, const double* d_guess, int count, const GicpParamsDev& prm,
-                      LmSched* sched, cudaStream_t s) {
-  k_gicp_init<<<1, 256, 0, s>>>(pairs, states, d_guess, count, prm, sched);
+void launch_gicp_init(const PairDev* pairs, PairState* states, const double* d_guess, LmCall* call, LmSched* sched, cudaStream_t s) {
+  k_gicp_init<<<1, 256, 0, s>>>(pairs, states, d_guess, call, sched);
 }
 
 // One LM step over every still-active pair = the search kernel + the accumulate kernel.  blocks_*: persistent grid sizes
 // (work items are strided over them); both kernels are correct for any value >= 1.  Returns the launches issued.
-int launch_gicp_step(const PairDev* pairs, PairState* states, int blocks_search, int blocks_accum, const GicpParamsDev& prm,
-                     LmSched* sched, cudaStream_t s) {
-  k_gicp_search<<<blocks_search, STEP_THREADS, 0, s>>>(pairs, states, prm, sched);
-  k_gicp_accum<<<blocks_accum, STEP_THREADS, 0, s>>>(pairs, states, prm, sched);
+int launch_gicp_step(const PairDev* pairs, PairState* states, int blocks_search, int blocks_accum, LmCall* call, LmSched* sched,
+                     cudaStream_t s) {
+  k_gicp_search<<<blocks_search, STEP_THREADS, 0, s>>>(pairs, states, call, sched);
+  k_gicp_accum<<<blocks_accum, STEP_THREADS, 0, s>>>(pairs, states, call, sched);
   return 2;
+}
+
+// The whole solve as ONE CUDA graph: init kernel, then a WHILE node whose body is the two step kernels; the accumulate
+// kernel's last block sets the loop condition (cudaGraphSetConditional) from the device-side schedule.  The host launches
+// the graph once per solve and synchronises once -- no polling, no chunking (round 1 polled a counter every 8 launches).
+// All kernel arguments are pointers into the context's persistent LM arena, so the executable graph is reused by every call
+// until the arena grows.
+cudaError_t lm_graph_build(LmGraph* g, const PairDev* pairs, PairState* states, const double* guess, LmCall* call, LmSched* sched,
+                           int blocks_search, int blocks_accum) {
+  cudaError_t e;
+  if ((e = cudaGraphCreate(&g->graph, 0)) != cudaSuccess) return e;
+  cudaGraphNode_t n_init, n_while, n_search, n_accum;
+  {
+    void* args[] = {(void*)&pairs, (void*)&states, (void*)&guess, (void*)&call, (void*)&sched};
+    cudaKernelNodeParams kp = {};
+    kp.func = (void*)k_gicp_init;
+    kp.gridDim = dim3(1);
+    kp.blockDim = dim3(256);
+    kp.kernelParams = args;
+    if ((e = cudaGraphAddKernelNode(&n_init, g->graph, nullptr, 0, &kp)) != cudaSuccess) return e;
+  }
+  cudaGraphConditionalHandle h;
+  if ((e = cudaGraphConditionalHandleCreate(&h, g->graph, 1, cudaGraphCondAssignDefault)) != cudaSuccess) return e;
+  g->cond_handle = (unsigned long long)h;
+  cudaGraphNodeParams wp = {};
+  wp.type = cudaGraphNodeTypeConditional;
+  wp.conditional.handle = h;
+  wp.conditional.type = cudaGraphCondTypeWhile;
+  wp.conditional.size = 1;
+  if ((e = cudaGraphAddNode(&n_while, g->graph, &n_init, 1, &wp)) != cudaSuccess) return e;
+  cudaGraph_t body = wp.conditional.phGraph_out[0];
+  {
+    const PairState* cstates = states;
+    const LmCall* ccall = call;
+    const LmSched* csched = sched;
+    void* args[] = {(void*)&pairs, (void*)&cstates, (void*)&ccall, (void*)&csched};
+    cudaKernelNodeParams kp = {};
+    kp.func = (void*)k_gicp_search;
+    kp.gridDim = dim3(blocks_search);
+    kp.blockDim = dim3(STEP_THREADS);
+    kp.kernelParams = args;
+    if ((e = cudaGraphAddKernelNode(&n_search, body, nullptr, 0, &kp)) != cudaSuccess) return e;
+  }
+  {
+    void* args[] = {(void*)&pairs, (void*)&states, (void*)&call, (void*)&sched};
+    cudaKernelNodeParams kp = {};
+    kp.func = (void*)k_gicp_accum;
+    kp.gridDim = dim3(blocks_accum);
+    kp.blockDim = dim3(STEP_THREADS);
+    kp.kernelParams = args;
+    if ((e = cudaGraphAddKernelNode(&n_accum, body, &n_search, 1, &kp)) != cudaSuccess) return e;
+  }
+  return cudaGraphInstantiate(&g->exec, g->graph, 0);
+}
+
+void lm_graph_destroy(LmGraph* g) {
+  if (g->exec) cudaGraphExecDestroy(g->exec);
+  if (g->graph) cudaGraphDestroy(g->graph);
+  g->exec = nullptr;
+  g->graph = nullptr;
+  g->cond_handle = 0;
 }
 
 int launch_knn_queries(const CloudDev& c, const float* d_q, int nq, int qstride, int k, int* idx, float* d2, cudaStream_t s, int brute) {

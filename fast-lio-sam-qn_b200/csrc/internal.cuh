@@ -110,12 +110,29 @@ struct LmSched {
   int* prefix;            // [n_pairs + 1] exclusive prefix of their block counts
 };
 
+// Per-call parameters of one batched LM solve, read by the kernels from device memory (not passed by value) so that the
+// CUDA graph of the solve can be instantiated once per context and re-launched for every call.
+struct LmCall {
+  int count;            // pairs of this call
+  int has_guess;        // guess16 holds count x 16 doubles (row-major); otherwise identity
+  int max_steps;        // safety cap on the number of step iterations of the device-side loop
+  int overrun;          // set by the device when max_steps was hit (a bug in the state machine, never expected)
+  unsigned long long cond_handle;  // cudaGraphConditionalHandle of the while node, 0 when the step kernels are launched directly
+  GicpParamsDev prm;
+};
+
 struct PairDev {
   CloudDev src, tgt;
   int* corr;       // [src.n] sorted target position or -1 (per sorted source position)
   float* sqd;      // [src.n]
   double* mahal;   // [6 * src.n]
   double* partial; // [nblocks * NRED]
+};
+
+struct LmGraph {  // host side: the instantiated graph of one context's LM solve (gicp.cu: lm_graph_build)
+  cudaGraph_t graph = nullptr;
+  cudaGraphExec_t exec = nullptr;
+  unsigned long long cond_handle = 0;
 };
 
 // ---- keyframe store / cloud assembly -------------------------------------------
