@@ -648,7 +648,21 @@ int b200reg_gicp_align(b200reg_ctx* c, int count, b200reg_cloud* const* src, b20
   hc.cond_handle = A.graph.cond_handle;
   hc.prm = prm;
   CU(cudaMemcpyAsync(A.d_call, A.h_call, sizeof(LmCall), cudaMemcpyHostToDevice, s));
-  {
+  static const bool no_graph = getenv("B200REG_LM_NO_GRAPH") != nullptr;  // profiling aid: Nsight Compute does not list kernels
+  if (no_graph) {                                                           // that run inside a conditional graph node
+    // the SAME kernels launched one by one, the host polling the schedule (what the while node does on the device)
+    ProfScope ps(c, CLS_STEP);
+    A.h_call->cond_handle = 0;
+    CU(cudaMemcpyAsync(A.d_call, A.h_call, sizeof(LmCall), cudaMemcpyHostToDevice, s));
+    launch_gicp_init(A.d_pairs, A.d_states, A.d_guess, A.d_call, A.d_sched, s);
+    for (;;) {
+      LmSched hs;
+      CU(cudaMemcpyAsync(&hs, A.d_sched, sizeof(LmSched), cudaMemcpyDeviceToHost, s));
+      CU(cudaStreamSynchronize(s));
+      if (hs.n_active == 0 || hs.steps > hc.max_steps) break;
+      launch_gicp_step(A.d_pairs, A.d_states, c->sm_count * 16, c->sm_count * 8, A.d_call, A.d_sched, s);
+    }
+  } else {
     // init kernel + device-side while loop over {search, accumulate}: ONE launch, ONE synchronisation per solve
     ProfScope ps(c, CLS_STEP);
     CU(cudaGraphLaunch(A.graph.exec, s));
