@@ -71,7 +71,7 @@ struct b200reg_ctx {
     int cap = 0;
     PairDev* d_pairs = nullptr;
     PairState* d_states = nullptr;
-    LmSched* d_sched = nullptr;  // header + active[cap] + prefix[cap + 1]
+    LmSched* d_sched = nullptr;  // header + slots[cap]
     double* d_guess = nullptr;   // [16 * cap]
     LmCall* d_call = nullptr;
     LmCall* h_call = nullptr;    // pinned staging
@@ -190,7 +190,7 @@ static int lm_arena_ensure(b200reg_ctx* c, int count) {
     const int cap = std::max(16, count + count / 2);
     CU(cudaMalloc(&a.d_pairs, sizeof(PairDev) * cap));
     CU(cudaMalloc(&a.d_states, sizeof(PairState) * cap));
-    CU(cudaMalloc((void**)&a.d_sched, 64 + sizeof(int) * (2 * (size_t)cap + 1)));
+    CU(cudaMalloc((void**)&a.d_sched, 64 + sizeof(LmSlot) * (size_t)cap));
     CU(cudaMalloc(&a.d_guess, sizeof(double) * 16 * cap));
     CU(cudaMalloc(&a.d_call, sizeof(LmCall)));
     CU(cudaMallocHost(&a.h_call, sizeof(LmCall)));
@@ -198,8 +198,7 @@ static int lm_arena_ensure(b200reg_ctx* c, int count) {
     LmSched hs;
     memset(&hs, 0, sizeof(hs));
     static_assert(sizeof(LmSched) <= 64, "LmSched header");
-    hs.active = (int*)((char*)a.d_sched + 64);
-    hs.prefix = hs.active + cap;
+    hs.slots = (LmSlot*)((char*)a.d_sched + 64);
     CU(cudaMemcpy(a.d_sched, &hs, sizeof(hs), cudaMemcpyHostToDevice));
     a.cap = cap;
   }
@@ -592,13 +591,12 @@ static int make_pair_work(b200reg_ctx* c, int count, b200reg_cloud* const* src, 
   w.call_host.max_steps = 1 << 30;
   w.call_host.prm = *prm;
   CU(cudaMemcpyAsync(w.d_call, &w.call_host, sizeof(LmCall), cudaMemcpyHostToDevice, s));
-  {  // schedule header + active[count] + prefix[count + 1]
+  {  // schedule header + slots[count]
     char* sm = nullptr;
-    CU(scratch.alloc((void**)&sm, 64 + sizeof(int) * (2 * (size_t)count + 1)));
+    CU(scratch.alloc((void**)&sm, 64 + sizeof(LmSlot) * (size_t)count));
     LmSched hs;
     memset(&hs, 0, sizeof(hs));
-    hs.active = (int*)(sm + 64);
-    hs.prefix = hs.active + count;
+    hs.slots = (LmSlot*)(sm + 64);
     w.d_sched = (LmSched*)sm;
     static_assert(sizeof(LmSched) <= 64, "LmSched header");
     w.sched_host = hs;

@@ -199,59 +199,45 @@ __device__ void lm_update(PairState* st, const double* sums, const GicpParamsDev
   }
 }
 
-// Rebuild the work-item schedule from the pairs' phases (one block, any size that is a multiple of 32).
+// Rebuild the slot list from the pairs' phases (one block, any size that is a multiple of 32); ascending pair order.
 __device__ void sched_rebuild(const PairDev* pairs, const PairState* states, LmSched* sched, LmCall* call) {
-  __shared__ int s_wsum[32];
   __shared__ int s_wcnt[32];
-  __shared__ int s_carry_items, s_carry_cnt;
+  __shared__ int s_carry_cnt, s_stride;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
   if (threadIdx.x == 0) {
-    s_carry_items = 0;
     s_carry_cnt = 0;
+    s_stride = 0;
   }
   __syncthreads();
   const int n = sched->n_pairs;
+  int my_max = 0;
   for (int base = 0; base < n; base += blockDim.x) {
     const int p = base + threadIdx.x;
-    int nblk = 0;
-    if (p < n && __ldcg(&states[p].phase) != PH_DONE) nblk = (pairs[p].src.n + STEP_THREADS - 1) / STEP_THREADS;
-    const int act = nblk > 0 ? 1 : 0;
-    int isum = nblk, csum = act;  // inclusive warp scans
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-      const int a = __shfl_up_sync(0xffffffffu, isum, o), b = __shfl_up_sync(0xffffffffu, csum, o);
-      if (lane >= o) {
-        isum += a;
-        csum += b;
-      }
+    int nblk = 0, phase = PH_DONE, seeded = 0;
+    if (p < n) {
+      nblk = (pairs[p].src.n + STEP_THREADS - 1) / STEP_THREADS;
+      my_max = max(my_max, nblk);
+      phase = __ldcg(&states[p].phase);
+      seeded = __ldcg(&states[p].n_lin) > 0;
     }
-    if (lane == 31) {
-      s_wsum[warp] = isum;
-      s_wcnt[warp] = csum;
-    }
+    const int act = (p < n && phase != PH_DONE) ? 1 : 0;
+    const unsigned bal = __ballot_sync(0xffffffffu, act);
+    if (lane == 0) s_wcnt[warp] = __popc(bal);
     __syncthreads();
-    int woff_i = s_carry_items, woff_c = s_carry_cnt;
-    for (int w = 0; w < warp; w++) {
-      woff_i += s_wsum[w];
-      woff_c += s_wcnt[w];
-    }
-    if (act) {
-      sched->active[woff_c + csum - 1] = p;
-      sched->prefix[woff_c + csum - 1] = woff_i + isum - nblk;
-    }
+    int woff = s_carry_cnt;
+    for (int w = 0; w < warp; w++) woff += s_wcnt[w];
+    if (act) sched->slots[woff + __popc(bal & ((1u << lane) - 1u))] = LmSlot{p, nblk, phase, seeded};
     __syncthreads();
-    if (threadIdx.x == 0) {
-      for (int w = 0; w < nw; w++) {
-        s_carry_items += s_wsum[w];
-        s_carry_cnt += s_wcnt[w];
-      }
-    }
+    if (threadIdx.x == 0)
+      for (int w = 0; w < nw; w++) s_carry_cnt += s_wcnt[w];
     __syncthreads();
   }
+  atomicMax(&s_stride, my_max);
+  __syncthreads();
   if (threadIdx.x == 0) {
-    sched->prefix[s_carry_cnt] = s_carry_items;
+    sched->stride = s_stride;
     sched->n_active = s_carry_cnt;
-    sched->total_items = s_carry_items;
+    sched->total_items = s_carry_cnt * s_stride;
     sched->arrive = 0;
     int again = s_carry_cnt > 0 ? 1 : 0;
     if (again && sched->steps > call->max_steps) {  // the state machine always terminates; this only guards the device loop
@@ -442,31 +428,38 @@ __global__ void __launch_bounds__(STEP_THREADS, (K <= 16 ? (HEAP ? 10 : 8) : 4))
 //                  App. A.6) and runs the LM controller; the last block of the STEP rebuilds the schedule from the pairs'
 //                  new phases -- no host round trip per iteration, finished pairs cost nothing from the next step on.
 // ---------------------------------------------------------------------------------------
-// work item -> (active pair, block of that pair): binary search of the exclusive prefix (block-uniform)
-__device__ __forceinline__ void locate_item(const LmSched* sched, int n_active, int item, int& pair_id, int& blk) {
-  int lo = 0, hi = n_active - 1;
-  while (lo < hi) {
-    const int mid = (lo + hi + 1) >> 1;
-    if (__ldg(&sched->prefix[mid]) <= item) lo = mid; else hi = mid - 1;
-  }
-  pair_id = __ldg(&sched->active[lo]);
-  blk = item - __ldg(&sched->prefix[lo]);
+// The step's slot list in shared memory (first LM_SMEM_SLOTS entries; beyond that straight from global memory).
+struct SlotView {
+  const LmSlot* g;
+  const LmSlot* sh;
+  __device__ __forceinline__ LmSlot get(int k) const { return k < LM_SMEM_SLOTS ? sh[k] : g[k]; }
+};
+__device__ __forceinline__ void load_slots(const LmSched* sched, int n_active, LmSlot* sh) {
+  const int4* src = reinterpret_cast<const int4*>(sched->slots);
+  int4* dst = reinterpret_cast<int4*>(sh);
+  for (int k = threadIdx.x; k < min(n_active, LM_SMEM_SLOTS); k += blockDim.x) dst[k] = __ldcg(&src[k]);
+  __syncthreads();
 }
 
 __global__ void __launch_bounds__(STEP_THREADS, 16) k_gicp_search(const PairDev* pairs, const PairState* states, const LmCall* call,
                                                                 const LmSched* sched) {
   __shared__ float s_Tf[12];
+  __shared__ __align__(16) LmSlot s_slots[LM_SMEM_SLOTS];
   const double max_corr_dist2 = call->prm.max_corr_dist2;
   const int total_items = sched->total_items;
   const int n_active = sched->n_active;
+  const int stride = sched->stride;
+  if ((int)blockIdx.x >= total_items) return;
+  load_slots(sched, n_active, s_slots);
+  const SlotView slots{sched->slots, s_slots};
   for (int item = blockIdx.x; item < total_items; item += gridDim.x) {
-    int pair_id, blk;
-    locate_item(sched, n_active, item, pair_id, blk);
-    const PairState* st = &states[pair_id];
-    const int phase = st->phase;
-    if (phase != PH_LINEARIZE && phase != PH_FITNESS) continue;  // block-uniform
-    const PairDev& P = pairs[pair_id];
-    const bool seeded = st->n_lin > 0;  // P.corr holds the previous linearization's correspondences
+    const int slot = item / stride, blk = item - slot * stride;
+    const LmSlot sl = slots.get(slot);
+    const int phase = sl.phase;
+    if (blk >= sl.nblk || (phase != PH_LINEARIZE && phase != PH_FITNESS)) continue;  // block-uniform
+    const PairState* st = &states[sl.pair];
+    const PairDev& P = pairs[sl.pair];
+    const bool seeded = sl.seeded != 0;  // P.corr holds the previous linearization's correspondences
     __syncthreads();
     if (threadIdx.x < 12) {
       const int r = threadIdx.x / 4, cc = threadIdx.x % 4;
@@ -507,17 +500,22 @@ __global__ void __launch_bounds__(STEP_THREADS, 8) k_gicp_accum(const PairDev* p
   __shared__ double s_T[12];
   __shared__ double s_red[STEP_THREADS / 32][NRED];
   __shared__ bool s_last;
+  __shared__ __align__(16) LmSlot s_slots[LM_SMEM_SLOTS];
   // the schedule is stable for the whole step: only the LAST block to finish rewrites it (see the end of the kernel)
   const int total_items = sched->total_items;
   const int n_active = sched->n_active;
+  const int stride = sched->stride;
+  load_slots(sched, n_active, s_slots);
+  const SlotView slots{sched->slots, s_slots};
   for (int item = blockIdx.x; item < total_items; item += gridDim.x) {
-  int pair_id, blk;
-  locate_item(sched, n_active, item, pair_id, blk);
-  const PairDev& P = pairs[pair_id];
-  PairState* st = &states[pair_id];
+  const int slot = item / stride, blk = item - slot * stride;
+  const LmSlot sl = slots.get(slot);
+  if (blk >= sl.nblk) continue;  // a shorter pair's padding item (block-uniform)
+  const PairDev& P = pairs[sl.pair];
+  PairState* st = &states[sl.pair];
   const int N = P.src.n;
-  const int nblk = (N + STEP_THREADS - 1) / STEP_THREADS;
-  const int phase = st->phase;  // written by the previous step's controller; PH_DONE pairs are not in the list
+  const int nblk = sl.nblk;
+  const int phase = sl.phase;  // written by the previous step's controller; PH_DONE pairs are not in the list
 
   __syncthreads();  // the previous item's shared state is no longer needed
   if (threadIdx.x < 12) {

@@ -96,18 +96,30 @@ struct PairState {
   int pad;
 };
 
-// Device-side schedule of one batched LM solve: the step kernel runs over WORK ITEMS (one 128-point block of one
-// still-active pair); the last block of every step rebuilds the list from the pairs' phases, so finished pairs cost
-// nothing from the next step on and the host (or a CUDA-graph while node) only ever looks at `done`.
+// Device-side schedule of one batched LM solve: the step kernels run over WORK ITEMS (one 128-point block of one
+// still-active pair).  Items are laid out with a uniform stride: item = slot * stride + block, slot indexing the list of
+// active pairs, stride = the largest block count of any pair of the call (a few items of a shorter pair are empty).
+// A block copies the slot list (pair id, block count, phase) into shared memory once, so locating an item costs no
+// global load.  The last block of every step rebuilds the list from the pairs' phases: finished pairs cost nothing from
+// the next step on, and the host (or the CUDA-graph while node) never looks at anything but the loop condition.
+struct LmSlot {
+  int pair;    // index into the call's pair array
+  int nblk;    // ceil(src.n / STEP_THREADS)
+  int phase;   // the pair's phase during this step
+  int seeded;  // n_lin > 0: corr[] holds the previous linearization's correspondences
+};
+constexpr int LM_SMEM_SLOTS = 512;  // slot entries cached per block (8 KB); larger batches read the rest from global memory
+
 struct LmSched {
   int n_pairs;
   int n_active;           // pairs whose phase != PH_DONE
-  int total_items;        // sum over active pairs of ceil(src.n / STEP_THREADS)
-  int done;               // pairs that reached PH_DONE (host polls this)
+  int stride;             // max over the call's pairs of their block count
+  int total_items;        // n_active * stride
+  int done;               // pairs that reached PH_DONE
   unsigned int arrive;    // blocks that finished the current step
-  int steps;              // step kernels executed
-  int* active;            // [n_pairs] ids of the active pairs, ascending
-  int* prefix;            // [n_pairs + 1] exclusive prefix of their block counts
+  int steps;              // step iterations executed
+  int pad;
+  LmSlot* slots;          // [n_pairs]
 };
 
 // Per-call parameters of one batched LM solve, read by the kernels from device memory (not passed by value) so that the

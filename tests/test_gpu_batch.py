@@ -143,7 +143,8 @@ def test_cxx_batch_and_comm_client(tmp_path, ctx, pairs):
     src.tofile(sp)
     dst.tofile(dp)
     world = min(2, torch.cuda.device_count())
-    out = json.loads(subprocess.check_output([exe, sp, dp, str(len(src)), str(len(dst)), str(world)], timeout=300).decode())
+    txt = subprocess.check_output([exe, sp, dp, str(len(src)), str(len(dst)), str(world)], timeout=300).decode()
+    out = json.loads([ln for ln in txt.splitlines() if ln.startswith("{")][-1])  # NCCL may print its version banner on stdout first
     assert out["status"] == 0 and out["identical"] and out["world"] == world
     want = ctx.icp_alignment([src], [dst])[0]
     assert np.array_equal(np.array(out["T"]).reshape(4, 4), want["T"]) and out["fitness"] == want["fitness"]
