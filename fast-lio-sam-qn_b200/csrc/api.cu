@@ -205,7 +205,7 @@ static int lm_arena_ensure(b200reg_ctx* c, int count) {
   if (!a.graph.exec) {
     // persistent grids: as many blocks as can be resident (search: 16 per SM at 32 registers, accumulate: 8 per SM);
     // blocks beyond the current number of work items exit at once
-    int bps = 16, bpa = 8;  // development knobs of this round (measurement of the occupancy trade-off)
+    int bps = 32, bpa = 32;  // development knobs of this round (measurement of the occupancy trade-off)
     if (const char* e1 = getenv("B200REG_SEARCH_BPS")) bps = std::max(1, atoi(e1));
     if (const char* e2 = getenv("B200REG_ACCUM_BPS")) bpa = std::max(1, atoi(e2));
     const cudaError_t e = lm_graph_build(&a.graph, a.d_pairs, a.d_states, a.d_guess, a.d_call, a.d_sched, c->sm_count * bps, c->sm_count * bpa);
@@ -571,7 +571,7 @@ static int make_pair_work(b200reg_ctx* c, int count, b200reg_cloud* const* src, 
     size_t o_sqd = align_up(o_corr + (size_t)N * 4, 256);
     size_t o_mah = align_up(o_sqd + (size_t)N * 4, 256);
     size_t o_par = align_up(o_mah + (size_t)N * 6 * 8, 256);
-    size_t total = align_up(o_par + (size_t)nblk * NRED * 8, 256);
+    size_t total = align_up(o_par + (size_t)((N + 31) / 32) * NRED * 8, 256);
     char* slab = nullptr;
     CU(scratch.alloc((void**)&slab, total));
     p.corr = (int*)(slab + o_corr);
@@ -658,7 +658,7 @@ int b200reg_gicp_align(b200reg_ctx* c, int count, b200reg_cloud* const* src, b20
       CU(cudaMemcpyAsync(&hs, A.d_sched, sizeof(LmSched), cudaMemcpyDeviceToHost, s));
       CU(cudaStreamSynchronize(s));
       if (hs.n_active == 0 || hs.steps > hc.max_steps) break;
-      launch_gicp_step(A.d_pairs, A.d_states, c->sm_count * 16, c->sm_count * 8, A.d_call, A.d_sched, s);
+      launch_gicp_step(A.d_pairs, A.d_states, c->sm_count * 32, c->sm_count * 32, A.d_call, A.d_sched, s);
     }
   } else {
     // init kernel + device-side while loop over {search, accumulate}: ONE launch, ONE synchronisation per solve
@@ -671,8 +671,8 @@ int b200reg_gicp_align(b200reg_ctx* c, int count, b200reg_cloud* const* src, b20
   LmSched hsched;
   CU(cudaMemcpyAsync(&hsched, A.d_sched, sizeof(LmSched), cudaMemcpyDeviceToHost, s));
   CU(cudaStreamSynchronize(s));
-  c->launches += 1 + 2 * (int64_t)hsched.steps;  // init + (search, accumulate) per executed step, counted by the device
-  if (c->profiling) c->prof_launches[CLS_STEP] += 1 + 2 * (int64_t)hsched.steps;
+  c->launches += 1 + 3 * (int64_t)hsched.steps;  // init + (search, accumulate, control) per executed step, counted by the device
+  if (c->profiling) c->prof_launches[CLS_STEP] += 1 + 3 * (int64_t)hsched.steps;
   if (A.h_call->overrun) return fail(B200REG_ESTATE, "LM state machine did not terminate");
   for (int i = 0; i < count; i++) {
     const PairState& st = states[i];
@@ -959,7 +959,7 @@ int b200reg_compute_error(b200reg_ctx* c, const b200reg_cloud* src, const b200re
   CU(cudaMemcpyAsync((char*)w.d_states + offsetof(PairState, Rt), Rt, sizeof(Rt), cudaMemcpyHostToDevice, s));
   CU(cudaMemcpyAsync((char*)w.d_states + offsetof(PairState, tt), tt, sizeof(tt), cudaMemcpyHostToDevice, s));
   launch_gicp_step(w.d_pairs, w.d_states, blocks, blocks, w.d_call, w.d_sched, s);  // compute_error at the trial pose
-  c->launches += 5;
+  c->launches += 7;
   PairState st;
   CU(cudaMemcpyAsync(&st, w.d_states, sizeof(PairState), cudaMemcpyDeviceToHost, s));
   CU(cudaStreamSynchronize(s));

@@ -496,53 +496,52 @@ __global__ void __launch_bounds__(STEP_THREADS, 16) k_gicp_search(const PairDev*
   }
 }
 
-__global__ void __launch_bounds__(STEP_THREADS, 8) k_gicp_accum(const PairDev* pairs, PairState* states, LmCall* call, LmSched* sched) {
-  __shared__ double s_T[12];
-  __shared__ double s_red[STEP_THREADS / 32][NRED];
-  __shared__ bool s_last;
+// Accumulate kernel: NO barrier, NO atomic, NO fence.  A work item is still a 128-point block of a pair, but every warp
+// reduces its own 32 points and writes its own partial row (28 doubles for a linearize pass, 1 otherwise); the controller
+// kernel sums the rows in a fixed order.  (Round 1 and the first version of this round reduced per block and let the
+// last-arriving block of a pair run the controller: four __syncthreads, a __threadfence and an atomic round trip per item
+// made the streaming phases barrier- and latency-bound, ncu: barrier 7.9 / long-scoreboard 17 stalled warps per issue.)
+__global__ void __launch_bounds__(STEP_THREADS, 8) k_gicp_accum(const PairDev* pairs, const PairState* states, const LmSched* sched) {
   __shared__ __align__(16) LmSlot s_slots[LM_SMEM_SLOTS];
-  // the schedule is stable for the whole step: only the LAST block to finish rewrites it (see the end of the kernel)
   const int total_items = sched->total_items;
   const int n_active = sched->n_active;
   const int stride = sched->stride;
+  if ((int)blockIdx.x >= total_items) return;
   load_slots(sched, n_active, s_slots);
   const SlotView slots{sched->slots, s_slots};
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   for (int item = blockIdx.x; item < total_items; item += gridDim.x) {
-  const int slot = item / stride, blk = item - slot * stride;
-  const LmSlot sl = slots.get(slot);
-  if (blk >= sl.nblk) continue;  // a shorter pair's padding item (block-uniform)
-  const PairDev& P = pairs[sl.pair];
-  PairState* st = &states[sl.pair];
-  const int N = P.src.n;
-  const int nblk = sl.nblk;
-  const int phase = sl.phase;  // written by the previous step's controller; PH_DONE pairs are not in the list
-
-  __syncthreads();  // the previous item's shared state is no longer needed
-  if (threadIdx.x < 12) {
-    const int r = threadIdx.x / 4, cc = threadIdx.x % 4;
-    double v;
-    if (phase == PH_TRIAL) v = cc < 3 ? st->Rt[3 * r + cc] : st->tt[r];
-    else v = cc < 3 ? st->R[3 * r + cc] : st->t[r];
-    s_T[threadIdx.x] = v;
-  }
-  __syncthreads();
-
-  const int i = blk * STEP_THREADS + threadIdx.x;
-  const int nred = phase == PH_LINEARIZE ? NRED : 1;
-  double v[NRED];
+    const int slot = item / stride, blk = item - slot * stride;
+    const LmSlot sl = slots.get(slot);
+    if (blk >= sl.nblk) continue;  // a shorter pair's padding item
+    const PairDev& P = pairs[sl.pair];
+    const PairState* st = &states[sl.pair];
+    const int N = P.src.n;
+    const int phase = sl.phase;
+    const int i0 = blk * STEP_THREADS + warp * 32;  // this warp's 32 points
+    if (i0 >= N) continue;
+    const int i = i0 + lane;
+    double* row = P.partial + (size_t)(blk * (STEP_THREADS / 32) + warp) * NRED;
+    // pose of this phase: x0 for the linearize pass, the trial pose for compute_error (same address for the whole warp)
+    double T[12];
+    if (phase != PH_FITNESS) {
+      const double* Rp = phase == PH_TRIAL ? st->Rt : st->R;
+      const double* tp = phase == PH_TRIAL ? st->tt : st->t;
 #pragma unroll
-  for (int k = 0; k < NRED; k++) v[k] = 0.0;
-
-  if (i < N) {
+      for (int r = 0; r < 3; r++) {
+#pragma unroll
+        for (int c = 0; c < 3; c++) T[4 * r + c] = Rp[3 * r + c];
+        T[4 * r + 3] = tp[r];
+      }
+    }
     if (phase == PH_LINEARIZE) {
-      const int pos = P.corr[i];  // this step's k_gicp_search
+      double v[NRED];
+#pragma unroll
+      for (int k = 0; k < NRED; k++) v[k] = 0.0;
+      const int pos = i < N ? P.corr[i] : -1;  // this step's k_gicp_search
       if (pos >= 0) {
         const float4 p = P.src.pts[i];
-        double R[9];
-#pragma unroll
-        for (int r = 0; r < 3; r++)
-#pragma unroll
-          for (int c = 0; c < 3; c++) R[3 * r + c] = s_T[4 * r + c];
+        const double R[9] = {T[0], T[1], T[2], T[4], T[5], T[6], T[8], T[9], T[10]};
         double ca[6], cb[6], rcr[6], M[6];
         const double2* pa = reinterpret_cast<const double2*>(P.src.cov + (size_t)i * 6);
         const double2* pb = reinterpret_cast<const double2*>(P.tgt.cov + (size_t)pos * 6);
@@ -562,8 +561,8 @@ __global__ void __launch_bounds__(STEP_THREADS, 8) k_gicp_accum(const PairDev* p
         pm[2] = make_double2(M[4], M[5]);
         const float4 pbt = __ldg(&P.tgt.pts[pos]);
         const double ax = p.x, ay = p.y, az = p.z;
-        const double ta[3] = {R[0] * ax + R[1] * ay + R[2] * az + s_T[3], R[3] * ax + R[4] * ay + R[5] * az + s_T[7],
-                              R[6] * ax + R[7] * ay + R[8] * az + s_T[11]};
+        const double ta[3] = {R[0] * ax + R[1] * ay + R[2] * az + T[3], R[3] * ax + R[4] * ay + R[5] * az + T[7],
+                              R[6] * ax + R[7] * ay + R[8] * az + T[11]};
         const double e[3] = {(double)pbt.x - ta[0], (double)pbt.y - ta[1], (double)pbt.z - ta[2]};
         const double Mf[3][3] = {{M[0], M[1], M[2]}, {M[1], M[3], M[4]}, {M[2], M[4], M[5]}};
         double Me[3];
@@ -585,72 +584,70 @@ __global__ void __launch_bounds__(STEP_THREADS, 8) k_gicp_accum(const PairDev* p
         for (int r = 0; r < 6; r++) v[21 + r] = J[0][r] * Me[0] + J[1][r] * Me[1] + J[2][r] * Me[2];
         v[27] = e[0] * Me[0] + e[1] * Me[1] + e[2] * Me[2];
       }
-    } else if (phase == PH_TRIAL) {
-      const int pos = P.corr[i];
-      if (pos >= 0) {
-        const float4 p = P.src.pts[i];
-        const float4 pbt = __ldg(&P.tgt.pts[pos]);
-        const double ax = p.x, ay = p.y, az = p.z;
-        const double e0 = (double)pbt.x - (s_T[0] * ax + s_T[1] * ay + s_T[2] * az + s_T[3]);
-        const double e1 = (double)pbt.y - (s_T[4] * ax + s_T[5] * ay + s_T[6] * az + s_T[7]);
-        const double e2 = (double)pbt.z - (s_T[8] * ax + s_T[9] * ay + s_T[10] * az + s_T[11]);
-        const double2* pm = reinterpret_cast<const double2*>(P.mahal + (size_t)i * 6);
-        const double2 m01 = pm[0], m23 = pm[1], m45 = pm[2];
-        const double Me0 = m01.x * e0 + m01.y * e1 + m23.x * e2;
-        const double Me1 = m01.y * e0 + m23.y * e1 + m45.x * e2;
-        const double Me2 = m23.x * e0 + m45.x * e1 + m45.y * e2;
-        v[0] = e0 * Me0 + e1 * Me1 + e2 * Me2;
+      // 28 values at once with a transposing butterfly: at step m every lane keeps half of its values and trades the other
+      // half, so after 5 steps lane L holds the warp total of value L (31 shuffles of doubles instead of 28 * 5)
+      double w[32];
+#pragma unroll
+      for (int k = 0; k < 32; k++) w[k] = k < NRED ? v[k] : 0.0;
+#pragma unroll
+      for (int m = 16; m >= 1; m >>= 1) {
+        const bool up = (lane & m) != 0;
+#pragma unroll
+        for (int k = 0; k < m; k++) {
+          const double keep = up ? w[k + m] : w[k];
+          const double send = up ? w[k] : w[k + m];
+          w[k] = keep + __shfl_xor_sync(0xffffffffu, send, m);
+        }
       }
-    } else {  // PH_FITNESS: mean of the 1-NN d^2 this step's k_gicp_search found
-      v[0] = (double)P.sqd[i];
+      if (lane < NRED) row[lane] = w[0];
+    } else {
+      double x = 0.0;
+      if (i < N) {
+        if (phase == PH_TRIAL) {
+          const int pos = P.corr[i];
+          if (pos >= 0) {
+            const float4 p = P.src.pts[i];
+            const float4 pbt = __ldg(&P.tgt.pts[pos]);
+            const double ax = p.x, ay = p.y, az = p.z;
+            const double e0 = (double)pbt.x - (T[0] * ax + T[1] * ay + T[2] * az + T[3]);
+            const double e1 = (double)pbt.y - (T[4] * ax + T[5] * ay + T[6] * az + T[7]);
+            const double e2 = (double)pbt.z - (T[8] * ax + T[9] * ay + T[10] * az + T[11]);
+            const double2* pm = reinterpret_cast<const double2*>(P.mahal + (size_t)i * 6);
+            const double2 m01 = pm[0], m23 = pm[1], m45 = pm[2];
+            const double Me0 = m01.x * e0 + m01.y * e1 + m23.x * e2;
+            const double Me1 = m01.y * e0 + m23.y * e1 + m45.x * e2;
+            const double Me2 = m23.x * e0 + m45.x * e1 + m45.y * e2;
+            x = e0 * Me0 + e1 * Me1 + e2 * Me2;
+          }
+        } else {  // PH_FITNESS: the 1-NN d^2 this step's k_gicp_search found
+          x = (double)P.sqd[i];
+        }
+      }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) x += __shfl_down_sync(0xffffffffu, x, o);
+      if (lane == 0) row[0] = x;
     }
   }
+}
 
-  // warp reduction -> shared -> block partial (fixed order).  LINEARIZE reduces 28 values at once with a
-  // transposing butterfly: at step m every lane keeps half of its values and trades the other half, so after
-  // 5 steps lane L holds the warp total of value L (31 shuffles of doubles instead of 28 * 5).
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  if (phase == PH_LINEARIZE) {
-    double w[32];
-#pragma unroll
-    for (int k = 0; k < 32; k++) w[k] = k < NRED ? v[k] : 0.0;
-#pragma unroll
-    for (int m = 16; m >= 1; m >>= 1) {
-      const bool up = (lane & m) != 0;
-#pragma unroll
-      for (int k = 0; k < m; k++) {
-        const double keep = up ? w[k + m] : w[k];
-        const double send = up ? w[k] : w[k + m];
-        w[k] = keep + __shfl_xor_sync(0xffffffffu, send, m);
-      }
-    }
-    if (lane < NRED) s_red[warp][lane] = w[0];
-  } else {
-    double x = v[0];
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) x += __shfl_down_sync(0xffffffffu, x, o);
-    if (lane == 0) s_red[warp][0] = x;
-  }
-  __syncthreads();
-  if ((int)threadIdx.x < nred) {
-    double x = 0;
-#pragma unroll
-    for (int w = 0; w < STEP_THREADS / 32; w++) x += s_red[w][threadIdx.x];
-    P.partial[(size_t)blk * NRED + threadIdx.x] = x;
-    __threadfence();
-  }
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    const unsigned prev = atomicAdd(&st->arrive, 1u);
-    s_last = (prev == (unsigned)(nblk - 1));
-  }
-  __syncthreads();
-  if (s_last) {  // last block of this pair: deterministic sum over blocks (4 interleaved chains, then a fixed 4-way add)
-    __threadfence();
-    const int j = threadIdx.x & 31, g = threadIdx.x >> 5;
+// Controller kernel: one block per active pair (strided over a fixed grid) sums the pair's partial rows in a FIXED order
+// (8 interleaved chains per column, then a fixed 8-way add: deterministic) and runs the LM state machine;
+// the last block to finish rebuilds the schedule and sets the loop condition of the solve's while node.
+constexpr int CTRL_THREADS = 256;
+__global__ void __launch_bounds__(CTRL_THREADS) k_gicp_control(const PairDev* pairs, PairState* states, LmCall* call, LmSched* sched) {
+  __shared__ double s_red[CTRL_THREADS / 32][NRED];
+  __shared__ bool s_last;
+  const int n_active = sched->n_active;
+  const int j = threadIdx.x & 31, g = threadIdx.x >> 5;
+  for (int slot = blockIdx.x; slot < n_active; slot += gridDim.x) {
+    const LmSlot sl = sched->slots[slot];
+    const PairDev& P = pairs[sl.pair];
+    const int N = P.src.n;
+    const int nrows = (N + 31) / 32;
+    const int nred = sl.phase == PH_LINEARIZE ? NRED : 1;
     double x = 0;
     if (j < nred)
-      for (int b = g; b < nblk; b += STEP_THREADS / 32) x += __ldcg(&P.partial[(size_t)b * NRED + j]);
+      for (int r = g; r < nrows; r += CTRL_THREADS / 32) x += __ldcg(&P.partial[(size_t)r * NRED + j]);
     __syncthreads();
     if (j < NRED) s_red[g][j] = x;
     __syncthreads();
@@ -658,15 +655,12 @@ __global__ void __launch_bounds__(STEP_THREADS, 8) k_gicp_accum(const PairDev* p
       double sums[NRED];
       for (int k = 0; k < nred; k++) {
         double s = 0;
-        for (int w = 0; w < STEP_THREADS / 32; w++) s += s_red[w][k];
+        for (int w = 0; w < CTRL_THREADS / 32; w++) s += s_red[w][k];
         sums[k] = s;
       }
-      st->arrive = 0;
-      lm_update(st, sums, call->prm, phase, N, &sched->done);
-      __threadfence();
+      lm_update(&states[sl.pair], sums, call->prm, sl.phase, N, &sched->done);
     }
   }
-  }  // work items
   // ---- end of the step: the last block to get here rebuilds the schedule from the pairs' new phases
   __syncthreads();
   if (threadIdx.x == 0) {
@@ -812,17 +806,19 @@ void launch_gicp_init(const PairDev* pairs, PairState* states, const double* d_g
   k_gicp_init<<<1, 256, 0, s>>>(pairs, states, d_guess, call, sched);
 }
 
-// One LM step over every still-active pair = the search kernel + the accumulate kernel.  blocks_*: persistent grid sizes
-// (work items are strided over them); both kernels are correct for any value >= 1.  Returns the launches issued.
+// One LM step over every still-active pair = search + accumulate + controller.  blocks_*: persistent grid sizes (work
+// items are strided over them); the kernels are correct for any value >= 1.  Returns the launches issued.
+constexpr int CTRL_BLOCKS = 64;
 int launch_gicp_step(const PairDev* pairs, PairState* states, int blocks_search, int blocks_accum, LmCall* call, LmSched* sched,
                      cudaStream_t s) {
   k_gicp_search<<<blocks_search, STEP_THREADS, 0, s>>>(pairs, states, call, sched);
-  k_gicp_accum<<<blocks_accum, STEP_THREADS, 0, s>>>(pairs, states, call, sched);
-  return 2;
+  k_gicp_accum<<<blocks_accum, STEP_THREADS, 0, s>>>(pairs, states, sched);
+  k_gicp_control<<<CTRL_BLOCKS, CTRL_THREADS, 0, s>>>(pairs, states, call, sched);
+  return 3;
 }
 
-// The whole solve as ONE CUDA graph: init kernel, then a WHILE node whose body is the two step kernels; the accumulate
-// kernel's last block sets the loop condition (cudaGraphSetConditional) from the device-side schedule.  The host launches
+// The whole solve as ONE CUDA graph: init kernel, then a WHILE node whose body is the three step kernels; the controller's
+// last block sets the loop condition (cudaGraphSetConditional) from the device-side schedule.  The host launches
 // the graph once per solve and synchronises once -- no polling, no chunking (round 1 polled a counter every 8 launches).
 // All kernel arguments are pointers into the context's persistent LM arena, so the executable graph is reused by every call
 // until the arena grows.
@@ -830,7 +826,7 @@ cudaError_t lm_graph_build(LmGraph* g, const PairDev* pairs, PairState* states, 
                            int blocks_search, int blocks_accum) {
   cudaError_t e;
   if ((e = cudaGraphCreate(&g->graph, 0)) != cudaSuccess) return e;
-  cudaGraphNode_t n_init, n_while, n_search, n_accum;
+  cudaGraphNode_t n_init, n_while, n_search, n_accum, n_ctrl;
   {
     void* args[] = {(void*)&pairs, (void*)&states, (void*)&guess, (void*)&call, (void*)&sched};
     cudaKernelNodeParams kp = {};
@@ -850,10 +846,10 @@ cudaError_t lm_graph_build(LmGraph* g, const PairDev* pairs, PairState* states, 
   wp.conditional.size = 1;
   if ((e = cudaGraphAddNode(&n_while, g->graph, &n_init, 1, &wp)) != cudaSuccess) return e;
   cudaGraph_t body = wp.conditional.phGraph_out[0];
+  const PairState* cstates = states;
+  const LmCall* ccall = call;
+  const LmSched* csched = sched;
   {
-    const PairState* cstates = states;
-    const LmCall* ccall = call;
-    const LmSched* csched = sched;
     void* args[] = {(void*)&pairs, (void*)&cstates, (void*)&ccall, (void*)&csched};
     cudaKernelNodeParams kp = {};
     kp.func = (void*)k_gicp_search;
@@ -863,13 +859,22 @@ cudaError_t lm_graph_build(LmGraph* g, const PairDev* pairs, PairState* states, 
     if ((e = cudaGraphAddKernelNode(&n_search, body, nullptr, 0, &kp)) != cudaSuccess) return e;
   }
   {
-    void* args[] = {(void*)&pairs, (void*)&states, (void*)&call, (void*)&sched};
+    void* args[] = {(void*)&pairs, (void*)&cstates, (void*)&csched};
     cudaKernelNodeParams kp = {};
     kp.func = (void*)k_gicp_accum;
     kp.gridDim = dim3(blocks_accum);
     kp.blockDim = dim3(STEP_THREADS);
     kp.kernelParams = args;
     if ((e = cudaGraphAddKernelNode(&n_accum, body, &n_search, 1, &kp)) != cudaSuccess) return e;
+  }
+  {
+    void* args[] = {(void*)&pairs, (void*)&states, (void*)&call, (void*)&sched};
+    cudaKernelNodeParams kp = {};
+    kp.func = (void*)k_gicp_control;
+    kp.gridDim = dim3(CTRL_BLOCKS);
+    kp.blockDim = dim3(CTRL_THREADS);
+    kp.kernelParams = args;
+    if ((e = cudaGraphAddKernelNode(&n_ctrl, body, &n_accum, 1, &kp)) != cudaSuccess) return e;
   }
   return cudaGraphInstantiate(&g->exec, g->graph, 0);
 }

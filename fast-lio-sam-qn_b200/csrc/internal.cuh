@@ -92,7 +92,7 @@ struct PairState {
   int lm_failed;
   int n_lin, n_err;
   int nr_iterations;
-  unsigned int arrive;  // block arrival counter for the last-block reduction
+  unsigned int arrive;  // (unused since the controller became its own kernel; kept for layout stability)
   int pad;
 };
 
@@ -138,7 +138,7 @@ struct PairDev {
   int* corr;       // [src.n] sorted target position or -1 (per sorted source position)
   float* sqd;      // [src.n]
   double* mahal;   // [6 * src.n]
-  double* partial; // [nblocks * NRED]
+  double* partial; // [ceil(src.n / 32) * NRED] one row per warp of the accumulate kernel
 };
 
 struct LmGraph {  // host side: the instantiated graph of one context's LM solve (gicp.cu: lm_graph_build)
