@@ -36,6 +36,7 @@ int launch_fetch_closest(const double* d_pos, const double* d_stamp, const int* 
                          int* d_out, cudaStream_t s);
 cudaError_t quatro_init_device();
 void launch_ingest_world(const float* d_raw, int stride, int n, const double* d_Tinv, float4* d_out, cudaStream_t s);
+void launch_pack_xyzi(const float* d_raw, int stride, int n, float4* d_out, cudaStream_t s);
 int launch_assemble_voxelize(const AssembleJob* d_jobs, const CloudDev* d_sort, int count, int max_total, const KeyframeDev* d_kfs,
                              const double* d_poses, float inv_leaf, cudaStream_t s);
 }  // namespace b200
@@ -1499,7 +1500,17 @@ int b200reg_keyframes_add(b200reg_ctx* c, b200reg_keyframes* kf, const float* xy
   CU(cudaSetDevice(c->device));
   float4* d = nullptr;
   CU(cudaMallocFromPoolAsync((void**)&d, n * 16, c->pool, c->stream));
-  CU(cudaMemcpy2DAsync(d, 16, xyzi, stride_bytes, 16, n, cudaMemcpyHostToDevice, c->stream));
+  if (stride_bytes == 16) {  // already packed (x, y, z, intensity): one linear copy (a 2-D copy of n 16-byte rows crawls)
+    CU(cudaMemcpyAsync(d, xyzi, n * 16, cudaMemcpyHostToDevice, c->stream));
+  } else {  // pcl::PointXYZI (32 B) and friends: upload the records as they are, repack on the device
+    Scratch scratch(c);
+    float* d_raw = nullptr;
+    CU(scratch.alloc((void**)&d_raw, n * stride_bytes));
+    CU(cudaMemcpyAsync(d_raw, xyzi, n * stride_bytes, cudaMemcpyHostToDevice, c->stream));
+    launch_pack_xyzi(d_raw, (int)(stride_bytes / 4), (int)n, d, c->stream);
+    c->launches++;
+    CU(cudaGetLastError());
+  }
   kf->pts.push_back(d);
   kf->n.push_back((int)n);
   kf->poses.insert(kf->poses.end(), pose16, pose16 + 16);

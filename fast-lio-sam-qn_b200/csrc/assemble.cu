@@ -181,8 +181,19 @@ __global__ void __launch_bounds__(256) k_ingest_world(const float* raw, int stri
   o.x = (float)(Tinv[0] * x + Tinv[1] * y + Tinv[2] * z + Tinv[3]);
   o.y = (float)(Tinv[4] * x + Tinv[5] * y + Tinv[6] * z + Tinv[7]);
   o.z = (float)(Tinv[8] * x + Tinv[9] * y + Tinv[10] * z + Tinv[11]);
-  o.w = p[3];
+  o.w = stride >= 8 ? p[4] : p[3];  // pcl::PointXYZI keeps the intensity in its second 16-byte lane
   out[i] = o;
+}
+
+// strided (x, y, z, ..., intensity at float 3 or, for pcl::PointXYZI's 32-byte records, float 4) -> packed float4
+__global__ void __launch_bounds__(256) k_pack_xyzi(const float* raw, int stride, int n, float4* out) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const float* p = raw + (size_t)i * stride;
+  out[i] = make_float4(p[0], p[1], p[2], stride >= 8 ? p[4] : p[3]);
+}
+void launch_pack_xyzi(const float* d_raw, int stride, int n, float4* d_out, cudaStream_t s) {
+  k_pack_xyzi<<<(n + 255) / 256, 256, 0, s>>>(d_raw, stride, n, d_out);
 }
 
 void launch_ingest_world(const float* d_raw, int stride, int n, const double* d_Tinv, float4* d_out, cudaStream_t s) {

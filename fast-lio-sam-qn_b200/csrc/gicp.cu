@@ -319,10 +319,9 @@ __global__ void __launch_bounds__(STEP_THREADS, (K <= 16 ? (HEAP ? 10 : 8) : 4))
   lo = max(0, hi - (K - 1));
   int nb[K];  // neighbour positions for the covariance (registers; for HEAP read back from shared memory)
   if (HEAP) {
-    KnnHeap<K> res;
+    KnnHeap<K, STEP_THREADS> res;
     res.hd = &s_hd[0][threadIdx.x];
     res.hp = &s_hp[0][threadIdx.x];
-    res.stride = STEP_THREADS;
 #pragma unroll
     for (int j = 0; j < K; j++) {
       if (lo + j <= hi) {
@@ -332,8 +331,8 @@ __global__ void __launch_bounds__(STEP_THREADS, (K <= 16 ? (HEAP ? 10 : 8) : 4))
         res.set(j, 3.402823466e+38f, -1);
       }
     }
-    res.heapify(c.pts);
-    knn_walk<KnnHeap<K>>(c, q.x, q.y, q.z, res, lo, hi);
+    res.heapify();
+    knn_walk<KnnHeap<K, STEP_THREADS>>(c, q.x, q.y, q.z, res, lo, hi);
     int m = K;
     while (m > k) m = res.pop(m, c.pts);  // k < K: drop the K - k farthest
 #pragma unroll

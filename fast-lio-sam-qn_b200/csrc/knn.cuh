@@ -44,6 +44,13 @@ struct KnnSet {
   }
   __device__ __forceinline__ float worst() const { return d[K - 1]; }
   __device__ __forceinline__ void offer(float cd, int cp, const float4* __restrict__ pts);  // candidate with cd <= worst()
+  // distance of leaf slot j out of the register-resident dl[]: a select chain (no dynamic register indexing)
+  __device__ __forceinline__ float leaf_distance(const float (&dl)[LEAF], int j, const float4* __restrict__, int, float, float, float) const {
+    float dj = dl[0];
+#pragma unroll
+    for (int t = 1; t < LEAF; t++) dj = (j == t) ? dl[t] : dj;
+    return dj;
+  }
 };
 
 __device__ __forceinline__ int orig_index(const float4* __restrict__ pts, int pos) {
@@ -99,15 +106,25 @@ __device__ __forceinline__ void KnnSet<K>::offer(float cd, int cp, const float4*
 
 // The K best candidates as a binary MAX-heap in shared memory, one column per thread ([slot][thread]: the bank is the
 // thread, so the divergent, dynamically indexed accesses of a sift-down are conflict free).  For consumers that need the
-// SET of neighbours and the current worst distance, not their order (the covariance pass): replacing the root costs
-// ~45 instructions against ~120 for the K-long register insertion chain, and the result set no longer occupies 2K
-// registers.  Order between equal distances follows the same rule as everywhere: (d2, ORIGINAL index), ties looked up cold.
-template <int K>
+// SET of neighbours and the current worst distance, not their order (the covariance pass); the result set no longer
+// occupies 2K registers.
+// The heap is ordered by DISTANCE ONLY: the hot sift-down is strict float compares and nothing else (the first version
+// carried the (d2, original index) rule through every compare and cost as much as the register insertion chain it
+// replaced: ncu, 43% of the kernel's warp instructions at 7-9 active lanes).  The tie rule matters in exactly one place --
+// a candidate at EXACTLY the current worst distance -- and is resolved there, cold: among the entries tied at that
+// distance the one with the highest original index is the true worst; the candidate overwrites it in place (same
+// distance: the heap stays a heap) iff its own index is lower.
+template <int K, int stride>
 struct KnnHeap {
-  float* hd;   // column base: slot j at hd[j * stride]
+  float* hd;   // column base: slot j at hd[j * stride] (stride = threads per block, a compile-time constant)
   int* hp;
-  int stride;
   float wd;    // cached root distance
+  // a leaf candidate's distance is recomputed from the (L1-resident) point instead of being selected out of eight registers
+  __device__ __forceinline__ float leaf_distance(const float (&)[LEAF], int, const float4* __restrict__ pts, int pos, float qx, float qy,
+                                                 float qz) const {
+    const float4 q = __ldg(&pts[pos]);
+    return dist2_rn(qx, qy, qz, q.x, q.y, q.z);
+  }
   __device__ __forceinline__ float worst() const { return wd; }
   __device__ __forceinline__ float d(int j) const { return hd[j * stride]; }
   __device__ __forceinline__ int p(int j) const { return hp[j * stride]; }
@@ -115,68 +132,70 @@ struct KnnHeap {
     hd[j * stride] = dd;
     hp[j * stride] = pp;
   }
-  // (da, pa) ordered after (db, pb)?
-  static __device__ __forceinline__ bool after(float da, int pa, float db, int pb, const float4* __restrict__ pts) {
-    return da > db || (da == db && orig_index(pts, pa) > orig_index(pts, pb));
-  }
-  // sink (cd, cp) from slot i to its place
-  __device__ __forceinline__ void sift(int i, float cd, int cp, const float4* __restrict__ pts) {
+  // sink (cd, cp) from slot i to its place among the first m slots; distance order only
+  __device__ __forceinline__ void sift(int i, float cd, int cp, int m) {
 #pragma unroll 1
     for (;;) {
       const int l = 2 * i + 1;
-      if (l >= K) break;
-      int ch = l;
+      if (l >= m) break;
       float dc = d(l);
-      if (l + 1 < K) {
+      int ch = l;
+      if (l + 1 < m) {
         const float dr = d(l + 1);
-        if (dr > dc || (dr == dc && after(dr, p(l + 1), dc, p(l), pts))) {
-          ch = l + 1;
+        if (dr > dc) {
           dc = dr;
+          ch = l + 1;
         }
       }
-      if (!(dc > cd || (dc == cd && after(dc, p(ch), cd, cp, pts)))) break;
+      if (!(dc > cd)) break;
       set(i, dc, p(ch));
       i = ch;
     }
     set(i, cd, cp);
   }
   // slots 0..K-1 hold arbitrary entries: make them a heap (Floyd)
-  __device__ __forceinline__ void heapify(const float4* __restrict__ pts) {
+  __device__ __forceinline__ void heapify() {
 #pragma unroll 1
-    for (int i = K / 2 - 1; i >= 0; i--) sift(i, d(i), p(i), pts);
+    for (int i = K / 2 - 1; i >= 0; i--) sift(i, d(i), p(i), K);
     wd = d(0);
   }
-  // candidate with cd <= worst(): replaces the root unless it ties with it on a higher original index
+  // candidate with cd <= worst()
   __device__ __forceinline__ void offer(float cd, int cp, const float4* __restrict__ pts) {
-    if (cd == wd && !(orig_index(pts, cp) < orig_index(pts, p(0)))) return;
-    sift(0, cd, cp, pts);
+    if (cd == wd) {  // cold: the (d2, original index) rule among everything tied at the worst distance
+      int worst_slot = -1, worst_idx = -1;
+#pragma unroll 1
+      for (int j = 0; j < K; j++)
+        if (d(j) == cd) {
+          const int oi = orig_index(pts, p(j));
+          if (oi > worst_idx) {
+            worst_idx = oi;
+            worst_slot = j;
+          }
+        }
+      if (orig_index(pts, cp) < worst_idx) hp[worst_slot * stride] = cp;
+      return;
+    }
+    sift(0, cd, cp, K);
     wd = d(0);
   }
-  // remove the current worst entry of a heap that holds `m` entries (slots 0..m-1); returns m - 1
+  // Remove the worst entry under the full (d2, original index) order from a heap holding m entries; returns m - 1.
+  // Only used when fewer neighbours than the capacity are wanted (k < K): cold.
   __device__ __forceinline__ int pop(int m, const float4* __restrict__ pts) {
-    const float ld = d(m - 1);
-    const int lp = p(m - 1);
-    set(m - 1, d(0), p(0));  // parked behind the live part, never read again
-    // sift with the live size m - 1
-    int i = 0;
+    const float top = d(0);
+    int victim = 0, vidx = orig_index(pts, p(0));
 #pragma unroll 1
-    for (;;) {
-      const int l = 2 * i + 1;
-      if (l >= m - 1) break;
-      int ch = l;
-      float dc = d(l);
-      if (l + 1 < m - 1) {
-        const float dr = d(l + 1);
-        if (dr > dc || (dr == dc && after(dr, p(l + 1), dc, p(l), pts))) {
-          ch = l + 1;
-          dc = dr;
+    for (int j = 1; j < m; j++)
+      if (d(j) == top) {
+        const int oi = orig_index(pts, p(j));
+        if (oi > vidx) {
+          vidx = oi;
+          victim = j;
         }
       }
-      if (!(dc > ld || (dc == ld && after(dc, p(ch), ld, lp, pts)))) break;
-      set(i, dc, p(ch));
-      i = ch;
-    }
-    if (m - 1 > 0) set(i, ld, lp);
+    if (victim != 0) hp[victim * stride] = p(0);  // same distance: swap the positions, the root is now the true worst
+    const float ld = d(m - 1);
+    const int lp = p(m - 1);
+    sift(0, ld, lp, m - 1);
     return m - 1;
   }
 };
@@ -274,9 +293,7 @@ __device__ __forceinline__ void knn_walk(const CloudDev& c, float qx, float qy, 
       while (mask) {
         const int j = __ffs(mask) - 1;
         mask &= mask - 1;
-        float dj = dl[0];
-#pragma unroll
-        for (int t = 1; t < LEAF; t++) dj = (j == t) ? dl[t] : dj;
+        const float dj = res.leaf_distance(dl, j, pts, base + j, qx, qy, qz);
         if (!(dj > res.worst())) res.offer(dj, base + j, pts);
       }
     }

@@ -210,8 +210,9 @@ void b200reg_default_loop_config(b200reg_loop_config* cfg);
 
 int b200reg_keyframes_create(b200reg_ctx* ctx, b200reg_keyframes** out);
 int b200reg_keyframes_destroy(b200reg_ctx* ctx, b200reg_keyframes* kf);
-/* PosePcd (fast_lio_sam_qn/include/pose_pcd.hpp:7-43): cloud in the LiDAR frame as (x, y, z, intensity) records
- * `stride_bytes` apart (host memory), its corrected pose (row-major 4x4) and timestamp.  Returns the index.   */
+/* PosePcd (fast_lio_sam_qn/include/pose_pcd.hpp:7-43): cloud in the LiDAR frame as fp32 records `stride_bytes` apart (host
+ * memory): packed (x, y, z, intensity) for strides below 32 bytes, the pcl::PointXYZI layout (x, y, z, 1, intensity, pad...)
+ * from 32 bytes on; its corrected pose (row-major 4x4) and timestamp.  Returns the index.                          */
 int b200reg_keyframes_add(b200reg_ctx* ctx, b200reg_keyframes* kf, const float* xyzi, size_t n, size_t stride_bytes,
                           const double* pose16, double timestamp);
 /* The PosePcd constructor itself (pose_pcd.hpp:21-43) as a device step: the scan arrives in the WORLD frame with the odometry
