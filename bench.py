@@ -510,8 +510,10 @@ def main():
             "gpu_launches": launches,
             "roofline": {"bound": "hbm", "kernel": fam, "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak, "traffic": ncu_traffic(fam, "gicp"), "peak_source": peak_src,
-                         "note": "algorithmic bytes per SURVEY.md §8(d) / CUDA-event time of that kernel family on the launching "
-                                 "stream, %d profiled 16-pair jobs on one context after the timed region" % prof_steps},
+                         "note": "dominant KERNEL of the step (largest total CUDA-event time among the kernels / single-kernel families): "
+                                 "algorithmic bytes per SURVEY.md §8(d) / its CUDA-event time on the launching stream, %d profiled 16-pair jobs "
+                                 "on one context after the timed region; while profiling, the LM loop's three kernels are launched one by one "
+                                 "instead of as one graph so that each gets its own events" % prof_steps},
             "kernels": family_table(prof, prof_steps),
             "clocks": clocks,
             "accuracy": accuracy,

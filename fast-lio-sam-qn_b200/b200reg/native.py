@@ -211,7 +211,7 @@ class Context:
     def get_profile(self):
         """{family: dict(ms, algo_bytes, launches)} from CUDA events on the launching stream."""
         out = {}
-        for f in range(6):
+        for f in range(9):
             name, ms, by, ln = C.c_char_p(), C.c_double(), C.c_double(), C.c_int64()
             _check(lib().b200reg_ctx_get_profile(self.h, f, C.byref(name), C.byref(ms), C.byref(by), C.byref(ln)))
             out[name.value.decode()] = dict(ms=ms.value, algo_bytes=by.value, launches=ln.value)

@@ -23,6 +23,9 @@ size_t radix_sort_ws_bytes(int n, int key_bits);
 int launch_covariances(const CloudDev* d_clouds, int count, int max_n, int k, int method, cudaStream_t s);
 void launch_gicp_init(const PairDev* pairs, PairState* states, const double* d_guess, LmCall* call, LmSched* sched, cudaStream_t s);
 int launch_gicp_step(const PairDev* pairs, PairState* states, int blocks_search, int blocks_accum, LmCall* call, LmSched* sched, cudaStream_t s);
+void launch_gicp_search(const PairDev* pairs, const PairState* states, int blocks, const LmCall* call, const LmSched* sched, cudaStream_t s);
+void launch_gicp_accum(const PairDev* pairs, const PairState* states, int blocks, const LmSched* sched, cudaStream_t s);
+void launch_gicp_control(const PairDev* pairs, PairState* states, LmCall* call, LmSched* sched, cudaStream_t s);
 cudaError_t lm_graph_build(LmGraph* g, const PairDev* pairs, PairState* states, const double* guess, LmCall* call, LmSched* sched,
                            int blocks_search, int blocks_accum);
 void lm_graph_destroy(LmGraph* g);
@@ -56,7 +59,7 @@ static int fail(int code, const std::string& msg) {
                                      std::to_string(__LINE__));                                               \
   } while (0)
 
-enum { CLS_BUILD = 0, CLS_COV = 1, CLS_STEP = 2, CLS_MISC = 3, CLS_FPFH = 4, CLS_MATCH = 5, NCLS = 6 };
+enum { CLS_BUILD = 0, CLS_COV = 1, CLS_STEP = 2, CLS_MISC = 3, CLS_FPFH = 4, CLS_MATCH = 5, CLS_SEARCH = 6, CLS_ACCUM = 7, CLS_CTRL = 8, NCLS = 9 };
 
 struct b200reg_ctx {
   int device = 0;
@@ -93,7 +96,10 @@ struct b200reg_ctx {
   int64_t prof_launches[NCLS] = {0};
 };
 
-static const char* kClassNames[NCLS] = {"index_build", "knn_covariance", "gicp_step", "misc", "fpfh", "quatro_match_solve"};
+// gicp_step = the whole LM loop of a solve when it runs as one graph launch; with profiling enabled the same kernels are
+// launched one by one and timed per kernel: gicp_search / gicp_accum / gicp_control (and gicp_step stays empty)
+static const char* kClassNames[NCLS] = {"index_build", "knn_covariance", "gicp_step", "misc", "fpfh", "quatro_match_solve",
+                                        "gicp_search", "gicp_accum", "gicp_control"};
 
 static cudaEvent_t prof_event(b200reg_ctx* c) {
   cudaEvent_t e;
@@ -647,10 +653,11 @@ int b200reg_gicp_align(b200reg_ctx* c, int count, b200reg_cloud* const* src, b20
   hc.cond_handle = A.graph.cond_handle;
   hc.prm = prm;
   CU(cudaMemcpyAsync(A.d_call, A.h_call, sizeof(LmCall), cudaMemcpyHostToDevice, s));
-  static const bool no_graph = getenv("B200REG_LM_NO_GRAPH") != nullptr;  // profiling aid: Nsight Compute does not list kernels
-  if (no_graph) {                                                           // that run inside a conditional graph node
-    // the SAME kernels launched one by one, the host polling the schedule (what the while node does on the device)
-    ProfScope ps(c, CLS_STEP);
+  static const bool env_no_graph = getenv("B200REG_LM_NO_GRAPH") != nullptr;  // Nsight Compute does not list kernels that run
+  const bool no_graph = env_no_graph || c->profiling;                          // inside a conditional graph node
+  if (no_graph) {
+    // Profiling / ncu aid: the SAME kernels launched one by one, the host polling the schedule (what the while node does
+    // on the device), each kernel bracketed by its own CUDA events
     A.h_call->cond_handle = 0;
     CU(cudaMemcpyAsync(A.d_call, A.h_call, sizeof(LmCall), cudaMemcpyHostToDevice, s));
     launch_gicp_init(A.d_pairs, A.d_states, A.d_guess, A.d_call, A.d_sched, s);
@@ -659,10 +666,25 @@ int b200reg_gicp_align(b200reg_ctx* c, int count, b200reg_cloud* const* src, b20
       CU(cudaMemcpyAsync(&hs, A.d_sched, sizeof(LmSched), cudaMemcpyDeviceToHost, s));
       CU(cudaStreamSynchronize(s));
       if (hs.n_active == 0 || hs.steps > hc.max_steps) break;
-      launch_gicp_step(A.d_pairs, A.d_states, c->sm_count * 32, c->sm_count * 32, A.d_call, A.d_sched, s);
+      {
+        ProfScope ps(c, CLS_SEARCH);
+        launch_gicp_search(A.d_pairs, A.d_states, c->sm_count * 32, A.d_call, A.d_sched, s);
+        c->launches++;
+      }
+      {
+        ProfScope ps(c, CLS_ACCUM);
+        launch_gicp_accum(A.d_pairs, A.d_states, c->sm_count * 32, A.d_sched, s);
+        c->launches++;
+      }
+      {
+        ProfScope ps(c, CLS_CTRL);
+        launch_gicp_control(A.d_pairs, A.d_states, A.d_call, A.d_sched, s);
+        c->launches++;
+      }
     }
+    c->launches++;
   } else {
-    // init kernel + device-side while loop over {search, accumulate}: ONE launch, ONE synchronisation per solve
+    // init kernel + device-side while loop over {search, accumulate, control}: ONE launch, ONE synchronisation per solve
     ProfScope ps(c, CLS_STEP);
     CU(cudaGraphLaunch(A.graph.exec, s));
   }
@@ -672,8 +694,7 @@ int b200reg_gicp_align(b200reg_ctx* c, int count, b200reg_cloud* const* src, b20
   LmSched hsched;
   CU(cudaMemcpyAsync(&hsched, A.d_sched, sizeof(LmSched), cudaMemcpyDeviceToHost, s));
   CU(cudaStreamSynchronize(s));
-  c->launches += 1 + 3 * (int64_t)hsched.steps;  // init + (search, accumulate, control) per executed step, counted by the device
-  if (c->profiling) c->prof_launches[CLS_STEP] += 1 + 3 * (int64_t)hsched.steps;
+  if (!no_graph) c->launches += 1 + 3 * (int64_t)hsched.steps;  // init + (search, accumulate, control) per executed step, counted by the device
   if (A.h_call->overrun) return fail(B200REG_ESTATE, "LM state machine did not terminate");
   for (int i = 0; i < count; i++) {
     const PairState& st = states[i];
@@ -699,8 +720,15 @@ int b200reg_gicp_align(b200reg_ctx* c, int count, b200reg_cloud* const* src, b20
     r.n_error = st.n_err;
     r.lm_failed = st.lm_failed;
     r.status = 0;
-    // K3 136*N per linearize, K4 132*N per compute_error, K5 16*N fitness
-    c->prof_bytes[CLS_STEP] += (136.0 * st.n_lin + 132.0 * st.n_err + 16.0) * w.pairs[i].src.n;
+    // K3 136*N per linearize, K4 132*N per compute_error, K5 16*N fitness.  Per kernel: the search reads the
+    // 16-byte points and writes the 8-byte correspondence record (24*N of K3; all 16*N of K5), the accumulate pass owns the rest
+    const double N = w.pairs[i].src.n;
+    if (no_graph) {
+      c->prof_bytes[CLS_SEARCH] += (24.0 * st.n_lin + 16.0) * N;
+      c->prof_bytes[CLS_ACCUM] += (112.0 * st.n_lin + 132.0 * st.n_err) * N;
+    } else {
+      c->prof_bytes[CLS_STEP] += (136.0 * st.n_lin + 132.0 * st.n_err + 16.0) * N;
+    }
   }
   return B200REG_OK;
 }

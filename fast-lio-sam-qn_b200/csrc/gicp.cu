@@ -630,9 +630,9 @@ __global__ void __launch_bounds__(STEP_THREADS, 8) k_gicp_accum(const PairDev* p
 }
 
 // Controller kernel: one block per active pair (strided over a fixed grid) sums the pair's partial rows in a FIXED order
-// (8 interleaved chains per column, then a fixed 8-way add: deterministic) and runs the LM state machine;
+// (32 interleaved chains per column, then a fixed 32-way add: deterministic) and runs the LM state machine;
 // the last block to finish rebuilds the schedule and sets the loop condition of the solve's while node.
-constexpr int CTRL_THREADS = 256;
+constexpr int CTRL_THREADS = 1024;  // 32 interleaved chains per column: the row sums are latency chains, not bandwidth
 __global__ void __launch_bounds__(CTRL_THREADS) k_gicp_control(const PairDev* pairs, PairState* states, LmCall* call, LmSched* sched) {
   __shared__ double s_red[CTRL_THREADS / 32][NRED];
   __shared__ bool s_last;
@@ -808,11 +808,20 @@ void launch_gicp_init(const PairDev* pairs, PairState* states, const double* d_g
 // One LM step over every still-active pair = search + accumulate + controller.  blocks_*: persistent grid sizes (work
 // items are strided over them); the kernels are correct for any value >= 1.  Returns the launches issued.
 constexpr int CTRL_BLOCKS = 64;
+void launch_gicp_search(const PairDev* pairs, const PairState* states, int blocks, const LmCall* call, const LmSched* sched, cudaStream_t s) {
+  k_gicp_search<<<blocks, STEP_THREADS, 0, s>>>(pairs, states, call, sched);
+}
+void launch_gicp_accum(const PairDev* pairs, const PairState* states, int blocks, const LmSched* sched, cudaStream_t s) {
+  k_gicp_accum<<<blocks, STEP_THREADS, 0, s>>>(pairs, states, sched);
+}
+void launch_gicp_control(const PairDev* pairs, PairState* states, LmCall* call, LmSched* sched, cudaStream_t s) {
+  k_gicp_control<<<CTRL_BLOCKS, CTRL_THREADS, 0, s>>>(pairs, states, call, sched);
+}
 int launch_gicp_step(const PairDev* pairs, PairState* states, int blocks_search, int blocks_accum, LmCall* call, LmSched* sched,
                      cudaStream_t s) {
-  k_gicp_search<<<blocks_search, STEP_THREADS, 0, s>>>(pairs, states, call, sched);
-  k_gicp_accum<<<blocks_accum, STEP_THREADS, 0, s>>>(pairs, states, sched);
-  k_gicp_control<<<CTRL_BLOCKS, CTRL_THREADS, 0, s>>>(pairs, states, call, sched);
+  launch_gicp_search(pairs, states, blocks_search, call, sched, s);
+  launch_gicp_accum(pairs, states, blocks_accum, sched, s);
+  launch_gicp_control(pairs, states, call, sched, s);
   return 3;
 }
 

@@ -242,33 +242,51 @@ __global__ void __launch_bounds__(SORT_THREADS) k_sort_pass(const CloudDev* clou
     for (int k = 0; k < DPT; k++) gbase[threadIdx.x * DPT + k] = excl + hv[k];
   }
   __syncthreads();
-  // per digit: exclusive prefix over the warps of this tile, publish the tile's count, look back over earlier tiles
+  // per digit: exclusive prefix over the warps of this tile, publish the tile's count, look back over earlier tiles.
+  // A thread owns DPT digits (strided: consecutive threads publish consecutive words) and walks back for all of them
+  // TOGETHER: the DPT loads of a step are independent, so a step costs one L2 round trip, not DPT.
+  {
+    uint32_t run[DPT], excl[DPT];
+    bool open_[DPT];
 #pragma unroll
-  for (int k = 0; k < DPT; k++) {
-    const int d = k * SORT_THREADS + threadIdx.x;  // strided: consecutive threads publish consecutive words
-    uint32_t run = 0;
+    for (int k = 0; k < DPT; k++) {
+      const int d = k * SORT_THREADS + threadIdx.x;
+      uint32_t r = 0;
 #pragma unroll
-    for (int ww = 0; ww < NW; ww++) {
-      const uint32_t t = cnt[ww][d];
-      cnt[ww][d] = (unsigned short)run;
-      run += t;
-    }
-    volatile uint32_t* mine = look + (size_t)tile * R + d;
-    uint32_t excl = 0;
-    if (tile == 0) {
-      *mine = LB_INC | run;
-    } else {
-      *mine = LB_AGG | run;
-      for (int t2 = tile - 1;; t2--) {
-        volatile uint32_t* p = look + (size_t)t2 * R + d;
-        uint32_t v = *p;
-        while ((v >> 30) == 0u) v = *p;
-        excl += v & LB_MASK;
-        if ((v >> 30) == 2u) break;
+      for (int ww = 0; ww < NW; ww++) {
+        const uint32_t t = cnt[ww][d];
+        cnt[ww][d] = (unsigned short)r;
+        r += t;
       }
-      *mine = LB_INC | (excl + run);
+      run[k] = r;
+      excl[k] = 0;
+      open_[k] = tile > 0;
+      *(volatile uint32_t*)(look + (size_t)tile * R + d) = (tile == 0 ? LB_INC : LB_AGG) | r;
     }
-    gbase[d] += excl;
+    for (int t2 = tile - 1; t2 >= 0; t2--) {
+      uint32_t v[DPT];
+      bool any_open = false;
+#pragma unroll
+      for (int k = 0; k < DPT; k++) {
+        v[k] = LB_INC;
+        if (open_[k]) v[k] = *(volatile uint32_t*)(look + (size_t)t2 * R + k * SORT_THREADS + threadIdx.x);
+      }
+#pragma unroll
+      for (int k = 0; k < DPT; k++) {
+        if (!open_[k]) continue;
+        while ((v[k] >> 30) == 0u) v[k] = *(volatile uint32_t*)(look + (size_t)t2 * R + k * SORT_THREADS + threadIdx.x);
+        excl[k] += v[k] & LB_MASK;
+        if ((v[k] >> 30) == 2u) open_[k] = false;
+        any_open |= open_[k];
+      }
+      if (!any_open) break;
+    }
+#pragma unroll
+    for (int k = 0; k < DPT; k++) {
+      const int d = k * SORT_THREADS + threadIdx.x;
+      if (tile > 0) *(volatile uint32_t*)(look + (size_t)tile * R + d) = LB_INC | (excl[k] + run[k]);
+      gbase[d] += excl[k];
+    }
   }
   __syncthreads();
 #pragma unroll

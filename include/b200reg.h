@@ -128,7 +128,10 @@ int b200reg_ctx_synchronize(b200reg_ctx* ctx);
 int64_t b200reg_ctx_launch_count(const b200reg_ctx* ctx);
 
 /* Per-kernel-family timing with CUDA events recorded on the launching stream (bench.py roofline).
- * Families: 0 index_build, 1 knn_covariance, 2 gicp_step, 3 misc.  algo_bytes follows SURVEY.md §8(d). */
+ * Families: 0 index_build, 1 knn_covariance, 2 gicp_step (the LM loop as ONE graph launch), 3 misc, 4 fpfh,
+ * 5 quatro_match_solve, 6 gicp_search, 7 gicp_accum, 8 gicp_control.  While profiling is enabled the LM loop is not run as
+ * a graph: its three kernels are launched one by one (host-polled) so that each gets its own events -- families 6-8 fill,
+ * family 2 stays empty.  algo_bytes follows SURVEY.md §8(d).                                                         */
 int b200reg_ctx_set_profiling(b200reg_ctx* ctx, int enable);
 int b200reg_ctx_reset_profile(b200reg_ctx* ctx);
 int b200reg_ctx_get_profile(b200reg_ctx* ctx, int family, const char** name, double* ms, double* algo_bytes,
