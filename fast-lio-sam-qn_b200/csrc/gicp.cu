@@ -11,8 +11,6 @@
 //       computeTransformation :88-115, is_converged :117-127, step_lm :160-208
 //   third_party/nano_gicp/include/nano_gicp/gicp/so3.hpp  so3_exp :99-118
 //   pcl::Registration::getFitnessScore (call site fast_lio_sam_qn/src/loop_closure.cpp:127)
-#include <cstdlib>
-
 #include "internal.cuh"
 #include "knn.cuh"
 #include "smallmath.cuh"
@@ -295,30 +293,22 @@ __global__ void __launch_bounds__(256) k_gicp_init(const PairDev* pairs, PairSta
 // ---------------------------------------------------------------------------------------
 // K is the CAPACITY of the result set; k <= K neighbours enter the covariance (the k nearest of the K nearest are the
 // k nearest), so every k in 1..32 is served by the next instantiated capacity.
-// HEAP = true: the result set is a max-heap in shared memory (KnnHeap, knn.cuh) -- the covariance needs the SET of
-// neighbours, not their order; HEAP = false: the sorted register list of round 1 (kept for the A/B measurement).
-template <int K, bool HEAP>
-struct CovResult;
+// The result set is a max-heap in shared memory (KnnHeap, knn.cuh): the covariance needs the SET of neighbours, not their
+// order.  (Round 1 kept a sorted list in registers: 1.98 ms for 32 x 100k points against 1.58 ms, profiles/r02/README.md.)
 template <int K>
-struct CovResult<K, false> {
-  KnnSet<K> set;
-  __device__ __forceinline__ int pos(int j) const { return set.p[j]; }
-};
-
-template <int K, bool HEAP>
-__global__ void __launch_bounds__(STEP_THREADS, (K <= 16 ? (HEAP ? 10 : 8) : 4)) k_covariance(const CloudDev* clouds, int k, int method) {
+__global__ void __launch_bounds__(STEP_THREADS, (K <= 16 ? 10 : 4)) k_covariance(const CloudDev* clouds, int k, int method) {
   const CloudDev& c = clouds[blockIdx.y];
   const int i = blockIdx.x * STEP_THREADS + threadIdx.x;
-  __shared__ float s_hd[HEAP ? K : 1][STEP_THREADS];
-  __shared__ int s_hp[HEAP ? K : 1][STEP_THREADS];
+  __shared__ float s_hd[K][STEP_THREADS];
+  __shared__ int s_hp[K][STEP_THREADS];
   if (i >= c.n) return;
   const float4 q = c.pts[i];
   // seed with the K points around i in Morton order (cheap, coalesced, usually most of the true neighbours): the
   // traversal then starts with a tight bound and only ever inserts improvements
   int lo = max(0, i - K / 2), hi = min(c.n - 1, lo + K - 1);
   lo = max(0, hi - (K - 1));
-  int nb[K];  // neighbour positions for the covariance (registers; for HEAP read back from shared memory)
-  if (HEAP) {
+  int nb[K];  // neighbour positions for the covariance
+  {
     KnnHeap<K, STEP_THREADS> res;
     res.hd = &s_hd[0][threadIdx.x];
     res.hp = &s_hp[0][threadIdx.x];
@@ -337,13 +327,6 @@ __global__ void __launch_bounds__(STEP_THREADS, (K <= 16 ? (HEAP ? 10 : 8) : 4))
     while (m > k) m = res.pop(m, c.pts);  // k < K: drop the K - k farthest
 #pragma unroll
     for (int j = 0; j < K; j++) nb[j] = res.p(j);
-  } else {
-    KnnSet<K> res;
-    res.init();
-    SeedLoop<K, 0>::run(res, c.pts, q.x, q.y, q.z, lo, hi);
-    knn_search<K>(c, q.x, q.y, q.z, res, lo, hi);
-#pragma unroll
-    for (int j = 0; j < K; j++) nb[j] = res.p[j];
   }
   // two passes over the K neighbours (second pass hits L1) instead of parking 3K doubles in registers
   double mx = 0, my = 0, mz = 0;
@@ -786,18 +769,10 @@ __global__ void __launch_bounds__(256) k_transform_out(CloudDev c, const float* 
 int launch_covariances(const CloudDev* d_clouds, int count, int max_n, int k, int method, cudaStream_t s) {
   dim3 grid((max_n + STEP_THREADS - 1) / STEP_THREADS, count);
   if (k < 1 || k > 32 || method < 0 || method > 4) return -1;
-  static const bool reg_list = getenv("B200REG_COV_REGLIST") != nullptr;  // A/B switch of the development round
-  if (reg_list) {
-    if (k <= 8) k_covariance<8, false><<<grid, STEP_THREADS, 0, s>>>(d_clouds, k, method);
-    else if (k <= 15) k_covariance<15, false><<<grid, STEP_THREADS, 0, s>>>(d_clouds, k, method);
-    else if (k <= 20) k_covariance<20, false><<<grid, STEP_THREADS, 0, s>>>(d_clouds, k, method);
-    else k_covariance<32, false><<<grid, STEP_THREADS, 0, s>>>(d_clouds, k, method);
-    return 1;
-  }
-  if (k <= 8) k_covariance<8, true><<<grid, STEP_THREADS, 0, s>>>(d_clouds, k, method);
-  else if (k <= 15) k_covariance<15, true><<<grid, STEP_THREADS, 0, s>>>(d_clouds, k, method);
-  else if (k <= 20) k_covariance<20, true><<<grid, STEP_THREADS, 0, s>>>(d_clouds, k, method);
-  else k_covariance<32, true><<<grid, STEP_THREADS, 0, s>>>(d_clouds, k, method);
+  if (k <= 8) k_covariance<8><<<grid, STEP_THREADS, 0, s>>>(d_clouds, k, method);
+  else if (k <= 15) k_covariance<15><<<grid, STEP_THREADS, 0, s>>>(d_clouds, k, method);
+  else if (k <= 20) k_covariance<20><<<grid, STEP_THREADS, 0, s>>>(d_clouds, k, method);
+  else k_covariance<32><<<grid, STEP_THREADS, 0, s>>>(d_clouds, k, method);
   return 1;
 }
 

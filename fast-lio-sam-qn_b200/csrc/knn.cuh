@@ -200,50 +200,6 @@ struct KnnHeap {
   }
 };
 
-// Seeding: insert into a set whose first S slots are occupied (slot S is still empty): the chain only has to
-// look at slots 0..S, so filling K seeds costs K^2/2 compare-selects instead of K^2.
-template <int K, int S>
-__device__ __forceinline__ void knn_insert_prefix(KnnSet<K>& s, float cd, int cp, const float4* __restrict__ pts) {
-  bool tie = false, placed = false;
-#pragma unroll
-  for (int j = 0; j <= S; j++) {
-    const bool lt = placed || cd < s.d[j];
-    tie |= (!placed && cd == s.d[j]);
-    placed = lt;
-    const float td = s.d[j];
-    const int tp = s.p[j];
-    s.d[j] = lt ? cd : td;
-    s.p[j] = lt ? cp : tp;
-    cd = lt ? td : cd;
-    cp = lt ? tp : cp;
-  }
-  if (tie) {
-#pragma unroll
-    for (int j = S; j > 0; j--) {
-      if (s.d[j] == s.d[j - 1] && s.p[j] >= 0 && orig_index(pts, s.p[j]) < orig_index(pts, s.p[j - 1])) {
-        const int t = s.p[j];
-        s.p[j] = s.p[j - 1];
-        s.p[j - 1] = t;
-      }
-    }
-  }
-}
-
-template <int K, int S>
-struct SeedLoop {
-  static __device__ __forceinline__ void run(KnnSet<K>& res, const float4* __restrict__ pts, float qx, float qy, float qz, int lo, int hi) {
-    if (lo + S <= hi) {
-      const float4 p = __ldg(&pts[lo + S]);
-      knn_insert_prefix<K, S>(res, dist2_rn(qx, qy, qz, p.x, p.y, p.z), lo + S, pts);
-    }
-    SeedLoop<K, S + 1>::run(res, pts, qx, qy, qz, lo, hi);
-  }
-};
-template <int K>
-struct SeedLoop<K, K> {
-  static __device__ __forceinline__ void run(KnnSet<K>&, const float4* __restrict__, float, float, float, int, int) {}
-};
-
 // Exact K-NN of (qx,qy,qz) in cloud c.  One thread per query; Morton-sorted queries keep
 // neighbouring lanes on neighbouring paths (coherent loads, low divergence).
 template <typename Res>
