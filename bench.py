@@ -70,11 +70,21 @@ def parse():
 # inputs
 # ---------------------------------------------------------------------------------------------------------------------
 def gen_pairs(seeds, n_points, mode="gicp", voxel=None, threads=None):
-    """synth.make_pair for every seed (the generator runs OpenMP inside; a few Python threads keep the cores busy)."""
+    """synth.make_pair for every seed (the generator runs OpenMP inside; a few Python threads keep the cores busy).
+    A seed whose procedural scene cannot return n_points echoes (the virtual sensor sits inside a building: one in a few
+    hundred) is replaced by seed + 100000, deterministically -- an input-generation matter, not a registration one."""
     from b200reg import synth
+
+    def one(s):
+        for k in range(4):
+            try:
+                return synth.make_pair(s + 100000 * k, n_points, n_points, mode=mode, voxel=voxel)
+            except RuntimeError:
+                continue
+        raise RuntimeError("no usable synthetic scene for seed %d" % s)
     threads = threads or max(1, min(16, (os.cpu_count() or 8) // 8))
     with ThreadPoolExecutor(threads) as ex:
-        return list(ex.map(lambda s: synth.make_pair(s, n_points, n_points, mode=mode, voxel=voxel), seeds))
+        return list(ex.map(one, seeds))
 
 
 def primary_seeds(rank):
@@ -748,4 +758,15 @@ def bench_batch512(args, runner, batch, ctx, dist, prm, rank, world):
 
 
 if __name__ == "__main__":
-    main()
+    try:
+        main()
+    except BaseException as e:  # noqa: BLE001
+        if isinstance(e, SystemExit) and e.code in (0, None):
+            raise
+        import traceback
+        traceback.print_exc()
+        sys.stderr.flush()
+        sys.stdout.flush()
+        # a rank that fails must not linger in destructors that wait for its peers (communicator teardown): exit hard, the
+        # launcher then stops the other ranks
+        os._exit(1 if not isinstance(e, SystemExit) else (e.code if isinstance(e.code, int) else 1))
