@@ -477,8 +477,9 @@ def main():
 
     sampler = ClockSampler(local_rank) if rank == 0 else None  # samples from the warm-up on: same load as the timed region
     warm_jobs = max(args.warmup, 3) * max(DISTINCT_JOBS, 2 * args.depth)  # every context sees every sub-batch, both arms
-    runner.run(warm_jobs, submit_icp(True))
-    runner.run(warm_jobs, submit_icp(False))
+    # (the warm-up includes the per-step gather: NCCL sets its channels up lazily on the first collective of a communicator)
+    runner.run(warm_jobs, submit_icp(True), max(DISTINCT_JOBS, 2 * args.depth), gather=world > 1)
+    runner.run(warm_jobs, submit_icp(False), max(DISTINCT_JOBS, 2 * args.depth), gather=world > 1)
     n_jobs = args.steps * JOBS_PER_STEP
     ms_dev, launches, res_dev, lat_dev, _ = runner.run(n_jobs, submit_icp(True), JOBS_PER_STEP, gather=world > 1)
     ms_e2e, _, res_e2e, lat_e2e, _ = runner.run(n_jobs, submit_icp(False), JOBS_PER_STEP, gather=world > 1)
