@@ -39,5 +39,34 @@ t_clean, nl, _ = run(clean)
 t_bad, nl2, cv2 = run(clean[:15] + [bad])
 print("clean 16-pair batch: %.2f ms (linearize passes %s)" % (t_clean, nl))
 print("15 clean pairs + seed 1104: %.2f ms (linearize passes %s, converged %s)" % (t_bad, nl2, cv2))
-print("ratio %.2f" % (t_bad / t_clean))
+print("latency ratio %.2f (the straggler's own chain of 32 x (linearize + trial) steps on 100k points is serial: ~50 us per step)" % (t_bad / t_clean))
 ctx.close()
+
+# throughput: the same two job types streamed through the batch driver (3 contexts, 6 jobs in flight): while one context
+# spins through its straggler's steps (782 work items of a 4736-block grid), the other contexts' jobs fill the machine
+batch = b200reg.Batch(0, depth=3)
+
+
+def stream(pairs, jobs=24):
+    ds = [torch.from_numpy(p[0]).cuda() for p in pairs]
+    dd = [torch.from_numpy(p[1]).cuda() for p in pairs]
+    args = ([t.data_ptr() for t in ds], [t.shape[0] for t in ds], [t.data_ptr() for t in dd], [t.shape[0] for t in dd], 16, 1)
+    for _ in range(2):
+        [batch.wait(t) for t in [batch.submit_icp(*args) for _ in range(6)]]
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    inflight = []
+    for j in range(jobs):
+        inflight.append(batch.submit_icp(*args))
+        if len(inflight) >= 6:
+            batch.wait(inflight.pop(0))
+    for t in inflight:
+        batch.wait(t)
+    return 16 * jobs / (time.perf_counter() - t0)
+
+
+p_clean = stream(clean)
+p_bad = stream(clean[:15] + [bad])
+print("streamed through b200reg_batch: clean jobs %.0f pairs/s, jobs with one 32-iteration pair each %.0f pairs/s: cost ratio %.2f"
+      % (p_clean, p_bad, p_clean / p_bad))
+batch.close()
