@@ -161,6 +161,25 @@ struct Scratch {
   }
 };
 
+// scope guards: events and cloud handles created inside a call are released on EVERY exit path (the CU() macro returns early)
+struct EventBag {
+  std::vector<cudaEvent_t> ev;
+  cudaError_t make(cudaEvent_t* e) {
+    const cudaError_t r = cudaEventCreateWithFlags(e, cudaEventDisableTiming);
+    if (r == cudaSuccess) ev.push_back(*e);
+    return r;
+  }
+  ~EventBag() {
+    for (cudaEvent_t e : ev) cudaEventDestroy(e);
+  }
+};
+struct CloudBag {
+  b200reg_ctx* c;
+  std::vector<b200reg_cloud*> cl;
+  explicit CloudBag(b200reg_ctx* c_) : c(c_) {}
+  ~CloudBag();
+};
+
 struct b200reg_cloud {
   CloudDev dev;            // device pointers + sizes
   void* slab = nullptr;    // persistent allocation (pts, tnodes, cov, rank)
@@ -174,6 +193,10 @@ struct b200reg_cloud {
 };
 
 static size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+CloudBag::~CloudBag() {
+  for (b200reg_cloud* p : cl) b200reg_cloud_destroy(c, p);
+}
 
 static void lm_arena_free(b200reg_ctx* c) {
   auto& a = c->lm;
@@ -462,6 +485,7 @@ int b200reg_clouds_create(b200reg_ctx* c, int count, const float* const* xyz, co
     d.parent_node = d.parent_leaf = nullptr;
     d.bbox = nullptr;
   }
+  if (!on_device) CU(cudaStreamSynchronize(s));  // host buffers have been consumed when the call returns (pinned or not)
   guard.ok = true;
   return B200REG_OK;
 }
@@ -780,8 +804,13 @@ int b200reg_icp_alignment(b200reg_ctx* c, int count, const float* const* src_xyz
   }
   char* stage = nullptr;
   CU(scratch.alloc((void**)&stage, total));
+  EventBag events;
+  struct CopyDrain {  // the uploads read the caller's buffers: they must have finished whenever this call returns
+    cudaStream_t cs;
+    ~CopyDrain() { cudaStreamSynchronize(cs); }
+  } drain{c->copy_stream};
   cudaEvent_t ready;
-  CU(cudaEventCreateWithFlags(&ready, cudaEventDisableTiming));
+  CU(events.make(&ready));
   CU(cudaEventRecord(ready, s));
   CU(cudaStreamWaitEvent(c->copy_stream, ready, 0));
   std::vector<cudaEvent_t> landed;
@@ -792,7 +821,7 @@ int b200reg_icp_alignment(b200reg_ctx* c, int count, const float* const* src_xyz
       CU(cudaMemcpyAsync(stage + off_t[i], tgt_xyz[i], tgt_n[i] * stride_bytes, cudaMemcpyHostToDevice, c->copy_stream));
     }
     cudaEvent_t e;
-    CU(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    CU(events.make(&e));
     CU(cudaEventRecord(e, c->copy_stream));
     landed.push_back(e);
   }
@@ -801,6 +830,7 @@ int b200reg_icp_alignment(b200reg_ctx* c, int count, const float* const* src_xyz
   int rc = B200REG_OK;
   int chunk = 0;
   std::vector<b200reg_cloud*> sc(count, nullptr), tc(count, nullptr);
+  CloudBag bag(c);
   for (int k0 = 0; k0 < count && !rc; k0 += per, chunk++) {
     const int k1 = std::min(count, k0 + per), m = k1 - k0;
     CU(cudaStreamWaitEvent(s, landed[chunk], 0));
@@ -814,6 +844,8 @@ int b200reg_icp_alignment(b200reg_ctx* c, int count, const float* const* src_xyz
       ns[m + i - k0] = tgt_n[i];
     }
     rc = b200reg_clouds_create(c, 2 * m, ptrs.data(), ns.data(), stride_bytes, 1, cl.data());
+    for (b200reg_cloud* p : cl)
+      if (p) bag.cl.push_back(p);
     for (int i = k0; i < k1; i++) {
       sc[i] = cl[i - k0];
       tc[i] = cl[m + i - k0];
@@ -821,14 +853,7 @@ int b200reg_icp_alignment(b200reg_ctx* c, int count, const float* const* src_xyz
     if (!rc) rc = b200reg_clouds_covariances_ex(c, 2 * m, cl.data(), params->k_correspondences, params->regularization);
   }
   if (!rc) rc = b200reg_gicp_align(c, count, sc.data(), tc.data(), nullptr, params, out);
-  for (int i = 0; i < count; i++) {
-    b200reg_cloud_destroy(c, sc[i]);
-    b200reg_cloud_destroy(c, tc[i]);
-  }
-  cudaStreamSynchronize(c->copy_stream);
-  for (cudaEvent_t e : landed) cudaEventDestroy(e);
-  cudaEventDestroy(ready);
-  return rc;
+  return rc;  // clouds, events and the copy stream are released / drained by the scope guards
 }
 
 int b200reg_transform_cloud(b200reg_ctx* c, const b200reg_cloud* cl, const float* Tf16, float* out_xyz) {
@@ -1261,10 +1286,8 @@ static int coarse_to_fine_on_clouds(b200reg_ctx* c, int count, b200reg_cloud* co
   cudaStream_t s = c->stream;
   Scratch scratch(c);
   std::vector<b200reg_quatro_info> qi(count);
-  std::vector<b200reg_cloud*> coarse;
-  auto cleanup = [&]() {
-    for (b200reg_cloud* cl : coarse) b200reg_cloud_destroy(c, cl);
-  };
+  CloudBag coarse_bag(c);  // the transformed source clouds are released on every exit path
+  std::vector<b200reg_cloud*>& coarse = coarse_bag.cl;
   int rc = b200reg_quatro_align(c, count, src, dst, qp, qi.data(), nullptr);
   if (rc) return rc;
   if (quatro_out) memcpy(quatro_out, qi.data(), sizeof(b200reg_quatro_info) * count);
@@ -1316,10 +1339,7 @@ static int coarse_to_fine_on_clouds(b200reg_ctx* c, int count, b200reg_cloud* co
     for (int k = 0; k < nv; k++) tg[k] = dst[vidx[k]];
     std::vector<b200reg_result> gres(nv);
     if (!rc) rc = b200reg_gicp_align(c, nv, coarse.data(), tg.data(), nullptr, gp, gres.data());
-    if (rc) {
-      cleanup();
-      return rc;
-    }
+    if (rc) return rc;
     for (int k = 0; k < nv; k++) {
       const int i = vidx[k];
       b200reg_result r = gres[k];
@@ -1343,7 +1363,6 @@ static int coarse_to_fine_on_clouds(b200reg_ctx* c, int count, b200reg_cloud* co
       out[i] = r;
     }
   }
-  cleanup();
   return B200REG_OK;
 }
 

@@ -21,6 +21,9 @@
  *     fast_lio_sam_qn/src/fast_lio_sam_qn.cpp:81);
  *   - point buffers are (x, y, z [, ...]) fp32 records `stride_bytes` apart, so
  *     pcl::PointXYZI (32 B: x,y,z,1,intensity,pad) uploads without repacking;
+ *   - host buffers passed to a call (pinned or pageable) have been consumed when the call returns; device buffers passed
+ *     with on_device != 0 must stay valid until the context's stream has been synchronised or the call has returned a result;
+ *   - b200reg_ctx_set_stream may only be called while the context is idle (everything it owns is ordered on ONE stream);
  *   - there is NO CPU fallback: if no sm_100 device is present b200reg_ctx_create fails.
  */
 #ifndef B200REG_H

@@ -186,3 +186,27 @@ def test_quatro_batch_equals_single_and_invalid_pairs(ctx, synth):
         assert np.array_equal(res[i]["T"], single[0]["T"]) and np.array_equal(res[i]["T"], res2[i]["T"])
         assert qi[i]["n_corr"] == qs[0]["n_corr"] == qi2[i]["n_corr"]
     assert not qi[3]["valid"] and np.array_equal(qi[3]["T"], np.eye(4)) and not res[3]["valid"]
+
+
+def test_isolated_points_normals_descriptors_and_matching(ctx, oracle, synth):
+    """Points with fewer than 3 neighbours inside the normal radius (isolated returns): NaN normal, all-zero descriptor on
+    both sides, and they take no part in the matching (the deliberate definition stated in DESIGN §6 / oracle_quatro.cpp --
+    PCL would bin NaN-normal neighbours into bin 0 and FLANN would still match all-zero descriptors)."""
+    src, dst, _ = synth.make_pair(2001, 6000, 6500, mode="quatro")
+    lone = np.array([[200.0 + 10 * i, -150.0, 40.0, 0.5] for i in range(6)], np.float32)  # far from everything, 10 m apart
+    dst2 = np.concatenate([dst[:3000], lone, dst[3000:]]).astype(np.float32)
+    cl, = ctx.create_clouds([dst2])
+    ctx.fpfh([cl], 0.9, 1.5)
+    gn, gf = ctx.get_fpfh(cl)
+    on, _, of = oracle.fpfh(dst2, 0.9, 1.5)
+    idx = np.arange(3000, 3006)
+    assert np.isnan(gn[idx]).all() and np.isnan(on[idx]).all()
+    assert (gf[idx] == 0).all() and (of[idx] == 0).all()
+    assert np.array_equal(np.isnan(gn[:, 0]), np.isnan(on[:, 0]))
+    assert np.array_equal(np.abs(gf).sum(1) == 0, np.abs(of).sum(1) == 0)
+    cl.destroy()
+    # the matcher on the GPU's descriptors: same mutual set and correspondences as the oracle, no isolated point in either
+    info, fs, fd = _gpu_stage(ctx, src, dst2)
+    corr, mutual = oracle.match(src, dst2, fs, fd)
+    assert info["n_mutual"] == len(mutual) and np.array_equal(info["corr"], corr)
+    assert not np.isin(corr[:, 1], idx).any()
