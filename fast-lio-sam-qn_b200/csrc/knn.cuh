@@ -159,6 +159,23 @@ struct KnnHeap {
     for (int i = K / 2 - 1; i >= 0; i--) sift(i, d(i), p(i), K);
     wd = d(0);
   }
+  // sift from the root of a PERFECT tree (K = 2^m - 1: every internal slot has two children), levels unrolled: no bounds
+  // checks, the first level's slots are immediates
+  template <int LEVELS>
+  __device__ __forceinline__ void sift_root_perfect(float cd, int cp) {
+    int i = 0;
+#pragma unroll
+    for (int lv = 0; lv < LEVELS; lv++) {
+      const int l = 2 * i + 1;
+      const float dl = d(l), dr = d(l + 1);
+      const int ch = dr > dl ? l + 1 : l;
+      const float dc = fmaxf(dl, dr);
+      if (!(dc > cd)) break;
+      set(i, dc, p(ch));
+      i = ch;
+    }
+    set(i, cd, cp);
+  }
   // candidate with cd <= worst()
   __device__ __forceinline__ void offer(float cd, int cp, const float4* __restrict__ pts) {
     if (cd == wd) {  // cold: the (d2, original index) rule among everything tied at the worst distance
@@ -175,7 +192,9 @@ struct KnnHeap {
       if (orig_index(pts, cp) < worst_idx) hp[worst_slot * stride] = cp;
       return;
     }
-    sift(0, cd, cp, K);
+    if (K == 15) sift_root_perfect<3>(cd, cp);
+    else if (K == 31) sift_root_perfect<4>(cd, cp);
+    else sift(0, cd, cp, K);
     wd = d(0);
   }
   // Remove the worst entry under the full (d2, original index) order from a heap holding m entries; returns m - 1.
