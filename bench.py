@@ -7,7 +7,7 @@
 
 Headline (configs[1]): one "step" = LoopClosure::icpAlignment (fast_lio_sam_qn/src/loop_closure.cpp:110-136: two index
 builds, two covariance passes, align, fitness) over 256 synthetic 100k x 100k pairs per rank, issued as 16 jobs of 16 pairs
-to the C ABI's batch driver (b200reg_batch_*, five engine contexts on C++ host threads).  The jobs rotate over 4 DISTINCT
+to the C ABI's batch driver (b200reg_batch_*, three engine contexts on C++ host threads).  The jobs rotate over 4 DISTINCT
 sub-batches (64 distinct pairs, 205 MB of raw points per rank -- more than the 126 MB L2), nothing is replaced or skipped.
 Prints ONE JSON line (rank 0):
 
@@ -57,9 +57,11 @@ def parse():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--points", type=int, default=N_POINTS)
-    ap.add_argument("--depth", type=int, default=int(os.environ.get("B200REG_PIPE_DEPTH", "5")),
-                    help="engine contexts of the batch driver (measured on this workload, value / e2e pairs/s: 2: 4420 / 3811, 3: 4640 / 4145, "
-                         "4: 3856 / 4290 -- four contexts over four rotating sub-batches fall into lockstep --, 5: 4724 / 4372)")
+    ap.add_argument("--depth", type=int, default=int(os.environ.get("B200REG_PIPE_DEPTH", "3")),
+                    help="engine contexts of the batch driver.  Measured on this workload (value / e2e pairs/s, 20 steps): 2: 4420 / 3811; "
+                         "3: 4639 / 4145, 4641 / 4144, 4591 / 4107 (stable); 4: 3856 / 4290 (four contexts over four rotating sub-batches "
+                         "fall into lockstep); 5: 4653 / 4383, 4724 / 4372, but also 4066 / 4395 -- more contexts hide more of the uploads "
+                         "yet can phase-lock on the device-resident arm, so the default stays at the stable 3")
     ap.add_argument("--secondary", default="all", help="comma list of secondary workloads: voxel,raw,sequence,batch512 | all | none")
     ap.add_argument("--keyframes", type=int, default=2761, help="sequence workload: keyframes generated (KITTI 05: 2761)")
     ap.add_argument("--matching", default="optimized", choices=["optimized", "advanced"])
