@@ -432,3 +432,20 @@ def test_all_regularization_methods(ctx, oracle, synth, pair5k):
     assert not np.array_equal(g["T"], p3["T"])  # a different weighting gives a (slightly) different optimum
     rot, tr = synth.se3_error(g["T"], Texp)
     assert rot < 2e-2 and tr < 0.3  # still lands on the ground truth
+
+
+def test_large_batch_beyond_the_shared_slot_cache(ctx, synth):
+    """More pairs than the LM schedule caches in shared memory (LM_SMEM_SLOTS = 512): the slot list's tail is read from global
+    memory; every pair of the batch must equal its single-pair result bit for bit, finished pairs dropping out at
+    different steps."""
+    rng = np.random.default_rng(7)
+    base = [synth.make_pair(1300 + i, 600 + 40 * i, 700 + 30 * i) for i in range(6)]
+    order = rng.integers(0, 6, 530)
+    srcs = [base[k][0] for k in order]
+    dsts = [base[k][1] for k in order]
+    batch = ctx.icp_alignment(srcs, dsts)
+    singles = [ctx.icp_alignment([b[0]], [b[1]])[0] for b in base]
+    assert len({s["n_linearize"] for s in singles}) > 1  # pairs finish at different steps
+    for r, k in zip(batch, order):
+        assert np.array_equal(r["T"], singles[k]["T"]) and r["fitness"] == singles[k]["fitness"]
+        assert r["n_linearize"] == singles[k]["n_linearize"] and r["converged"] == singles[k]["converged"]
