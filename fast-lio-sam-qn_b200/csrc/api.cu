@@ -430,9 +430,9 @@ int b200reg_clouds_create(b200reg_ctx* c, int count, const float* const* xyz, co
     d.nrm = nullptr;
     d.spfh = nullptr;
     d.fpfh = nullptr;
-    d.fnorm = nullptr;
+    d.fproj = nullptr;
     d.fpfh_s = nullptr;
-    d.fnorm_s = nullptr;
+    d.fproj_s = nullptr;
     d.ftile = nullptr;
     d.fcode_s = nullptr;
     // temporary slab (sort buffers, tree scratch, bbox partials, and the raw records when uploading)
@@ -1066,30 +1066,40 @@ int b200reg_clouds_fpfh(b200reg_ctx* c, int count, b200reg_cloud* const* clouds,
       cl->dev.nrm = (float4*)(fs + o_n);
       cl->dev.spfh = (float*)(fs + o_s);
       cl->dev.fpfh = (float*)(fs + o_f);
-      cl->dev.fnorm = (float4*)(fs + o_fn);
+      cl->dev.fproj = (float4*)(fs + o_fn);
       cl->dev.fpfh_s = cl->dev.spfh;  // the SPFH table is dead once k_fpfh has consumed it
-      cl->dev.fnorm_s = (float4*)(fs + o_fns);
+      cl->dev.fproj_s = (float4*)(fs + o_fns);
       cl->dev.ftile = (float4*)(fs + o_ft);
       cl->dev.fcode_s = (uint32_t*)(fs + o_fc);
     }
     todo.push_back(cl);
     descs.push_back(cl->dev);
-    {  // sort buffers of the norm-code ordering (scratch: only this call uses them)
-      CloudDev& d = descs.back();
-      const size_t n = d.n;
-      const size_t s_k = align_up(n * 4, 256), s_ws = align_up(radix_sort_ws_bytes((int)n, 30), 256);
-      char* sb = nullptr;
-      CU(scratch.alloc((void**)&sb, 4 * s_k + s_ws));
-      d.keys[0] = (uint32_t*)sb;
-      d.keys[1] = (uint32_t*)(sb + s_k);
-      d.vals[0] = (uint32_t*)(sb + 2 * s_k);
-      d.vals[1] = (uint32_t*)(sb + 3 * s_k);
-      d.hist = (uint32_t*)(sb + 4 * s_k);
-      CU(cudaMemsetAsync(d.hist, 0, s_ws, s));
-    }
     max_n = std::max(max_n, cl->dev.n);
   }
   if (todo.empty()) return B200REG_OK;
+  {  // sort buffers of the filter-code ordering (scratch: only this call uses them); the work memory of all clouds is one
+     // region, zeroed by one memset
+    size_t ws_total = 0, k_total = 0;
+    for (auto& d : descs) {
+      ws_total += align_up(radix_sort_ws_bytes(d.n, 32), 256);
+      k_total += 4 * align_up((size_t)d.n * 4, 256);
+    }
+    char* sb = nullptr;
+    CU(scratch.alloc((void**)&sb, ws_total + k_total));
+    CU(cudaMemsetAsync(sb, 0, ws_total, s));
+    char* ws = sb;
+    char* kb = sb + ws_total;
+    for (auto& d : descs) {
+      const size_t s_k = align_up((size_t)d.n * 4, 256);
+      d.hist = (uint32_t*)ws;
+      ws += align_up(radix_sort_ws_bytes(d.n, 32), 256);
+      d.keys[0] = (uint32_t*)kb;
+      d.keys[1] = (uint32_t*)(kb + s_k);
+      d.vals[0] = (uint32_t*)(kb + 2 * s_k);
+      d.vals[1] = (uint32_t*)(kb + 3 * s_k);
+      kb += 4 * s_k;
+    }
+  }
   CloudDev* d_descs = nullptr;
   CU(scratch.alloc((void**)&d_descs, sizeof(CloudDev) * descs.size()));
   CU(cudaMemcpyAsync(d_descs, descs.data(), sizeof(CloudDev) * descs.size(), cudaMemcpyHostToDevice, s));

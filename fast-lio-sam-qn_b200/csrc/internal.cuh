@@ -41,14 +41,15 @@ struct CloudDev {
   // Quatro features (allocated by b200reg_clouds_fpfh; sorted order)
   float4* nrm;         // [n] unit normal, w = 1 valid / 0 invalid (< 3 neighbours)
   float* spfh;         // [FPAD * n]
-  float* fpfh;         // [FPAD * n]; slot 33 = original index (int bits), slot 34 = 1.0 if the descriptor is usable
-  float4* fnorm;       // [n] L2 norms of the three 11-bin blocks (x, y, z): lower bound ||a-b||^2 >= sum_k (|a_k| - |b_k|)^2
-  // the matcher's view of the descriptors: records re-ordered by the Morton code of their three block norms, so that a
-  // tile of 64 consecutive records is a small box in norm space and whole tiles can be skipped per query
-  float* fpfh_s;       // [FPAD * n] (aliases spfh, which is dead once k_fpfh has run); unusable records last
-  float4* fnorm_s;     // [n]
-  float4* ftile;       // [2 * ceil(n / 64)] per tile: (min norms, #usable) and (max norms, -)
-  uint32_t* fcode_s;   // [n] sorted norm codes (0x3FFFFFFF+ for unusable records)
+  float* fpfh;         // [FPAD * n]; slot 33 = original index (int bits), slot 34 = 1.0 if the descriptor is usable, slot 35 = hash of its bits
+  float4* fproj;       // [n] filter coordinates (fpfh_basis.cuh): 3 projections + residual norm, ||a-b||^2 >= their squared distance
+  // the matcher's view of the descriptors: records re-ordered by the Morton code of their filter coordinates, so that a
+  // tile of 64 consecutive records is a small box in filter space and whole tiles can be skipped per query
+  float* fpfh_s;       // [FPAD * n] (aliases spfh, which is dead once k_fpfh has run); unusable records last; slot 34 = 1 base
+                       // record / 2 duplicate of its predecessor (query only), slot 35 = index a base record answers with
+  float4* fproj_s;     // [n]
+  float4* ftile;       // [2 * ceil(n / 64)] per tile: min and max filter coordinates of its base records (+inf / -inf if none)
+  uint32_t* fcode_s;   // [n] sorted keys: 28-bit filter-space Morton code, 4 hash bits (0xFFFFFFFF for unusable records)
   // build-time temporaries (freed after the build)
   uint32_t* keys[2];   // sort ping-pong
   uint32_t* vals[2];

@@ -16,6 +16,7 @@
 //      k_big_*                           the same solve over a global-memory workspace for > 512 correspondences
 // Deliberate definitions where the reference is seed- or race-dependent are listed in oracle/oracle_quatro.cpp.
 #include "internal.cuh"
+#include "fpfh_basis.cuh"
 #include "knn.cuh"
 #include "smallmath.cuh"
 
@@ -188,14 +189,29 @@ __global__ void __launch_bounds__(STEP_THREADS) k_fpfh(const CloudDev* clouds, f
   }
   out[33] = p.w;  // original index (int bits)
   out[34] = any ? 1.f : 0.f;
-  out[35] = 0.f;
-  float n0 = 0.f, n1 = 0.f, n2 = 0.f;
+  // the matcher's filter coordinates (fpfh_basis.cuh): projections on three fixed orthonormal directions and the norm of
+  // the residual, computed from the residual VECTOR (no cancellation of large sums); plus a hash of the record's bits
+  float x[FDIM];
+  float c0 = 0.f, c1 = 0.f, c2 = 0.f;
+  uint32_t hsh = 0x811C9DC5u;
 #pragma unroll
-  for (int k = 0; k < 11; k++) {
-    const float a = h[k] * sc0, b = h[11 + k] * sc1, cc = h[22 + k] * sc2;
-    n0 += a * a; n1 += b * b; n2 += cc * cc;
+  for (int k = 0; k < FDIM; k++) {
+    const float v = h[k] * (k < 11 ? sc0 : (k < 22 ? sc1 : sc2));
+    hsh = (hsh ^ __float_as_uint(v)) * 0x01000193u;
+    hsh ^= hsh >> 15;
+    x[k] = v - FB_MU[k];
+    c0 += x[k] * FB_U[0][k];
+    c1 += x[k] * FB_U[1][k];
+    c2 += x[k] * FB_U[2][k];
   }
-  c.fnorm[i] = make_float4(sqrtf(n0), sqrtf(n1), sqrtf(n2), 0.f);
+  float rr = 0.f;
+#pragma unroll
+  for (int k = 0; k < FDIM; k++) {
+    const float e = x[k] - ((c0 * FB_U[0][k] + c1 * FB_U[1][k]) + c2 * FB_U[2][k]);
+    rr += e * e;
+  }
+  out[35] = __uint_as_float(hsh);
+  c.fproj[i] = make_float4(c0, c1, c2, sqrtf(rr));
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -228,91 +244,148 @@ constexpr int NN_THREADS = 128;  // 4 warps, each owning 32 queries (measured: 6
 constexpr int NN_TILE = 64;      // base descriptors per smem tile: 64 * 144 B = 9216 B per cp.async.bulk
 constexpr int NN_QCAP = 96;      // per-warp survivor queue (drained whenever it holds >= 32 entries)
 
-// ---- norm-space ordering of the descriptors (the matcher's view) -------------------------------------------------
-__device__ __forceinline__ uint32_t spread10(uint32_t v) {
-  v = (v | (v << 16)) & 0x030000FFu;
-  v = (v | (v << 8)) & 0x0300F00Fu;
-  v = (v | (v << 4)) & 0x030C30C3u;
-  v = (v | (v << 2)) & 0x09249249u;
-  return v;
+// ---- filter-space ordering of the descriptors (the matcher's view) ------------------------------------------------
+// fixed quantiser of the filter coordinates (half-ranges from the spread of real descriptors; outliers clamp -- the code
+// only orders the records, exactness never depends on it)
+__device__ __forceinline__ uint32_t fcode_of(const float4 f) {
+  const int q0 = min(127, max(0, (int)((f.x + 60.f) * (128.f / 120.f)))), q1 = min(127, max(0, (int)((f.y + 40.f) * (128.f / 80.f)))),
+            q2 = min(127, max(0, (int)((f.z + 30.f) * (128.f / 60.f)))), q3 = min(127, max(0, (int)(f.w * (128.f / 60.f))));
+  uint32_t c = 0;
+#pragma unroll
+  for (int b = 0; b < 7; b++)
+    c |= (((uint32_t)q0 >> b) & 1u) << (4 * b) | (((uint32_t)q1 >> b) & 1u) << (4 * b + 1) | (((uint32_t)q2 >> b) & 1u) << (4 * b + 2) |
+         (((uint32_t)q3 >> b) & 1u) << (4 * b + 3);
+  return c;
 }
-// sort key of sorted position p: Morton code of the three block norms (each in [0, 100]) at 10 bits; unusable
+// sort key of sorted position p: 28-bit Morton code of the four filter coordinates, then 4 hash bits so that bitwise
+// identical descriptors (planar patches all produce the same histogram) end up next to each other; unusable
 // descriptors go to the end
 __global__ void __launch_bounds__(256) k_fcode(const CloudDev* clouds) {
   const CloudDev& c = clouds[blockIdx.y];
   const int p = blockIdx.x * blockDim.x + threadIdx.x;
   if (p >= c.n) return;
-  const float4 nr = c.fnorm[p];
-  const bool ok = c.fpfh[(size_t)p * FPAD + 34] != 0.f;
-  const uint32_t q0 = min(1023u, (uint32_t)(nr.x * 10.23f)), q1 = min(1023u, (uint32_t)(nr.y * 10.23f)), q2 = min(1023u, (uint32_t)(nr.z * 10.23f));
-  c.keys[0][p] = ok ? ((spread10(q2) << 2) | (spread10(q1) << 1) | spread10(q0)) : 0x3FFFFFFFu;
+  const float4 tail = *reinterpret_cast<const float4*>(c.fpfh + (size_t)p * FPAD + 32);  // slots 32..35
+  const bool ok = tail.z != 0.f;
+  c.keys[0][p] = ok ? ((fcode_of(c.fproj[p]) << 4) | (__float_as_uint(tail.w) & 15u)) : 0xFFFFFFFFu;
   c.vals[0][p] = (uint32_t)p;
 }
-// gather the records into code order and box every tile of NN_TILE records in norm space.  One 64-thread block per tile.
+// gather the records into code order, collapse runs of bitwise identical descriptors and box every tile of NN_TILE
+// records in filter space.  One 64-thread block per tile.
+//   A run (consecutive identical records inside one tile) keeps its first record as a BASE record, carrying the run's
+//   lowest original index in slot 35 -- exactly what the lowest-index tie rule would pick among them; the others get
+//   flag 2: still queries, never candidates.  Runs that a tile border or a hash collision splits simply keep two heads.
 __global__ void __launch_bounds__(NN_TILE) k_fgather(const CloudDev* clouds) {
   const CloudDev& c = clouds[blockIdx.y];
   const int t = blockIdx.x;
   if (t * NN_TILE >= c.n) return;
   const int r = t * NN_TILE + threadIdx.x;
-  float lo[3] = {INFINITY, INFINITY, INFINITY}, hi[3] = {-INFINITY, -INFINITY, -INFINITY};
-  int usable = 0;
-  if (r < c.n) {
-    const int p = (int)c.vals[1][r];  // radix_sort_result_buf()
-    const float4* s4 = reinterpret_cast<const float4*>(c.fpfh + (size_t)p * FPAD);
-    float4* d4 = reinterpret_cast<float4*>(c.fpfh_s + (size_t)r * FPAD);
-    float4 last;
+  __shared__ int s_p[NN_TILE];
+  __shared__ int s_same[NN_TILE];
+  __shared__ int s_min[NN_TILE];
+  float lo[4] = {INFINITY, INFINITY, INFINITY, INFINITY}, hi[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
+  float4 rec[9];
 #pragma unroll
-    for (int k = 0; k < 9; k++) {
-      last = s4[k];
-      d4[k] = last;
-    }
-    const float4 nr = c.fnorm[p];
-    c.fnorm_s[r] = nr;
-    c.fcode_s[r] = c.keys[1][r];
-    if (last.z != 0.f) {  // slot 34
-      usable = 1;
-      lo[0] = hi[0] = nr.x; lo[1] = hi[1] = nr.y; lo[2] = hi[2] = nr.z;
+  for (int k = 0; k < 9; k++) rec[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+  float4 fp = make_float4(0.f, 0.f, 0.f, 0.f);
+  int p = -1;
+  bool usable = false;
+  if (r < c.n) {
+    p = (int)c.vals[1][r];  // radix_sort_result_buf()
+    const float4* s4 = reinterpret_cast<const float4*>(c.fpfh + (size_t)p * FPAD);
+#pragma unroll
+    for (int k = 0; k < 9; k++) rec[k] = s4[k];
+    fp = c.fproj[p];
+    usable = rec[8].z != 0.f;  // slot 34
+  }
+  s_p[threadIdx.x] = usable ? p : -1;
+  s_min[threadIdx.x] = __float_as_int(rec[8].y);  // own original index
+  __syncthreads();
+  bool same = false;
+  if (usable && threadIdx.x > 0 && s_p[threadIdx.x - 1] >= 0) {
+    const float4* q4 = reinterpret_cast<const float4*>(c.fpfh + (size_t)s_p[threadIdx.x - 1] * FPAD);
+    const float4 qt = q4[8];
+    same = __float_as_uint(qt.w) == __float_as_uint(rec[8].w) && __float_as_uint(qt.x) == __float_as_uint(rec[8].x);  // hash, slot 32
+    for (int k = 0; same && k < 8; k++) {
+      const float4 v = q4[k];
+      same = __float_as_uint(v.x) == __float_as_uint(rec[k].x) && __float_as_uint(v.y) == __float_as_uint(rec[k].y) &&
+             __float_as_uint(v.z) == __float_as_uint(rec[k].z) && __float_as_uint(v.w) == __float_as_uint(rec[k].w);
     }
   }
-  __shared__ float red[2][7];
+  s_same[threadIdx.x] = same ? 1 : 0;
+  __syncthreads();
+  if (same) {
+    int h = threadIdx.x - 1;
+    while (s_same[h]) h--;  // s_same[0] == 0
+    atomicMin(&s_min[h], __float_as_int(rec[8].y));
+  }
+  __syncthreads();
+  if (r < c.n) {
+    rec[8].z = !usable ? 0.f : (same ? 2.f : 1.f);
+    rec[8].w = __int_as_float(s_min[threadIdx.x]);  // base index: the run's lowest original index (heads), own otherwise
+    float4* d4 = reinterpret_cast<float4*>(c.fpfh_s + (size_t)r * FPAD);
+#pragma unroll
+    for (int k = 0; k < 9; k++) d4[k] = rec[k];
+    c.fproj_s[r] = fp;
+    c.fcode_s[r] = c.keys[1][r];
+    if (usable && !same) {
+      lo[0] = hi[0] = fp.x; lo[1] = hi[1] = fp.y; lo[2] = hi[2] = fp.z; lo[3] = hi[3] = fp.w;
+    }
+  }
+  __shared__ float red[2][8];
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) {
 #pragma unroll
-    for (int d = 0; d < 3; d++) {
+    for (int d = 0; d < 4; d++) {
       lo[d] = fminf(lo[d], __shfl_xor_sync(0xffffffffu, lo[d], o));
       hi[d] = fmaxf(hi[d], __shfl_xor_sync(0xffffffffu, hi[d], o));
     }
-    usable += __shfl_xor_sync(0xffffffffu, usable, o);
   }
   if ((threadIdx.x & 31) == 0) {
     float* w = red[threadIdx.x >> 5];
-    w[0] = lo[0]; w[1] = lo[1]; w[2] = lo[2]; w[3] = hi[0]; w[4] = hi[1]; w[5] = hi[2]; w[6] = (float)usable;
+#pragma unroll
+    for (int d = 0; d < 4; d++) {
+      w[d] = lo[d];
+      w[4 + d] = hi[d];
+    }
   }
   __syncthreads();
-  if (threadIdx.x == 0) {
-    c.ftile[2 * t] = make_float4(fminf(red[0][0], red[1][0]), fminf(red[0][1], red[1][1]), fminf(red[0][2], red[1][2]), red[0][6] + red[1][6]);
-    c.ftile[2 * t + 1] = make_float4(fmaxf(red[0][3], red[1][3]), fmaxf(red[0][4], red[1][4]), fmaxf(red[0][5], red[1][5]), 0.f);
+  if (threadIdx.x == 0) {  // a tile without base records keeps lo = +inf: its lower bound is +inf, nobody visits it
+    c.ftile[2 * t] = make_float4(fminf(red[0][0], red[1][0]), fminf(red[0][1], red[1][1]), fminf(red[0][2], red[1][2]), fminf(red[0][3], red[1][3]));
+    c.ftile[2 * t + 1] = make_float4(fmaxf(red[0][4], red[1][4]), fmaxf(red[0][5], red[1][5]), fmaxf(red[0][6], red[1][6]), fmaxf(red[0][7], red[1][7]));
   }
 }
 
-// lower bound of the filter's record test over every record of a tile: distance from the query's norm triple to the
+// filter test of one record: squared distance of the filter coordinates
+__device__ __forceinline__ float filt_lb(const float4& q, const float4& b) {
+  const float e0 = q.x - b.x, e1 = q.y - b.y, e2 = q.z - b.z, e3 = q.w - b.w;
+  return ((e0 * e0 + e1 * e1) + e2 * e2) + e3 * e3;
+}
+// lower bound of the filter's record test over every record of a tile: distance from the query's coordinates to the
 // tile's box.  Same operation order as the record test and rounding is monotone, so box_lb <= record lower bound.
-__device__ __forceinline__ float tile_lb(const float4& qn, const float4& lo, const float4& hi) {
-  const float e0 = fmaxf(fmaxf(lo.x - qn.x, qn.x - hi.x), 0.f), e1 = fmaxf(fmaxf(lo.y - qn.y, qn.y - hi.y), 0.f),
-              e2 = fmaxf(fmaxf(lo.z - qn.z, qn.z - hi.z), 0.f);
-  return (e0 * e0 + e1 * e1) + e2 * e2;
+__device__ __forceinline__ float tile_lb(const float4& q, const float4& lo, const float4& hi) {
+  const float e0 = fmaxf(fmaxf(lo.x - q.x, q.x - hi.x), 0.f), e1 = fmaxf(fmaxf(lo.y - q.y, q.y - hi.y), 0.f),
+              e2 = fmaxf(fmaxf(lo.z - q.z, q.z - hi.z), 0.f), e3 = fmaxf(fmaxf(lo.w - q.w, q.w - hi.w), 0.f);
+  return ((e0 * e0 + e1 * e1) + e2 * e2) + e3 * e3;
+}
+// acceptance threshold of the filter for a query whose best squared distance so far is `best`.  The filter value is a
+// true lower bound of the distance up to fp32 rounding of the coordinates (worst case 2.4e-3 in distance for |a - mu| <=
+// 173, measured 7e-5: profiles/emulate_projected_bound_margin.py) and of the refine's sum (4e-6 relative).
+__device__ __forceinline__ float filt_bound(float best) {
+  const float sb = sqrtf(best) * 1.00001f + 4e-3f;
+  return sb * sb;
 }
 
-// Exact 33-D 1-NN by filter-and-refine over norm-ordered tiles.
-//  * Both clouds are held in the order of the Morton code of their three block norms (k_fcode / k_fgather), so the 128
-//    queries of a block are similar and a base tile of 64 records is a small box in norm space.
+// Exact 33-D 1-NN by filter-and-refine over filter-ordered tiles.
+//  * Both clouds are held in the order of the Morton code of their four filter coordinates (k_fcode / k_fgather), so the
+//    128 queries of a block are similar and a base tile of 64 records is a small box in filter space; bitwise identical
+//    base records are collapsed to one candidate per run (k_fgather).
 //  * A block starts at the base tile nearest to its own queries (binary search of the code) and sweeps up, then down:
 //    good matches are found in the first tiles and the bound is tight from then on.
 //  * Per tile: every lane tests ITS query against the tile box (one test instead of 64); tiles nobody in the block
 //    needs are not even fetched (__syncthreads_or), tiles are fetched by cp.async.bulk (TMA) one ahead.
-//  * Per (needed query, tile): the 32 lanes test 32+32 records against the block-norm lower bound
-//    sum_k (|a_k| - |b_k|)^2 <= |a - b|^2, ballot-compact the survivors into a per-warp queue, and refine 32 queued
-//    pairs at a time with the full fp32 distance in the oracle's operation order.
+//  * Per (needed query, tile): the 32 lanes test 32+32 records against the projected lower bound
+//    sum_i (u_i.(a - b))^2 + (|r_a| - |r_b|)^2 <= |a - b|^2 (fpfh_basis.cuh), ballot-compact the survivors into a
+//    per-warp queue, and refine 32 queued pairs at a time with the full fp32 distance in the oracle's operation order.
 // Exact: both bounds are true lower bounds applied with a margin against rounding; ties go to the lower original index
 // through the packed (d2 bits, index) 64-bit minimum, so the visiting order does not matter.
 // mode 0: queries = fj, base = fi; writes nn/dis by ORIGINAL j
@@ -352,7 +425,7 @@ __global__ void __launch_bounds__(NN_THREADS) k_feat_nn(const MatchDev* pairs, i
     }
     qorig = __float_as_int(last.y);
     qok = inrange && last.z != 0.f;
-    if (inrange) qn = Q.fnorm_s[qi];
+    if (inrange) qn = Q.fproj_s[qi];
     // reverse search: i was reached from j0 = first_j[i] at distance dis[j0], and the metric is symmetric, so that
     // very pair is a valid starting candidate -- the filter is tight from the first tile on
     unsigned long long init = ((unsigned long long)__float_as_uint(lim) << 32) | 0xFFFFFFFFull;
@@ -361,7 +434,6 @@ __global__ void __launch_bounds__(NN_THREADS) k_feat_nn(const MatchDev* pairs, i
       if (j0 == 0x7FFFFFFF) qok = false;  // nobody asked for this point
       else init = ((unsigned long long)__float_as_uint(P.dis[j0]) << 32) | (unsigned)j0;
     }
-    qn.w = qok ? 1.f : 0.f;
     sqn[warp][lane] = qn;
     sbest[warp][lane] = init;
   }
@@ -395,10 +467,8 @@ __global__ void __launch_bounds__(NN_THREADS) k_feat_nn(const MatchDev* pairs, i
   // does this thread's query still need tile t?
   auto my_need = [&](int t) {
     if (!qok) return false;
-    const float4 lo4 = __ldg(&boxes[2 * t]), hi4 = __ldg(&boxes[2 * t + 1]);
-    if (lo4.w == 0.f) return false;  // no usable record in the tile
-    const float bound = fminf(lim, __uint_as_float((unsigned)(sbest[warp][lane] >> 32))) * 1.0001f + 1e-3f;
-    return tile_lb(qn, lo4, hi4) <= bound;
+    const float4 lo4 = __ldg(&boxes[2 * t]), hi4 = __ldg(&boxes[2 * t + 1]);  // lo = +inf when the tile has no base record
+    return tile_lb(qn, lo4, hi4) <= filt_bound(fminf(lim, __uint_as_float((unsigned)(sbest[warp][lane] >> 32))));
   };
   // first visit index >= k whose tile somebody in the block needs (ntiles if none).  Always at least one barrier: it
   // also orders "every warp is done with the buffer about to be refilled" before the refill.
@@ -414,7 +484,7 @@ __global__ void __launch_bounds__(NN_THREADS) k_feat_nn(const MatchDev* pairs, i
     const unsigned bytes = (unsigned)cnt * FPAD * 4, nbytes = (unsigned)cnt * 16;
     mbar_expect_tx(&full[buf], bytes + nbytes);
     bulk_g2s(tile[buf], B.fpfh_s + (size_t)t * NN_TILE * FPAD, bytes, &full[buf]);
-    bulk_g2s(tnorm[buf], B.fnorm_s + (size_t)t * NN_TILE, nbytes, &full[buf]);
+    bulk_g2s(tnorm[buf], B.fproj_s + (size_t)t * NN_TILE, nbytes, &full[buf]);
   };
   int qn_count = 0;  // entries in this warp's queue (warp-uniform)
   // refine up to 32 queued (query, record) pairs: one per lane
@@ -443,7 +513,7 @@ __global__ void __launch_bounds__(NN_THREADS) k_feat_nn(const MatchDev* pairs, i
         d += e0 * e0;
       }
       // most refined pairs do not beat the current best (near-duplicate descriptors): look before the atomic
-      const unsigned long long cand = ((unsigned long long)__float_as_uint(d) << 32) | (unsigned)__float_as_int(y.y);
+      const unsigned long long cand = ((unsigned long long)__float_as_uint(d) << 32) | (unsigned)__float_as_int(y.w);  // slot 35
       if (d < lim && cand < sbest[warp][ql]) atomicMin(&sbest[warp][ql], cand);
     }
     __syncwarp();
@@ -470,26 +540,24 @@ __global__ void __launch_bounds__(NN_THREADS) k_feat_nn(const MatchDev* pairs, i
       const float* tb = tile[it & 1];
       const float4* tn = tnorm[it & 1];
       const int cnt = min(NN_TILE, nb - t * NN_TILE);
-      // this lane's two base records of the tile: block norms and usability
+      // this lane's two base records of the tile: filter coordinates and whether they are candidates (flag 1: not a duplicate)
       float4 bn0 = make_float4(0.f, 0.f, 0.f, 0.f), bn1 = bn0;
       bool ok0 = false, ok1 = false;
       if (lane < cnt) {
         bn0 = tn[lane];
-        ok0 = tb[lane * FPAD + 34] != 0.f;
+        ok0 = tb[lane * FPAD + 34] == 1.f;
       }
       if (lane + 32 < cnt) {
         bn1 = tn[lane + 32];
-        ok1 = tb[(lane + 32) * FPAD + 34] != 0.f;
+        ok1 = tb[(lane + 32) * FPAD + 34] == 1.f;
       }
       while (mask) {
         const int ql = __ffs(mask) - 1;
         mask &= mask - 1;
         const float4 qv = sqn[warp][ql];  // broadcast
-        const float bound = fminf(lim, __uint_as_float((unsigned)(sbest[warp][ql] >> 32))) * 1.0001f + 1e-3f;
-        float e0 = qv.x - bn0.x, e1 = qv.y - bn0.y, e2 = qv.z - bn0.z;
-        const bool p0 = ok0 && ((e0 * e0 + e1 * e1) + e2 * e2 <= bound);
-        e0 = qv.x - bn1.x; e1 = qv.y - bn1.y; e2 = qv.z - bn1.z;
-        const bool p1 = ok1 && ((e0 * e0 + e1 * e1) + e2 * e2 <= bound);
+        const float bound = filt_bound(fminf(lim, __uint_as_float((unsigned)(sbest[warp][ql] >> 32))));
+        const bool p0 = ok0 && filt_lb(qv, bn0) <= bound;
+        const bool p1 = ok1 && filt_lb(qv, bn1) <= bound;
         const unsigned m0 = __ballot_sync(0xffffffffu, p0), m1 = __ballot_sync(0xffffffffu, p1);
         const unsigned lt = (1u << lane) - 1u;
         if (p0) queue[warp][qn_count + __popc(m0 & lt)] = (unsigned short)((ql << 8) | lane);
@@ -1634,9 +1702,9 @@ int launch_fpfh(const CloudDev* d_clouds, int count, int max_n, float normal_r2,
   k_normals<<<grid, STEP_THREADS, 0, s>>>(d_clouds, normal_r2);
   k_spfh<<<grid, STEP_THREADS, 0, s>>>(d_clouds, fpfh_r2);
   k_fpfh<<<grid, STEP_THREADS, 0, s>>>(d_clouds, fpfh_r2);
-  // the matcher's view: records in the order of their block-norm Morton code, boxed per tile
+  // the matcher's view: records in the order of their filter-space Morton code, duplicates collapsed, boxed per tile
   k_fcode<<<dim3((max_n + 255) / 256, count), 256, 0, s>>>(d_clouds);
-  const int ls = launch_radix_sort(d_clouds, count, max_n, 30, s);  // 30-bit keys, 3 passes of 10 bits: result in keys[1] / vals[1]
+  const int ls = launch_radix_sort(d_clouds, count, max_n, 32, s);  // 32-bit keys, 3 passes of 11 bits: result in keys[1] / vals[1]
   k_fgather<<<dim3((max_n + NN_TILE - 1) / NN_TILE, count), NN_TILE, 0, s>>>(d_clouds);
   return 5 + ls;
 }
