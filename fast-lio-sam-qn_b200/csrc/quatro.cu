@@ -402,8 +402,10 @@ __global__ void __launch_bounds__(NN_THREADS) k_feat_nn(const MatchDev* pairs, i
   __shared__ __align__(16) float sq[NN_THREADS / 32][32 * FPAD];
   __shared__ __align__(16) float4 sqn[NN_THREADS / 32][32];
   __shared__ unsigned long long sbest[NN_THREADS / 32][32];
+  __shared__ int sbound[NN_THREADS / 32][32];  // filt_bound(best d2) as int bits (positive floats order like ints): atomicMin
   __shared__ unsigned short queue[NN_THREADS / 32][NN_QCAP];
   __shared__ __align__(8) unsigned long long full[2];
+  __shared__ unsigned s_need[3];  // block-level need masks of the current / next chunks of tile visits
   __shared__ int s_t0;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const float lim = __int_as_float(__float_as_int(thr2) + 1);  // nextafter(thr2, +inf): d2 == thr2 still qualifies
@@ -436,6 +438,8 @@ __global__ void __launch_bounds__(NN_THREADS) k_feat_nn(const MatchDev* pairs, i
     }
     sqn[warp][lane] = qn;
     sbest[warp][lane] = init;
+    sbound[warp][lane] = __float_as_int(filt_bound(fminf(lim, __uint_as_float((unsigned)(init >> 32)))));
+    if (threadIdx.x < 3) s_need[threadIdx.x] = 0u;
   }
   if (!__syncthreads_or(qok ? 1 : 0)) {  // nothing to search for in this block
     if (mode == 0 && qi < nq && qorig >= 0) {
@@ -464,19 +468,55 @@ __global__ void __launch_bounds__(NN_THREADS) k_feat_nn(const MatchDev* pairs, i
   const int t0 = s_t0, up = ntiles - t0;
   auto visit = [&](int k) { return k < up ? t0 + k : t0 - 1 - (k - up); };
   const float4* boxes = B.ftile;
-  // does this thread's query still need tile t?
+  // does this thread's query still need tile t?  (lo = +inf when the tile has no base record)
   auto my_need = [&](int t) {
     if (!qok) return false;
-    const float4 lo4 = __ldg(&boxes[2 * t]), hi4 = __ldg(&boxes[2 * t + 1]);  // lo = +inf when the tile has no base record
-    return tile_lb(qn, lo4, hi4) <= filt_bound(fminf(lim, __uint_as_float((unsigned)(sbest[warp][lane] >> 32))));
+    const float4 lo4 = __ldg(&boxes[2 * t]), hi4 = __ldg(&boxes[2 * t + 1]);
+    return tile_lb(qn, lo4, hi4) <= __int_as_float(sbound[warp][lane]);
   };
-  // first visit index >= k whose tile somebody in the block needs (ntiles if none).  Always at least one barrier: it
-  // also orders "every warp is done with the buffer about to be refilled" before the refill.
+  // First visit index >= k whose tile somebody in the block needs (ntiles if none).  The decision is taken for a CHUNK
+  // of visits at a time (every thread tests its query against the chunk's boxes with its current bound, one block-wide
+  // OR per chunk instead of one barrier per tile); the bound only tightens afterwards, so the mask is a superset and the
+  // warps re-test at the visit.  The first chunks are short: a forward search starts with the gate as its bound.
+  // Always at least one barrier per call: it also orders "every warp is done with the buffer about to be refilled"
+  // before the refill.
+  int cbase = 0, clen = 0, cslot = 0;
+  unsigned cmask = 0u;
   auto next_needed = [&](int k) {
+    bool synced = false;
     for (;;) {
-      const int any = __syncthreads_or((k < ntiles && my_need(visit(k))) ? 1 : 0);
-      if (any || k >= ntiles) return k;
-      k++;
+      if (k >= ntiles) {
+        if (!synced) __syncthreads();
+        return ntiles;
+      }
+      if (k >= cbase + clen) {  // open the chunk that starts at visit k
+        const int len = min(ntiles - k, clen == 0 ? 2 : (clen == 2 ? 6 : 32));
+        unsigned m = 0u;
+        if (qok) {
+          const float bnd = __int_as_float(sbound[warp][lane]);
+          for (int j = 0; j < len; j++) {
+            const int t = visit(k + j);
+            const float4 lo4 = __ldg(&boxes[2 * t]), hi4 = __ldg(&boxes[2 * t + 1]);
+            if (tile_lb(qn, lo4, hi4) <= bnd) m |= 1u << j;
+          }
+        }
+        m = __reduce_or_sync(0xffffffffu, m);
+        if (lane == 0 && m) atomicOr(&s_need[cslot], m);
+        __syncthreads();
+        synced = true;
+        cmask = s_need[cslot];
+        cbase = k;
+        clen = len;
+        // the slot of the chunk after next is cleared now: its atomicOr's come after the NEXT chunk's barrier
+        if (threadIdx.x == 0) s_need[(cslot + 2) % 3] = 0u;
+        cslot = (cslot + 1) % 3;
+      }
+      const unsigned rem = cmask >> (k - cbase);
+      if (rem) {
+        if (!synced) __syncthreads();
+        return k + __ffs(rem) - 1;
+      }
+      k = cbase + clen;
     }
   };
   auto issue = [&](int t, int buf) {
@@ -514,7 +554,10 @@ __global__ void __launch_bounds__(NN_THREADS) k_feat_nn(const MatchDev* pairs, i
       }
       // most refined pairs do not beat the current best (near-duplicate descriptors): look before the atomic
       const unsigned long long cand = ((unsigned long long)__float_as_uint(d) << 32) | (unsigned)__float_as_int(y.w);  // slot 35
-      if (d < lim && cand < sbest[warp][ql]) atomicMin(&sbest[warp][ql], cand);
+      if (d < lim && cand < sbest[warp][ql]) {
+        atomicMin(&sbest[warp][ql], cand);
+        atomicMin(&sbound[warp][ql], __float_as_int(filt_bound(d)));
+      }
     }
     __syncwarp();
     // compact the rest of the queue to the front
@@ -555,7 +598,7 @@ __global__ void __launch_bounds__(NN_THREADS) k_feat_nn(const MatchDev* pairs, i
         const int ql = __ffs(mask) - 1;
         mask &= mask - 1;
         const float4 qv = sqn[warp][ql];  // broadcast
-        const float bound = filt_bound(fminf(lim, __uint_as_float((unsigned)(sbest[warp][ql] >> 32))));
+        const float bound = __int_as_float(sbound[warp][ql]);
         const bool p0 = ok0 && filt_lb(qv, bn0) <= bound;
         const bool p1 = ok1 && filt_lb(qv, bn1) <= bound;
         const unsigned m0 = __ballot_sync(0xffffffffu, p0), m1 = __ballot_sync(0xffffffffu, p1);
