@@ -405,4 +405,77 @@ __device__ __forceinline__ void radius_visit_warp(const CloudDev& c, bool active
   flush();
 }
 
+// The same warp-shared walk, with the hits of all 32 queries POOLED in one per-warp ring and processed 32 at a time by
+// whichever lane is free: f(owner_lane, position) runs for entry e on lane e.  For per-pair work whose result is
+// order-independent (integer histograms in shared memory) this keeps every lane busy -- with per-lane hit lists the
+// lockstep processing ran at 12.5 of 32 lanes (profiles/r02: the lanes of a warp fill at different rates).
+// on_hit(position) runs on the OWNER lane when the hit is found (cheap bookkeeping such as a neighbour count).
+// ring: RV_RING unsigned per warp.  Must be called by every thread of the warp; control flow is warp-uniform.
+constexpr int RV_RING = 64;
+template <typename H, typename F>
+__device__ __forceinline__ void radius_visit_warp_pooled(const CloudDev& c, bool active, float qx, float qy, float qz, float r2,
+                                                         unsigned* ring, int* wstack, H&& on_hit, F&& f) {
+  const float4* __restrict__ pts = c.pts;
+  const float4* __restrict__ tn = c.tnodes;
+  constexpr unsigned FULL = 0xffffffffu;
+  const int lane = threadIdx.x & 31;
+  const unsigned lt = (1u << lane) - 1u;
+  int sp = 0;
+  int ref = c.root_ref;
+  int head = 0, tail = 0;  // warp-uniform: entries [head, tail) of the ring are pending
+  auto process = [&](int take) {
+    if (lane < take) {
+      const unsigned e = ring[(head + lane) & (RV_RING - 1)];
+      f((int)(e & 31u), (int)(e >> 5));
+    }
+    head += take;
+    __syncwarp();
+  };
+  if (!__any_sync(FULL, active)) return;
+  for (;;) {
+    while (ref >= 0) {
+      const float4 a0 = __ldg(&tn[4 * ref]), a1 = __ldg(&tn[4 * ref + 1]);
+      const float4 b0 = __ldg(&tn[4 * ref + 2]), b1 = __ldg(&tn[4 * ref + 3]);
+      const bool in0 = __any_sync(FULL, active && box_dist2_rn(qx, qy, qz, a0, a1) < r2);
+      const bool in1 = __any_sync(FULL, active && box_dist2_rn(qx, qy, qz, b0, b1) < r2);
+      const int r0 = __float_as_int(a0.w), r1 = __float_as_int(b0.w);
+      if (in0 && in1) {
+        wstack[sp++] = r1;  // every lane writes the same value
+        ref = r0;
+      } else if (in0) {
+        ref = r0;
+      } else if (in1) {
+        ref = r1;
+      } else {
+        ref = 0x7FFFFFFF;  // dead end
+        break;
+      }
+    }
+    if (ref < 0) {
+      const int code = -1 - ref;
+      const int base = code >> 4, n = code & 15;
+      for (int j = 0; j < n; j++) {
+        const float4 p = __ldg(&pts[base + j]);
+        const bool hit = active && dist2_rn(qx, qy, qz, p.x, p.y, p.z) < r2;
+        const unsigned m = __ballot_sync(FULL, hit);
+        if (hit) {
+          ring[(tail + __popc(m & lt)) & (RV_RING - 1)] = ((unsigned)(base + j) << 5) | (unsigned)lane;
+          on_hit(base + j);
+        }
+        tail += __popc(m);
+        if (tail - head >= 32) {  // at most 31 + 32 pending: the ring never overflows
+          __syncwarp();
+          process(32);
+        }
+      }
+    }
+    if (sp == 0) break;
+    __syncwarp();  // the pushes of this round are visible to every lane ...
+    ref = wstack[--sp];
+    __syncwarp();  // ... and every lane has popped before the slot can be pushed again
+  }
+  __syncwarp();
+  if (tail > head) process(tail - head);
+}
+
 }  // namespace b200

@@ -98,33 +98,43 @@ __device__ __forceinline__ int bin11(float v) {
 }
 
 // ------------------------------------------------------------------------------------------------
-// Q2 SPFH: per-thread 33-bin integer histogram in shared memory (bin-major => conflict free)
+// Q2 SPFH: per-point 33-bin integer histogram in shared memory (bin-major: the column is the point's thread).  The
+// (point, neighbour) pairs of a warp are pooled and processed 32 at a time by whichever lane is free
+// (radius_visit_warp_pooled); the increments are integer shared-memory atomics, so the order does not matter.
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(STEP_THREADS) k_spfh(const CloudDev* clouds, float r2) {
   const CloudDev& c = clouds[blockIdx.y];
   const int i = blockIdx.x * STEP_THREADS + threadIdx.x;
   __shared__ unsigned int hist[FDIM][STEP_THREADS];  // 32-bit: an un-voxelised cloud can hold > 65535 neighbours in the radius
-  __shared__ int spos[RV_BUF * STEP_THREADS];
+  __shared__ float4 s_p[STEP_THREADS], s_n[STEP_THREADS];
+  __shared__ unsigned ring[STEP_THREADS / 32][RV_RING];
   __shared__ int wstack[STEP_THREADS / 32][MAX_STACK];
 #pragma unroll
   for (int k = 0; k < FDIM; k++) hist[k][threadIdx.x] = 0;
   const bool inrange = i < c.n;
   const float4 p = inrange ? c.pts[i] : make_float4(0.f, 0.f, 0.f, 0.f);
   const float4 np = inrange ? c.nrm[i] : make_float4(0.f, 0.f, 0.f, 0.f);
+  s_p[threadIdx.x] = p;
+  s_n[threadIdx.x] = np;
+  __syncwarp();
   int cnt = 0;
   const float d_pi = 1.0f / (2.0f * 3.14159265358979323846f);
-  radius_visit_warp<RV_BUF>(c, inrange && np.w != 0.f, p.x, p.y, p.z, r2, spos, nullptr, wstack[threadIdx.x >> 5], [&](int pos, float) {
-    cnt++;
-    if (pos == i) return;
-    const float4 nq = __ldg(&c.nrm[pos]);
-    if (nq.w == 0.f) return;
-    const float4 q = __ldg(&c.pts[pos]);
-    float f1, f2, f3;
-    if (!pair_features(p, np, q, nq, f1, f2, f3)) return;
-    hist[bin11(11.0f * ((f1 + 3.14159265358979323846f) * d_pi))][threadIdx.x]++;
-    hist[11 + bin11(11.0f * ((f2 + 1.0f) * 0.5f))][threadIdx.x]++;
-    hist[22 + bin11(11.0f * ((f3 + 1.0f) * 0.5f))][threadIdx.x]++;
-  });
+  const int wbase = threadIdx.x & ~31, ibase = blockIdx.x * STEP_THREADS + wbase;
+  radius_visit_warp_pooled(
+      c, inrange && np.w != 0.f, p.x, p.y, p.z, r2, ring[threadIdx.x >> 5], wstack[threadIdx.x >> 5], [&](int) { cnt++; },
+      [&](int owner, int pos) {
+        if (pos == ibase + owner) return;
+        const float4 nq = __ldg(&c.nrm[pos]);
+        if (nq.w == 0.f) return;
+        const float4 q = __ldg(&c.pts[pos]);
+        float f1, f2, f3;
+        if (!pair_features(s_p[wbase + owner], s_n[wbase + owner], q, nq, f1, f2, f3)) return;
+        const int col = wbase + owner;
+        atomicAdd(&hist[bin11(11.0f * ((f1 + 3.14159265358979323846f) * d_pi))][col], 1u);
+        atomicAdd(&hist[11 + bin11(11.0f * ((f2 + 1.0f) * 0.5f))][col], 1u);
+        atomicAdd(&hist[22 + bin11(11.0f * ((f3 + 1.0f) * 0.5f))][col], 1u);
+      });
+  __syncwarp();
   if (!inrange) return;
   float* out = c.spfh + (size_t)i * FPAD;
   const float incr = cnt >= 2 ? 100.0f / (float)(cnt - 1) : 0.f;
@@ -147,7 +157,6 @@ __global__ void __launch_bounds__(STEP_THREADS) k_fpfh(const CloudDev* clouds, f
   float h[FDIM];
 #pragma unroll
   for (int k = 0; k < FDIM; k++) h[k] = 0.f;
-  float s0 = 0.f, s1 = 0.f, s2 = 0.f;
   radius_visit_warp<RV_BUF_D2>(c, inrange && c.nrm[inrange ? i : 0].w != 0.f, p.x, p.y, p.z, r2, spos, sd2, wstack[threadIdx.x >> 5], [&](int pos, float d2) {
     if (d2 == 0.f) return;
     const float w = 1.0f / d2;
@@ -159,25 +168,18 @@ __global__ void __launch_bounds__(STEP_THREADS) k_fpfh(const CloudDev* clouds, f
       s[4 * k] = v.x; s[4 * k + 1] = v.y; s[4 * k + 2] = v.z; s[4 * k + 3] = v.w;
     }
 #pragma unroll
-    for (int k = 0; k < 11; k++) {
-      const float v = s[k] * w;
-      s0 += v;
-      h[k] += v;
-    }
-#pragma unroll
-    for (int k = 11; k < 22; k++) {
-      const float v = s[k] * w;
-      s1 += v;
-      h[k] += v;
-    }
-#pragma unroll
-    for (int k = 22; k < 33; k++) {
-      const float v = s[k] * w;
-      s2 += v;
-      h[k] += v;
-    }
+    for (int k = 0; k < FDIM; k++) h[k] += s[k] * w;
   });
   if (!inrange) return;
+  // block sums taken once at the end (the reference adds them up pair by pair; neither order is privileged, and the
+  // neighbour order already differs from the kd-tree's)
+  float s0 = 0.f, s1 = 0.f, s2 = 0.f;
+#pragma unroll
+  for (int k = 0; k < 11; k++) {
+    s0 += h[k];
+    s1 += h[11 + k];
+    s2 += h[22 + k];
+  }
   const float sc0 = s0 != 0.f ? 100.0f / s0 : 0.f, sc1 = s1 != 0.f ? 100.0f / s1 : 0.f, sc2 = s2 != 0.f ? 100.0f / s2 : 0.f;
   float* out = c.fpfh + (size_t)i * FPAD;
   bool any = false;
