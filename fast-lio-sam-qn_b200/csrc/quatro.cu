@@ -168,7 +168,7 @@ __global__ void __launch_bounds__(STEP_THREADS) k_fpfh(const CloudDev* clouds, f
       s[4 * k] = v.x; s[4 * k + 1] = v.y; s[4 * k + 2] = v.z; s[4 * k + 3] = v.w;
     }
 #pragma unroll
-    for (int k = 0; k < FDIM; k++) h[k] += s[k] * w;
+    for (int k = 0; k < FDIM; k++) h[k] = __fmaf_rn(s[k], w, h[k]);  // one rounding per term instead of two
   });
   if (!inrange) return;
   // block sums taken once at the end (the reference adds them up pair by pair; neither order is privileged, and the
