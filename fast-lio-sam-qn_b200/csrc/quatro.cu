@@ -360,14 +360,14 @@ __global__ void __launch_bounds__(NN_TILE) k_fgather(const CloudDev* clouds) {
 // filter test of one record: squared distance of the filter coordinates
 __device__ __forceinline__ float filt_lb(const float4& q, const float4& b) {
   const float e0 = q.x - b.x, e1 = q.y - b.y, e2 = q.z - b.z, e3 = q.w - b.w;
-  return ((e0 * e0 + e1 * e1) + e2 * e2) + e3 * e3;
+  return __fmaf_rn(e3, e3, __fmaf_rn(e2, e2, __fmaf_rn(e1, e1, e0 * e0)));  // a filter, not a parity-relevant value: fused
 }
 // lower bound of the filter's record test over every record of a tile: distance from the query's coordinates to the
 // tile's box.  Same operation order as the record test and rounding is monotone, so box_lb <= record lower bound.
 __device__ __forceinline__ float tile_lb(const float4& q, const float4& lo, const float4& hi) {
   const float e0 = fmaxf(fmaxf(lo.x - q.x, q.x - hi.x), 0.f), e1 = fmaxf(fmaxf(lo.y - q.y, q.y - hi.y), 0.f),
               e2 = fmaxf(fmaxf(lo.z - q.z, q.z - hi.z), 0.f), e3 = fmaxf(fmaxf(lo.w - q.w, q.w - hi.w), 0.f);
-  return ((e0 * e0 + e1 * e1) + e2 * e2) + e3 * e3;
+  return __fmaf_rn(e3, e3, __fmaf_rn(e2, e2, __fmaf_rn(e1, e1, e0 * e0)));
 }
 // acceptance threshold of the filter for a query whose best squared distance so far is `best`.  The filter value is a
 // true lower bound of the distance up to fp32 rounding of the coordinates (worst case 2.4e-3 in distance for |a - mu| <=
