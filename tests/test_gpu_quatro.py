@@ -210,3 +210,34 @@ def test_isolated_points_normals_descriptors_and_matching(ctx, oracle, synth):
     corr, mutual = oracle.match(src, dst2, fs, fd)
     assert info["n_mutual"] == len(mutual) and np.array_equal(info["corr"], corr)
     assert not np.isin(corr[:, 1], idx).any()
+
+
+@pytest.mark.parametrize("mode", ["optimized", "advanced"])
+def test_matching_with_runs_of_identical_descriptors(ctx, oracle, native, mode):
+    """Noise-free planes: thousands of points share ONE bitwise-identical descriptor (runs far longer than a 64-record
+    tile, runs cut by tile borders), next to a few hundred distinct ones.  The matcher collapses such runs to one base
+    record that answers with the run's lowest original index (k_fgather); the correspondences must still equal the
+    oracle's brute-force matcher on the same descriptors, order included."""
+    rng = np.random.default_rng(5)
+
+    def scene(shift):
+        g = np.stack(np.meshgrid(np.arange(70) * 0.3, np.arange(70) * 0.3, indexing="ij"), -1).reshape(-1, 2)
+        floor = np.c_[g, np.zeros(len(g))]
+        wall = np.c_[g[:, 0], np.full(len(g), 21.0), g[:, 1] * 0.5 + 0.3]
+        blob = rng.uniform(0, 1, (400, 3)) * [6.0, 6.0, 3.0] + [5.0, 8.0, 0.3]
+        pts = np.concatenate([floor, wall, blob]) + shift
+        return np.c_[pts, np.zeros(len(pts))].astype(np.float32)
+    src = scene(np.array([-10.0, -12.0, -1.5]))
+    dst = scene(np.array([-10.4, -11.7, -1.5]))[::-1].copy()  # other order: the lowest-index rule is exercised
+    prm = native.default_quatro_params()
+    prm.use_optimized_matching = 1 if mode == "optimized" else 0
+    info, fs, fd = _gpu_stage(ctx, src, dst, prm)
+    u = np.unique(fd[(fd != 0).any(1)], axis=0)
+    assert (fd != 0).any(1).sum() - len(u) > 2000, "the scene is meant to produce long runs of identical descriptors"
+    if mode == "optimized":
+        corr, mutual = oracle.match(src, dst, fs, fd)
+        assert info["n_mutual"] == len(mutual)
+    else:
+        corr = oracle.match_advanced(src, dst, fs, fd)
+    assert info["n_corr"] == len(corr)
+    assert np.array_equal(info["corr"], corr)
