@@ -401,7 +401,6 @@ __global__ void __launch_bounds__(NN_THREADS) k_feat_nn(const MatchDev* pairs, i
   if (q0 >= nq) return;
   __shared__ __align__(128) float tile[2][NN_TILE * FPAD];
   __shared__ __align__(16) float4 tnorm[2][NN_TILE];
-  __shared__ __align__(16) float sq[NN_THREADS / 32][32 * FPAD];
   __shared__ __align__(16) float4 sqn[NN_THREADS / 32][32];
   __shared__ unsigned long long sbest[NN_THREADS / 32][32];
   __shared__ int sbound[NN_THREADS / 32][32];  // filt_bound(best d2) as int bits (positive floats order like ints): atomicMin
@@ -419,14 +418,7 @@ __global__ void __launch_bounds__(NN_THREADS) k_feat_nn(const MatchDev* pairs, i
   {
     const bool inrange = qi < nq;
     const float4* q4 = reinterpret_cast<const float4*>(Q.fpfh_s + (size_t)(inrange ? qi : 0) * FPAD);
-    float4* d4 = reinterpret_cast<float4*>(&sq[warp][lane * FPAD]);
-    float4 last = make_float4(0.f, 0.f, 0.f, 0.f);
-#pragma unroll
-    for (int k = 0; k < 9; k++) {
-      const float4 v = inrange ? q4[k] : make_float4(0.f, 0.f, 0.f, 0.f);
-      d4[k] = v;
-      if (k == 8) last = v;
-    }
+    const float4 last = inrange ? q4[8] : make_float4(0.f, 0.f, 0.f, 0.f);  // slots 32..35
     qorig = __float_as_int(last.y);
     qok = inrange && last.z != 0.f;
     if (inrange) qn = Q.fproj_s[qi];
@@ -534,13 +526,14 @@ __global__ void __launch_bounds__(NN_THREADS) k_feat_nn(const MatchDev* pairs, i
     if (lane < take) {
       const unsigned e = queue[warp][lane];
       const int ql = e >> 8, r = e & 255;
-      const float4* a4 = reinterpret_cast<const float4*>(&sq[warp][ql * FPAD]);
+      // the query records stay in global memory (18 KB per block: L1-resident); shared memory is what limits the occupancy
+      const float4* a4 = reinterpret_cast<const float4*>(Q.fpfh_s + (size_t)min(nq - 1, q0 + warp * 32 + ql) * FPAD);
       const float4* b4 = reinterpret_cast<const float4*>(tb + r * FPAD);
       float d = 0.f;
       float4 x, y;
 #pragma unroll
       for (int k = 0; k < 8; k++) {
-        x = a4[k];
+        x = __ldg(&a4[k]);
         y = b4[k];
         float e0;
         e0 = x.x - y.x; d += e0 * e0;
@@ -548,7 +541,7 @@ __global__ void __launch_bounds__(NN_THREADS) k_feat_nn(const MatchDev* pairs, i
         e0 = x.z - y.z; d += e0 * e0;
         e0 = x.w - y.w; d += e0 * e0;
       }
-      x = a4[8];
+      x = __ldg(&a4[8]);
       y = b4[8];
       {
         const float e0 = x.x - y.x;
