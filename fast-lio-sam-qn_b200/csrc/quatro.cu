@@ -899,26 +899,24 @@ struct SolveSmem {
   int stop;
 };
 
+// block reductions in a fixed order: butterfly inside each warp, then over the SV_THREADS / 32 warp results (two
+// barriers per reduction; a shared-memory tree cost nine, and the GNC loop does six reductions per iteration)
 __device__ __forceinline__ double block_sum(SolveSmem& sm, double v) {
-  sm.red[threadIdx.x] = v;
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  __syncthreads();  // the previous reduction's readers are done with sm.red
+  if ((threadIdx.x & 31) == 0) sm.red[threadIdx.x >> 5] = v;
   __syncthreads();
-  for (int o = SV_THREADS / 2; o > 0; o >>= 1) {
-    if ((int)threadIdx.x < o) sm.red[threadIdx.x] += sm.red[threadIdx.x + o];
-    __syncthreads();
-  }
-  const double r = sm.red[0];
-  __syncthreads();
+  double r = (threadIdx.x & 31) < SV_THREADS / 32 ? sm.red[threadIdx.x & 31] : 0.0;
+  for (int o = 16; o > 0; o >>= 1) r += __shfl_xor_sync(0xffffffffu, r, o);
   return r;
 }
-__device__ __forceinline__ double block_max(SolveSmem& sm, double v) {
-  sm.red[threadIdx.x] = v;
+__device__ __forceinline__ double block_max(SolveSmem& sm, double v) {  // of non-negative values
+  for (int o = 16; o > 0; o >>= 1) v = fmax(v, __shfl_xor_sync(0xffffffffu, v, o));
   __syncthreads();
-  for (int o = SV_THREADS / 2; o > 0; o >>= 1) {
-    if ((int)threadIdx.x < o) sm.red[threadIdx.x] = fmax(sm.red[threadIdx.x], sm.red[threadIdx.x + o]);
-    __syncthreads();
-  }
-  const double r = sm.red[0];
+  if ((threadIdx.x & 31) == 0) sm.red[threadIdx.x >> 5] = v;
   __syncthreads();
+  double r = (threadIdx.x & 31) < SV_THREADS / 32 ? sm.red[threadIdx.x & 31] : 0.0;
+  for (int o = 16; o > 0; o >>= 1) r = fmax(r, __shfl_xor_sync(0xffffffffu, r, o));
   return r;
 }
 
@@ -1162,8 +1160,10 @@ __global__ void __launch_bounds__(SV_THREADS) k_teaser_solve(const MatchDev* pai
   __syncthreads();
   // translation: per-axis TLS adaptive voting over dst_i - R src_i on the clique members
   const double range = prm.noise_bound;
+  int sn = 2;  // sort size: the power of two that holds the 2m interval ends (not always 2 * MAXC)
+  while (sn < 2 * m) sn <<= 1;
   for (int d = 0; d < 3; d++) {
-    for (int k = tid; k < 2 * MAXC; k += SV_THREADS) {
+    for (int k = tid; k < sn; k += SV_THREADS) {
       sm.hval[k] = INFINITY;
       sm.hidx[k] = 0;
     }
@@ -1178,9 +1178,9 @@ __global__ void __launch_bounds__(SV_THREADS) k_teaser_solve(const MatchDev* pai
     }
     __syncthreads();
     // bitonic sort by (value, original slot) == std::stable_sort by value
-    for (int k = 2; k <= 2 * MAXC; k <<= 1)
+    for (int k = 2; k <= sn; k <<= 1)
       for (int j = k >> 1; j > 0; j >>= 1) {
-        for (int i = tid; i < 2 * MAXC; i += SV_THREADS) {
+        for (int i = tid; i < sn; i += SV_THREADS) {
           const int l = i ^ j;
           if (l > i) {
             const double a = sm.hval[i], b = sm.hval[l];
