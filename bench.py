@@ -62,6 +62,9 @@ def parse():
                          "3: 4639 / 4145, 4641 / 4144, 4591 / 4107 (stable); 4: 3856 / 4290 (four contexts over four rotating sub-batches "
                          "fall into lockstep); 5: 4653 / 4383, 4724 / 4372, but also 4066 / 4395 -- more contexts hide more of the uploads "
                          "yet can phase-lock on the device-resident arm, so the default stays at the stable 3")
+    ap.add_argument("--depth-e2e", type=int, default=int(os.environ.get("B200REG_PIPE_DEPTH_E2E", "5")),
+                    help="engine contexts of the batch driver of the from-host arm: it has uploads to hide, and the sweep above shows its "
+                         "throughput rising steadily with the depth (3811 / 4145 / 4290 / 4383) where the device-resident arm does not")
     ap.add_argument("--secondary", default="all", help="comma list of secondary workloads: voxel,raw,sequence,batch512 | all | none")
     ap.add_argument("--keyframes", type=int, default=2761, help="sequence workload: keyframes generated (KITTI 05: 2761)")
     ap.add_argument("--matching", default="optimized", choices=["optimized", "advanced"])
@@ -483,17 +486,24 @@ def main():
     pairs = gen_pairs(primary_seeds(), args.points)
     arena = Arena(pairs, JOB_PAIRS)
 
+    # the from-host arm runs on its own batch driver with more contexts (--depth-e2e): more uploads in flight
+    batch_h = batch if args.depth_e2e == args.depth else b200reg.Batch(local_rank, depth=args.depth_e2e)
+    runner_h = runner if batch_h is batch else Runner(batch_h, ctx, dist, stream, args.depth_e2e)
+
     def submit_icp(on_device):
-        return lambda j: batch.submit_icp(*arena.job(j + rank, on_device), prm)
+        b = batch if on_device else batch_h
+        return lambda j: b.submit_icp(*arena.job(j + rank, on_device), prm)
 
     sampler = ClockSampler(local_rank) if rank == 0 else None  # samples from the warm-up on: same load as the timed region
-    warm_jobs = max(args.warmup, 3) * max(DISTINCT_JOBS, 2 * args.depth)  # every context sees every sub-batch, both arms
+    # every context sees every sub-batch, both arms
     # (the warm-up includes the per-step gather: NCCL sets its channels up lazily on the first collective of a communicator)
-    runner.run(warm_jobs, submit_icp(True), max(DISTINCT_JOBS, 2 * args.depth), gather=world > 1)
-    runner.run(warm_jobs, submit_icp(False), max(DISTINCT_JOBS, 2 * args.depth), gather=world > 1)
+    for r_, dev_, depth_ in ((runner, True, args.depth), (runner_h, False, args.depth_e2e)):
+        r_.run(max(args.warmup, 3) * max(DISTINCT_JOBS, 2 * depth_), submit_icp(dev_), max(DISTINCT_JOBS, 2 * depth_), gather=world > 1)
     n_jobs = args.steps * JOBS_PER_STEP
     ms_dev, launches, res_dev, lat_dev, _ = runner.run(n_jobs, submit_icp(True), JOBS_PER_STEP, gather=world > 1)
-    ms_e2e, _, res_e2e, lat_e2e, _ = runner.run(n_jobs, submit_icp(False), JOBS_PER_STEP, gather=world > 1)
+    ms_e2e, _, res_e2e, lat_e2e, _ = runner_h.run(n_jobs, submit_icp(False), JOBS_PER_STEP, gather=world > 1)
+    if batch_h is not batch:
+        batch_h.close()
     clocks = sampler.stop() if sampler else None
 
     # one result per distinct pair (jobs 0..3 of the device arm), bit-identical across repeats and arms
@@ -527,8 +537,8 @@ def main():
             "warmup": args.warmup, "ms_per_step": ms_dev / args.steps, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32 points+kNN / f64 covariance+solver", "data": "synthetic",
             "config": cfg, "parallelism": parallelism,
-            "driver": "b200reg_batch (C ABI, csrc/batch.cu): %d engine contexts on C++ host threads, %d-pair jobs, at most %d jobs in flight"
-                      % (args.depth, JOB_PAIRS, 2 * args.depth),
+            "driver": "b200reg_batch (C ABI, csrc/batch.cu): %d engine contexts on C++ host threads, %d-pair jobs, at most %d jobs in flight "
+                      "(from-host arm: %d contexts, %d jobs in flight)" % (args.depth, JOB_PAIRS, 2 * args.depth, args.depth_e2e, 2 * args.depth_e2e),
             "timed_region_s": ms_dev * 1e-3,
             "e2e": {"value": total_pairs / (ms_e2e * 1e-3), "unit": UNIT, "ms_per_step": ms_e2e / args.steps,
                     "h2d_bytes_per_step": sum(arena.h2d_bytes(j) for j in range(JOBS_PER_STEP)),
@@ -544,7 +554,8 @@ def main():
             "clocks": clocks,
             "accuracy": accuracy,
             "job_latency_ms_under_load": {"device_resident": percentiles(lat_dev), "from_host": percentiles(lat_e2e),
-                                          "note": "submit -> completion of one 16-pair job with up to %d jobs in flight" % (2 * args.depth)},
+                                          "note": "submit -> completion of one 16-pair job with up to %d (device_resident) / %d (from_host) "
+                                                  "jobs in flight" % (2 * args.depth, 2 * args.depth_e2e)},
         }
 
     # ---- single-pair latency through ONE C-ABI call on an idle GPU (the reference's "ms per ICP" view) ---------------------
