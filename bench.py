@@ -123,6 +123,7 @@ class Arena:
 
     def __init__(self, pairs, per_job):
         import torch
+        rebind_cpus()
         self.pairs = pairs
         self.hs = [torch.from_numpy(np.ascontiguousarray(p[0])).pin_memory() for p in pairs]
         self.hd = [torch.from_numpy(np.ascontiguousarray(p[1])).pin_memory() for p in pairs]
@@ -146,6 +147,47 @@ class Arena:
 # ---------------------------------------------------------------------------------------------------------------------
 # host / clocks
 # ---------------------------------------------------------------------------------------------------------------------
+_ALL_CPUS = None
+_NEAR_CPUS = None
+
+
+def bind_near_gpu(dev):
+    """Run this rank's host threads (and so first-touch its pinned buffers) on the CPUs local to its GPU's PCIe root --
+    what `numactl --cpunodebind` does for a production rank.  Returns the cpulist string, None if the topology is not exposed."""
+    global _ALL_CPUS, _NEAR_CPUS
+    try:
+        import torch
+        p = torch.cuda.get_device_properties(dev)
+        bus = "%04x:%02x:%02x.0" % (p.pci_domain_id, p.pci_bus_id, p.pci_device_id)
+        with open("/sys/bus/pci/devices/%s/local_cpulist" % bus) as f:
+            txt = f.read().strip()
+        cpus = set()
+        for part in txt.split(","):
+            a, _, b = part.partition("-")
+            cpus.update(range(int(a), int(b or a) + 1))
+        cpus &= os.sched_getaffinity(0)
+        if not cpus:
+            return None
+        _ALL_CPUS = os.sched_getaffinity(0)
+        _NEAR_CPUS = cpus
+        os.sched_setaffinity(0, cpus)
+        return txt
+    except (OSError, ValueError, AttributeError, RuntimeError):
+        return None
+
+
+def unbind_cpus():
+    """The CPU baselines use every core of the box."""
+    if _ALL_CPUS:
+        os.sched_setaffinity(0, _ALL_CPUS)
+
+
+def rebind_cpus():
+    """Back next to the GPU after a CPU baseline (the batch driver's worker threads never left)."""
+    if _NEAR_CPUS:
+        os.sched_setaffinity(0, _NEAR_CPUS)
+
+
 def cpu_info():
     model = "unknown"
     try:
@@ -248,6 +290,7 @@ def peaks():
 # the CPU arm (oracle port; kNN through the reference's own nanoflann when oracle/_ref is built)
 # ---------------------------------------------------------------------------------------------------------------------
 def oracle_setup():
+    unbind_cpus()
     from oracle import oracle as orc
     orc.lib()
     used_ref = orc.use_ref_nanoflann(True) == 0
@@ -334,6 +377,7 @@ class Runner:
         step's result records over the context's communicator.  Returns (ms, launches, results per job, job latencies)."""
         import torch
         from b200reg import native
+        rebind_cpus()
         dist = self.dist
         if dist is not None:
             dist.barrier()
@@ -450,6 +494,7 @@ def main():
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device -- the b200 arm has no CPU fallback")
     torch.cuda.set_device(local_rank)
+    affinity = bind_near_gpu(local_rank)
     dist = None
     if world > 1:
         import torch.distributed as dist
@@ -539,7 +584,7 @@ def main():
             "config": cfg, "parallelism": parallelism,
             "driver": "b200reg_batch (C ABI, csrc/batch.cu): %d engine contexts on C++ host threads, %d-pair jobs, at most %d jobs in flight "
                       "(from-host arm: %d contexts, %d jobs in flight)" % (args.depth, JOB_PAIRS, 2 * args.depth, args.depth_e2e, 2 * args.depth_e2e),
-            "timed_region_s": ms_dev * 1e-3,
+            "timed_region_s": ms_dev * 1e-3, "host_affinity": affinity,
             "e2e": {"value": total_pairs / (ms_e2e * 1e-3), "unit": UNIT, "ms_per_step": ms_e2e / args.steps,
                     "h2d_bytes_per_step": sum(arena.h2d_bytes(j) for j in range(JOBS_PER_STEP)),
                     "d2h_bytes_per_step": JOB_PAIRS * JOBS_PER_STEP * res_bytes, "timed_region_s": ms_e2e * 1e-3},
