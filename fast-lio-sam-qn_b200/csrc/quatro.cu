@@ -6,7 +6,7 @@
 //   Q1 k_normals        pcl::NormalEstimation, radius 0.9, viewpoint (0,0,0)       third_party/Quatro/src/fpfh.cc:27-32
 //   Q2 k_spfh           FPFHEstimationOMP::computePointSPFHSignature                fpfh.cc:35-39
 //   Q3 k_fpfh           FPFHEstimationOMP::weightPointSPFHSignature                 fpfh.cc:35-39
-//      k_fcode / k_fgather               the matcher's view: descriptors in block-norm Morton order, boxed per 64-record tile
+//      k_fcode / k_fgather               the matcher's view: descriptors in filter-space Morton order, identical records collapsed, boxed per 64-record tile
 //   Q4 k_feat_nn        FLANN KDTreeSingleIndex exact 1-NN in 33-D (both directions) third_party/Quatro/src/matcher.cc:378-399, 597-636
 //      k_first_hit / k_mutual            gate + first-hit reverse search + mutual check   matcher.cc:412-455
 //      k_cloud_sum / k_cloud_scale       Matcher::normalizePoints                         matcher.cc:58-116
