@@ -278,6 +278,14 @@ def ncu_traffic(kernel_family, workload):
     return t.get(workload, {}).get(kernel_family)
 
 
+def traffic_fields(kernel_family, workload):
+    """-> (`roofline.traffic`: bytes per launch or None, the capture's details)."""
+    d = ncu_traffic(kernel_family, workload)
+    if not d:
+        return None, None
+    return d.get("dram_bytes_per_launch"), d
+
+
 def peaks():
     p = os.path.join(REPO, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -590,7 +598,9 @@ def main():
                     "d2h_bytes_per_step": JOB_PAIRS * JOBS_PER_STEP * res_bytes, "timed_region_s": ms_e2e * 1e-3},
             "gpu_launches": launches,
             "roofline": {"bound": "hbm", "kernel": fam, "achieved": achieved, "peak": peak, "unit": "GB/s",
-                         "frac": achieved / peak, "traffic": ncu_traffic(fam, "gicp"), "peak_source": peak_src,
+                         "frac": achieved / peak, "traffic": traffic_fields(fam, "gicp")[0], "traffic_unit": "bytes per launch",
+                         "traffic_capture": traffic_fields(fam, "gicp")[1], "algorithmic_bytes_per_launch": f["algo_bytes"] / max(1, f["launches"]),
+                         "peak_source": peak_src,
                          "note": "dominant KERNEL of the step (largest total CUDA-event time among the kernels / single-kernel families): "
                                  "algorithmic bytes per SURVEY.md §8(d) / its CUDA-event time on the launching stream, %d profiled 16-pair jobs "
                                  "on one context after the timed region; while profiling, the LM loop's three kernels are launched one by one "
