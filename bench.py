@@ -155,6 +155,8 @@ def bind_near_gpu(dev):
     """Run this rank's host threads (and so first-touch its pinned buffers) on the CPUs local to its GPU's PCIe root --
     what `numactl --cpunodebind` does for a production rank.  Returns the cpulist string, None if the topology is not exposed."""
     global _ALL_CPUS, _NEAR_CPUS
+    if os.environ.get("B200REG_BENCH_NO_AFFINITY"):
+        return None
     try:
         import torch
         p = torch.cuda.get_device_properties(dev)
@@ -550,10 +552,14 @@ def main():
     sampler = ClockSampler(local_rank) if rank == 0 else None  # samples from the warm-up on: same load as the timed region
     # every context sees every sub-batch, both arms
     # (the warm-up includes the per-step gather: NCCL sets its channels up lazily on the first collective of a communicator)
-    for r_, dev_, depth_ in ((runner, True, args.depth), (runner_h, False, args.depth_e2e)):
-        r_.run(max(args.warmup, 3) * max(DISTINCT_JOBS, 2 * depth_), submit_icp(dev_), max(DISTINCT_JOBS, 2 * depth_), gather=world > 1)
+    # Each arm: W (>= 3) full warm-up steps plus a fixed spin-up of SPIN_STEPS steps right before ITS timed region -- the
+    # first process on a fresh box measured 30 % low for about a second (page-ins, memory pools, host threads waking up).
+    SPIN_STEPS = 12
+    n_warm = (max(args.warmup, 3) + SPIN_STEPS) * JOBS_PER_STEP
     n_jobs = args.steps * JOBS_PER_STEP
+    runner.run(n_warm, submit_icp(True), JOBS_PER_STEP, gather=world > 1)
     ms_dev, launches, res_dev, lat_dev, _ = runner.run(n_jobs, submit_icp(True), JOBS_PER_STEP, gather=world > 1)
+    runner_h.run(n_warm, submit_icp(False), JOBS_PER_STEP, gather=world > 1)
     ms_e2e, _, res_e2e, lat_e2e, _ = runner_h.run(n_jobs, submit_icp(False), JOBS_PER_STEP, gather=world > 1)
     if batch_h is not batch:
         batch_h.close()
@@ -592,7 +598,7 @@ def main():
             "config": cfg, "parallelism": parallelism,
             "driver": "b200reg_batch (C ABI, csrc/batch.cu): %d engine contexts on C++ host threads, %d-pair jobs, at most %d jobs in flight "
                       "(from-host arm: %d contexts, %d jobs in flight)" % (args.depth, JOB_PAIRS, 2 * args.depth, args.depth_e2e, 2 * args.depth_e2e),
-            "timed_region_s": ms_dev * 1e-3, "host_affinity": affinity,
+            "timed_region_s": ms_dev * 1e-3, "host_affinity": affinity, "spin_up_steps_before_each_timed_region": SPIN_STEPS,
             "e2e": {"value": total_pairs / (ms_e2e * 1e-3), "unit": UNIT, "ms_per_step": ms_e2e / args.steps,
                     "h2d_bytes_per_step": sum(arena.h2d_bytes(j) for j in range(JOBS_PER_STEP)),
                     "d2h_bytes_per_step": JOB_PAIRS * JOBS_PER_STEP * res_bytes, "timed_region_s": ms_e2e * 1e-3},
