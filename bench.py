@@ -782,9 +782,18 @@ def bench_sequence(args, ctx, stream):
         step(i, False)
     steps = len(batches)  # every candidate of the sequence exactly once
     ms_dev, launches, nvalid = timed(False, steps)
-    for i in range(3):  # the ingest path warms up too (the store's memory pool grows on the first appended keyframes)
+    # the ingest path warms up too: the keyframe memory comes out of the context's pool, which a long-running node has grown
+    # long before its 2761st keyframe (here: a scratch store of as many keyframes as the timed region appends, released again),
+    # then spin-up steps as for the headline (a fresh box answers slowly for its first second)
+    e2e_steps = min(steps, 48)
+    tmp = ctx.keyframes()
+    for j in range(B * (e2e_steps + 24)):
+        tmp.add(pinned[j % len(pinned)].numpy(), seq["poses"][0], 0.0)
+    ctx.synchronize()
+    tmp.destroy()
+    for i in range(20):
         step(i, True)
-    ms_e2e, _, _ = timed(True, min(steps, 16))
+    ms_e2e, _, _ = timed(True, e2e_steps)
     prof = profile_families(ctx, lambda i: step(i, False), min(4, steps))
     res = {"metric": "loop_closure_attempts_per_sec_kitti05_shaped_sequence", "unit": UNIT,
            "workload": "configs[4]: loopTimerFunc over a synthetic KITTI-05-shaped sequence of %d keyframes x %dk points kept on the device: "
@@ -792,7 +801,7 @@ def bench_sequence(args, ctx, stream):
                        "loop candidate, %d per call" % (args.keyframes, pts // 1000, B),
            "keyframes": args.keyframes, "candidates": int(len(cand)), "attempts_timed": B * steps, "valid_loops": int(nvalid),
            "value": B * steps / (ms_dev * 1e-3), "timed_region_s": ms_dev * 1e-3, "ms_per_attempt": ms_dev / (B * steps),
-           "e2e": {"value": B * min(steps, 16) / (ms_e2e * 1e-3), "unit": UNIT, "h2d_bytes_per_call": B * pts * 16,
+           "e2e": {"value": B * e2e_steps / (ms_e2e * 1e-3), "unit": UNIT, "calls_timed": e2e_steps, "h2d_bytes_per_call": B * pts * 16,
                    "d2h_bytes_per_call": B * ctypes.sizeof(b200reg.Result),
                    "note": "the 16 query keyframes of every call are ingested from pinned host memory first"},
            "gpu_launches": launches, "kernels": family_table(prof, min(4, steps))}
