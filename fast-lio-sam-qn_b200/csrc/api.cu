@@ -220,6 +220,7 @@ static int lm_arena_ensure(b200reg_ctx* c, int count) {
     const int cap = std::max(16, count + count / 2);
     CU(cudaMalloc(&a.d_pairs, sizeof(PairDev) * cap));
     CU(cudaMalloc(&a.d_states, sizeof(PairState) * cap));
+    CU(cudaMemsetAsync(a.d_states, 0, sizeof(PairState) * cap, c->stream));  // the records travel to the host whole: no stale bytes
     CU(cudaMalloc((void**)&a.d_sched, 64 + sizeof(LmSlot) * (size_t)cap));
     CU(cudaMalloc(&a.d_guess, sizeof(double) * 16 * cap));
     CU(cudaMalloc(&a.d_call, sizeof(LmCall)));
@@ -613,6 +614,7 @@ static int make_pair_work(b200reg_ctx* c, int count, b200reg_cloud* const* src, 
   if (!own_arrays) return B200REG_OK;  // b200reg_gicp_align: the argument arrays live in the context's LM arena
   CU(scratch.alloc((void**)&w.d_pairs, sizeof(PairDev) * count));
   CU(scratch.alloc((void**)&w.d_states, sizeof(PairState) * count));
+  CU(cudaMemsetAsync(w.d_states, 0, sizeof(PairState) * count, c->stream));
   CU(scratch.alloc((void**)&w.d_call, sizeof(LmCall)));
   memset(&w.call_host, 0, sizeof(LmCall));
   w.call_host.count = count;

@@ -274,6 +274,7 @@ __global__ void __launch_bounds__(256) k_gicp_init(const PairDev* pairs, PairSta
     st->n_err = 0;
     st->nr_iterations = 0;
     st->arrive = 0;
+    st->pad = 0;
     if (prm.max_iterations <= 0) lm_finish(st, 0);
   }
   if (threadIdx.x == 0) {
