@@ -168,7 +168,7 @@ def bind_near_gpu(dev):
             a, _, b = part.partition("-")
             cpus.update(range(int(a), int(b or a) + 1))
         cpus &= os.sched_getaffinity(0)
-        if not cpus:
+        if len(cpus) < 16:  # a cpuset that leaves only a few local CPUs: the remote socket is the better place
             return None
         _ALL_CPUS = os.sched_getaffinity(0)
         _NEAR_CPUS = cpus
