@@ -384,7 +384,8 @@ __device__ __forceinline__ float filt_bound(float best) {
 //  * A block starts at the base tile nearest to its own queries (binary search of the code) and sweeps up, then down:
 //    good matches are found in the first tiles and the bound is tight from then on.
 //  * Per tile: every lane tests ITS query against the tile box (one test instead of 64); tiles nobody in the block
-//    needs are not even fetched (__syncthreads_or), tiles are fetched by cp.async.bulk (TMA) one ahead.
+//    needs are not even fetched (block-wide OR of per-thread need masks, taken per chunk of visits), tiles are fetched
+//    by cp.async.bulk (TMA) one ahead.
 //  * Per (needed query, tile): the 32 lanes test 32+32 records against the projected lower bound
 //    sum_i (u_i.(a - b))^2 + (|r_a| - |r_b|)^2 <= |a - b|^2 (fpfh_basis.cuh), ballot-compact the survivors into a
 //    per-warp queue, and refine 32 queued pairs at a time with the full fp32 distance in the oracle's operation order.
