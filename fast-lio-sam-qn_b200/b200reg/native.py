@@ -73,7 +73,7 @@ EXPORTS = [
     "b200reg_get_covariances", "b200reg_linearize", "b200reg_ctx_set_profiling", "b200reg_ctx_reset_profile",
     "b200reg_ctx_get_profile", "b200reg_default_quatro_params", "b200reg_clouds_fpfh", "b200reg_get_fpfh",
     "b200reg_quatro_align", "b200reg_loop_closure", "b200reg_default_loop_config", "b200reg_keyframes_create",
-    "b200reg_keyframes_destroy", "b200reg_keyframes_add", "b200reg_keyframes_set_pose", "b200reg_keyframes_size",
+    "b200reg_keyframes_destroy", "b200reg_keyframes_reserve", "b200reg_keyframes_add", "b200reg_keyframes_set_pose", "b200reg_keyframes_size",
     "b200reg_knn_bruteforce", "b200reg_fetch_closest_keyframes", "b200reg_assemble_clouds", "b200reg_cloud_points", "b200reg_perform_loop_closure",
     "b200reg_loop_factor_from_poses", "b200reg_loop_factors", "b200reg_compute_error", "b200reg_assemble_clouds_at",
     "b200reg_struct_size", "b200reg_set_last_error", "b200reg_set_covariances",
@@ -500,6 +500,10 @@ class Keyframes:
 
     def __len__(self):
         return int(lib().b200reg_keyframes_size(self.h))
+
+    def reserve(self, n_points):
+        """Device room for n_points more points, allocated now (adds allocate nothing until it is used up)."""
+        _check(lib().b200reg_keyframes_reserve(self.ctx.h, self.h, C.c_size_t(int(n_points))))
 
     def add(self, cloud_xyzi, pose, stamp):
         a = np.ascontiguousarray(cloud_xyzi, np.float32)

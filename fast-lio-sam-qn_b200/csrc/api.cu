@@ -1514,12 +1514,36 @@ int b200reg_allgather_results(b200reg_ctx* c, const b200reg_result* local, int n
 }
 
 // ---- "next" rows: keyframe store, candidate search, cloud assembly ----------------------------
+// Keyframe clouds live in SLABS of their own (plain cudaMalloc, never the context's stream-ordered pool): a store only
+// grows, while every registration call takes and returns hundreds of MB of scratch from the pool; 480 KB keyframes carved
+// out of the pool's free scratch blocks between two calls fragmented it, and the pool then grew by a fresh block in almost
+// every call (tens of ms each: profiles/diag_sequence_e2e.py measured 5.4 -> 11 ... 37 ms per 16-attempt step).
+struct KfSlab {
+  float4* base = nullptr;
+  size_t cap = 0, used = 0;  // points
+};
 struct b200reg_keyframes {
   std::vector<float4*> pts;
   std::vector<int> n;
   std::vector<double> poses;   // 16 per keyframe, row-major
   std::vector<double> stamps;
+  std::vector<KfSlab> slabs;
 };
+constexpr size_t KF_SLAB_POINTS = (size_t)8 << 20;  // 8 Mi points = 128 MB per slab unless reserved otherwise
+
+// room for n more points: the tail of the last slab, else a new slab (cudaMalloc: a rare, synchronous event)
+static int kf_alloc(b200reg_keyframes* kf, size_t n, size_t min_slab, float4** out) {
+  if (kf->slabs.empty() || kf->slabs.back().cap - kf->slabs.back().used < n) {
+    KfSlab sl;
+    sl.cap = std::max(n, min_slab);
+    CU(cudaMalloc((void**)&sl.base, sl.cap * sizeof(float4)));
+    kf->slabs.push_back(sl);
+  }
+  KfSlab& sl = kf->slabs.back();
+  *out = sl.base + sl.used;
+  sl.used += n;
+  return B200REG_OK;
+}
 
 void b200reg_default_loop_config(b200reg_loop_config* cfg) {
   if (!cfg) return;
@@ -1544,8 +1568,21 @@ int b200reg_keyframes_destroy(b200reg_ctx* c, b200reg_keyframes* kf) {
   if (!kf) return B200REG_OK;
   if (!c) return fail(B200REG_EINVAL, "ctx is NULL");
   CU(cudaSetDevice(c->device));
-  for (float4* p : kf->pts) CU(cudaFreeAsync(p, c->stream));
+  CU(cudaStreamSynchronize(c->stream));  // nothing in flight may still read a keyframe
+  for (KfSlab& sl : kf->slabs) CU(cudaFree(sl.base));
   delete kf;
+  return B200REG_OK;
+}
+
+int b200reg_keyframes_reserve(b200reg_ctx* c, b200reg_keyframes* kf, size_t n_points) {
+  if (!c || !kf) return fail(B200REG_EINVAL, "bad argument");
+  CU(cudaSetDevice(c->device));
+  if (!kf->slabs.empty() && kf->slabs.back().cap - kf->slabs.back().used >= n_points) return B200REG_OK;
+  if (n_points == 0) return B200REG_OK;
+  KfSlab sl;
+  sl.cap = n_points;
+  CU(cudaMalloc((void**)&sl.base, sl.cap * sizeof(float4)));
+  kf->slabs.push_back(sl);
   return B200REG_OK;
 }
 
@@ -1556,7 +1593,10 @@ int b200reg_keyframes_add(b200reg_ctx* c, b200reg_keyframes* kf, const float* xy
   if (!c || !kf || !xyzi || n == 0 || !pose16 || stride_bytes < 16 || stride_bytes % 4) return fail(B200REG_EINVAL, "bad argument");
   CU(cudaSetDevice(c->device));
   float4* d = nullptr;
-  CU(cudaMallocFromPoolAsync((void**)&d, n * 16, c->pool, c->stream));
+  {
+    const int rc = kf_alloc(kf, n, KF_SLAB_POINTS, &d);
+    if (rc) return rc;
+  }
   if (stride_bytes == 16) {  // already packed (x, y, z, intensity): one linear copy (a 2-D copy of n 16-byte rows crawls)
     CU(cudaMemcpyAsync(d, xyzi, n * 16, cudaMemcpyHostToDevice, c->stream));
   } else {  // pcl::PointXYZI (32 B) and friends: upload the records as they are, repack on the device
@@ -1624,7 +1664,10 @@ int b200reg_keyframes_add_world(b200reg_ctx* c, b200reg_keyframes* kf, const flo
   float4* d_out = nullptr;
   CU(scratch.alloc((void**)&d_raw, n * stride_bytes));
   CU(scratch.alloc((void**)&d_T, 128));
-  CU(cudaMallocFromPoolAsync((void**)&d_out, n * 16, c->pool, s));
+  {
+    const int rc = kf_alloc(kf, n, KF_SLAB_POINTS, &d_out);
+    if (rc) return rc;
+  }
   CU(cudaMemcpyAsync(d_raw, xyzi_world, n * stride_bytes, cudaMemcpyHostToDevice, s));
   CU(cudaMemcpyAsync(d_T, Tinv, 128, cudaMemcpyHostToDevice, s));
   launch_ingest_world(d_raw, (int)(stride_bytes / 4), (int)n, d_T, d_out, s);

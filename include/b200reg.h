@@ -216,6 +216,10 @@ void b200reg_default_loop_config(b200reg_loop_config* cfg);
 
 int b200reg_keyframes_create(b200reg_ctx* ctx, b200reg_keyframes** out);
 int b200reg_keyframes_destroy(b200reg_ctx* ctx, b200reg_keyframes* kf);
+/* Keyframe clouds are kept in device slabs of their own (128 MB unless reserved), apart from the context's scratch pool.
+ * A node that knows roughly how many points its map will hold reserves them once at start (std::vector::reserve for
+ * keyframes_, fast_lio_sam_qn.h:63): no keyframe added afterwards allocates until the reservation is used up.        */
+int b200reg_keyframes_reserve(b200reg_ctx* ctx, b200reg_keyframes* kf, size_t n_points);
 /* PosePcd (fast_lio_sam_qn/include/pose_pcd.hpp:7-43): cloud in the LiDAR frame as fp32 records `stride_bytes` apart (host
  * memory): packed (x, y, z, intensity) for strides below 32 bytes, the pcl::PointXYZI layout (x, y, z, 1, intensity, pad...)
  * from 32 bytes on; its corrected pose (row-major 4x4) and timestamp.  Returns the index.                          */

@@ -165,3 +165,20 @@ def test_pose_pcd_ingest_matches_oracle(ctx, oracle, synth, seq):
         worst = max(worst, np.abs(got[:, :3] - lidar[:, :3]).max())
     assert worst < 2e-5  # back in the LiDAR frame: the original scan up to the float round trip through the world frame
     kf.destroy()
+
+
+def test_keyframe_store_slabs_and_reserve(ctx, synth):
+    """Keyframes live in slabs apart from the scratch pool: a reservation that runs out rolls over to a new slab, and
+    every keyframe reads back exactly as it was added, before and after registration calls used the scratch pool."""
+    seq = synth.make_sequence(3, 9, pts_per_keyframe=4000, spacing=5.0)
+    kf = ctx.keyframes()
+    kf.reserve(2 * 4000 + 100)  # room for two keyframes and a bit: the third one opens a new slab
+    for c, T, t in zip(seq["clouds"], seq["poses"], seq["stamps"]):
+        kf.add(c, T, t)
+    kf.reserve(0)
+    q = np.array([8], np.int32)
+    kf.perform_loop_closure(q, np.array([0], np.int32))
+    for i, (c, T, t) in enumerate(zip(seq["clouds"], seq["poses"], seq["stamps"])):
+        pts, pose, ts = kf.get(i)
+        assert np.array_equal(pts, c[:, :4].astype(np.float32)) and np.array_equal(pose, T) and ts == t
+    kf.destroy()
