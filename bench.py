@@ -601,7 +601,8 @@ def main():
             "config": cfg, "parallelism": parallelism,
             "driver": "b200reg_batch (C ABI, csrc/batch.cu): %d engine contexts on C++ host threads, %d-pair jobs, at most %d jobs in flight "
                       "(from-host arm: %d contexts, %d jobs in flight)" % (args.depth, JOB_PAIRS, 2 * args.depth, args.depth_e2e, 2 * args.depth_e2e),
-            "timed_region_s": ms_dev * 1e-3, "host_affinity": affinity, "spin_up_steps_before_each_timed_region": SPIN_STEPS,
+            "timed_region_s": ms_dev * 1e-3, "host_affinity": affinity,
+            "lm_as_cuda_graph": not os.environ.get("B200REG_LM_NO_GRAPH"), "retried_after_failure": bool(os.environ.get("B200REG_BENCH_RETRIED")), "spin_up_steps_before_each_timed_region": SPIN_STEPS,
             "e2e": {"value": total_pairs / (ms_e2e * 1e-3), "unit": UNIT, "ms_per_step": ms_e2e / args.steps,
                     "h2d_bytes_per_step": sum(arena.h2d_bytes(j) for j in range(JOBS_PER_STEP)),
                     "d2h_bytes_per_step": JOB_PAIRS * JOBS_PER_STEP * res_bytes, "timed_region_s": ms_e2e * 1e-3},
@@ -922,7 +923,9 @@ if __name__ == "__main__":
         if (not isinstance(e, SystemExit) and os.environ.get("WORLD_SIZE", "1") == "1" and not os.environ.get("B200REG_BENCH_RETRIED")
                 and "--impl" not in " ".join(sys.argv[1:]).replace("--impl b200", "")):
             os.environ["B200REG_BENCH_RETRIED"] = "1"
-            sys.stderr.write("bench.py: the run failed before its JSON line was printed -- retrying ONCE in a fresh process\n")
+            os.environ["B200REG_LM_NO_GRAPH"] = "1"  # the retry launches the LM kernels one by one (no conditional graph nodes)
+            sys.stderr.write("bench.py: the run failed before its JSON line was printed -- retrying ONCE in a fresh process, "
+                             "without the LM graph\n")
             sys.stderr.flush()
             os.execv(sys.executable, [sys.executable] + sys.argv)
         # a rank that fails must not linger in destructors that wait for its peers (communicator teardown): exit hard, the
