@@ -67,7 +67,10 @@ def parse():
                          "It has uploads to hide and rises steadily with the depth (3811 / 4145 / 4290 / 4383 pairs/s at 2 / 3 / 4 / 5; 4420-4434 "
                          "measured at 5 over ~30 runs), but ONE of those runs ended in a CUDA 'illegal memory access' that could not be "
                          "reproduced or explained (profiles/README.md), so the default stays with the configuration that has never failed")
-    ap.add_argument("--depth-lc", type=int, default=6, help="engine contexts of the batch driver of the loop-closure secondaries")
+    ap.add_argument("--depth-lc", type=int, default=3,
+                    help="engine contexts of the batch driver of the loop-closure secondaries (default: the headline's driver; the coarse "
+                         "stage has latency-bound kernels and gains from more contexts in flight -- 4613 / 4745 / 4810 / 4870 pairs/s on the "
+                         "voxelised workload at 3 / 5 / 6 / 8 -- but see --depth-e2e for why the defaults stay at 3)")
     ap.add_argument("--secondary", default="all", help="comma list of secondary workloads: voxel,raw,sequence,batch512 | all | none")
     ap.add_argument("--keyframes", type=int, default=2761, help="sequence workload: keyframes generated (KITTI 05: 2761)")
     ap.add_argument("--matching", default="optimized", choices=["optimized", "advanced"])
@@ -688,17 +691,16 @@ def run_secondaries(args, sec, secondary, world, rank, local_rank, runner, batch
     import b200reg
     if world == 1:
         if "voxel" in sec or "raw" in sec:
-            # the coarse stage has latency-bound kernels (one CTA per pair in the solver): more contexts in flight fill the
-            # GPU better than the headline's three (measured on the voxelised workload: 4613 / 4745 / 4870 pairs/s at 3 / 5 / 8)
-            batch_lc = b200reg.Batch(local_rank, depth=args.depth_lc)
-            runner_lc = Runner(batch_lc, ctx, dist, stream, args.depth_lc)
+            own = args.depth_lc != args.depth
+            batch_lc = b200reg.Batch(local_rank, depth=args.depth_lc) if own else batch
+            runner_lc = Runner(batch_lc, ctx, dist, stream, args.depth_lc) if own else runner
         if "voxel" in sec:
             secondary["loop_closure_voxelised"] = bench_loop_closure(args, runner_lc, batch_lc, ctx, qprm, prm, voxel=0.3, n_pairs=64,
                                                                      per_job=16, jobs=192, cpu_pairs=3)
         if "raw" in sec:
             secondary["loop_closure_raw_100k"] = bench_loop_closure(args, runner_lc, batch_lc, ctx, qprm, prm, voxel=None, n_pairs=8, per_job=4,
                                                                     jobs=16, cpu_pairs=1)
-        if "voxel" in sec or "raw" in sec:
+        if ("voxel" in sec or "raw" in sec) and own:
             batch_lc.close()
         if "sequence" in sec:
             secondary["sequence_kitti05_shaped"] = bench_sequence(args, ctx, stream)
